@@ -1,0 +1,158 @@
+/* hdsm.h - C ABI of the B200 (sm_100a) batched trajectory-optimisation library.
+ *
+ * Drop-in boundary for ONE hot path of lis-epfl/multi_agent_pkgs: the per-agent receding-horizon
+ * trajectory optimisation of multi_agent_planner.  The reference has no plugin / FFI interface for
+ * it - the solver is three private member functions of class Agent plus private Gurobi members
+ * (multi_agent_planner/include/agent_class.hpp:63-70, 100-104, 407-432) - so the seam is defined
+ * here, one entry point per reference call site:
+ *
+ *   hdsm_create              replaces  Agent::InitializeGurobi + Agent::CreateGurobiModel +
+ *                                      Agent::InitializePlannerParameters
+ *                                      (agent_class.cpp:2063-2069, :2071-2153, :2169-2188)
+ *   hdsm_solve_batch         replaces  Agent::GenerateTimeAwareSafeCorridor (:1086-1215) followed by
+ *                                      Agent::SolveOptimizationProblem (:858-1023), i.e. the two
+ *                                      calls at agent_class.cpp:168 and :174, incl. GRBModel::optimize (:959)
+ *   hdsm_solve_batch_device  same, device pointers, stream ordered (synthetic-swarm harness)
+ *   hdsm_comm_* / hdsm_allgather_positions
+ *                            replaces  the ROS2 broadcast of Trajectory messages between agents
+ *                                      (publisher :645-677, subscriber :629-643) inside the harness
+ *   hdsm_destroy             replaces  ~GRBModel / ~GRBEnv (members at agent_class.hpp:409-410)
+ *
+ * Conventions: plain pointers and sizes, row-major contiguous arrays, IEEE double like the
+ * reference (decomp_basis/data_type.h:50).  No exceptions cross the ABI: every function returns
+ * HDSM_OK or a negative error code (hdsm_last_error gives text); per-agent solver outcomes are in
+ * hdsm_result.status and the caller keeps the reference's fallback (:997-1019) for anything
+ * that is not HDSM_OPTIMAL / HDSM_NODE_LIMIT-with-incumbent.  The library keeps no pointer after
+ * a call returns.  One handle per calling thread; calls on one handle are not re-entrant.
+ * There is no CPU fallback: without a CUDA device hdsm_create fails.
+ */
+#ifndef HDSM_H_
+#define HDSM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDSM_VERSION 100
+
+/* library return codes */
+#define HDSM_OK 0
+#define HDSM_ERR_INVALID (-1)   /* bad argument / unsupported parameter value */
+#define HDSM_ERR_CUDA (-2)      /* CUDA runtime error, see hdsm_last_error */
+#define HDSM_ERR_CAPACITY (-3)  /* n_local / n_rob exceed what the handle was created for */
+#define HDSM_ERR_NCCL (-4)      /* NCCL missing or failed */
+
+/* per-agent solver status (hdsm_result.status) */
+#define HDSM_OPTIMAL 0       /* optimum of the mixed-integer problem proven */
+#define HDSM_INFEASIBLE 1    /* no assignment of polytopes admits a trajectory (GRB infeasible -> :988) */
+#define HDSM_MAX_ITER 2      /* interior point hit max_iter without converging */
+#define HDSM_NUMERICAL 3     /* factorisation broke down / non-finite iterate / degenerate plane */
+#define HDSM_NODE_LIMIT 4    /* search stopped at max_nodes; traj holds the incumbent if obj is finite
+                                (the reference accepts a TimeLimit incumbent the same way, :952-987) */
+#define HDSM_ROW_OVERFLOW 5  /* more active constraint rows than the handle's shared-memory budget */
+
+#define HDSM_MAX_HOR 12
+#define HDSM_MAX_POLY 8
+
+/* POD mirror of the ROS parameters that enter the optimisation (agent_class.cpp:2190-2248;
+ * values e.g. multi_agent_planner/config/agent_agile_config.yaml). */
+typedef struct hdsm_params {
+  int32_t n_hor;             /* n_hor: horizon N, 3..HDSM_MAX_HOR (n_x = 9, n_u = 3 fixed: ModelODE :2155) */
+  int32_t poly_hor;          /* poly_hor: polytopes per step P, 1..HDSM_MAX_POLY */
+  int32_t max_rows_per_poly; /* row stride Rmax of poly_A / poly_b, <= 32 */
+  int32_t rk4;               /* rk4: 0 = Euler (:2140-2151), 1 = RK4 (:2123-2139) */
+  int32_t max_iter;          /* interior-point iterations per QP (0 -> 60) */
+  int32_t max_nodes;         /* branch-and-bound nodes per agent (0 -> 64); plays the role of TimeLimit */
+  int32_t prune;             /* 1 = drop rows that can never be active inside the reachable box (exact) */
+  int32_t reserved;
+  double dt;                 /* dt */
+  double drag[3];            /* drag_coeff */
+  double r_u;                /* r_u  (:2098) */
+  double r_x[6];             /* r_x[0..5] (:878-881; acceleration weights are never applied) */
+  double r_n[6];             /* r_n[0..5] (:873-876) */
+  double max_vel;            /* :2181-2184 */
+  double min_acc_xy, max_acc_xy, min_acc_z, max_acc_z;
+  double max_jerk;           /* :2185-2186 */
+  double drone_radius;       /* :1161-1163 */
+  double drone_z_offset;
+  double tilt;               /* var_tmp = 0.1 (:1180) */
+  double tol;                /* KKT tolerance of a QP solve (0 -> 1e-8) */
+} hdsm_params;
+
+typedef struct hdsm_result {
+  int32_t status; /* HDSM_OPTIMAL ... */
+  int32_t iters;  /* interior-point iterations summed over nodes */
+  int32_t nodes;  /* QP relaxations solved */
+  int32_t rows;   /* largest number of position rows handed to one QP (after pruning) */
+  double obj;     /* objective incl. the constant ref^2 terms, comparable with Gurobi ObjVal */
+  double kkt_res; /* max scaled KKT residual of the returned solution */
+} hdsm_result;
+
+typedef struct hdsm_handle hdsm_handle;
+
+int hdsm_version(void);
+
+/* max_agents: largest n_local of a later call.  max_neighbours: largest number of neighbour
+ * candidates (nbr_end - nbr_begin, or n_rob) of a later call; sizes the per-block row buffers. */
+int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, int device, hdsm_handle** out);
+void hdsm_destroy(hdsm_handle* h);
+const char* hdsm_last_error(const hdsm_handle* h);
+
+/* One replanning step for n_local agents; HOST pointers; synchronous.
+ *
+ *  global_id     [n_local]            index of each agent in all_pos (own slot is skipped like the
+ *                                     empty own entry of traj_other_agents_, :1132-1134)
+ *  nbr_begin/end [n_local] or NULL    neighbour candidates = all_pos[nbr_begin, nbr_end) (NULL: 0..n_rob)
+ *  x0            [n_local][9]         state_curr_ (:886-889)  (px py pz vx vy vz ax ay az)
+ *  ref           [n_local][N][6]      traj_ref_curr_[0..N-1], pos+vel (:871-883)
+ *  poly_A        [n_local][P][Rmax][3]  poly_const_vec_: A x <= b rows (polyhedron.h:98-147)
+ *  poly_b        [n_local][P][Rmax]
+ *  poly_rows     [n_local][P]         rows per polytope, 0 = absent (P_eff = leading non-zero count, :913)
+ *  prev_self_pos [n_local][N+1][3]    own previous plan positions traj_curr_[k][0..2] (:1103-1110);
+ *                                     state_ini_ repeated before the first solve
+ *  all_pos       [n_rob][N+1][3]      last received plans of all agents (states[k].position, :1147-1149)
+ *  all_valid     [n_rob]              plan received? (traj.states.size() != 0, :1134)
+ *  assign_in     [n_local][N] or NULL per-step polytope index to force, -1 = search
+ *  traj          [n_local][N+1][9]    traj_curr_ (:962-973)
+ *  ctrl          [n_local][N][3]      control_curr_ (:975-978)
+ *  poly_used     [n_local][P]         poly_used_idx_ (:981-985)
+ *  assign_out    [n_local][N]         polytope chosen per step (the binaries b[k][p])
+ *  res           [n_local]
+ */
+int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
+                     const int32_t* nbr_end, const double* x0, const double* ref, const double* poly_A,
+                     const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,
+                     const double* all_pos, const uint8_t* all_valid, int n_rob, const int32_t* assign_in,
+                     double* traj, double* ctrl, uint8_t* poly_used, int32_t* assign_out, hdsm_result* res);
+
+/* Same with DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL = the handle's stream), no
+ * host synchronisation.  pos_out [n_local][N+1][3] (may be NULL) receives the packed positions of
+ * the new plans - the send buffer of the trajectory exchange, written by the solver's epilogue;
+ * agents without a usable result get their previous plan shifted by one step (:1004-1013). */
+int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
+                            const int32_t* nbr_end, const double* x0, const double* ref, const double* poly_A,
+                            const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,
+                            const double* all_pos, const uint8_t* all_valid, int n_rob,
+                            const int32_t* assign_in, double* traj, double* ctrl, uint8_t* poly_used,
+                            int32_t* assign_out, hdsm_result* res, double* pos_out, void* stream);
+
+/* Number of kernels the library launched on this handle so far (bench.py's gpu_launches). */
+int64_t hdsm_launch_count(const hdsm_handle* h);
+/* Dynamic shared memory per thread block of the solver kernel, bytes. */
+int hdsm_smem_bytes(const hdsm_handle* h);
+
+/* ---- trajectory exchange between the GPUs of one box (one process per GPU) ------------------
+ * hdsm_comm_unique_id fills a 128-byte NCCL id on rank 0; the caller broadcasts it by any means;
+ * every rank then calls hdsm_comm_init.  hdsm_allgather_positions is one ncclAllGather of
+ * n_local*(N+1)*3 doubles per rank on `stream` (device pointers; recv holds n_ranks such blocks). */
+int hdsm_comm_unique_id(uint8_t id_out[128]);
+int hdsm_comm_init(hdsm_handle* h, int n_ranks, int rank, const uint8_t id[128]);
+int hdsm_allgather_positions(hdsm_handle* h, const double* send, double* recv, int n_local, void* stream);
+void hdsm_comm_destroy(hdsm_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDSM_H_ */

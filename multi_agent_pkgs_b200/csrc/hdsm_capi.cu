@@ -1,0 +1,334 @@
+// C ABI of libhdsm (see include/hdsm.h).  Host side only: argument checks, device memory,
+// one pinned staging arena per direction, kernel dispatch on the horizon length, and the NCCL
+// trajectory exchange (NCCL is resolved with dlopen so the library loads without it).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/hdsm.h"
+#include "hdsm_kernel.cuh"
+
+using namespace hdsm;
+
+namespace {
+
+struct Id128 {  // ncclUniqueId, passed by value
+  char internal[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.lib ? &api : nullptr;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return nullptr;
+  api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<int (*)(void**, int, Id128, int)>(dlsym(api.lib, "ncclCommInitRank"));
+  api.AllGather =
+      reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(api.lib, "ncclAllGather"));
+  api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) {
+    api.lib = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+
+}  // namespace
+
+struct hdsm_handle {
+  hdsm_params prm{};
+  Tables host_tables{};
+  Tables* dev_tables = nullptr;
+  int device = 0, max_agents = 0, max_neighbours = 0;
+  int nbr_cap = 0, stat_cap = 0, smem_bytes = 0;
+  cudaStream_t stream = nullptr;
+  // staging for the host-pointer entry point
+  unsigned char *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
+  size_t in_cap = 0, out_cap = 0;
+  int64_t launches = 0;
+  std::string err;
+  void* comm = nullptr;
+  int n_ranks = 1;
+};
+
+namespace {
+
+int fail(hdsm_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+int cuda_fail(hdsm_handle* h, cudaError_t e, const char* what) {
+  return fail(h, HDSM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                              \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);    \
+  } while (0)
+
+template <int N>
+cudaError_t launch(hdsm_handle* h, const KernelArgs& a, cudaStream_t s) {
+  static int configured_for = -1;  // per instantiation; smem attribute is per device function
+  if (configured_for < h->smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(hdsm_solve_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured_for = h->smem_bytes;
+  }
+  hdsm_solve_kernel<N><<<a.n_local, 32, h->smem_bytes, s>>>(h->dev_tables, a);
+  return cudaGetLastError();
+}
+
+cudaError_t dispatch(hdsm_handle* h, const KernelArgs& a, cudaStream_t s) {
+  switch (h->prm.n_hor) {
+#define HDSM_CASE(n) \
+  case n:            \
+    return launch<n>(h, a, s);
+    HDSM_CASE(5)
+    HDSM_CASE(6)
+    HDSM_CASE(7)
+    HDSM_CASE(8)
+    HDSM_CASE(9)
+    HDSM_CASE(10)
+    HDSM_CASE(11)
+    HDSM_CASE(12)
+#undef HDSM_CASE
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+extern "C" {
+
+int hdsm_version(void) { return HDSM_VERSION; }
+
+int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, int device, hdsm_handle** out) {
+  if (!params || !out || max_agents < 1 || max_neighbours < 0) return HDSM_ERR_INVALID;
+  *out = nullptr;
+  hdsm_handle* h = new (std::nothrow) hdsm_handle();
+  if (!h) return HDSM_ERR_INVALID;
+  h->prm = *params;
+  if (h->prm.max_iter <= 0) h->prm.max_iter = 60;
+  if (h->prm.max_nodes <= 0) h->prm.max_nodes = 64;
+  if (!(h->prm.tol > 0)) h->prm.tol = 1e-8;
+  if (h->prm.n_hor < 5 || h->prm.n_hor > HDSM_MAX_HOR || build_tables(h->prm, h->host_tables) != 0) {
+    delete h;
+    return HDSM_ERR_INVALID;
+  }
+  h->device = device, h->max_agents = max_agents, h->max_neighbours = max_neighbours;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) {  // no CPU fallback: fail loudly
+    delete h;
+    return HDSM_ERR_CUDA;
+  }
+  auto bail = [&](cudaError_t err, const char* what) {
+    std::fprintf(stderr, "hdsm_create: %s: %s\n", what, cudaGetErrorString(err));
+    hdsm_destroy(h);
+    return HDSM_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  if ((e = cudaMalloc(&h->dev_tables, sizeof(Tables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+  if ((e = cudaMemcpy(h->dev_tables, &h->host_tables, sizeof(Tables), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return bail(e, "copy tables");
+  // shared-memory budget: all rows that can exist when nothing is pruned, capped by what one SM
+  // can give several resident blocks; beyond the cap exact pruning has to make room (else ROW_OVERFLOW)
+  const int nkp = h->host_tables.nkp, rmax = h->prm.max_rows_per_poly;
+  h->stat_cap = h->prm.prune ? std::min(2 * rmax * nkp, 6 * rmax + 4 * nkp) : 2 * rmax * nkp;
+  const long worst_nbr = 2L * max_neighbours * nkp;
+  int smem_max = 0;
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const int base = plan_smem(h->prm.n_hor, h->prm.poly_hor, rmax, 0, h->stat_cap).total_doubles * 8;
+  const long budget_rows = std::max(0L, (long)(smem_max - base - 1024) / 48);
+  h->nbr_cap = (int)std::min(worst_nbr, std::min(budget_rows, 1024L));
+  h->nbr_cap = std::max(h->nbr_cap, 8);
+  h->smem_bytes = plan_smem(h->prm.n_hor, h->prm.poly_hor, rmax, h->nbr_cap, h->stat_cap).total_doubles * 8;
+  *out = h;
+  return HDSM_OK;
+}
+
+void hdsm_destroy(hdsm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  hdsm_comm_destroy(h);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->dev_tables);
+  cudaFree(h->d_in);
+  cudaFree(h->d_out);
+  cudaFreeHost(h->h_in);
+  cudaFreeHost(h->h_out);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* hdsm_last_error(const hdsm_handle* h) { return h ? h->err.c_str() : "null handle"; }
+int64_t hdsm_launch_count(const hdsm_handle* h) { return h ? h->launches : 0; }
+int hdsm_smem_bytes(const hdsm_handle* h) { return h ? h->smem_bytes : 0; }
+
+int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
+                            const int32_t* nbr_end, const double* x0, const double* ref, const double* poly_A,
+                            const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,
+                            const double* all_pos, const uint8_t* all_valid, int n_rob, const int32_t* assign_in,
+                            double* traj, double* ctrl, uint8_t* poly_used, int32_t* assign_out, hdsm_result* res,
+                            double* pos_out, void* stream) {
+  if (!h) return HDSM_ERR_INVALID;
+  if (n_local == 0) return HDSM_OK;
+  if (n_local < 0 || n_rob < 0 || !global_id || !x0 || !ref || !poly_A || !poly_b || !poly_rows || !prev_self_pos ||
+      !traj || !ctrl || !poly_used || !assign_out || !res || (n_rob > 0 && (!all_pos || !all_valid)) ||
+      ((nbr_begin == nullptr) != (nbr_end == nullptr)))
+    return fail(h, HDSM_ERR_INVALID, "hdsm_solve_batch: null or inconsistent argument");
+  if (n_local > h->max_agents) return fail(h, HDSM_ERR_CAPACITY, "n_local exceeds max_agents of the handle");
+  CU(cudaSetDevice(h->device));
+  KernelArgs a{};
+  a.n_local = n_local, a.n_rob = n_rob, a.rmax = h->prm.max_rows_per_poly, a.P = h->prm.poly_hor;
+  a.global_id = global_id, a.nbr_begin = nbr_begin, a.nbr_end = nbr_end, a.poly_rows = poly_rows, a.assign_in = assign_in;
+  a.x0 = x0, a.ref = ref, a.poly_A = poly_A, a.poly_b = poly_b, a.prev = prev_self_pos, a.all_pos = all_pos;
+  a.all_valid = all_valid, a.traj = traj, a.ctrl = ctrl, a.pos_out = pos_out, a.poly_used = poly_used;
+  a.assign_out = assign_out, a.res = res, a.nbr_cap = h->nbr_cap, a.stat_cap = h->stat_cap;
+  a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  CU(dispatch(h, a, s));
+  h->launches += 1;
+  return HDSM_OK;
+}
+
+int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
+                     const int32_t* nbr_end, const double* x0, const double* ref, const double* poly_A,
+                     const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,
+                     const double* all_pos, const uint8_t* all_valid, int n_rob, const int32_t* assign_in, double* traj,
+                     double* ctrl, uint8_t* poly_used, int32_t* assign_out, hdsm_result* res) {
+  if (!h) return HDSM_ERR_INVALID;
+  if (n_local == 0) return HDSM_OK;
+  if (n_local < 0 || n_rob < 0 || !global_id || !x0 || !ref || !poly_A || !poly_b || !poly_rows || !prev_self_pos ||
+      !traj || !ctrl || !poly_used || !assign_out || !res || (n_rob > 0 && (!all_pos || !all_valid)) ||
+      ((nbr_begin == nullptr) != (nbr_end == nullptr)))
+    return fail(h, HDSM_ERR_INVALID, "hdsm_solve_batch: null or inconsistent argument");
+  if (n_local > h->max_agents) return fail(h, HDSM_ERR_CAPACITY, "n_local exceeds max_agents of the handle");
+  CU(cudaSetDevice(h->device));
+  const int N = h->prm.n_hor, P = h->prm.poly_hor, R = h->prm.max_rows_per_poly;
+  const size_t n = n_local;
+  // ---- input arena: one pinned block, one H2D copy
+  struct Seg {
+    const void* src;
+    size_t bytes, off;
+  };
+  Seg in[] = {
+      {global_id, n * 4, 0},
+      {nbr_begin, nbr_begin ? n * 4 : 0, 0},
+      {nbr_end, nbr_end ? n * 4 : 0, 0},
+      {poly_rows, n * P * 4, 0},
+      {assign_in, assign_in ? n * N * 4 : 0, 0},
+      {x0, n * 9 * 8, 0},
+      {ref, n * N * 6 * 8, 0},
+      {poly_A, n * P * R * 3 * 8, 0},
+      {poly_b, n * P * R * 8, 0},
+      {prev_self_pos, n * (N + 1) * 3 * 8, 0},
+      {all_pos, (size_t)n_rob * (N + 1) * 3 * 8, 0},
+      {all_valid, (size_t)n_rob, 0},
+  };
+  size_t in_bytes = 0;
+  for (Seg& s : in) s.off = in_bytes, in_bytes += align256(s.bytes);
+  const size_t o_traj = 0, o_ctrl = o_traj + align256(n * (N + 1) * 9 * 8), o_res = o_ctrl + align256(n * N * 3 * 8),
+               o_asg = o_res + align256(n * sizeof(hdsm_result)), o_used = o_asg + align256(n * N * 4),
+               out_bytes = o_used + align256(n * P);
+  if (in_bytes > h->in_cap) {
+    cudaFree(h->d_in), cudaFreeHost(h->h_in);
+    h->d_in = h->h_in = nullptr, h->in_cap = 0;
+    CU(cudaMalloc(&h->d_in, in_bytes));
+    CU(cudaMallocHost(&h->h_in, in_bytes));
+    h->in_cap = in_bytes;
+  }
+  if (out_bytes > h->out_cap) {
+    cudaFree(h->d_out), cudaFreeHost(h->h_out);
+    h->d_out = h->h_out = nullptr, h->out_cap = 0;
+    CU(cudaMalloc(&h->d_out, out_bytes));
+    CU(cudaMallocHost(&h->h_out, out_bytes));
+    h->out_cap = out_bytes;
+  }
+  for (const Seg& s : in)
+    if (s.bytes) std::memcpy(h->h_in + s.off, s.src, s.bytes);
+  CU(cudaMemcpyAsync(h->d_in, h->h_in, in_bytes, cudaMemcpyHostToDevice, h->stream));
+  auto dp = [&](int i) -> const void* { return in[i].bytes ? h->d_in + in[i].off : nullptr; };
+  int rc = hdsm_solve_batch_device(
+      h, n_local, (const int32_t*)dp(0), (const int32_t*)dp(1), (const int32_t*)dp(2), (const double*)dp(5),
+      (const double*)dp(6), (const double*)dp(7), (const double*)dp(8), (const int32_t*)dp(3), (const double*)dp(9),
+      (const double*)dp(10), (const uint8_t*)dp(11), n_rob, (const int32_t*)dp(4), (double*)(h->d_out + o_traj),
+      (double*)(h->d_out + o_ctrl), (uint8_t*)(h->d_out + o_used), (int32_t*)(h->d_out + o_asg),
+      (hdsm_result*)(h->d_out + o_res), nullptr, h->stream);
+  if (rc != HDSM_OK) return rc;
+  CU(cudaMemcpyAsync(h->h_out, h->d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::memcpy(traj, h->h_out + o_traj, n * (N + 1) * 9 * 8);
+  std::memcpy(ctrl, h->h_out + o_ctrl, n * N * 3 * 8);
+  std::memcpy(res, h->h_out + o_res, n * sizeof(hdsm_result));
+  std::memcpy(assign_out, h->h_out + o_asg, n * N * 4);
+  std::memcpy(poly_used, h->h_out + o_used, n * P);
+  return HDSM_OK;
+}
+
+int hdsm_comm_unique_id(uint8_t id_out[128]) {
+  NcclApi* n = nccl_api();
+  if (!n || !id_out) return HDSM_ERR_NCCL;
+  Id128 id;
+  if (n->GetUniqueId(&id) != 0) return HDSM_ERR_NCCL;
+  std::memcpy(id_out, &id, 128);
+  return HDSM_OK;
+}
+
+int hdsm_comm_init(hdsm_handle* h, int n_ranks, int rank, const uint8_t id[128]) {
+  if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return HDSM_ERR_INVALID;
+  NcclApi* n = nccl_api();
+  if (!n) return fail(h, HDSM_ERR_NCCL, "libnccl.so.2 not found");
+  CU(cudaSetDevice(h->device));
+  Id128 uid;
+  std::memcpy(&uid, id, 128);
+  int rc = n->CommInitRank(&h->comm, n_ranks, uid, rank);
+  if (rc != 0) return fail(h, HDSM_ERR_NCCL, std::string("ncclCommInitRank: ") + (n->GetErrorString ? n->GetErrorString(rc) : "?"));
+  h->n_ranks = n_ranks;
+  return HDSM_OK;
+}
+
+int hdsm_allgather_positions(hdsm_handle* h, const double* send, double* recv, int n_local, void* stream) {
+  if (!h || !send || !recv || n_local < 0) return HDSM_ERR_INVALID;
+  NcclApi* n = nccl_api();
+  if (!n || !h->comm) return fail(h, HDSM_ERR_NCCL, "communicator not initialised");
+  const size_t count = (size_t)n_local * (h->prm.n_hor + 1) * 3;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  int rc = n->AllGather(send, recv, count, /*ncclFloat64*/ 8, h->comm, s);
+  if (rc != 0) return fail(h, HDSM_ERR_NCCL, std::string("ncclAllGather: ") + (n->GetErrorString ? n->GetErrorString(rc) : "?"));
+  h->launches += 1;
+  return HDSM_OK;
+}
+
+void hdsm_comm_destroy(hdsm_handle* h) {
+  if (!h || !h->comm) return;
+  NcclApi* n = nccl_api();
+  if (n) n->CommDestroy(h->comm);
+  h->comm = nullptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,986 @@
+// Batched trajectory optimisation for sm_100a: one agent per thread block (one warp).
+//
+// Replaces, per agent and per replanning step (multi_agent_planner/src/agent_class.cpp):
+//   K1  GenerateTimeAwareSafeCorridor  :1086-1215   inter-agent separating planes, built on device
+//   K2  SolveOptimizationProblem       :858-1023    + GRBModel::optimize :959  (primal-dual interior point)
+//   K3  the binaries b[k][p] / indicator rows :928-940  (exact branch and bound over candidate sets)
+//   K4  PublishTrajectoryFull payload  :645-677     positions packed for the trajectory exchange
+//
+// Layout: every per-agent quantity lives in shared memory for the whole solve; HBM is touched once
+// for the inputs (coalesced per-agent blocks + the neighbour table, which is L2 resident) and once
+// for the outputs.  The 3(N-2)-square KKT matrix (the terminal equalities are eliminated by a
+// null-space basis, see hdsm_tables.h) is assembled, factorised (Cholesky) and solved by the warp
+// with one matrix row per lane held in registers.  FP64 throughout - the reference is double
+// (decomp_basis/data_type.h:50) and cond(K) reaches 1e14 near convergence.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hdsm_tables.h"
+
+namespace hdsm {
+
+constexpr double kFeasTol = 1e-6;      // Gurobi FeasibilityTol: constant rows are checked, not solved
+constexpr double kPruneMargin = 1e-6;  // a row is dropped only if it keeps this slack everywhere reachable
+constexpr double kContainTol = 1e-7;   // segment-in-polytope test on a node optimum
+constexpr double kPruneRel = 1e-7;     // bound pruning, relative
+constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still inside the 1e-6 KKT target
+constexpr int kStackCap = 48;          // >= 1 + N * ceil(log2 P) open nodes
+constexpr unsigned kFull = 0xffffffffu;
+
+struct KernelArgs {
+  int n_local, n_rob, rmax, P;
+  const int32_t *global_id, *nbr_begin, *nbr_end, *poly_rows, *assign_in;
+  const double *x0, *ref, *poly_A, *poly_b, *prev, *all_pos;
+  const uint8_t* all_valid;
+  double *traj, *ctrl, *pos_out;
+  uint8_t* poly_used;
+  int32_t* assign_out;
+  hdsm_result* res;
+  int nbr_cap, stat_cap;
+  int max_iter, max_nodes, prune;
+  double tol;
+};
+
+// Shared-memory plan, in doubles, shared by host (size) and device (carving).
+struct SmemPlan {
+  int poly, nrow, ns, nl, srow, ss, sl, Ls, bs, bl, DQ, TQ, FQ, qv, dq, dqc, qbar, Mk, Tk, Fk, p, dp, dpc, pbar, plo,
+      phi, w, dw, dwc, g, bestw, s0, viol, scal, ints, total_doubles;
+};
+HDSM_HD inline SmemPlan plan_smem(int N, int P, int rmax, int nbr_cap, int stat_cap) {
+  const int NW = 3 * (N - 2), NQ3 = 3 * (3 * N - 2), K3 = 3 * (N + 1);
+  SmemPlan s;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += n; return r; };
+  s.poly = take(P * rmax * 4);
+  s.nrow = take(nbr_cap * 4), s.ns = take(nbr_cap), s.nl = take(nbr_cap);
+  s.srow = take(stat_cap * 4), s.ss = take(stat_cap), s.sl = take(stat_cap);
+  s.Ls = take(NW * (NW + 1));
+  s.bs = take(NQ3 * 2), s.bl = take(NQ3 * 2);
+  s.DQ = take(NQ3), s.TQ = take(NQ3), s.FQ = take(NQ3), s.qv = take(NQ3), s.dq = take(NQ3), s.dqc = take(NQ3),
+  s.qbar = take(NQ3);
+  s.Mk = take((N + 1) * 6), s.Tk = take(K3), s.Fk = take(K3);
+  s.p = take(K3), s.dp = take(K3), s.dpc = take(K3), s.pbar = take(K3), s.plo = take(K3), s.phi = take(K3);
+  s.w = take(NW), s.dw = take(NW), s.dwc = take(NW), s.g = take(NW), s.bestw = take(NW);
+  s.s0 = take(10), s.viol = take(N * kMaxP), s.scal = take(16);
+  s.ints = take((2 * (N + 2) + 4 * N + kStackCap * 4 + 16) / 2 + 1);  // int32 region, counted in doubles
+  s.total_doubles = o;
+  return s;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ double quad_sum(unsigned gmask, double v) {
+  v += __shfl_xor_sync(gmask, v, 1);
+  v += __shfl_xor_sync(gmask, v, 2);
+  return v;
+}
+
+// Separating plane between own point pc and neighbour point po: agent_class.cpp:1152-1205, pert = 0.
+// Returns false for coincident points (the reference produces NaN rows there).
+__device__ __forceinline__ bool interagent_plane(const hdsm_params& P, const double pc[3], const double po[3], double nf[3],
+                                                 double& b) {
+  const double nx = po[0] - pc[0], ny = po[1] - pc[1], nz = po[2] - pc[2];
+  const double nrm = sqrt(nx * nx + ny * ny + nz * nz);
+  if (!(nrm > 0.0)) return false;
+  const double ux = nx / nrm, uy = ny / nrm, uz = nz / nrm;
+  const double ang = M_PI_2 - fabs(acos(fmin(1.0, fmax(-1.0, uz))));
+  const double t = atan(P.drone_radius / P.drone_z_offset * tan(ang));
+  const double sd = hypot(P.drone_radius * cos(t), P.drone_z_offset * sin(t));
+  const double h = fmin(2.0 * sd, nrm) / 2.0;
+  const double px = (pc[0] + po[0]) / 2 - h * ux, py = (pc[1] + po[1]) / 2 - h * uy, pz = (pc[2] + po[2]) / 2 - h * uz;
+  // right = u x (0,0,1) + u x (0,1,0) = (uy - uz, -ux, ux);  up_final = u x (0,1,0) = (-uz, 0, ux)
+  nf[0] = P.tilt * (uy - uz) + P.tilt * (-uz) + ux;
+  nf[1] = P.tilt * (-ux) + uy;
+  nf[2] = P.tilt * ux + P.tilt * ux + uz;
+  b = nf[0] * px + nf[1] * py + nf[2] * pz;
+  return true;
+}
+
+template <int N>
+struct Solver {
+  static constexpr int NZ = N - 2, NW = 3 * NZ, NQ = 3 * N - 2, NQ3 = 3 * NQ, K3 = 3 * (N + 1), LD = NW + 1;
+
+  const Tables& T;
+  const KernelArgs& A;
+  const int lane, grp, sub;
+  const unsigned gmask;
+  // shared memory views
+  double *poly, *nrow, *ns, *nl, *srow, *ss, *sl, *Ls, *bs, *bl, *DQ, *TQ, *FQ, *qv, *dq, *dqc, *qbar, *Mk, *Tk, *Fk, *p,
+      *dp, *dpc, *pbar, *plo, *phi, *w, *dw, *dwc, *g, *bestw, *s0, *viol, *scal;
+  int *nbeg, *sbeg, *bestsig, *prow_n;
+  unsigned char* stack;  // kStackCap entries of 16 bytes: per-step candidate masks
+  unsigned char* cur;    // current node's masks [N]
+  double c0;
+  int nkp, Peff;
+
+  __device__ Solver(const Tables& t, const KernelArgs& a, double* sm)
+      : T(t), A(a), lane(threadIdx.x), grp(threadIdx.x >> 2), sub(threadIdx.x & 3), gmask(0xFu << (threadIdx.x & ~3)) {
+    const SmemPlan s = plan_smem(N, a.P, a.rmax, a.nbr_cap, a.stat_cap);
+    poly = sm + s.poly, nrow = sm + s.nrow, ns = sm + s.ns, nl = sm + s.nl, srow = sm + s.srow, ss = sm + s.ss,
+    sl = sm + s.sl, Ls = sm + s.Ls, bs = sm + s.bs, bl = sm + s.bl, DQ = sm + s.DQ, TQ = sm + s.TQ, FQ = sm + s.FQ,
+    qv = sm + s.qv, dq = sm + s.dq, dqc = sm + s.dqc, qbar = sm + s.qbar, Mk = sm + s.Mk, Tk = sm + s.Tk, Fk = sm + s.Fk,
+    p = sm + s.p, dp = sm + s.dp, dpc = sm + s.dpc, pbar = sm + s.pbar, plo = sm + s.plo, phi = sm + s.phi, w = sm + s.w,
+    dw = sm + s.dw, dwc = sm + s.dwc, g = sm + s.g, bestw = sm + s.bestw, s0 = sm + s.s0, viol = sm + s.viol,
+    scal = sm + s.scal;
+    int* ip = reinterpret_cast<int*>(sm + s.ints);
+    nbeg = ip, sbeg = ip + (N + 2), bestsig = ip + 2 * (N + 2), prow_n = bestsig + N;
+    cur = reinterpret_cast<unsigned char*>(prow_n + kMaxP);
+    stack = cur + 16;
+    nkp = T.nkp;
+  }
+
+  // ---------------------------------------------------------------- small dense products
+  // out[k][a] = (bar ? bar[k][a] : 0) + QP[a][k] . x[a*NZ ...]
+  __device__ void positions_of(const double* x, const double* bar, double* out) const {
+    for (int idx = lane; idx < K3; idx += 32) {
+      const int k = idx / 3, a = idx - 3 * k;
+      double v = bar ? bar[idx] : 0.0;
+#pragma unroll
+      for (int z = 0; z < NZ; ++z) v += T.QP[a][k][z] * x[a * NZ + z];
+      out[idx] = v;
+    }
+  }
+  __device__ void quantities_of(const double* x, const double* bar, double* out) const {
+    for (int idx = lane; idx < NQ3; idx += 32) {
+      const int a = idx / NQ, q = idx - a * NQ;
+      double v = bar ? bar[idx] : 0.0;
+#pragma unroll
+      for (int z = 0; z < NZ; ++z) v += T.EQ[a][q][z] * x[a * NZ + z];
+      out[idx] = v;
+    }
+  }
+
+  // can n.p_kp <= b ever be active inside the reachable box of p_kp?  (exact pruning)
+  __device__ __forceinline__ bool reachable(const double n[3], double b, int kp) const {
+    double mx = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) mx += n[a] >= 0 ? n[a] * phi[3 * kp + a] : n[a] * plo[3 * kp + a];
+    return !(mx <= b - kPruneMargin);
+  }
+
+  template <class F>
+  __device__ __forceinline__ void for_slot_rows(int slot, F&& f) {
+    for (int i = nbeg[slot] + sub; i < nbeg[slot + 1]; i += 4) f(nrow + 4 * i, ns[i], nl[i]);
+    for (int i = sbeg[slot] + sub; i < sbeg[slot + 1]; i += 4) f(srow + 4 * i, ss[i], sl[i]);
+  }
+
+  // ---------------------------------------------------------------- per-agent set-up
+  // returns 0 ok, else an HDSM_* status
+  __device__ int setup(int agent) {
+    const hdsm_params& P = T.prm;
+    if (lane < 9) s0[lane] = A.x0[(size_t)agent * 9 + lane];  // x0 = (p, v, a): s0^a = (x0[a], x0[3+a], x0[6+a])
+    for (int i = lane; i < A.P * A.rmax; i += 32) {
+      const size_t base = (size_t)agent * A.P * A.rmax + i;
+      poly[4 * i + 0] = A.poly_A[base * 3 + 0];
+      poly[4 * i + 1] = A.poly_A[base * 3 + 1];
+      poly[4 * i + 2] = A.poly_A[base * 3 + 2];
+      poly[4 * i + 3] = A.poly_b[base];
+    }
+    if (lane < kMaxP) prow_n[lane] = lane < A.P ? A.poly_rows[(size_t)agent * A.P + lane] : 0;
+    __syncwarp();
+    Peff = 0;
+    while (Peff < A.P && prow_n[Peff] > 0) ++Peff;  // P_eff = leading present polytopes (:913)
+    const double* ref = A.ref + (size_t)agent * N * 6;
+    // gradient and constant of the condensed objective (:870-883, :2098)
+    double gi = 0, cpart = 0;
+    if (lane < NW) {
+      const int a = lane / NZ, r = lane - a * NZ;
+      const double sp = s0[a], sv = s0[3 + a], sa = s0[6 + a];
+      for (int k = 0; k < N; ++k) {
+        const double up = T.Up[a][k][0] * sp + T.Up[a][k][1] * sv + T.Up[a][k][2] * sa;
+        gi += 2 * P.r_u * T.Z[a][k][r] * up;
+        if (r == 0) cpart += P.r_u * up * up;
+      }
+      for (int i = 1; i <= N; ++i) {
+        const double* wt = i == N ? P.r_n : P.r_x;
+        const double ep = T.cP[a][i][0] * sp + T.cP[a][i][1] * sv + T.cP[a][i][2] * sa - ref[(i - 1) * 6 + a];
+        const double ev = T.cV[a][i][0] * sp + T.cV[a][i][1] * sv + T.cV[a][i][2] * sa - ref[(i - 1) * 6 + 3 + a];
+        gi += 2 * wt[a] * T.QP[a][i][r] * ep + 2 * wt[3 + a] * T.QV[a][i][r] * ev;
+        if (r == 0) cpart += wt[a] * ep * ep + wt[3 + a] * ev * ev;
+      }
+      g[lane] = gi;
+    }
+    c0 = warp_sum(cpart);
+    for (int idx = lane; idx < K3; idx += 32) {
+      const int k = idx / 3, a = idx - 3 * k;
+      pbar[idx] = T.cP[a][k][0] * s0[a] + T.cP[a][k][1] * s0[3 + a] + T.cP[a][k][2] * s0[6 + a];
+    }
+    for (int idx = lane; idx < NQ3; idx += 32) {
+      const int a = idx / NQ, q = idx - a * NQ;
+      qbar[idx] = T.cQ[a][q][0] * s0[a] + T.cQ[a][q][1] * s0[3 + a] + T.cQ[a][q][2] * s0[6 + a];
+    }
+    // reachable box of p_k by interval propagation through the one-step map under the boxes
+    if (lane < 3) {
+      const int a = lane;
+      double lo[3] = {s0[a], s0[3 + a], s0[6 + a]}, hi[3] = {lo[0], lo[1], lo[2]};
+      const double alo = a < 2 ? P.min_acc_xy : P.min_acc_z, ahi = a < 2 ? P.max_acc_xy : P.max_acc_z;
+      plo[a] = phi[a] = lo[0];
+      for (int k = 0; k < N; ++k) {
+        double nlo[3], nhi[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double l = 0, h = 0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double c = T.A1[a][i][j];
+            l += c >= 0 ? c * lo[j] : c * hi[j];
+            h += c >= 0 ? c * hi[j] : c * lo[j];
+          }
+          const double bj = fabs(T.B1[a][i]) * P.max_jerk;
+          nlo[i] = l - bj, nhi[i] = h + bj;
+        }
+        if (k + 1 < N) {  // boxes hold for k = 1..N-1 (:2083-2086)
+          nlo[1] = fmax(nlo[1], -P.max_vel), nhi[1] = fmin(nhi[1], P.max_vel);
+          nlo[2] = fmax(nlo[2], alo), nhi[2] = fmin(nhi[2], ahi);
+          if (nlo[1] > nhi[1]) nlo[1] = nhi[1] = 0.5 * (nlo[1] + nhi[1]);
+          if (nlo[2] > nhi[2]) nlo[2] = nhi[2] = 0.5 * (nlo[2] + nhi[2]);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) lo[i] = nlo[i], hi[i] = nhi[i];
+        plo[3 * (k + 1) + a] = lo[0], phi[3 * (k + 1) + a] = hi[0];
+      }
+    }
+    __syncwarp();
+    // constant box quantities (v_1 under Euler): feasibility check only
+    int bad = 0;
+    for (int idx = lane; idx < NQ3; idx += 32) {
+      const int a = idx / NQ, q = idx - a * NQ;
+      if (T.qconst[a][q] && (qbar[idx] - T.qhi[a][q] > kFeasTol || T.qlo[a][q] - qbar[idx] > kFeasTol)) bad = 1;
+    }
+    if (__any_sync(kFull, bad)) return HDSM_INFEASIBLE;
+    if (Peff == 0) return HDSM_INFEASIBLE;  // sum over an empty set of binaries == 1 (:939-940)
+    return -1;
+  }
+
+  // ---------------------------------------------------------------- K1: inter-agent rows, packed by position step
+  __device__ int build_neighbour_rows(int agent) {
+    const hdsm_params& P = T.prm;
+    const int gid = A.global_id[agent];
+    const int nb0 = A.nbr_begin ? A.nbr_begin[agent] : 0, nb1 = A.nbr_end ? A.nbr_end[agent] : A.n_rob;
+    const double* prev = A.prev + (size_t)agent * K3;
+    const double smax = fmax(P.drone_radius, P.drone_z_offset);
+    const double nfmax = 1.0 + 3.0 * fabs(P.tilt);  // |n_f| <= |u| + tilt (|right| + |up|)
+    int cnt = 0, status = -1;
+    const unsigned lt = (1u << lane) - 1;
+    for (int kp = 0; kp <= N; ++kp) {
+      const int slot = T.slot_of_kp[kp];
+      if (slot >= 0) nbeg[slot] = cnt;
+      for (int k = kp - 1; k <= kp; ++k) {
+        if (k < 0 || k >= N) continue;
+        const double ps[3] = {prev[3 * (k + 1)], prev[3 * (k + 1) + 1], prev[3 * (k + 1) + 2]};
+        // quick reject: |x - ps| <= rho for every reachable x, and the plane keeps distance
+        // |n|/2 - smax from ps along u, n_f.u = 1  =>  inactive if nfmax*rho < |n|/2 - smax - margin
+        double rho2 = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double d = fmax(fabs(plo[3 * kp + a] - ps[a]), fabs(phi[3 * kp + a] - ps[a]));
+          rho2 += d * d;
+        }
+        const double thr = 2.0 * (nfmax * sqrt(rho2) + smax + 1e-3);
+        const double thr2 = thr * thr;
+        for (int j0 = nb0; j0 < nb1; j0 += 32) {
+          const int j = j0 + lane;
+          bool valid = j < nb1 && j != gid && A.all_valid[j] != 0;
+          double nf[3] = {0, 0, 0}, b = 0;
+          if (valid) {
+            const double* q = A.all_pos + ((size_t)j * (N + 1) + k + 1) * 3;
+            const double po[3] = {q[0], q[1], q[2]};
+            const double dx = po[0] - ps[0], dy = po[1] - ps[1], dz = po[2] - ps[2];
+            if (A.prune && dx * dx + dy * dy + dz * dz > thr2) {
+              valid = false;
+            } else if (!interagent_plane(P, ps, po, nf, b)) {
+              status = HDSM_NUMERICAL;
+              valid = false;
+            } else if (slot < 0) {  // constant point: the row is a number (agent_class.cpp rows on p_0..)
+              if (nf[0] * pbar[3 * kp] + nf[1] * pbar[3 * kp + 1] + nf[2] * pbar[3 * kp + 2] - b > kFeasTol)
+                status = HDSM_INFEASIBLE;
+              valid = false;
+            } else if (A.prune && !reachable(nf, b, kp)) {
+              valid = false;
+            }
+          }
+          const unsigned m = __ballot_sync(kFull, valid);
+          if (valid) {
+            const int pos = cnt + __popc(m & lt);
+            if (pos < A.nbr_cap) {
+              nrow[4 * pos] = nf[0], nrow[4 * pos + 1] = nf[1], nrow[4 * pos + 2] = nf[2], nrow[4 * pos + 3] = b;
+            }
+          }
+          cnt += __popc(m);
+        }
+      }
+    }
+    nbeg[nkp] = cnt;
+    status = __reduce_max_sync(kFull, status);
+    if (cnt > A.nbr_cap) return HDSM_ROW_OVERFLOW;
+    __syncwarp();
+    return status;
+  }
+
+  // candidate sets of the root node: polytopes whose rows hold at the constant points (p_0, p_1, ...)
+  __device__ bool root_sets(int agent) {
+    bool any_empty = false;
+    for (int k = 0; k < N; ++k) {
+      unsigned mask = 0;
+      const int forced = A.assign_in ? A.assign_in[(size_t)agent * N + k] : -1;
+      for (int j = 0; j < Peff; ++j) {
+        if (forced >= 0 && forced != j) continue;
+        int bad = 0;
+        for (int kp = k; kp <= k + 1; ++kp) {
+          if (T.slot_of_kp[kp] >= 0) continue;
+          if (lane < prow_n[j]) {
+            const double* r = poly + 4 * (j * A.rmax + lane);
+            if (r[0] * pbar[3 * kp] + r[1] * pbar[3 * kp + 1] + r[2] * pbar[3 * kp + 2] - r[3] > kFeasTol) bad = 1;
+          }
+        }
+        if (!__any_sync(kFull, bad)) mask |= 1u << j;
+      }
+      if (lane == 0) cur[k] = (unsigned char)mask;
+      any_empty |= mask == 0;
+    }
+    __syncwarp();
+    return !any_empty;
+  }
+
+  // rows of a candidate set at lane `r`: the polytope's own row (singleton) or the union-hull row
+  // (normal shared bit-identically by every member, offset = max over members of their tightest)
+  __device__ __forceinline__ bool set_row(unsigned mask, int r, double n[3], double& b) const {
+    const int first = __ffs(mask) - 1;
+    if (r >= prow_n[first]) return false;
+    const double* a = poly + 4 * (first * A.rmax + r);
+    n[0] = a[0], n[1] = a[1], n[2] = a[2], b = a[3];
+    if ((mask & (mask - 1)) == 0) return true;
+    for (int r2 = 0; r2 < r; ++r2) {  // duplicate normal inside the first member: handled by the first occurrence
+      const double* c = poly + 4 * (first * A.rmax + r2);
+      if (c[0] == n[0] && c[1] == n[1] && c[2] == n[2]) return false;
+    }
+    double bmax = -INFINITY;
+    for (int j = first; j < Peff; ++j) {
+      if (!(mask >> j & 1)) continue;
+      double bmin = INFINITY;
+      for (int r2 = 0; r2 < prow_n[j]; ++r2) {
+        const double* c = poly + 4 * (j * A.rmax + r2);
+        if (c[0] == n[0] && c[1] == n[1] && c[2] == n[2]) bmin = fmin(bmin, c[3]);
+      }
+      if (bmin == INFINITY) return false;
+      bmax = fmax(bmax, bmin);
+    }
+    b = bmax;
+    return true;
+  }
+
+  // static corridor rows of the current node, packed by position step; returns row count or -1 on overflow
+  __device__ int build_static_rows() {
+    int cnt = 0;
+    const unsigned lt = (1u << lane) - 1;
+    for (int slot = 0; slot < nkp; ++slot) {
+      const int kp = T.kp_of_slot[slot];
+      sbeg[slot] = cnt;
+      for (int k = kp - 1; k <= kp; ++k) {
+        if (k < 0 || k >= N) continue;
+        if (k == kp && kp >= 1 && cur[kp - 1] == cur[kp]) continue;  // same rows already put on p_kp by step kp-1
+        double n[3], b;
+        bool valid = set_row(cur[k], lane, n, b);
+        if (valid && A.prune) valid = reachable(n, b, kp);
+        const unsigned m = __ballot_sync(kFull, valid);
+        if (valid) {
+          const int pos = cnt + __popc(m & lt);
+          if (pos < A.stat_cap) srow[4 * pos] = n[0], srow[4 * pos + 1] = n[1], srow[4 * pos + 2] = n[2], srow[4 * pos + 3] = b;
+        }
+        cnt += __popc(m);
+      }
+    }
+    sbeg[nkp] = cnt;
+    __syncwarp();
+    return cnt > A.stat_cap ? -1 : cnt;
+  }
+
+  // ---------------------------------------------------------------- K2: Mehrotra predictor-corrector
+  // box row helpers: side 0 = upper (q <= hi), side 1 = lower (lo <= q); coefficient sign +1 / -1
+  __device__ __forceinline__ double box_slack(int idx, int side, int a, int q) const {
+    return side == 0 ? T.qhi[a][q] - qv[idx] : qv[idx] - T.qlo[a][q];
+  }
+
+  // Cholesky of the matrix whose row `lane` is in K[], in place (lower part), then two triangular
+  // solves per call of solve().  Lanes >= NW carry zero rows.
+  __device__ __forceinline__ bool factor(double (&K)[NW], double& myinv) {
+    // A pivot that lost all its digits to cancellation (<= 1e-13 of the original diagonal) marks a
+    // direction the barrier has pinned: the variable is frozen for this solve (inverse pivot 0)
+    // instead of aborting.  Only a NaN / non-positive original diagonal is a failure.
+    bool ok = true;
+    double dorig = 0.0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j)
+      if (lane == j) dorig = K[j];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+      const double djj = __shfl_sync(kFull, K[j], j);
+      const double dor = __shfl_sync(kFull, dorig, j);
+      ok &= dor > 0.0;
+      const double inv = djj > 1e-13 * dor ? rsqrt(djj) : 0.0;
+      const double lij = K[j] * inv;  // lane j: sqrt(djj)
+      K[j] = lij;
+      if (lane == j) myinv = inv;
+#pragma unroll
+      for (int k = j + 1; k < NW; ++k) {
+        const double lkj = __shfl_sync(kFull, lij, k);
+        if (lane >= k) K[k] -= lij * lkj;
+      }
+    }
+    if (lane < NW) {
+#pragma unroll
+      for (int j = 0; j < NW; ++j) Ls[lane * LD + j] = K[j];
+    }
+    __syncwarp();
+    return ok;
+  }
+  __device__ __forceinline__ double solve(const double (&K)[NW], double myinv, double rhs) const {
+    double acc = rhs, x = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {  // L y = rhs
+      const double yj = __shfl_sync(kFull, acc * myinv, j);
+      if (lane > j) acc -= K[j] * yj;
+      if (lane == j) acc = yj;
+    }
+#pragma unroll
+    for (int i = NW - 1; i >= 0; --i) {  // L' x = y
+      const double xi = __shfl_sync(kFull, acc * myinv, i);
+      if (lane < i) acc -= Ls[i * LD + lane] * xi;
+      if (lane == i) x = xi, acc = 0;
+    }
+    return x;
+  }
+
+  struct QpOut {
+    int status, iters;
+    double obj, kkt;
+  };
+
+  __device__ QpOut solve_qp() {
+    QpOut out{HDSM_MAX_ITER, 0, INFINITY, INFINITY};
+    const double tol = A.tol;
+    // count rows
+    int nbox = 0;
+    for (int idx = lane; idx < NQ3; idx += 32) {
+      const int a = idx / NQ, q = idx - a * NQ;
+      nbox += T.qconst[a][q] ? 0 : 2;
+    }
+    nbox = __reduce_add_sync(kFull, nbox);
+    const int mtot = nbox + nbeg[nkp] + sbeg[nkp];
+    const double inv_m = 1.0 / (mtot > 0 ? mtot : 1);
+    // start: unconstrained minimiser of the objective
+    if (lane < NW) {
+      const int a = lane / NZ, r = lane - a * NZ;
+      double v = 0;
+#pragma unroll
+      for (int c = 0; c < NZ; ++c) v -= T.HwInv[a][r][c] * g[a * NZ + c];
+      w[lane] = v;
+    }
+    const double gmax = warp_max(lane < NW ? fabs(g[lane]) : 0.0);
+    __syncwarp();
+    positions_of(w, pbar, p);
+    quantities_of(w, qbar, qv);
+    __syncwarp();
+    for (int slot = grp; slot < nkp; slot += 8) {
+      const int kp = T.kp_of_slot[slot];
+      const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+      for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+        const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
+        s = fmax(slk, 1.0);
+        l = 1.0 / s;
+      });
+    }
+    for (int idx = lane; idx < NQ3; idx += 32) {
+      const int a = idx / NQ, q = idx - a * NQ;
+      if (T.qconst[a][q]) continue;
+      const double sc = 0.05 * (T.qhi[a][q] - T.qlo[a][q]);
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const double s = fmax(box_slack(idx, side, a, q), sc);
+        bs[2 * idx + side] = s, bl[2 * idx + side] = 1.0 / s;
+      }
+    }
+    __syncwarp();
+
+    for (int it = 0;; ++it) {
+      // ---- pass 1: residuals and barrier blocks
+      double mu = 0, rcmax = 0, lamsl = 0, lamsum = 0;
+      for (int slot = grp; slot < nkp; slot += 8) {
+        const int kp = T.kp_of_slot[slot];
+        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+        double m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, t0 = 0, t1 = 0, t2 = 0, f0 = 0, f1 = 0, f2 = 0;
+        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+          const double nx = r[0], ny = r[1], nz = r[2];
+          const double slk = r[3] - (nx * px + ny * py + nz * pz);
+          const double rc = s - slk, d = l / s, t = d * rc;
+          mu += s * l, rcmax = fmax(rcmax, fabs(rc)), lamsl += l * slk, lamsum += l;
+          m0 += d * nx * nx, m1 += d * nx * ny, m2 += d * nx * nz, m3 += d * ny * ny, m4 += d * ny * nz, m5 += d * nz * nz;
+          t0 += t * nx, t1 += t * ny, t2 += t * nz;
+          f0 += l * nx, f1 += l * ny, f2 += l * nz;
+        });
+        m0 = quad_sum(gmask, m0), m1 = quad_sum(gmask, m1), m2 = quad_sum(gmask, m2), m3 = quad_sum(gmask, m3);
+        m4 = quad_sum(gmask, m4), m5 = quad_sum(gmask, m5);
+        t0 = quad_sum(gmask, t0), t1 = quad_sum(gmask, t1), t2 = quad_sum(gmask, t2);
+        f0 = quad_sum(gmask, f0), f1 = quad_sum(gmask, f1), f2 = quad_sum(gmask, f2);
+        if (sub == 0) {
+          double* M = Mk + 6 * slot;
+          M[0] = m0, M[1] = m1, M[2] = m2, M[3] = m3, M[4] = m4, M[5] = m5;
+          Tk[3 * slot] = t0, Tk[3 * slot + 1] = t1, Tk[3 * slot + 2] = t2;
+          Fk[3 * slot] = f0, Fk[3 * slot + 1] = f1, Fk[3 * slot + 2] = f2;
+        }
+      }
+      for (int idx = lane; idx < NQ3; idx += 32) {
+        const int a = idx / NQ, q = idx - a * NQ;
+        double dsum = 0, tsum = 0, fsum = 0;
+        if (!T.qconst[a][q]) {
+          const double range = T.qhi[a][q] - T.qlo[a][q];
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
+            const double rc = s - slk, d = l / s, sg = side == 0 ? 1.0 : -1.0;
+            mu += s * l, rcmax = fmax(rcmax, fabs(rc) / range), lamsl += l * slk, lamsum += l;
+            dsum += d, tsum += sg * d * rc, fsum += sg * l;
+          }
+        }
+        DQ[idx] = dsum, TQ[idx] = tsum, FQ[idx] = fsum;
+      }
+      __syncwarp();
+      mu = warp_sum(mu) * inv_m, rcmax = warp_max(rcmax), lamsl = warp_sum(lamsl), lamsum = warp_sum(lamsum);
+
+      // ---- smooth gradient, dual residual, objective, right-hand side of the predictor
+      double hg = 0, fi = 0, ti = 0, wi = 0;
+      int ax = 0, rr = 0;
+      if (lane < NW) {
+        ax = lane / NZ, rr = lane - ax * NZ;
+        wi = w[lane];
+        hg = g[lane];
+#pragma unroll
+        for (int c = 0; c < NZ; ++c) hg += T.Hw[ax][rr][c] * w[ax * NZ + c];
+        for (int slot = 0; slot < nkp; ++slot) {
+          const double qp = T.QP[ax][T.kp_of_slot[slot]][rr];
+          fi += Fk[3 * slot + ax] * qp, ti += Tk[3 * slot + ax] * qp;
+        }
+        for (int q = 0; q < NQ; ++q) {
+          const double e = T.EQ[ax][q][rr];
+          fi += FQ[ax * NQ + q] * e, ti += TQ[ax * NQ + q] * e;
+        }
+      }
+      const double rdmax = warp_max(fabs(hg + fi));
+      const double fmaxv = warp_max(fabs(fi));
+      const double wf = warp_sum(wi * fi);
+      const double obj = c0 + 0.5 * warp_sum(lane < NW ? wi * (hg + g[lane]) : 0.0);
+      const auto accept = [&](double tl) {
+        return rdmax <= tl * (1 + gmax) && rcmax <= tl && mu <= 0.1 * tl * fmax(1.0, fabs(obj));
+      };
+      if (accept(tol) || (it >= A.max_iter && accept(kLooseTol))) {
+        out.status = HDSM_OPTIMAL, out.iters = it, out.obj = obj;
+        out.kkt = fmax(rdmax / (1 + gmax), fmax(rcmax, mu));
+        return out;
+      }
+      if (mtot > 0 && lamsum > 0 && it >= 3) {  // Farkas certificate: lam >= 0, C'lam ~ 0, d'lam < 0
+        const double dlam = (lamsl + wf) / lamsum;
+        if (fmaxv / lamsum < 1e-9 * fmax(1.0, -dlam * 1e3) && dlam < -1e-7) {
+          out.status = HDSM_INFEASIBLE, out.iters = it;
+          return out;
+        }
+      }
+      if (it >= A.max_iter) {
+        out.iters = it;
+        return out;
+      }
+
+      // ---- K = Hw + sum_slots QP' M QP + sum_q DQ EQ EQ'   (row `lane` in registers)
+      double K[NW];
+#pragma unroll
+      for (int c = 0; c < NW; ++c) K[c] = 0.0;
+      double myinv = 0.0;
+      if (lane < NW) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          if (b == ax) {
+#pragma unroll
+            for (int c = 0; c < NZ; ++c) K[b * NZ + c] = T.Hw[ax][rr][c];
+            for (int q = 0; q < NQ; ++q) {
+              const double f = DQ[ax * NQ + q] * T.EQ[ax][q][rr];
+#pragma unroll
+              for (int c = 0; c < NZ; ++c) K[b * NZ + c] += f * T.EQ[ax][q][c];
+            }
+          }
+        }
+        for (int slot = 0; slot < nkp; ++slot) {
+          const int kp = T.kp_of_slot[slot];
+          const double* M = Mk + 6 * slot;
+          const double qr = T.QP[ax][kp][rr];
+          // symmetric 3x3 block stored as (00,01,02,11,12,22)
+          const double mx = ax == 0 ? M[0] : ax == 1 ? M[1] : M[2];
+          const double my = ax == 0 ? M[1] : ax == 1 ? M[3] : M[4];
+          const double mz = ax == 0 ? M[2] : ax == 1 ? M[4] : M[5];
+          const double fx = mx * qr, fy = my * qr, fz = mz * qr;
+#pragma unroll
+          for (int c = 0; c < NZ; ++c) {
+            K[c] += fx * T.QP[0][kp][c];
+            K[NZ + c] += fy * T.QP[1][kp][c];
+            K[2 * NZ + c] += fz * T.QP[2][kp][c];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NW; ++c) K[c] = 0.0;
+      }
+      if (!factor(K, myinv)) {
+        out.status = HDSM_NUMERICAL, out.iters = it;
+        return out;
+      }
+
+      // ---- predictor
+      const double dwa = solve(K, myinv, -hg - ti);
+      if (lane < NW) dw[lane] = dwa;
+      __syncwarp();
+      positions_of(dw, nullptr, dp);
+      quantities_of(dw, nullptr, dq);
+      __syncwarp();
+      double alpha = 1.0, s_sl = 0, s_x = 0, s_dd = 0;
+      for (int slot = grp; slot < nkp; slot += 8) {
+        const int kp = T.kp_of_slot[slot];
+        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+        const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
+        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+          const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
+          const double ds = -(s - slk) - (r[0] * dx + r[1] * dy + r[2] * dz);
+          const double dl = -l - l * ds / s;
+          if (ds < 0) alpha = fmin(alpha, -s / ds);
+          if (dl < 0) alpha = fmin(alpha, -l / dl);
+          s_sl += s * l, s_x += s * dl + l * ds, s_dd += ds * dl;
+        });
+      }
+      for (int idx = lane; idx < NQ3; idx += 32) {
+        const int a = idx / NQ, q = idx - a * NQ;
+        if (T.qconst[a][q]) continue;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
+          const double cdw = side == 0 ? dq[idx] : -dq[idx];
+          const double ds = -(s - slk) - cdw;
+          const double dl = -l - l * ds / s;
+          if (ds < 0) alpha = fmin(alpha, -s / ds);
+          if (dl < 0) alpha = fmin(alpha, -l / dl);
+          s_sl += s * l, s_x += s * dl + l * ds, s_dd += ds * dl;
+        }
+      }
+      __syncwarp();
+      alpha = warp_min(alpha), s_sl = warp_sum(s_sl), s_x = warp_sum(s_x), s_dd = warp_sum(s_dd);
+      const double mu_aff = fmax((s_sl + alpha * s_x + alpha * alpha * s_dd) * inv_m, 0.0);
+      const double ratio = mu > 0 ? mu_aff / mu : 0.0;
+      const double smu = ratio * ratio * ratio * mu;
+
+      // ---- corrector right-hand side
+      for (int slot = grp; slot < nkp; slot += 8) {
+        const int kp = T.kp_of_slot[slot];
+        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+        const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
+        double t0 = 0, t1 = 0, t2 = 0;
+        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+          const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
+          const double rc = s - slk;
+          const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
+          const double dla = -l - l * dsa / s;
+          const double t = (l * rc - (dsa * dla - smu)) / s;
+          t0 += t * r[0], t1 += t * r[1], t2 += t * r[2];
+        });
+        t0 = quad_sum(gmask, t0), t1 = quad_sum(gmask, t1), t2 = quad_sum(gmask, t2);
+        if (sub == 0) Tk[3 * slot] = t0, Tk[3 * slot + 1] = t1, Tk[3 * slot + 2] = t2;
+      }
+      for (int idx = lane; idx < NQ3; idx += 32) {
+        const int a = idx / NQ, q = idx - a * NQ;
+        double tsum = 0;
+        if (!T.qconst[a][q]) {
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
+            const double cdw = side == 0 ? dq[idx] : -dq[idx];
+            const double rc = s - slk, dsa = -rc - cdw, dla = -l - l * dsa / s;
+            const double t = (l * rc - (dsa * dla - smu)) / s;
+            tsum += side == 0 ? t : -t;
+          }
+        }
+        TQ[idx] = tsum;
+      }
+      __syncwarp();
+      double tc = 0;
+      if (lane < NW) {
+        for (int slot = 0; slot < nkp; ++slot) tc += Tk[3 * slot + ax] * T.QP[ax][T.kp_of_slot[slot]][rr];
+        for (int q = 0; q < NQ; ++q) tc += TQ[ax * NQ + q] * T.EQ[ax][q][rr];
+      }
+      const double dwv = solve(K, myinv, -hg - tc);
+      if (lane < NW) dwc[lane] = dwv;
+      __syncwarp();
+      positions_of(dwc, nullptr, dpc);
+      quantities_of(dwc, nullptr, dqc);
+      __syncwarp();
+
+      // ---- step length of the combined direction
+      alpha = 1.0;
+      for (int slot = grp; slot < nkp; slot += 8) {
+        const int kp = T.kp_of_slot[slot];
+        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+        const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
+        const double ex = dpc[3 * kp], ey = dpc[3 * kp + 1], ez = dpc[3 * kp + 2];
+        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+          const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
+          const double rc = s - slk;
+          const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
+          const double dla = -l - l * dsa / s;
+          const double ds = -rc - (r[0] * ex + r[1] * ey + r[2] * ez);
+          const double dl = -(s * l + (dsa * dla - smu) + l * ds) / s;
+          if (ds < 0) alpha = fmin(alpha, -s / ds);
+          if (dl < 0) alpha = fmin(alpha, -l / dl);
+        });
+      }
+      for (int idx = lane; idx < NQ3; idx += 32) {
+        const int a = idx / NQ, q = idx - a * NQ;
+        if (T.qconst[a][q]) continue;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
+          const double sg = side == 0 ? 1.0 : -1.0;
+          const double rc = s - slk, dsa = -rc - sg * dq[idx], dla = -l - l * dsa / s;
+          const double ds = -rc - sg * dqc[idx];
+          const double dl = -(s * l + (dsa * dla - smu) + l * ds) / s;
+          if (ds < 0) alpha = fmin(alpha, -s / ds);
+          if (dl < 0) alpha = fmin(alpha, -l / dl);
+        }
+      }
+      __syncwarp();
+      alpha = warp_min(alpha);
+      const double al = fmin(1.0, 0.995 * alpha);
+
+      // ---- update
+      for (int slot = grp; slot < nkp; slot += 8) {
+        const int kp = T.kp_of_slot[slot];
+        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+        const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
+        const double ex = dpc[3 * kp], ey = dpc[3 * kp + 1], ez = dpc[3 * kp + 2];
+        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+          const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
+          const double rc = s - slk;
+          const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
+          const double dla = -l - l * dsa / s;
+          const double ds = -rc - (r[0] * ex + r[1] * ey + r[2] * ez);
+          const double dl = -(s * l + (dsa * dla - smu) + l * ds) / s;
+          s += al * ds, l += al * dl;
+        });
+      }
+      for (int idx = lane; idx < NQ3; idx += 32) {
+        const int a = idx / NQ, q = idx - a * NQ;
+        if (T.qconst[a][q]) continue;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
+          const double sg = side == 0 ? 1.0 : -1.0;
+          const double rc = s - slk, dsa = -rc - sg * dq[idx], dla = -l - l * dsa / s;
+          const double ds = -rc - sg * dqc[idx];
+          const double dl = -(s * l + (dsa * dla - smu) + l * ds) / s;
+          bs[2 * idx + side] = s + al * ds, bl[2 * idx + side] = l + al * dl;
+        }
+      }
+      bool finite = true;
+      if (lane < NW) {
+        const double v = w[lane] + al * dwv;
+        finite = isfinite(v);
+        w[lane] = v;
+      }
+      __syncwarp();
+      if (!__all_sync(kFull, finite)) {
+        out.status = HDSM_NUMERICAL, out.iters = it;
+        return out;
+      }
+      positions_of(w, pbar, p);
+      quantities_of(w, qbar, qv);
+      __syncwarp();
+    }
+  }
+
+  // ---------------------------------------------------------------- K3 + epilogue
+  __device__ void run(int agent) {
+    hdsm_result R{HDSM_INFEASIBLE, 0, 0, 0, INFINITY, INFINITY};
+    int st = setup(agent);
+    if (st < 0) st = build_neighbour_rows(agent);
+    if (st < 0 && !root_sets(agent)) st = HDSM_INFEASIBLE;
+    double best = INFINITY, bestkkt = INFINITY;
+    int nodes = 0, iters = 0, maxrows = 0, fail = 0;
+    bool exhausted = true;
+    if (st < 0) {
+      int top = 0;
+      if (lane < 16) stack[lane] = lane < N ? cur[lane] : 0;
+      top = 1;
+      __syncwarp();
+      while (top > 0) {
+        if (nodes >= A.max_nodes) {
+          exhausted = false;
+          break;
+        }
+        --top;
+        if (lane < 16) cur[lane] = stack[top * 16 + lane];
+        __syncwarp();
+        const int nstat = build_static_rows();
+        if (nstat < 0) {
+          fail = HDSM_ROW_OVERFLOW;
+          continue;
+        }
+        maxrows = max(maxrows, nstat + nbeg[nkp]);
+        const QpOut q = solve_qp();
+        ++nodes;
+        iters += q.iters;
+        if (q.status != HDSM_OPTIMAL) {
+          if (q.status != HDSM_INFEASIBLE) fail = q.status;
+          continue;
+        }
+        if (q.obj >= best - kPruneRel * fmax(1.0, fabs(best))) continue;
+        // coverage of every segment (p_k, p_k+1) by one member of its candidate set
+        for (int idx = lane; idx < N * Peff; idx += 32) {
+          const int k = idx / Peff, j = idx - k * Peff;
+          double v = INFINITY;
+          if (cur[k] >> j & 1) {
+            v = -INFINITY;
+            const double ax_ = p[3 * k], ay = p[3 * k + 1], az = p[3 * k + 2];
+            const double bx = p[3 * k + 3], by = p[3 * k + 4], bz = p[3 * k + 5];
+            for (int r = 0; r < prow_n[j]; ++r) {
+              const double* c = poly + 4 * (j * A.rmax + r);
+              v = fmax(v, fmax(c[0] * ax_ + c[1] * ay + c[2] * az, c[0] * bx + c[1] * by + c[2] * bz) - c[3]);
+            }
+          }
+          viol[k * kMaxP + j] = v;
+        }
+        __syncwarp();
+        int bk = -1;
+        int full[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          full[k] = -1;
+          for (int j = 0; j < Peff; ++j)
+            if (full[k] < 0 && viol[k * kMaxP + j] <= kContainTol) full[k] = j;
+          if (full[k] < 0 && bk < 0) bk = k;
+        }
+        if (bk < 0) {  // node optimum is feasible for the mixed-integer problem: new incumbent
+          best = q.obj, bestkkt = q.kkt;
+          if (lane < NW) bestw[lane] = w[lane];
+#pragma unroll
+          for (int k = 0; k < N; ++k)
+            if (lane == 0) bestsig[k] = full[k];
+          __syncwarp();
+          continue;
+        }
+        // split the candidate set of step bk in two halves ordered by (violation, index)
+        int order[kMaxP], no = 0;
+        double vv[kMaxP];
+        for (int j = 0; j < Peff; ++j)
+          if (cur[bk] >> j & 1) order[no] = j, vv[no++] = viol[bk * kMaxP + j];
+        for (int x = 1; x < no; ++x)
+          for (int y = x; y > 0 && vv[y] < vv[y - 1]; --y) {
+            const double tv = vv[y];
+            vv[y] = vv[y - 1], vv[y - 1] = tv;
+            const int to = order[y];
+            order[y] = order[y - 1], order[y - 1] = to;
+          }
+        if (no <= 1) continue;
+        const int h = (no + 1) / 2;
+        unsigned lo_m = 0, hi_m = 0;
+        for (int x = 0; x < no; ++x) {
+          if (x < h) lo_m |= 1u << order[x];
+          else hi_m |= 1u << order[x];
+        }
+        if (top + 2 > kStackCap) {
+          exhausted = false;
+          break;
+        }
+        if (lane < 16) {
+          const unsigned char c = cur[lane];
+          stack[top * 16 + lane] = lane == bk ? (unsigned char)hi_m : c;
+          stack[(top + 1) * 16 + lane] = lane == bk ? (unsigned char)lo_m : c;  // least violated half first
+        }
+        top += 2;
+        __syncwarp();
+      }
+      R.nodes = nodes, R.iters = iters, R.rows = maxrows;
+      if (best < INFINITY) {
+        R.status = (exhausted && !fail) ? HDSM_OPTIMAL : HDSM_NODE_LIMIT;  // a lost node leaves the optimum unproven
+        R.obj = best, R.kkt_res = bestkkt;
+      } else {
+        R.status = !exhausted ? HDSM_NODE_LIMIT : (fail ? fail : HDSM_INFEASIBLE);
+      }
+    } else {
+      R.status = st;
+    }
+    write_outputs(agent, R, best < INFINITY);
+  }
+
+  // read-back (agent_class.cpp:962-987) and K4 position pack; failed agents get the shifted previous
+  // plan in pos_out (:1004-1013) and zeros elsewhere
+  __device__ void write_outputs(int agent, const hdsm_result& R, bool have) {
+    double* traj = A.traj + (size_t)agent * (N + 1) * 9;
+    double* ctrl = A.ctrl + (size_t)agent * N * 3;
+    for (int idx = lane; idx < K3; idx += 32) {
+      const int k = idx / 3, a = idx - 3 * k;
+      double pp = 0, vv = 0, aa = 0;
+      if (have) {
+        pp = pbar[idx];
+        vv = T.cV[a][k][0] * s0[a] + T.cV[a][k][1] * s0[3 + a] + T.cV[a][k][2] * s0[6 + a];
+        aa = T.cA[a][k][0] * s0[a] + T.cA[a][k][1] * s0[3 + a] + T.cA[a][k][2] * s0[6 + a];
+#pragma unroll
+        for (int z = 0; z < NZ; ++z) {
+          const double wz = bestw[a * NZ + z];
+          pp += T.QP[a][k][z] * wz, vv += T.QV[a][k][z] * wz, aa += T.QA[a][k][z] * wz;
+        }
+        if (k == 0) pp = s0[a], vv = s0[3 + a], aa = s0[6 + a];  // fixed to state_curr_ (:886-889)
+        if (k == N) vv = 0.0, aa = 0.0;                          // fixed to zero (:2078-2081)
+      }
+      traj[k * 9 + a] = pp, traj[k * 9 + 3 + a] = vv, traj[k * 9 + 6 + a] = aa;
+      if (A.pos_out) {
+        const double* prev = A.prev + (size_t)agent * K3;
+        A.pos_out[(size_t)agent * K3 + idx] = have ? pp : prev[3 * (k < N ? k + 1 : N) + a];
+      }
+    }
+    for (int idx = lane; idx < 3 * N; idx += 32) {
+      const int k = idx / 3, a = idx - 3 * k;
+      double u = 0;
+      if (have) {
+        u = T.Up[a][k][0] * s0[a] + T.Up[a][k][1] * s0[3 + a] + T.Up[a][k][2] * s0[6 + a];
+#pragma unroll
+        for (int z = 0; z < NZ; ++z) u += T.Z[a][k][z] * bestw[a * NZ + z];
+      }
+      ctrl[idx] = u;
+    }
+    if (lane < N) A.assign_out[(size_t)agent * N + lane] = have ? bestsig[lane] : -1;
+    if (lane < A.P) {
+      int used = 0;
+      if (have)
+        for (int k = 0; k < N; ++k) used |= bestsig[k] == lane;
+      A.poly_used[(size_t)agent * A.P + lane] = (uint8_t)used;
+    }
+    if (lane == 0) A.res[agent] = R;
+  }
+};
+
+template <int N>
+__global__ void __launch_bounds__(32) hdsm_solve_kernel(const Tables* __restrict__ tables, const KernelArgs args) {
+  extern __shared__ double smem[];
+  const int agent = blockIdx.x;
+  if (agent >= args.n_local) return;
+  Solver<N> s(*tables, args, smem);
+  s.run(agent);
+}
+
+}  // namespace hdsm

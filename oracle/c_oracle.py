@@ -53,7 +53,7 @@ def lib():
     return _LIB
 
 
-def make_params(d, max_iter=60, max_nodes=100000, prune=True, tol=1e-9):
+def make_params(d, max_iter=60, max_nodes=100000, prune=True, tol=1e-8):
     p = OrcParams()
     p.n_hor, p.poly_hor, p.rk4 = int(d["n_hor"]), int(d["poly_hor"]), int(bool(d["rk4"]))
     p.max_iter, p.max_nodes, p.prune = max_iter, max_nodes, int(prune)

@@ -34,6 +34,7 @@
 #define MAXQ (3 * MAXN - 2)
 #define FEAS_TOL 1e-6
 #define PRUNE_MARGIN 1e-6
+#define LOOSE_TOL 1e-6 /* accepted when the iteration limit is reached: still inside the 1e-6 KKT target */
 
 enum { ORC_OPTIMAL = 0, ORC_INFEASIBLE = 1, ORC_MAX_ITER = 2, ORC_NUMERICAL = 3, ORC_NODE_LIMIT = 4 };
 
@@ -64,11 +65,19 @@ typedef struct {
 } tables_t;
 
 /* ------------------------------------------------------------------ small dense helpers */
-static int chol(int n, double *A, int lda) { /* in place lower Cholesky; returns 0 ok */
+/* In-place lower Cholesky.  A pivot that lost all its digits to cancellation (<= 1e-13 of the
+ * original diagonal) marks a direction the barrier has pinned: that variable is frozen for this
+ * solve (column zeroed, diagonal stored as 0) instead of aborting.  strict != 0: fail instead. */
+static int chol(int n, double *A, int lda, int strict) {
   for (int j = 0; j < n; j++) {
-    double d = A[j * lda + j];
+    double orig = A[j * lda + j], d = orig;
     for (int k = 0; k < j; k++) d -= A[j * lda + k] * A[j * lda + k];
-    if (!(d > 0.0)) return 1;
+    if (!(d > 1e-13 * orig) || !(orig > 0.0)) {
+      if (strict || !(orig == orig)) return 1;
+      A[j * lda + j] = 0.0;
+      for (int i = j + 1; i < n; i++) A[i * lda + j] = 0.0;
+      continue;
+    }
     d = sqrt(d);
     A[j * lda + j] = d;
     for (int i = j + 1; i < n; i++) {
@@ -83,12 +92,12 @@ static void chol_solve(int n, const double *L, int lda, double *x) {
   for (int i = 0; i < n; i++) {
     double v = x[i];
     for (int k = 0; k < i; k++) v -= L[i * lda + k] * x[k];
-    x[i] = v / L[i * lda + i];
+    x[i] = L[i * lda + i] > 0 ? v / L[i * lda + i] : 0.0;
   }
   for (int i = n - 1; i >= 0; i--) {
     double v = x[i];
     for (int k = i + 1; k < n; k++) v -= L[k * lda + i] * x[k];
-    x[i] = v / L[i * lda + i];
+    x[i] = L[i * lda + i] > 0 ? v / L[i * lda + i] : 0.0;
   }
 }
 
@@ -256,7 +265,7 @@ static int build_tables(const orc_params *P, tables_t *T) {
       }
     double L[MAXNZ][MAXNZ];
     memcpy(L, T->Hw[a], sizeof(L));
-    if (chol(nz, &L[0][0], MAXNZ)) return 4;
+    if (chol(nz, &L[0][0], MAXNZ, 1)) return 4;
     for (int c = 0; c < nz; c++) {
       double e2[MAXNZ] = {0};
       e2[c] = 1;
@@ -503,7 +512,10 @@ static void solve_qp(prob_t *pb, qp_out *out) {
       }
     double obj = pb->c0;
     for (int i = 0; i < nw; i++) obj += 0.5 * w[i] * (hg[i] + pb->g[i]);
-    if (rdmax <= tol * (1 + gmax) && rcmax <= tol && mu <= tol * fmax(1.0, fabs(obj)) * 1e-1) {
+    if (getenv("ORC_TRACE") && atoi(getenv("ORC_TRACE")) > 1)
+      fprintf(stderr, "   it %d rd %.2e rc %.2e mu %.2e obj %.9f lamsum %.2e\n", it, rdmax / (1 + gmax), rcmax, mu, obj, lamsum);
+#define ACCEPT(TOL) (rdmax <= (TOL) * (1 + gmax) && rcmax <= (TOL) && mu <= 0.1 * (TOL) * fmax(1.0, fabs(obj)))
+    if (ACCEPT(tol) || (it == P->max_iter && ACCEPT(LOOSE_TOL))) {
       out->status = ORC_OPTIMAL, out->iters = it, out->obj = obj, out->kkt = fmax(rdmax / (1 + gmax), fmax(rcmax, mu));
       memcpy(out->w, w, sizeof(double) * nw);
       return;
@@ -540,7 +552,7 @@ static void solve_qp(prob_t *pb, qp_out *out) {
           }
         }
     }
-    if (chol(nw, &K[0][0], MAXNW)) {
+    if (chol(nw, &K[0][0], MAXNW, 0)) {
       out->status = ORC_NUMERICAL, out->iters = it, out->obj = INFINITY;
       return;
     }
@@ -813,6 +825,11 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
     solve_qp(&pb, &q);
     nodes++;
     iters += q.iters;
+    if (getenv("ORC_TRACE")) {
+      fprintf(stderr, "node %d sets", nodes);
+      for (int k = 0; k < N; k++) fprintf(stderr, " %x", sets[k]);
+      fprintf(stderr, " rows %d status %d it %d obj %.6f best %.6f\n", pb.m, q.status, q.iters, q.obj, best);
+    }
     if (q.status != ORC_OPTIMAL) {
       if (q.status != ORC_INFEASIBLE) anyfail = q.status;
       continue;
@@ -871,7 +888,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
   }
   res->nodes = nodes, res->iters = iters, res->rows = maxrows;
   if (best < INFINITY) {
-    res->status = exhausted ? ORC_OPTIMAL : ORC_NODE_LIMIT;
+    res->status = (exhausted && !anyfail) ? ORC_OPTIMAL : ORC_NODE_LIMIT; /* a lost node leaves the optimum unproven */
     res->obj = best;
     /* read-back (agent_class.cpp:962-987): u = Up s0 + Z w, states by the affine maps */
     for (int k = 0; k <= N; k++)

@@ -1,0 +1,70 @@
+"""The C-ABI library: it builds, loads, exports every symbol include/hdsm.h declares, and its
+struct layouts match the ctypes mirrors.  No compute calls here (those are the gpu tests)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+from multi_agent_pkgs_b200 import _build, _lib, scenarios as sc
+
+
+def test_library_builds_and_loads():
+    path = _build.build_lib()
+    assert os.path.exists(path) and path.startswith(os.path.join(ROOT, "multi_agent_pkgs_b200"))
+    L = _lib.load()
+    assert L.hdsm_version() == 100
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "hdsm.h")).read()
+    declared = sorted(set(re.findall(r"\b(hdsm_[a-z_]+)\s*\(", hdr)))
+    assert declared == sorted(_lib.EXPORTS)
+    L = _lib.load()
+    for sym in declared:
+        assert hasattr(L, sym), sym
+
+
+def test_header_cites_reference_lines():
+    hdr = open(os.path.join(ROOT, "include", "hdsm.h")).read()
+    for cite in (":2071-2153", ":1086-1215", ":858-1023", ":645-677"):
+        assert cite in hdr
+
+
+def test_struct_layouts():
+    assert C.sizeof(_lib.HdsmResult) == 32 and _lib.RESULT_DTYPE.itemsize == 32
+    assert C.sizeof(_lib.HdsmParams) == 8 * 4 + 8 * (1 + 3 + 1 + 6 + 6 + 6 + 3 + 1)
+    p = _lib.make_params(sc.agile_params())
+    assert (p.n_hor, p.poly_hor, p.max_rows_per_poly) == (10, 4, 18) and p.max_jerk == 60.0
+
+
+def test_create_rejects_bad_arguments():
+    L = _lib.load()
+    h = C.c_void_p()
+    bad = _lib.make_params(sc.agile_params())
+    bad.n_hor = 40
+    assert L.hdsm_create(C.byref(bad), 1, 1, 0, C.byref(h)) == -1 and not h.value
+    assert L.hdsm_create(None, 1, 1, 0, C.byref(h)) == -1
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_device():
+    """The product path must fail loudly when there is no CUDA device."""
+    from multi_agent_pkgs_b200.planner import HdsmError, TrajectoryPlanner
+    L = _lib.load()
+    h = C.c_void_p()
+    ok = _lib.make_params(sc.agile_params())
+    assert L.hdsm_create(C.byref(ok), 4, 10, 0, C.byref(h)) == -2  # HDSM_ERR_CUDA
+    with pytest.raises(HdsmError):
+        TrajectoryPlanner(sc.agile_params(), 4, 10)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "multi_agent_pkgs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle-free", ""), f
