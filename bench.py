@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the replaced hot path: agent-QP solves per second at horizon N = 10.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--swarms S]
+
+Workload (BASELINE.json configs[1]): 10-agent circular exchange over the forest map, horizon 10,
+replicated as S independent swarm instances per GPU (frozen closed-loop snapshots at steps
+{1, 6, 12, 18}, rotated between timed iterations; L2 flushed between iterations).  One "step" is one
+replanning step of every agent of every instance: inter-agent plane assembly, exact assignment
+search, interior-point solves, position pack - one kernel launch - plus, for N > 1, one NCCL
+all-gather of the new plans' positions (the trajectory exchange of the reference).
+
+`value`   agent-QP solves/s with inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     the same through hdsm_solve_batch with HOST buffers (pinned staging, H2D, D2H inside).
+`--impl reference`  the CPU arm: the reference's own solver is Gurobi 10 (closed source, absent), so
+          this times the C port of the oracle (oracle/hdsm_oracle.c, kind "port") on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from multi_agent_pkgs_b200 import scenarios as sc  # noqa: E402
+
+SNAP_STEPS = (1, 6, 12, 18)
+DISTINCT_SWARMS = 24
+MAX_NODES = 64
+METRIC = "agent-QP solves/sec (horizon N=10)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------
+def tile_batch(b, reps):
+    """Replicate a batch of independent swarm instances `reps` times (neighbour ranges re-based)."""
+    n, n_rob = b.n, b.all_pos.shape[0]
+    idx = np.tile(np.arange(n), reps)
+    off = np.repeat(np.arange(reps) * n_rob, n).astype(np.int32)
+    t = b.take(idx)
+    t.global_id = (t.global_id + off).astype(np.int32)
+    t.nbr_begin = (t.nbr_begin + off).astype(np.int32)
+    t.nbr_end = (t.nbr_end + off).astype(np.int32)
+    t.all_pos = np.tile(b.all_pos, (reps, 1, 1))
+    t.all_valid = np.tile(b.all_valid, reps)
+    return t
+
+
+def make_snapshots(solve, seed, n_swarms):
+    """Closed-loop simulation of DISTINCT_SWARMS instances; returns the frozen input batches at
+    SNAP_STEPS, each tiled up to n_swarms instances.  `solve(batch)` -> dict(traj, ctrl, res)."""
+    sw = sc.config2_circle(seed=seed, n_swarms=min(DISTINCT_SWARMS, n_swarms))
+    reps = -(-n_swarms // (sw.n // 10))
+    snaps = []
+    for step in range(max(SNAP_STEPS) + 1):
+        b = sw.make_batch()
+        if step in SNAP_STEPS:
+            t = tile_batch(b, reps)
+            snaps.append(t.take(np.arange(n_swarms * 10)) if t.n > n_swarms * 10 else t)
+        out = solve(b)
+        st = out["res"]["status"]
+        sw.advance(out["traj"], out["ctrl"], (st == 0) | ((st == 4) & np.isfinite(out["res"]["obj"])))
+    for s in snaps:  # take() keeps the full table; trim it to the instances actually used
+        n_rob = int(s.nbr_end.max())
+        s.all_pos, s.all_valid = s.all_pos[:n_rob], s.all_valid[:n_rob]
+    return snaps
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], 0.0, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm (oracle port): bench.py may execute oracle/ only here
+# ----------------------------------------------------------------------------------------------
+def cpu_solve_rate(snaps, min_seconds, max_agents=None):
+    from oracle import c_oracle as co
+    cores = co.max_threads()
+    n = t = 0
+    i = 0
+    while t < min_seconds:
+        b = snaps[i % len(snaps)]
+        if max_agents and b.n > max_agents:
+            b = b.take(np.arange(max_agents))
+        t0 = time.perf_counter()
+        co.solve_batch(b, max_nodes=MAX_NODES, n_threads=cores)
+        t += time.perf_counter() - t0
+        n += b.n
+        i += 1
+    return n / t, cores, n, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import c_oracle as co
+    co.build()
+    n_swarms = args.swarms
+    snaps = make_snapshots(lambda b: co.solve_batch(b, max_nodes=MAX_NODES), args.seed, min(n_swarms, 4 * DISTINCT_SWARMS))
+    sample = snaps[0].n  # bounded sample of the workload per step (96 swarm instances = 960 agent QPs)
+    for _ in range(args.warmup):
+        co.solve_batch(snaps[0].take(np.arange(sample)), max_nodes=MAX_NODES)
+    times = []
+    for k in range(args.steps):
+        b = snaps[k % len(snaps)].take(np.arange(sample))
+        t0 = time.perf_counter()
+        co.solve_batch(b, max_nodes=MAX_NODES)
+        times.append(time.perf_counter() - t0)
+    total = float(np.sum(times))
+    value = sample * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, world),
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": co.max_threads(), "kind": "port",
+                             "sample": f"{sample} agent QPs per step (first instances of the workload), "
+                                       f"C port of the oracle, Gurobi not available"},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, world):
+    return {"workload": f"config2: 10-agent circular exchange, forest map, N=10, {args.swarms} independent swarm "
+                        f"instances per GPU ({args.swarms * 10} agent QPs per GPU per step)",
+            "n_hor": 10, "poly_hor": 4, "agents_per_swarm": 10, "swarms_per_gpu": args.swarms,
+            "max_nodes": MAX_NODES, "snapshots": list(SNAP_STEPS), "l2": "flushed between timed iterations (512 MiB write)",
+            "parallelism": f"agents sharded over {world} GPU(s), one NCCL all-gather of plan positions per step"}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
+    from multi_agent_pkgs_b200.swarm import DeviceBatch, Exchange, algorithmic_bytes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n_swarms = args.swarms
+    n_local = n_swarms * 10
+    params = sc.agile_params(10)
+    gen = TrajectoryPlanner(params, max_agents=DISTINCT_SWARMS * 10, max_neighbours=10, device=local_rank,
+                            max_nodes=MAX_NODES)
+    t0 = time.time()
+    snaps = make_snapshots(gen.solve_batch, args.seed + 1000 * rank, n_swarms)
+    gen.close()
+    log(f"[rank {rank}] {len(snaps)} snapshots x {snaps[0].n} agent QPs generated in {time.time() - t0:.1f}s")
+
+    pl = TrajectoryPlanner(params, max_agents=n_local, max_neighbours=10, device=local_rank, max_nodes=MAX_NODES)
+    n_rob_global = n_local * world
+    ex = Exchange(n_rob_global, 10, world, rank, dev, pl)
+    dbs = [DeviceBatch(s, dev) for s in snaps]
+    balg = float(np.mean([algorithmic_bytes(s).mean() for s in snaps]))
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step(db):
+        pl.solve_batch_device(db.t, db.n_rob, sp)
+        if world > 1:
+            ex.allgather(db.t["pos_out"], sp)
+
+    for k in range(max(args.warmup, 3)):
+        step(dbs[k % len(dbs)])
+    torch.cuda.synchronize()
+    # quality of what is being timed: statuses and KKT residuals of one pass over the snapshots
+    stat = np.zeros(6, int)
+    kkt = 0.0
+    iters = nodes = 0
+    for db in dbs:
+        step(db)
+        torch.cuda.synchronize()
+        r = db.results()
+        stat += np.bincount(r["status"], minlength=6)
+        good = r["status"] == 0
+        kkt = max(kkt, float(r["kkt_res"][good].max()) if good.any() else 0.0)
+        iters += int(r["iters"].sum())
+        nodes += int(r["nodes"].sum())
+
+    # ---- device-resident timing: K steps, CUDA events on the launching stream, L2 flushed between
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    launches0 = pl.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        step(dbs[k % len(dbs)])
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clk = clocks.stop()
+    launches = pl.launch_count - launches0
+    ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(ms.sum())
+    if dist:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = n_local * world * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-pointer C ABI call (pinned staging, H2D + D2H inside)
+    for k in range(2):
+        pl.solve_batch(snaps[k % len(snaps)])
+    if dist:
+        dist.barrier()
+    t_e2e = 0.0
+    for k in range(args.steps):
+        b = snaps[k % len(snaps)]
+        t1 = time.perf_counter()
+        out = pl.solve_batch(b)
+        t_e2e += time.perf_counter() - t1
+    if dist:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = n_local * world * args.steps / t_e2e
+    h2d = dbs[0].input_bytes()
+    d2h = int(sum(out[k].nbytes for k in ("traj", "ctrl", "poly_used", "assign", "res")))
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+        kernel_ms = total_ms / args.steps
+        achieved = balg * n_local / (kernel_ms * 1e-3) / 1e9
+        cpu_rate, cores, cpu_n, cpu_t = cpu_solve_rate(snaps, min_seconds=args.cpu_seconds, max_agents=20000)
+        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(args, world),
+                "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_solve": balg,
+                             "note": "the solve is FP64-latency bound, not HBM bound (DESIGN.md section 5); "
+                                     "traffic from ncu is in profiles/"},
+                "cpu_baseline": {"value": cpu_rate, "unit": "solves/s", "cores": cores, "kind": "port",
+                                 "sample": f"{cpu_n} agent QPs of the same snapshots in {cpu_t:.1f}s, C port of the "
+                                           f"oracle on all host threads (Gurobi not available)"},
+                "clocks": clk,
+                "quality": {"status_counts": {k: int(v) for k, v in zip(
+                    ("optimal", "infeasible", "max_iter", "numerical", "node_limit", "row_overflow"), stat)},
+                    "max_kkt_residual": kkt, "ipm_iters_per_solve": iters / max(1, stat.sum()),
+                    "qp_relaxations_per_solve": nodes / max(1, stat.sum())},
+                "smem_bytes_per_block": pl.smem_bytes}
+        print(json.dumps(line), flush=True)
+    pl.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--swarms", type=int, default=2048, help="independent 10-agent swarm instances per GPU")
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

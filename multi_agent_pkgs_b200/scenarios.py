@@ -505,7 +505,7 @@ def config5_random(seed=5, n_rob=4096, n_hor=10, side=200.0):
     for i in range(n_rob):
         while True:
             g = np.array([*rng.uniform(0, side, 2), rng.uniform(1.0, 3.0)])
-            if np.linalg.norm(g[:2] - starts[i, :2]) >= 50.0:
+            if np.linalg.norm(g[:2] - starts[i, :2]) >= min(50.0, side / 2):
                 goals[i] = g
                 break
     return _mk_swarm(params, world, starts, goals, [(0, n_rob)], rng)
