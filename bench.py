@@ -208,7 +208,8 @@ def run_ours(args, rank, world, local_rank):
     dbs = [DeviceBatch(s, dev) for s in snaps]
     balg = float(np.mean([algorithmic_bytes(s).mean() for s in snaps]))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: NULL means "the handle's own stream" in the ABI
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
 
     def step(db):

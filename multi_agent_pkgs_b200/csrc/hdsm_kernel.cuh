@@ -868,14 +868,20 @@ struct Solver {
           viol[k * kMaxP + j] = v;
         }
         __syncwarp();
+        // branch on the uncovered step that is farthest from all of its candidates
         int bk = -1;
+        double bkv = 0.0;
         int full[N];
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           full[k] = -1;
-          for (int j = 0; j < Peff; ++j)
-            if (full[k] < 0 && viol[k * kMaxP + j] <= kContainTol) full[k] = j;
-          if (full[k] < 0 && bk < 0) bk = k;
+          double vmin = INFINITY;
+          for (int j = 0; j < Peff; ++j) {
+            const double v = viol[k * kMaxP + j];
+            vmin = fmin(vmin, v);
+            if (full[k] < 0 && v <= kContainTol) full[k] = j;
+          }
+          if (full[k] < 0 && (bk < 0 || vmin > bkv)) bk = k, bkv = vmin;
         }
         if (bk < 0) {  // node optimum is feasible for the mixed-integer problem: new incumbent
           best = q.obj, bestkkt = q.kkt;

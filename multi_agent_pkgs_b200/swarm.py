@@ -133,6 +133,8 @@ class ShardedSwarm:
         self.planner = TrajectoryPlanner(swarm.params, self.hi - self.lo, nn, dev_index, max_nodes=max_nodes, **kw)
         self.exchange = Exchange(swarm.n, swarm.params["n_hor"], world, rank, device, self.planner)
         self.have = np.zeros(swarm.n, np.uint8)
+        import torch
+        self.stream = torch.cuda.Stream(device=device)  # non-NULL: NULL selects the handle's own stream
 
     def step(self):
         """One replanning step of the whole swarm; returns this rank's hdsm_result array."""
@@ -142,9 +144,11 @@ class ShardedSwarm:
         db = DeviceBatch(batch, self.device)
         db.t["all_pos"] = self.exchange.table          # the table rebuilt by the previous exchange
         db.t["all_valid"] = torch.from_numpy(self.have.copy()).to(self.device)
-        self.planner.solve_batch_device(db.t, self.swarm.n, torch.cuda.current_stream().cuda_stream)
-        self.exchange.allgather(db.t["pos_out"], torch.cuda.current_stream().cuda_stream)
-        torch.cuda.current_stream().synchronize()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.planner.solve_batch_device(db.t, self.swarm.n, self.stream.cuda_stream)
+            self.exchange.allgather(db.t["pos_out"], self.stream.cuda_stream)
+        self.stream.synchronize()
         res = db.results()
         ok = (res["status"] == 0) | ((res["status"] == 4) & np.isfinite(res["obj"]))
         self.swarm.advance(db.t["traj"].cpu().numpy(), db.t["ctrl"].cpu().numpy(), ok, ids)

@@ -843,7 +843,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
     double p[MAXN + 1][3];
     positions(&pb, q.w, p, 1);
     int full[MAXN], bk = -1, order[MAXP], no = 0;
-    double viol[MAXP];
+    double viol[MAXP], bkv = 0;
     for (int k = 0; k < N; k++) {
       full[k] = -1;
       double v[MAXP];
@@ -854,7 +854,13 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
           if (full[k] < 0 && v[j] <= 1e-7) full[k] = j;
         }
       }
-      if (full[k] < 0 && bk < 0) {
+      double vmin = INFINITY;
+      for (int j = 0; j < Peff; j++) vmin = fmin(vmin, v[j]);
+      /* branch on the uncovered step that is farthest from all of its candidates: ~4x fewer nodes
+       * than "first uncovered" on the config-2 closed loop */
+      int take = full[k] < 0 && (bk < 0 || vmin > bkv);
+      if (take) {
+        bkv = vmin;
         bk = k;
         no = 0;
         for (int j = 0; j < Peff; j++)

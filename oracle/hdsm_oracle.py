@@ -600,8 +600,8 @@ def solve_miqp_bnb(p: Params, x0, ref, polys, planes, solver=solve_qp_pdip,
     whose rows at step k are union_hull_rows(S_k) (all rows of the polytope when |S_k| = 1) -
     a valid relaxation of "the segment lies in one member of S_k".  If every segment
     (p_k, p_{k+1}) of the node optimum already lies inside one member of S_k the node optimum is
-    MIQP-feasible and the node is fathomed; otherwise the first uncovered step's set is split in
-    two halves ordered by violation, least-violated half explored first.  Any split rule is exact;
+    MIQP-feasible and the node is fathomed; otherwise the set of the most violated uncovered step is
+    split in two halves ordered by violation, least-violated half explored first.  Any split rule is exact;
     this one collapses near-identical overlapping cells into a single subtree.
     """
     N = p.n_hor
@@ -634,14 +634,14 @@ def solve_miqp_bnb(p: Params, x0, ref, polys, planes, solver=solve_qp_pdip,
             continue
         xs, _ = qp.split(r.z)
         full = [-1] * N
-        branch_k = -1
+        branch_k, branch_v = -1, 0.0
         for k in range(N):
             viol = {j: segment_violation(polys[j], xs[k, :3], xs[k + 1, :3]) for j in sets[k]}
             ok = [j for j in sets[k] if viol[j] <= contain_tol]
             if ok:
                 full[k] = ok[0]
-            elif branch_k < 0:
-                branch_k = k
+            elif branch_k < 0 or min(viol.values()) > branch_v:  # farthest from all its candidates
+                branch_k, branch_v = k, min(viol.values())
                 order = sorted(sets[k], key=lambda j: (viol[j], j))
         if branch_k < 0:
             best = MIQPResult(OPTIMAL, full, r.obj, qp=r)

@@ -3,7 +3,8 @@
 Tolerances (north star: <= 1e-4 relative objective gap, KKT residual reported):
   * objective: 1e-6 relative against the NumPy-oracle golden vectors and the C port;
   * KKT residual of every returned solution <= 1e-6 (scaled as in SURVEY 8(d));
-  * trajectory 2e-3 m (the optimum is unique but flat along weakly weighted directions);
+  * positions 1e-3 m, velocities / accelerations 2e-2 (the optimum is unique but flat along the
+    weakly weighted directions: r_u = 0.01, no acceleration weight);
   * statuses and chosen assignments: exact, assignments up to ties (validated geometrically).
 """
 import numpy as np
@@ -17,7 +18,12 @@ from multi_agent_pkgs_b200.planner import AgentSolver, TrajectoryPlanner
 pytestmark = pytest.mark.gpu
 
 OBJ_RTOL = 1e-6
-TRAJ_ATOL = 2e-3
+POS_ATOL = 1e-3
+STATE_ATOL = 2e-2
+
+
+def _traj_close(a, b):
+    return np.abs(a[..., :3] - b[..., :3]).max() <= POS_ATOL and np.abs(a - b).max() <= STATE_ATOL
 
 
 def _planner(b, **kw):
@@ -65,7 +71,7 @@ def test_golden_parity(golden_names):
         ok = exp["status"] == OPTIMAL
         gap = np.abs(r["obj"][ok] - exp["obj"][ok]) / np.maximum(1, np.abs(exp["obj"][ok]))
         assert gap.max() <= OBJ_RTOL, (name, gap.max())
-        assert np.abs(out["traj"][ok] - exp["traj"][ok]).max() <= TRAJ_ATOL, name
+        assert _traj_close(out["traj"][ok], exp["traj"][ok]), name
         assert r["kkt_res"][ok].max() <= 1e-6
         _check_properties(b, out, np.nonzero(ok)[0])
         assert (r["nodes"][~ok] >= 0).all() and not np.isfinite(r["obj"][~ok]).any()
@@ -87,7 +93,7 @@ def test_matches_c_port_closed_loop(prune):
         ok = ref["res"]["status"] == OPTIMAL
         gap = np.abs(out["res"]["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1, np.abs(ref["res"]["obj"][ok]))
         assert gap.max() <= OBJ_RTOL, (step, gap.max())
-        assert np.abs(out["traj"][ok] - ref["traj"][ok]).max() <= TRAJ_ATOL
+        assert _traj_close(out["traj"][ok], ref["traj"][ok])
         if prune:
             assert out["res"]["rows"].max() < 140
         sw.advance(ref["traj"], ref["ctrl"], ok)
@@ -110,7 +116,7 @@ def test_first_step_has_no_planes_and_single_agent():
         assert ag.SolveOptimizationProblem() and not ag.optimization_failed_
         ref = co.solve_batch(b)
         assert abs(ag.last_result["obj"] - ref["res"]["obj"][0]) <= OBJ_RTOL * max(1, ref["res"]["obj"][0])
-        assert np.abs(ag.traj_curr_ - ref["traj"][0]).max() <= TRAJ_ATOL
+        assert _traj_close(ag.traj_curr_, ref["traj"][0])
         sw.advance(ref["traj"], ref["ctrl"], ref["res"]["status"] == 0)
     assert np.linalg.norm(sw.state[0, :3] - np.array([0, 0, 1.5])) > 1.0  # it actually flies
 

