@@ -352,6 +352,8 @@ class Swarm:
     rng: Optional[np.random.Generator] = None
     rmax: int = 18
     extra_chamfers: bool = True
+    seed: int = 0
+    step_count: int = 0
 
     @property
     def n(self):
@@ -375,7 +377,9 @@ class Swarm:
             pos = self.state[i, :3]
             path = plan_path(pos, self.goal[i], self.world)
             refs[r] = sample_path(path, self.path_vel[i], N, self.params["dt"])[:N]
-            polys_all.append(corridor(pos, path, self.world, self.rng, P, self.rmax, self.extra_chamfers))
+            # per-agent, per-step stream: a shard of the swarm generates the same inputs as the whole
+            rng_i = np.random.default_rng([self.seed, self.step_count, int(i)])
+            polys_all.append(corridor(pos, path, self.world, rng_i, P, self.rmax, self.extra_chamfers))
             if self.have_plan[i]:
                 prev[r] = self.traj[i, :, :3]
             else:
@@ -390,6 +394,7 @@ class Swarm:
         n = self.n
         N = self.params["n_hor"]
         ids = np.arange(n) if ids is None else np.asarray(ids)
+        self.step_count += 1
         if self.traj is None:
             self.traj = np.zeros((n, N + 1, 9))
             self.traj[:] = self.state[:, None, :]
@@ -406,7 +411,7 @@ class Swarm:
                 self.state[i] = self.traj[i, 1]
 
 
-def _mk_swarm(params, world, starts, goals, groups, rng, extra_chamfers=True):
+def _mk_swarm(params, world, starts, goals, groups, rng, extra_chamfers=True, seed=0):
     n = len(starts)
     state = np.zeros((n, 9))
     state[:, :3] = starts
@@ -418,7 +423,8 @@ def _mk_swarm(params, world, starts, goals, groups, rng, extra_chamfers=True):
     for (a, b) in groups:
         gb[a:b] = a
         ge[a:b] = b
-    return Swarm(params, world, state, np.asarray(goals, float), vel, gb, ge, rng=rng, extra_chamfers=extra_chamfers)
+    return Swarm(params, world, state, np.asarray(goals, float), vel, gb, ge, rng=rng, extra_chamfers=extra_chamfers,
+                 seed=seed)
 
 
 def config1_single_agent(seed=1, n_hor=10):
@@ -426,7 +432,7 @@ def config1_single_agent(seed=1, n_hor=10):
     rng = np.random.default_rng(seed)
     params = agile_params(n_hor)
     return _mk_swarm(params, Forest.empty(), np.array([[0.0, 0.0, 1.5]]), np.array([[42.15, 42.15, 1.5]]),
-                     [(0, 1)], rng, extra_chamfers=False)
+                     [(0, 1)], rng, extra_chamfers=False, seed=seed)
 
 
 def config2_circle(seed=2, n_swarms=1, n_rob=10, n_hor=10, radius=22.0, centre=(18.0, 15.0)):
@@ -449,7 +455,7 @@ def config2_circle(seed=2, n_swarms=1, n_rob=10, n_hor=10, radius=22.0, centre=(
         goals.append(pts[(np.arange(n_rob) + n_rob // 2) % n_rob])
         groups.append((s * n_rob, (s + 1) * n_rob))
     world = Forest(np.concatenate(cols))
-    return _mk_swarm(params, world, np.concatenate(starts), np.concatenate(goals), groups, rng)
+    return _mk_swarm(params, world, np.concatenate(starts), np.concatenate(goals), groups, rng, seed=seed)
 
 
 def config3_line(seed=3, n_rob=10, n_hor=10):
@@ -466,7 +472,7 @@ def config3_line(seed=3, n_rob=10, n_hor=10):
     world = Forest(np.concatenate([f1, wall, f2]))
     starts = np.array([[0.0, 5 + 2.01 * i, 1.0] for i in range(n_rob)])
     goals = starts + np.array([96.01, 0.0, 0.0])
-    return _mk_swarm(params, world, starts, goals, [(0, n_rob)], rng)
+    return _mk_swarm(params, world, starts, goals, [(0, n_rob)], rng, seed=seed)
 
 
 def config4_circle256(seed=4, n_rob=256, n_hor=10, radius=60.0):
@@ -477,7 +483,7 @@ def config4_circle256(seed=4, n_rob=256, n_hor=10, radius=60.0):
     ang = 2 * math.pi * np.arange(n_rob) / n_rob
     starts = np.stack([radius * np.cos(ang), radius * np.sin(ang), np.full(n_rob, 1.5)], 1)
     goals = starts[(np.arange(n_rob) + n_rob // 2) % n_rob]
-    return _mk_swarm(params, world, starts, goals, [(0, n_rob)], rng)
+    return _mk_swarm(params, world, starts, goals, [(0, n_rob)], rng, seed=seed)
 
 
 def config5_random(seed=5, n_rob=4096, n_hor=10, side=200.0):
@@ -508,4 +514,4 @@ def config5_random(seed=5, n_rob=4096, n_hor=10, side=200.0):
             if np.linalg.norm(g[:2] - starts[i, :2]) >= min(50.0, side / 2):
                 goals[i] = g
                 break
-    return _mk_swarm(params, world, starts, goals, [(0, n_rob)], rng)
+    return _mk_swarm(params, world, starts, goals, [(0, n_rob)], rng, seed=seed)
