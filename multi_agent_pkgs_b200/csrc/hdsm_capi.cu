@@ -162,11 +162,11 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   const long worst_nbr = 2L * max_neighbours * nkp;
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const int base = plan_smem(h->prm.n_hor, h->prm.poly_hor, rmax, 0, h->stat_cap).total_doubles * 8;
+  const int base = smem_doubles(h->prm.n_hor, h->prm.poly_hor, rmax, 0, h->stat_cap) * 8;
   const long budget_rows = std::max(0L, (long)(smem_max - base - 1024) / 48);
   h->nbr_cap = (int)std::min(worst_nbr, std::min(budget_rows, 1024L));
   h->nbr_cap = std::max(h->nbr_cap, 8);
-  h->smem_bytes = plan_smem(h->prm.n_hor, h->prm.poly_hor, rmax, h->nbr_cap, h->stat_cap).total_doubles * 8;
+  h->smem_bytes = smem_doubles(h->prm.n_hor, h->prm.poly_hor, rmax, h->nbr_cap, h->stat_cap) * 8;
   *out = h;
   return HDSM_OK;
 }

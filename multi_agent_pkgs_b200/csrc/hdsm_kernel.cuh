@@ -42,30 +42,55 @@ struct KernelArgs {
   double tol;
 };
 
-// Shared-memory plan, in doubles, shared by host (size) and device (carving).
-struct SmemPlan {
-  int poly, nrow, ns, nl, srow, ss, sl, Ls, bs, bl, DQ, TQ, FQ, qv, dq, dqc, qbar, Mk, Tk, Fk, p, dp, dpc, pbar, plo,
-      phi, w, dw, dwc, g, bestw, s0, viol, scal, ints, total_doubles;
+// Shared-memory layout in doubles.  Everything whose size depends only on the horizon sits at a
+// compile-time offset (no registers spent on pointers); the polytope and row buffers, sized at run
+// time, follow.
+struct FixedLayout {
+  int Ks, invd, diag0, bs, bl, DQ, TQ, FQ, qv, dq, dqc, qbar, Mk, Tk, Fk, p, dp, dpc, pbar, plo, phi, w, dw, dwc, g, bestw, s0,
+      viol, ints, var;
 };
-HDSM_HD inline SmemPlan plan_smem(int N, int P, int rmax, int nbr_cap, int stat_cap) {
+HDSM_HD constexpr FixedLayout make_layout(int N) {
   const int NW = 3 * (N - 2), NQ3 = 3 * (3 * N - 2), K3 = 3 * (N + 1);
-  SmemPlan s;
+  FixedLayout s{};
   int o = 0;
-  auto take = [&](int n) { int r = o; o += n; return r; };
-  s.poly = take(P * rmax * 4);
-  s.nrow = take(nbr_cap * 4), s.ns = take(nbr_cap), s.nl = take(nbr_cap);
-  s.srow = take(stat_cap * 4), s.ss = take(stat_cap), s.sl = take(stat_cap);
-  s.Ls = take(NW * (NW + 1));
-  s.bs = take(NQ3 * 2), s.bl = take(NQ3 * 2);
-  s.DQ = take(NQ3), s.TQ = take(NQ3), s.FQ = take(NQ3), s.qv = take(NQ3), s.dq = take(NQ3), s.dqc = take(NQ3),
-  s.qbar = take(NQ3);
-  s.Mk = take((N + 1) * 6), s.Tk = take(K3), s.Fk = take(K3);
-  s.p = take(K3), s.dp = take(K3), s.dpc = take(K3), s.pbar = take(K3), s.plo = take(K3), s.phi = take(K3);
-  s.w = take(NW), s.dw = take(NW), s.dwc = take(NW), s.g = take(NW), s.bestw = take(NW);
-  s.s0 = take(10), s.viol = take(N * kMaxP), s.scal = take(16);
-  s.ints = take((2 * (N + 2) + 4 * N + kStackCap * 4 + 16) / 2 + 1);  // int32 region, counted in doubles
-  s.total_doubles = o;
+  s.Ks = o, o += NW * (NW + 1);
+  s.invd = o, o += NW;
+  s.diag0 = o, o += NW;
+  s.bs = o, o += NQ3 * 2;
+  s.bl = o, o += NQ3 * 2;
+  s.DQ = o, o += NQ3;
+  s.TQ = o, o += NQ3;
+  s.FQ = o, o += NQ3;
+  s.qv = o, o += NQ3;
+  s.dq = o, o += NQ3;
+  s.dqc = o, o += NQ3;
+  s.qbar = o, o += NQ3;
+  s.Mk = o, o += (N + 1) * 6;
+  s.Tk = o, o += K3;
+  s.Fk = o, o += K3;
+  s.p = o, o += K3;
+  s.dp = o, o += K3;
+  s.dpc = o, o += K3;
+  s.pbar = o, o += K3;
+  s.plo = o, o += K3;
+  s.phi = o, o += K3;
+  s.w = o, o += NW;
+  s.dw = o, o += NW;
+  s.dwc = o, o += NW;
+  s.g = o, o += NW;
+  s.bestw = o, o += NW;
+  s.s0 = o, o += 10;
+  s.viol = o, o += N * kMaxP;
+  s.ints = o;
+  // int32 region: segment tables 4(N+2), bestsig N, fullsig N, prow_n 8, cur 16 B, stack, pair table u16
+  const int int_words = 4 * (N + 2) + 2 * N + kMaxP + 4 + kStackCap * 4 + (NW * (NW + 1) / 2 + 1) / 2 + 2;
+  o += (int_words + 1) / 2;
+  s.var = o;
   return s;
+}
+// run-time part after FixedLayout::var: poly [P*rmax*4], rown [rows*4], rs [rows], rl [rows], nid [P*rmax bytes]
+HDSM_HD inline int smem_doubles(int N, int P, int rmax, int nbr_cap, int stat_cap) {
+  return make_layout(N).var + P * rmax * 4 + (nbr_cap + stat_cap) * 6 + (P * rmax + 7) / 8;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -118,35 +143,43 @@ struct Solver {
   const KernelArgs& A;
   const int lane, grp, sub;
   const unsigned gmask;
-  // shared memory views
-  double *poly, *nrow, *ns, *nl, *srow, *ss, *sl, *Ls, *bs, *bl, *DQ, *TQ, *FQ, *qv, *dq, *dqc, *qbar, *Mk, *Tk, *Fk, *p,
-      *dp, *dpc, *pbar, *plo, *phi, *w, *dw, *dwc, *g, *bestw, *s0, *viol, *scal;
-  int *nbeg, *sbeg, *bestsig, *prow_n;
-  unsigned char* stack;  // kStackCap entries of 16 bytes: per-step candidate masks
-  unsigned char* cur;    // current node's masks [N]
+  static constexpr FixedLayout L = make_layout(N);
+  // shared memory views: fixed-offset arrays are sm + constant, only the last five need registers
+  double* const sm;
+  double *const Ks = sm + L.Ks, *const invd = sm + L.invd, *const diag0 = sm + L.diag0, *const bs = sm + L.bs,
+                *const bl = sm + L.bl, *const DQ = sm + L.DQ, *const TQ = sm + L.TQ, *const FQ = sm + L.FQ,
+                *const qv = sm + L.qv, *const dq = sm + L.dq, *const dqc = sm + L.dqc, *const qbar = sm + L.qbar,
+                *const Mk = sm + L.Mk, *const Tk = sm + L.Tk, *const Fk = sm + L.Fk, *const p = sm + L.p,
+                *const dp = sm + L.dp, *const dpc = sm + L.dpc, *const pbar = sm + L.pbar, *const plo = sm + L.plo,
+                *const phi = sm + L.phi, *const w = sm + L.w, *const dw = sm + L.dw, *const dwc = sm + L.dwc,
+                *const g = sm + L.g, *const bestw = sm + L.bestw, *const s0 = sm + L.s0, *const viol = sm + L.viol;
+  int* const ip = reinterpret_cast<int*>(sm + L.ints);
+  int *const segb = ip, *const sege = ip + 2 * (N + 2), *const bestsig = ip + 4 * (N + 2), *const fullsig = bestsig + N,
+             *const prow_n = fullsig + N;  // segb/sege[2*slot + {0: inter-agent, 1: corridor}]
+  unsigned char* const cur = reinterpret_cast<unsigned char*>(prow_n + kMaxP);  // current node's masks [N]
+  unsigned char* const stack = cur + 16;  // kStackCap entries of 16 bytes: per-step candidate masks
+  unsigned short* const tab = reinterpret_cast<unsigned short*>(stack + kStackCap * 16);  // pairs (i << 8 | k)
+  double *poly, *rown, *rs, *rl;
+  unsigned char* nid;  // per polytope row: id of the first row with the same normal
   double c0;
-  int nkp, Peff;
+  int nkp, Peff, n_nbr_rows;
 
-  __device__ Solver(const Tables& t, const KernelArgs& a, double* sm)
-      : T(t), A(a), lane(threadIdx.x), grp(threadIdx.x >> 2), sub(threadIdx.x & 3), gmask(0xFu << (threadIdx.x & ~3)) {
-    const SmemPlan s = plan_smem(N, a.P, a.rmax, a.nbr_cap, a.stat_cap);
-    poly = sm + s.poly, nrow = sm + s.nrow, ns = sm + s.ns, nl = sm + s.nl, srow = sm + s.srow, ss = sm + s.ss,
-    sl = sm + s.sl, Ls = sm + s.Ls, bs = sm + s.bs, bl = sm + s.bl, DQ = sm + s.DQ, TQ = sm + s.TQ, FQ = sm + s.FQ,
-    qv = sm + s.qv, dq = sm + s.dq, dqc = sm + s.dqc, qbar = sm + s.qbar, Mk = sm + s.Mk, Tk = sm + s.Tk, Fk = sm + s.Fk,
-    p = sm + s.p, dp = sm + s.dp, dpc = sm + s.dpc, pbar = sm + s.pbar, plo = sm + s.plo, phi = sm + s.phi, w = sm + s.w,
-    dw = sm + s.dw, dwc = sm + s.dwc, g = sm + s.g, bestw = sm + s.bestw, s0 = sm + s.s0, viol = sm + s.viol,
-    scal = sm + s.scal;
-    int* ip = reinterpret_cast<int*>(sm + s.ints);
-    nbeg = ip, sbeg = ip + (N + 2), bestsig = ip + 2 * (N + 2), prow_n = bestsig + N;
-    cur = reinterpret_cast<unsigned char*>(prow_n + kMaxP);
-    stack = cur + 16;
+  __device__ Solver(const Tables& t, const KernelArgs& a, double* smem)
+      : T(t), A(a), lane(threadIdx.x), grp(threadIdx.x >> 2), sub(threadIdx.x & 3), gmask(0xFu << (threadIdx.x & ~3)),
+        sm(smem) {
+    const int rows = a.nbr_cap + a.stat_cap;
+    poly = sm + L.var;
+    rown = poly + a.P * a.rmax * 4;
+    rs = rown + rows * 4;
+    rl = rs + rows;
+    nid = reinterpret_cast<unsigned char*>(rl + rows);
     nkp = T.nkp;
   }
 
   // ---------------------------------------------------------------- small dense products
-  // out[k][a] = (bar ? bar[k][a] : 0) + QP[a][k] . x[a*NZ ...]
-  __device__ void positions_of(const double* x, const double* bar, double* out) const {
-    for (int idx = lane; idx < K3; idx += 32) {
+  // out[k][a] = (bar ? bar[k][a] : 0) + QP[a][k] . x[a*NZ ...]   (static + noinline: one copy, no `this`)
+  __device__ __forceinline__ static void positions_of(const Tables& T, const double* x, const double* bar, double* out) {
+    for (int idx = threadIdx.x; idx < K3; idx += 32) {
       const int k = idx / 3, a = idx - 3 * k;
       double v = bar ? bar[idx] : 0.0;
 #pragma unroll
@@ -154,8 +187,8 @@ struct Solver {
       out[idx] = v;
     }
   }
-  __device__ void quantities_of(const double* x, const double* bar, double* out) const {
-    for (int idx = lane; idx < NQ3; idx += 32) {
+  __device__ __forceinline__ static void quantities_of(const Tables& T, const double* x, const double* bar, double* out) {
+    for (int idx = threadIdx.x; idx < NQ3; idx += 32) {
       const int a = idx / NQ, q = idx - a * NQ;
       double v = bar ? bar[idx] : 0.0;
 #pragma unroll
@@ -172,10 +205,15 @@ struct Solver {
     return !(mx <= b - kPruneMargin);
   }
 
+  // rows acting on the position of `slot`: two segments (inter-agent, corridor), strided over the quad
   template <class F>
   __device__ __forceinline__ void for_slot_rows(int slot, F&& f) {
-    for (int i = nbeg[slot] + sub; i < nbeg[slot + 1]; i += 4) f(nrow + 4 * i, ns[i], nl[i]);
-    for (int i = sbeg[slot] + sub; i < sbeg[slot + 1]; i += 4) f(srow + 4 * i, ss[i], sl[i]);
+#pragma unroll 1
+    for (int sg = 0; sg < 2; ++sg) {
+      const int end = sege[2 * slot + sg];
+#pragma unroll 1
+      for (int i = segb[2 * slot + sg] + sub; i < end; i += 4) f(rown + 4 * i, rs[i], rl[i]);
+    }
   }
 
   // ---------------------------------------------------------------- per-agent set-up
@@ -194,6 +232,22 @@ struct Solver {
     __syncwarp();
     Peff = 0;
     while (Peff < A.P && prow_n[Peff] > 0) ++Peff;  // P_eff = leading present polytopes (:913)
+    // id of a row's normal = flat index of the first row (over all polytopes) with bit-identical normal
+    for (int i = lane; i < A.P * A.rmax; i += 32) {
+      int id = i;
+      for (int i2 = 0; i2 < i; ++i2)
+        if (poly[4 * i2] == poly[4 * i] && poly[4 * i2 + 1] == poly[4 * i + 1] && poly[4 * i2 + 2] == poly[4 * i + 2]) {
+          id = i2;
+          break;
+        }
+      nid[i] = (unsigned char)id;
+    }
+    // lower-triangle pairs ordered by column descending: the trailing update of Cholesky step j
+    // touches exactly the first (NW-1-j)(NW-j)/2 entries
+    for (int k = NW - 1; k >= 0; --k) {
+      const int base = (NW - 1 - k) * (NW - k) / 2;
+      for (int i = k + lane; i < NW; i += 32) tab[base + (i - k)] = (unsigned short)((i << 8) | k);
+    }
     const double* ref = A.ref + (size_t)agent * N * 6;
     // gradient and constant of the condensed objective (:870-883, :2098)
     double gi = 0, cpart = 0;
@@ -278,7 +332,7 @@ struct Solver {
     const unsigned lt = (1u << lane) - 1;
     for (int kp = 0; kp <= N; ++kp) {
       const int slot = T.slot_of_kp[kp];
-      if (slot >= 0) nbeg[slot] = cnt;
+      if (slot >= 0) segb[2 * slot] = cnt;
       for (int k = kp - 1; k <= kp; ++k) {
         if (k < 0 || k >= N) continue;
         const double ps[3] = {prev[3 * (k + 1)], prev[3 * (k + 1) + 1], prev[3 * (k + 1) + 2]};
@@ -317,14 +371,15 @@ struct Solver {
           if (valid) {
             const int pos = cnt + __popc(m & lt);
             if (pos < A.nbr_cap) {
-              nrow[4 * pos] = nf[0], nrow[4 * pos + 1] = nf[1], nrow[4 * pos + 2] = nf[2], nrow[4 * pos + 3] = b;
+              rown[4 * pos] = nf[0], rown[4 * pos + 1] = nf[1], rown[4 * pos + 2] = nf[2], rown[4 * pos + 3] = b;
             }
           }
           cnt += __popc(m);
         }
       }
+      if (slot >= 0) sege[2 * slot] = cnt;
     }
-    nbeg[nkp] = cnt;
+    n_nbr_rows = cnt;
     status = __reduce_max_sync(kFull, status);
     if (cnt > A.nbr_cap) return HDSM_ROW_OVERFLOW;
     __syncwarp();
@@ -364,18 +419,15 @@ struct Solver {
     const double* a = poly + 4 * (first * A.rmax + r);
     n[0] = a[0], n[1] = a[1], n[2] = a[2], b = a[3];
     if ((mask & (mask - 1)) == 0) return true;
-    for (int r2 = 0; r2 < r; ++r2) {  // duplicate normal inside the first member: handled by the first occurrence
-      const double* c = poly + 4 * (first * A.rmax + r2);
-      if (c[0] == n[0] && c[1] == n[1] && c[2] == n[2]) return false;
-    }
+    const int myid = nid[first * A.rmax + r];
+    for (int r2 = 0; r2 < r; ++r2)  // duplicate normal inside `first`: handled by its first occurrence
+      if (nid[first * A.rmax + r2] == myid) return false;
     double bmax = -INFINITY;
     for (int j = first; j < Peff; ++j) {
       if (!(mask >> j & 1)) continue;
       double bmin = INFINITY;
-      for (int r2 = 0; r2 < prow_n[j]; ++r2) {
-        const double* c = poly + 4 * (j * A.rmax + r2);
-        if (c[0] == n[0] && c[1] == n[1] && c[2] == n[2]) bmin = fmin(bmin, c[3]);
-      }
+      for (int r2 = 0; r2 < prow_n[j]; ++r2)
+        if (nid[j * A.rmax + r2] == myid) bmin = fmin(bmin, poly[4 * (j * A.rmax + r2) + 3]);
       if (bmin == INFINITY) return false;
       bmax = fmax(bmax, bmin);
     }
@@ -387,24 +439,31 @@ struct Solver {
   __device__ int build_static_rows() {
     int cnt = 0;
     const unsigned lt = (1u << lane) - 1;
+    double pn[3] = {0, 0, 0}, pb = 0;  // rows of the previous step's set, reused when the set repeats
+    bool pvalid = false;
+    int pk = -2;
     for (int slot = 0; slot < nkp; ++slot) {
       const int kp = T.kp_of_slot[slot];
-      sbeg[slot] = cnt;
+      segb[2 * slot + 1] = A.nbr_cap + cnt;
       for (int k = kp - 1; k <= kp; ++k) {
         if (k < 0 || k >= N) continue;
         if (k == kp && kp >= 1 && cur[kp - 1] == cur[kp]) continue;  // same rows already put on p_kp by step kp-1
-        double n[3], b;
-        bool valid = set_row(cur[k], lane, n, b);
-        if (valid && A.prune) valid = reachable(n, b, kp);
+        if (!(pk >= 0 && cur[pk] == cur[k])) pvalid = set_row(cur[k], lane, pn, pb);
+        pk = k;
+        bool valid = pvalid;
+        if (valid && A.prune) valid = reachable(pn, pb, kp);
         const unsigned m = __ballot_sync(kFull, valid);
         if (valid) {
           const int pos = cnt + __popc(m & lt);
-          if (pos < A.stat_cap) srow[4 * pos] = n[0], srow[4 * pos + 1] = n[1], srow[4 * pos + 2] = n[2], srow[4 * pos + 3] = b;
+          if (pos < A.stat_cap) {
+            double* r = rown + 4 * (A.nbr_cap + pos);
+            r[0] = pn[0], r[1] = pn[1], r[2] = pn[2], r[3] = pb;
+          }
         }
         cnt += __popc(m);
       }
+      sege[2 * slot + 1] = A.nbr_cap + min(cnt, A.stat_cap);
     }
-    sbeg[nkp] = cnt;
     __syncwarp();
     return cnt > A.stat_cap ? -1 : cnt;
   }
@@ -415,51 +474,47 @@ struct Solver {
     return side == 0 ? T.qhi[a][q] - qv[idx] : qv[idx] - T.qlo[a][q];
   }
 
-  // Cholesky of the matrix whose row `lane` is in K[], in place (lower part), then two triangular
-  // solves per call of solve().  Lanes >= NW carry zero rows.
-  __device__ __forceinline__ bool factor(double (&K)[NW], double& myinv) {
-    // A pivot that lost all its digits to cancellation (<= 1e-13 of the original diagonal) marks a
-    // direction the barrier has pinned: the variable is frozen for this solve (inverse pivot 0)
-    // instead of aborting.  Only a NaN / non-positive original diagonal is a failure.
+  // Cholesky of Ks (lower part, in place).  A pivot that lost all its digits to cancellation
+  // (<= 1e-13 of the original diagonal) marks a direction the barrier has pinned: the variable is
+  // frozen for this solve (inverse pivot 0) instead of aborting.  Only a non-positive / NaN original
+  // diagonal is a failure.  Work per step j: scale column j (one lane per row), then the trailing
+  // update spread over all 32 lanes through the pair table.
+  __device__ __forceinline__ static bool factor(double* Ks, double* invd, const double* diag0, const unsigned short* tab) {
+    const int lane = threadIdx.x;
     bool ok = true;
-    double dorig = 0.0;
-#pragma unroll
-    for (int j = 0; j < NW; ++j)
-      if (lane == j) dorig = K[j];
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < NW; ++j) {
-      const double djj = __shfl_sync(kFull, K[j], j);
-      const double dor = __shfl_sync(kFull, dorig, j);
+      const double djj = Ks[j * LD + j], dor = diag0[j];
       ok &= dor > 0.0;
       const double inv = djj > 1e-13 * dor ? rsqrt(djj) : 0.0;
-      const double lij = K[j] * inv;  // lane j: sqrt(djj)
-      K[j] = lij;
-      if (lane == j) myinv = inv;
-#pragma unroll
-      for (int k = j + 1; k < NW; ++k) {
-        const double lkj = __shfl_sync(kFull, lij, k);
-        if (lane >= k) K[k] -= lij * lkj;
+      if (lane > j && lane < NW) Ks[lane * LD + j] *= inv;
+      __syncwarp();
+      if (lane == j) Ks[j * LD + j] = djj * inv, invd[j] = inv;
+      const int T_j = (NW - 1 - j) * (NW - j) / 2;
+#pragma unroll 2
+      for (int t = lane; t < T_j; t += 32) {
+        const int ik = tab[t], i = ik >> 8, k = ik & 255;
+        Ks[i * LD + k] -= Ks[i * LD + j] * Ks[k * LD + j];
       }
+      __syncwarp();
     }
-    if (lane < NW) {
-#pragma unroll
-      for (int j = 0; j < NW; ++j) Ls[lane * LD + j] = K[j];
-    }
-    __syncwarp();
     return ok;
   }
-  __device__ __forceinline__ double solve(const double (&K)[NW], double myinv, double rhs) const {
-    double acc = rhs, x = 0;
-#pragma unroll
+  // two triangular solves with the factor in Ks; rhs and result live one entry per lane
+  __device__ __forceinline__ static double solve(const double* Ks, const double* invd, double rhs) {
+    const int lane = threadIdx.x;
+    const double myinv = lane < NW ? invd[lane] : 0.0;
+    double acc = lane < NW ? rhs : 0.0, x = 0;
+#pragma unroll 1
     for (int j = 0; j < NW; ++j) {  // L y = rhs
       const double yj = __shfl_sync(kFull, acc * myinv, j);
-      if (lane > j) acc -= K[j] * yj;
+      if (lane > j && lane < NW) acc -= Ks[lane * LD + j] * yj;
       if (lane == j) acc = yj;
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = NW - 1; i >= 0; --i) {  // L' x = y
       const double xi = __shfl_sync(kFull, acc * myinv, i);
-      if (lane < i) acc -= Ls[i * LD + lane] * xi;
+      if (lane < i) acc -= Ks[i * LD + lane] * xi;
       if (lane == i) x = xi, acc = 0;
     }
     return x;
@@ -470,31 +525,45 @@ struct Solver {
     double obj, kkt;
   };
 
+  // One row of the complementarity system.  Everything a pass needs from (s, lam, slack, C.dw):
+  //   rc = s - slack, ds = -rc - cdw, dl = -lam - (corr + lam ds) / s      (corr = 0 for the predictor)
+  struct RowStep {
+    double ds, dl, inv_s, inv_l;
+  };
+  __device__ __forceinline__ static RowStep row_step(double s, double l, double slk, double cdw, double corr) {
+    RowStep r;
+    const double rsl = 1.0 / (s * l);  // one division per row and pass
+    r.inv_s = l * rsl, r.inv_l = s * rsl;
+    r.ds = -(s - slk) - cdw;
+    r.dl = -l - (corr + l * r.ds) * r.inv_s;
+    return r;
+  }
+
   __device__ QpOut solve_qp() {
     QpOut out{HDSM_MAX_ITER, 0, INFINITY, INFINITY};
     const double tol = A.tol;
-    // count rows
-    int nbox = 0;
+    int nbox = 0, npos = 0;
     for (int idx = lane; idx < NQ3; idx += 32) {
       const int a = idx / NQ, q = idx - a * NQ;
       nbox += T.qconst[a][q] ? 0 : 2;
     }
-    nbox = __reduce_add_sync(kFull, nbox);
-    const int mtot = nbox + nbeg[nkp] + sbeg[nkp];
+    if (lane < 2 * nkp) npos = sege[lane] - segb[lane];
+    const int mtot = __reduce_add_sync(kFull, nbox + npos);
     const double inv_m = 1.0 / (mtot > 0 ? mtot : 1);
+    const int ax = lane < NW ? lane / NZ : 0, rr = lane < NW ? lane - ax * NZ : 0;
     // start: unconstrained minimiser of the objective
     if (lane < NW) {
-      const int a = lane / NZ, r = lane - a * NZ;
       double v = 0;
 #pragma unroll
-      for (int c = 0; c < NZ; ++c) v -= T.HwInv[a][r][c] * g[a * NZ + c];
+      for (int c = 0; c < NZ; ++c) v -= T.HwInv[ax][rr][c] * g[ax * NZ + c];
       w[lane] = v;
     }
     const double gmax = warp_max(lane < NW ? fabs(g[lane]) : 0.0);
     __syncwarp();
-    positions_of(w, pbar, p);
-    quantities_of(w, qbar, qv);
+    positions_of(T, w, pbar, p);
+    quantities_of(T, w, qbar, qv);
     __syncwarp();
+#pragma unroll 1
     for (int slot = grp; slot < nkp; slot += 8) {
       const int kp = T.kp_of_slot[slot];
       const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
@@ -504,11 +573,12 @@ struct Solver {
         l = 1.0 / s;
       });
     }
+#pragma unroll 1
     for (int idx = lane; idx < NQ3; idx += 32) {
       const int a = idx / NQ, q = idx - a * NQ;
       if (T.qconst[a][q]) continue;
       const double sc = 0.05 * (T.qhi[a][q] - T.qlo[a][q]);
-#pragma unroll
+#pragma unroll 1
       for (int side = 0; side < 2; ++side) {
         const double s = fmax(box_slack(idx, side, a, q), sc);
         bs[2 * idx + side] = s, bl[2 * idx + side] = 1.0 / s;
@@ -516,9 +586,11 @@ struct Solver {
     }
     __syncwarp();
 
+#pragma unroll 1
     for (int it = 0;; ++it) {
       // ---- pass 1: residuals and barrier blocks
       double mu = 0, rcmax = 0, lamsl = 0, lamsum = 0;
+#pragma unroll 1
       for (int slot = grp; slot < nkp; slot += 8) {
         const int kp = T.kp_of_slot[slot];
         const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
@@ -528,7 +600,8 @@ struct Solver {
           const double slk = r[3] - (nx * px + ny * py + nz * pz);
           const double rc = s - slk, d = l / s, t = d * rc;
           mu += s * l, rcmax = fmax(rcmax, fabs(rc)), lamsl += l * slk, lamsum += l;
-          m0 += d * nx * nx, m1 += d * nx * ny, m2 += d * nx * nz, m3 += d * ny * ny, m4 += d * ny * nz, m5 += d * nz * nz;
+          const double dx = d * nx, dy = d * ny, dz = d * nz;
+          m0 += dx * nx, m1 += dx * ny, m2 += dx * nz, m3 += dy * ny, m4 += dy * nz, m5 += dz * nz;
           t0 += t * nx, t1 += t * ny, t2 += t * nz;
           f0 += l * nx, f1 += l * ny, f2 += l * nz;
         });
@@ -543,16 +616,17 @@ struct Solver {
           Fk[3 * slot] = f0, Fk[3 * slot + 1] = f1, Fk[3 * slot + 2] = f2;
         }
       }
+#pragma unroll 1
       for (int idx = lane; idx < NQ3; idx += 32) {
         const int a = idx / NQ, q = idx - a * NQ;
         double dsum = 0, tsum = 0, fsum = 0;
         if (!T.qconst[a][q]) {
-          const double range = T.qhi[a][q] - T.qlo[a][q];
-#pragma unroll
+          const double irange = 1.0 / (T.qhi[a][q] - T.qlo[a][q]);
+#pragma unroll 1
           for (int side = 0; side < 2; ++side) {
             const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
             const double rc = s - slk, d = l / s, sg = side == 0 ? 1.0 : -1.0;
-            mu += s * l, rcmax = fmax(rcmax, fabs(rc) / range), lamsl += l * slk, lamsum += l;
+            mu += s * l, rcmax = fmax(rcmax, fabs(rc) * irange), lamsl += l * slk, lamsum += l;
             dsum += d, tsum += sg * d * rc, fsum += sg * l;
           }
         }
@@ -563,17 +637,17 @@ struct Solver {
 
       // ---- smooth gradient, dual residual, objective, right-hand side of the predictor
       double hg = 0, fi = 0, ti = 0, wi = 0;
-      int ax = 0, rr = 0;
       if (lane < NW) {
-        ax = lane / NZ, rr = lane - ax * NZ;
         wi = w[lane];
         hg = g[lane];
 #pragma unroll
         for (int c = 0; c < NZ; ++c) hg += T.Hw[ax][rr][c] * w[ax * NZ + c];
+#pragma unroll 1
         for (int slot = 0; slot < nkp; ++slot) {
           const double qp = T.QP[ax][T.kp_of_slot[slot]][rr];
           fi += Fk[3 * slot + ax] * qp, ti += Tk[3 * slot + ax] * qp;
         }
+#pragma unroll 2
         for (int q = 0; q < NQ; ++q) {
           const double e = T.EQ[ax][q][rr];
           fi += FQ[ax * NQ + q] * e, ti += TQ[ax * NQ + q] * e;
@@ -603,91 +677,85 @@ struct Solver {
         return out;
       }
 
-      // ---- K = Hw + sum_slots QP' M QP + sum_q DQ EQ EQ'   (row `lane` in registers)
-      double K[NW];
-#pragma unroll
-      for (int c = 0; c < NW; ++c) K[c] = 0.0;
-      double myinv = 0.0;
+      // ---- K = Hw + sum_slots QP' M QP + sum_q DQ EQ EQ'   (row `lane`, written to shared memory)
       if (lane < NW) {
-#pragma unroll
+#pragma unroll 1
         for (int b = 0; b < 3; ++b) {
+          double acc[NZ];
+#pragma unroll
+          for (int c = 0; c < NZ; ++c) acc[c] = 0.0;
           if (b == ax) {
 #pragma unroll
-            for (int c = 0; c < NZ; ++c) K[b * NZ + c] = T.Hw[ax][rr][c];
+            for (int c = 0; c < NZ; ++c) acc[c] = T.Hw[ax][rr][c];
+#pragma unroll 1
             for (int q = 0; q < NQ; ++q) {
               const double f = DQ[ax * NQ + q] * T.EQ[ax][q][rr];
 #pragma unroll
-              for (int c = 0; c < NZ; ++c) K[b * NZ + c] += f * T.EQ[ax][q][c];
+              for (int c = 0; c < NZ; ++c) acc[c] += f * T.EQ[ax][q][c];
             }
           }
-        }
-        for (int slot = 0; slot < nkp; ++slot) {
-          const int kp = T.kp_of_slot[slot];
-          const double* M = Mk + 6 * slot;
-          const double qr = T.QP[ax][kp][rr];
-          // symmetric 3x3 block stored as (00,01,02,11,12,22)
-          const double mx = ax == 0 ? M[0] : ax == 1 ? M[1] : M[2];
-          const double my = ax == 0 ? M[1] : ax == 1 ? M[3] : M[4];
-          const double mz = ax == 0 ? M[2] : ax == 1 ? M[4] : M[5];
-          const double fx = mx * qr, fy = my * qr, fz = mz * qr;
+          // symmetric 3x3 block stored as (00,01,02,11,12,22): entry (ax, b)
+          const int mi = ax == b ? (ax == 0 ? 0 : ax == 1 ? 3 : 5) : (ax + b == 1 ? 1 : ax + b == 2 ? 2 : 4);
+#pragma unroll 1
+          for (int slot = 0; slot < nkp; ++slot) {
+            const int kp = T.kp_of_slot[slot];
+            const double f = Mk[6 * slot + mi] * T.QP[ax][kp][rr];
 #pragma unroll
-          for (int c = 0; c < NZ; ++c) {
-            K[c] += fx * T.QP[0][kp][c];
-            K[NZ + c] += fy * T.QP[1][kp][c];
-            K[2 * NZ + c] += fz * T.QP[2][kp][c];
+            for (int c = 0; c < NZ; ++c) acc[c] += f * T.QP[b][kp][c];
           }
-        }
-      } else {
 #pragma unroll
-        for (int c = 0; c < NW; ++c) K[c] = 0.0;
+          for (int c = 0; c < NZ; ++c) Ks[lane * LD + b * NZ + c] = acc[c];
+        }
+        diag0[lane] = Ks[lane * LD + lane];
       }
-      if (!factor(K, myinv)) {
+      __syncwarp();
+      if (!factor(Ks, invd, diag0, tab)) {
         out.status = HDSM_NUMERICAL, out.iters = it;
         return out;
       }
 
       // ---- predictor
-      const double dwa = solve(K, myinv, -hg - ti);
+      const double dwa = solve(Ks, invd, -hg - ti);
       if (lane < NW) dw[lane] = dwa;
       __syncwarp();
-      positions_of(dw, nullptr, dp);
-      quantities_of(dw, nullptr, dq);
+      positions_of(T, dw, nullptr, dp);
+      quantities_of(T, dw, nullptr, dq);
       __syncwarp();
-      double alpha = 1.0, s_sl = 0, s_x = 0, s_dd = 0;
+      // largest relative decrease of any s or lam along the step: alpha_max = 1 / rmax
+      double rmax = 0.0, s_sl = 0, s_x = 0, s_dd = 0;
+#pragma unroll 1
       for (int slot = grp; slot < nkp; slot += 8) {
         const int kp = T.kp_of_slot[slot];
         const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
         const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
         for_slot_rows(slot, [&](const double* r, double& s, double& l) {
           const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
-          const double ds = -(s - slk) - (r[0] * dx + r[1] * dy + r[2] * dz);
-          const double dl = -l - l * ds / s;
-          if (ds < 0) alpha = fmin(alpha, -s / ds);
-          if (dl < 0) alpha = fmin(alpha, -l / dl);
-          s_sl += s * l, s_x += s * dl + l * ds, s_dd += ds * dl;
+          const RowStep e = row_step(s, l, slk, r[0] * dx + r[1] * dy + r[2] * dz, 0.0);
+          rmax = fmax(rmax, fmax(-e.ds * e.inv_s, -e.dl * e.inv_l));
+          s_sl += s * l, s_x += s * e.dl + l * e.ds, s_dd += e.ds * e.dl;
         });
       }
+#pragma unroll 1
       for (int idx = lane; idx < NQ3; idx += 32) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
-#pragma unroll
+#pragma unroll 1
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
-          const double cdw = side == 0 ? dq[idx] : -dq[idx];
-          const double ds = -(s - slk) - cdw;
-          const double dl = -l - l * ds / s;
-          if (ds < 0) alpha = fmin(alpha, -s / ds);
-          if (dl < 0) alpha = fmin(alpha, -l / dl);
-          s_sl += s * l, s_x += s * dl + l * ds, s_dd += ds * dl;
+          const RowStep e = row_step(s, l, slk, side == 0 ? dq[idx] : -dq[idx], 0.0);
+          rmax = fmax(rmax, fmax(-e.ds * e.inv_s, -e.dl * e.inv_l));
+          s_sl += s * l, s_x += s * e.dl + l * e.ds, s_dd += e.ds * e.dl;
         }
       }
       __syncwarp();
-      alpha = warp_min(alpha), s_sl = warp_sum(s_sl), s_x = warp_sum(s_x), s_dd = warp_sum(s_dd);
+      rmax = warp_max(rmax), s_sl = warp_sum(s_sl), s_x = warp_sum(s_x), s_dd = warp_sum(s_dd);
+      double alpha = rmax > 1.0 ? 1.0 / rmax : 1.0;
       const double mu_aff = fmax((s_sl + alpha * s_x + alpha * alpha * s_dd) * inv_m, 0.0);
       const double ratio = mu > 0 ? mu_aff / mu : 0.0;
       const double smu = ratio * ratio * ratio * mu;
 
       // ---- corrector right-hand side
+#pragma unroll 1
       for (int slot = grp; slot < nkp; slot += 8) {
         const int kp = T.kp_of_slot[slot];
         const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
@@ -695,25 +763,23 @@ struct Solver {
         double t0 = 0, t1 = 0, t2 = 0;
         for_slot_rows(slot, [&](const double* r, double& s, double& l) {
           const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
-          const double rc = s - slk;
-          const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
-          const double dla = -l - l * dsa / s;
-          const double t = (l * rc - (dsa * dla - smu)) / s;
+          const RowStep e = row_step(s, l, slk, r[0] * dx + r[1] * dy + r[2] * dz, 0.0);
+          const double t = (l * (s - slk) - (e.ds * e.dl - smu)) * e.inv_s;
           t0 += t * r[0], t1 += t * r[1], t2 += t * r[2];
         });
         t0 = quad_sum(gmask, t0), t1 = quad_sum(gmask, t1), t2 = quad_sum(gmask, t2);
         if (sub == 0) Tk[3 * slot] = t0, Tk[3 * slot + 1] = t1, Tk[3 * slot + 2] = t2;
       }
+#pragma unroll 1
       for (int idx = lane; idx < NQ3; idx += 32) {
         const int a = idx / NQ, q = idx - a * NQ;
         double tsum = 0;
         if (!T.qconst[a][q]) {
-#pragma unroll
+#pragma unroll 1
           for (int side = 0; side < 2; ++side) {
             const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
-            const double cdw = side == 0 ? dq[idx] : -dq[idx];
-            const double rc = s - slk, dsa = -rc - cdw, dla = -l - l * dsa / s;
-            const double t = (l * rc - (dsa * dla - smu)) / s;
+            const RowStep e = row_step(s, l, slk, side == 0 ? dq[idx] : -dq[idx], 0.0);
+            const double t = (l * (s - slk) - (e.ds * e.dl - smu)) * e.inv_s;
             tsum += side == 0 ? t : -t;
           }
         }
@@ -722,18 +788,21 @@ struct Solver {
       __syncwarp();
       double tc = 0;
       if (lane < NW) {
+#pragma unroll 1
         for (int slot = 0; slot < nkp; ++slot) tc += Tk[3 * slot + ax] * T.QP[ax][T.kp_of_slot[slot]][rr];
+#pragma unroll 2
         for (int q = 0; q < NQ; ++q) tc += TQ[ax * NQ + q] * T.EQ[ax][q][rr];
       }
-      const double dwv = solve(K, myinv, -hg - tc);
+      const double dwv = solve(Ks, invd, -hg - tc);
       if (lane < NW) dwc[lane] = dwv;
       __syncwarp();
-      positions_of(dwc, nullptr, dpc);
-      quantities_of(dwc, nullptr, dqc);
+      positions_of(T, dwc, nullptr, dpc);
+      quantities_of(T, dwc, nullptr, dqc);
       __syncwarp();
 
       // ---- step length of the combined direction
-      alpha = 1.0;
+      rmax = 0.0;
+#pragma unroll 1
       for (int slot = grp; slot < nkp; slot += 8) {
         const int kp = T.kp_of_slot[slot];
         const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
@@ -743,34 +812,35 @@ struct Solver {
           const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
           const double rc = s - slk;
           const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
-          const double dla = -l - l * dsa / s;
-          const double ds = -rc - (r[0] * ex + r[1] * ey + r[2] * ez);
-          const double dl = -(s * l + (dsa * dla - smu) + l * ds) / s;
-          if (ds < 0) alpha = fmin(alpha, -s / ds);
-          if (dl < 0) alpha = fmin(alpha, -l / dl);
+          const RowStep e0 = row_step(s, l, slk, r[0] * ex + r[1] * ey + r[2] * ez, 0.0);
+          const double dla = -l - l * dsa * e0.inv_s;
+          const double dl = -l - ((dsa * dla - smu) + l * e0.ds) * e0.inv_s;
+          rmax = fmax(rmax, fmax(-e0.ds * e0.inv_s, -dl * e0.inv_l));
         });
       }
+#pragma unroll 1
       for (int idx = lane; idx < NQ3; idx += 32) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
-#pragma unroll
+#pragma unroll 1
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
           const double sg = side == 0 ? 1.0 : -1.0;
-          const double rc = s - slk, dsa = -rc - sg * dq[idx], dla = -l - l * dsa / s;
-          const double ds = -rc - sg * dqc[idx];
-          const double dl = -(s * l + (dsa * dla - smu) + l * ds) / s;
-          if (ds < 0) alpha = fmin(alpha, -s / ds);
-          if (dl < 0) alpha = fmin(alpha, -l / dl);
+          const double dsa = -(s - slk) - sg * dq[idx];
+          const RowStep e0 = row_step(s, l, slk, sg * dqc[idx], 0.0);
+          const double dla = -l - l * dsa * e0.inv_s;
+          const double dl = -l - ((dsa * dla - smu) + l * e0.ds) * e0.inv_s;
+          rmax = fmax(rmax, fmax(-e0.ds * e0.inv_s, -dl * e0.inv_l));
         }
       }
       __syncwarp();
-      alpha = warp_min(alpha);
+      rmax = warp_max(rmax);
       // 0.97 of the way to the boundary: 0.995 leaves the blocking pair so far off the central path
       // that predictor and centring steps alternate without reducing mu on ~0.4% of the QPs
-      const double al = fmin(1.0, kStepFrac * alpha);
+      const double al = rmax > kStepFrac ? kStepFrac / rmax : 1.0;
 
       // ---- update
+#pragma unroll 1
       for (int slot = grp; slot < nkp; slot += 8) {
         const int kp = T.kp_of_slot[slot];
         const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
@@ -778,24 +848,25 @@ struct Solver {
         const double ex = dpc[3 * kp], ey = dpc[3 * kp + 1], ez = dpc[3 * kp + 2];
         for_slot_rows(slot, [&](const double* r, double& s, double& l) {
           const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
-          const double rc = s - slk;
+          const double rc = s - slk, inv_s = 1.0 / s;
           const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
-          const double dla = -l - l * dsa / s;
+          const double dla = -l - l * dsa * inv_s;
           const double ds = -rc - (r[0] * ex + r[1] * ey + r[2] * ez);
-          const double dl = -(s * l + (dsa * dla - smu) + l * ds) / s;
+          const double dl = -l - ((dsa * dla - smu) + l * ds) * inv_s;
           s += al * ds, l += al * dl;
         });
       }
+#pragma unroll 1
       for (int idx = lane; idx < NQ3; idx += 32) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
-#pragma unroll
+#pragma unroll 1
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
-          const double sg = side == 0 ? 1.0 : -1.0;
-          const double rc = s - slk, dsa = -rc - sg * dq[idx], dla = -l - l * dsa / s;
+          const double sg = side == 0 ? 1.0 : -1.0, inv_s = 1.0 / s;
+          const double rc = s - slk, dsa = -rc - sg * dq[idx], dla = -l - l * dsa * inv_s;
           const double ds = -rc - sg * dqc[idx];
-          const double dl = -(s * l + (dsa * dla - smu) + l * ds) / s;
+          const double dl = -l - ((dsa * dla - smu) + l * ds) * inv_s;
           bs[2 * idx + side] = s + al * ds, bl[2 * idx + side] = l + al * dl;
         }
       }
@@ -810,8 +881,8 @@ struct Solver {
         out.status = HDSM_NUMERICAL, out.iters = it;
         return out;
       }
-      positions_of(w, pbar, p);
-      quantities_of(w, qbar, qv);
+      positions_of(T, w, pbar, p);
+      quantities_of(T, w, qbar, qv);
       __syncwarp();
     }
   }
@@ -843,7 +914,7 @@ struct Solver {
           fail = HDSM_ROW_OVERFLOW;
           continue;
         }
-        maxrows = max(maxrows, nstat + nbeg[nkp]);
+        maxrows = max(maxrows, nstat + n_nbr_rows);
         const QpOut q = solve_qp();
         ++nodes;
         iters += q.iters;
@@ -871,24 +942,24 @@ struct Solver {
         // branch on the uncovered step that is farthest from all of its candidates
         int bk = -1;
         double bkv = 0.0;
-        int full[N];
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < N; ++k) {
-          full[k] = -1;
+          int fk = -1;
           double vmin = INFINITY;
+#pragma unroll 1
           for (int j = 0; j < Peff; ++j) {
             const double v = viol[k * kMaxP + j];
             vmin = fmin(vmin, v);
-            if (full[k] < 0 && v <= kContainTol) full[k] = j;
+            if (fk < 0 && v <= kContainTol) fk = j;
           }
-          if (full[k] < 0 && (bk < 0 || vmin > bkv)) bk = k, bkv = vmin;
+          if (lane == 0) fullsig[k] = fk;
+          if (fk < 0 && (bk < 0 || vmin > bkv)) bk = k, bkv = vmin;
         }
+        __syncwarp();
         if (bk < 0) {  // node optimum is feasible for the mixed-integer problem: new incumbent
           best = q.obj, bestkkt = q.kkt;
           if (lane < NW) bestw[lane] = w[lane];
-#pragma unroll
-          for (int k = 0; k < N; ++k)
-            if (lane == 0) bestsig[k] = full[k];
+          if (lane < N) bestsig[lane] = fullsig[lane];
           __syncwarp();
           continue;
         }
