@@ -60,7 +60,8 @@ struct hdsm_handle {
   Tables host_tables{};
   Tables* dev_tables = nullptr;
   int device = 0, max_agents = 0, max_neighbours = 0;
-  int nbr_cap = 0, stat_cap = 0, smem_bytes = 0;
+  int row_cap = 0, smem_bytes = 0;          // first pass: typical row count, many blocks per SM
+  int row_cap_big = 0, smem_bytes_big = 0;  // second pass for ROW_OVERFLOW agents: worst case (0 = not needed)
   cudaStream_t stream = nullptr;
   // staging for the host-pointer entry point
   unsigned char *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
@@ -87,14 +88,22 @@ int cuda_fail(hdsm_handle* h, cudaError_t e, const char* what) {
   } while (0)
 
 template <int N>
-cudaError_t launch(hdsm_handle* h, const KernelArgs& a, cudaStream_t s) {
-  static int configured_for = -1;  // per instantiation; smem attribute is per device function
-  if (configured_for < h->smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(hdsm_solve_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
+cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
+  static int configured_for = -1;  // per instantiation; the smem attribute is per device function
+  const int need = std::max(h->smem_bytes, h->smem_bytes_big);
+  if (configured_for < need) {
+    cudaError_t e = cudaFuncSetAttribute(hdsm_solve_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
     if (e != cudaSuccess) return e;
-    configured_for = h->smem_bytes;
+    configured_for = need;
   }
+  a.row_cap = h->row_cap, a.only_status = -1;
   hdsm_solve_kernel<N><<<a.n_local, 32, h->smem_bytes, s>>>(h->dev_tables, a);
+  h->launches += 1;
+  if (h->row_cap_big > 0) {  // agents whose rows did not fit the small pool
+    a.row_cap = h->row_cap_big, a.only_status = HDSM_ROW_OVERFLOW;
+    hdsm_solve_kernel<N><<<a.n_local, 32, h->smem_bytes_big, s>>>(h->dev_tables, a);
+    h->launches += 1;
+  }
   return cudaGetLastError();
 }
 
@@ -155,18 +164,22 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   if ((e = cudaMalloc(&h->dev_tables, sizeof(Tables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
   if ((e = cudaMemcpy(h->dev_tables, &h->host_tables, sizeof(Tables), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail(e, "copy tables");
-  // shared-memory budget: all rows that can exist when nothing is pruned, capped by what one SM
-  // can give several resident blocks; beyond the cap exact pruning has to make room (else ROW_OVERFLOW)
-  const int nkp = h->host_tables.nkp, rmax = h->prm.max_rows_per_poly;
-  h->stat_cap = h->prm.prune ? std::min(2 * rmax * nkp, 6 * rmax + 4 * nkp) : 2 * rmax * nkp;
-  const long worst_nbr = 2L * max_neighbours * nkp;
+  // Shared-memory budget.  Worst case per agent: 2 planes per neighbour and variable position step
+  // plus two polytopes' rows per step.  Exact pruning usually leaves a few dozen rows, so the first
+  // pass runs with a small row pool (more resident blocks per SM); agents that overflow it are
+  // re-solved by a second launch with the worst-case pool (or what one SM can hold).
+  const int nkp = h->host_tables.nkp, rmax = h->prm.max_rows_per_poly, N = h->prm.n_hor, P = h->prm.poly_hor;
+  const long worst = 2L * max_neighbours * nkp + 2L * rmax * nkp;
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const int base = smem_doubles(h->prm.n_hor, h->prm.poly_hor, rmax, 0, h->stat_cap) * 8;
-  const long budget_rows = std::max(0L, (long)(smem_max - base - 1024) / 48);
-  h->nbr_cap = (int)std::min(worst_nbr, std::min(budget_rows, 1024L));
-  h->nbr_cap = std::max(h->nbr_cap, 8);
-  h->smem_bytes = smem_doubles(h->prm.n_hor, h->prm.poly_hor, rmax, h->nbr_cap, h->stat_cap) * 8;
+  const long fit = std::max(16L, (long)(smem_max - smem_doubles(N, P, rmax, 0) * 8 - 1024) / 48);
+  const long small = h->prm.prune ? 96 : worst;
+  h->row_cap = (int)std::min(std::min(worst, small), fit);
+  h->smem_bytes = smem_doubles(N, P, rmax, h->row_cap) * 8;
+  if (worst > h->row_cap) {
+    h->row_cap_big = (int)std::min(worst, fit);
+    h->smem_bytes_big = smem_doubles(N, P, rmax, h->row_cap_big) * 8;
+  }
   *out = h;
   return HDSM_OK;
 }
@@ -208,11 +221,10 @@ int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_i
   a.global_id = global_id, a.nbr_begin = nbr_begin, a.nbr_end = nbr_end, a.poly_rows = poly_rows, a.assign_in = assign_in;
   a.x0 = x0, a.ref = ref, a.poly_A = poly_A, a.poly_b = poly_b, a.prev = prev_self_pos, a.all_pos = all_pos;
   a.all_valid = all_valid, a.traj = traj, a.ctrl = ctrl, a.pos_out = pos_out, a.poly_used = poly_used;
-  a.assign_out = assign_out, a.res = res, a.nbr_cap = h->nbr_cap, a.stat_cap = h->stat_cap;
+  a.assign_out = assign_out, a.res = res;
   a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   CU(dispatch(h, a, s));
-  h->launches += 1;
   return HDSM_OK;
 }
 

@@ -37,7 +37,8 @@ struct KernelArgs {
   uint8_t* poly_used;
   int32_t* assign_out;
   hdsm_result* res;
-  int nbr_cap, stat_cap;
+  int row_cap;     // rows (inter-agent + corridor) one block can hold in shared memory
+  int only_status; // >= 0: solve only agents whose res[].status equals this (second, large-memory pass)
   int max_iter, max_nodes, prune;
   double tol;
 };
@@ -89,8 +90,8 @@ HDSM_HD constexpr FixedLayout make_layout(int N) {
   return s;
 }
 // run-time part after FixedLayout::var: poly [P*rmax*4], rown [rows*4], rs [rows], rl [rows], nid [P*rmax bytes]
-HDSM_HD inline int smem_doubles(int N, int P, int rmax, int nbr_cap, int stat_cap) {
-  return make_layout(N).var + P * rmax * 4 + (nbr_cap + stat_cap) * 6 + (P * rmax + 7) / 8;
+HDSM_HD inline int smem_doubles(int N, int P, int rmax, int row_cap) {
+  return make_layout(N).var + P * rmax * 4 + row_cap * 6 + (P * rmax + 7) / 8;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -167,7 +168,7 @@ struct Solver {
   __device__ Solver(const Tables& t, const KernelArgs& a, double* smem)
       : T(t), A(a), lane(threadIdx.x), grp(threadIdx.x >> 2), sub(threadIdx.x & 3), gmask(0xFu << (threadIdx.x & ~3)),
         sm(smem) {
-    const int rows = a.nbr_cap + a.stat_cap;
+    const int rows = a.row_cap;
     poly = sm + L.var;
     rown = poly + a.P * a.rmax * 4;
     rs = rown + rows * 4;
@@ -370,7 +371,7 @@ struct Solver {
           const unsigned m = __ballot_sync(kFull, valid);
           if (valid) {
             const int pos = cnt + __popc(m & lt);
-            if (pos < A.nbr_cap) {
+            if (pos < A.row_cap) {
               rown[4 * pos] = nf[0], rown[4 * pos + 1] = nf[1], rown[4 * pos + 2] = nf[2], rown[4 * pos + 3] = b;
             }
           }
@@ -381,7 +382,7 @@ struct Solver {
     }
     n_nbr_rows = cnt;
     status = __reduce_max_sync(kFull, status);
-    if (cnt > A.nbr_cap) return HDSM_ROW_OVERFLOW;
+    if (cnt > A.row_cap) return HDSM_ROW_OVERFLOW;
     __syncwarp();
     return status;
   }
@@ -420,12 +421,15 @@ struct Solver {
     n[0] = a[0], n[1] = a[1], n[2] = a[2], b = a[3];
     if ((mask & (mask - 1)) == 0) return true;
     const int myid = nid[first * A.rmax + r];
+#pragma unroll 1
     for (int r2 = 0; r2 < r; ++r2)  // duplicate normal inside `first`: handled by its first occurrence
       if (nid[first * A.rmax + r2] == myid) return false;
     double bmax = -INFINITY;
+#pragma unroll 1
     for (int j = first; j < Peff; ++j) {
       if (!(mask >> j & 1)) continue;
       double bmin = INFINITY;
+#pragma unroll 2
       for (int r2 = 0; r2 < prow_n[j]; ++r2)
         if (nid[j * A.rmax + r2] == myid) bmin = fmin(bmin, poly[4 * (j * A.rmax + r2) + 3]);
       if (bmin == INFINITY) return false;
@@ -438,13 +442,14 @@ struct Solver {
   // static corridor rows of the current node, packed by position step; returns row count or -1 on overflow
   __device__ int build_static_rows() {
     int cnt = 0;
+    const int stat_cap = A.row_cap - n_nbr_rows;
     const unsigned lt = (1u << lane) - 1;
     double pn[3] = {0, 0, 0}, pb = 0;  // rows of the previous step's set, reused when the set repeats
     bool pvalid = false;
     int pk = -2;
     for (int slot = 0; slot < nkp; ++slot) {
       const int kp = T.kp_of_slot[slot];
-      segb[2 * slot + 1] = A.nbr_cap + cnt;
+      segb[2 * slot + 1] = n_nbr_rows + cnt;
       for (int k = kp - 1; k <= kp; ++k) {
         if (k < 0 || k >= N) continue;
         if (k == kp && kp >= 1 && cur[kp - 1] == cur[kp]) continue;  // same rows already put on p_kp by step kp-1
@@ -455,17 +460,17 @@ struct Solver {
         const unsigned m = __ballot_sync(kFull, valid);
         if (valid) {
           const int pos = cnt + __popc(m & lt);
-          if (pos < A.stat_cap) {
-            double* r = rown + 4 * (A.nbr_cap + pos);
+          if (pos < stat_cap) {
+            double* r = rown + 4 * (n_nbr_rows + pos);
             r[0] = pn[0], r[1] = pn[1], r[2] = pn[2], r[3] = pb;
           }
         }
         cnt += __popc(m);
       }
-      sege[2 * slot + 1] = A.nbr_cap + min(cnt, A.stat_cap);
+      sege[2 * slot + 1] = n_nbr_rows + min(cnt, stat_cap);
     }
     __syncwarp();
-    return cnt > A.stat_cap ? -1 : cnt;
+    return cnt > stat_cap ? -1 : cnt;
   }
 
   // ---------------------------------------------------------------- K2: Mehrotra predictor-corrector
@@ -895,7 +900,7 @@ struct Solver {
     if (st < 0 && !root_sets(agent)) st = HDSM_INFEASIBLE;
     double best = INFINITY, bestkkt = INFINITY;
     int nodes = 0, iters = 0, maxrows = 0, fail = 0;
-    bool exhausted = true;
+    bool exhausted = true, overflow = false;
     if (st < 0) {
       int top = 0;
       if (lane < 16) stack[lane] = lane < N ? cur[lane] : 0;
@@ -910,9 +915,9 @@ struct Solver {
         if (lane < 16) cur[lane] = stack[top * 16 + lane];
         __syncwarp();
         const int nstat = build_static_rows();
-        if (nstat < 0) {
-          fail = HDSM_ROW_OVERFLOW;
-          continue;
+        if (nstat < 0) {  // the row pool is too small for this agent: the large-memory pass redoes it
+          overflow = true;
+          break;
         }
         maxrows = max(maxrows, nstat + n_nbr_rows);
         const QpOut q = solve_qp();
@@ -995,7 +1000,10 @@ struct Solver {
         __syncwarp();
       }
       R.nodes = nodes, R.iters = iters, R.rows = maxrows;
-      if (best < INFINITY) {
+      if (overflow) {
+        best = INFINITY;
+        R.status = HDSM_ROW_OVERFLOW;
+      } else if (best < INFINITY) {
         R.status = (exhausted && !fail) ? HDSM_OPTIMAL : HDSM_NODE_LIMIT;  // a lost node leaves the optimum unproven
         R.obj = best, R.kkt_res = bestkkt;
       } else {
@@ -1059,6 +1067,7 @@ __global__ void __launch_bounds__(32) hdsm_solve_kernel(const Tables* __restrict
   extern __shared__ double smem[];
   const int agent = blockIdx.x;
   if (agent >= args.n_local) return;
+  if (args.only_status >= 0 && args.res[agent].status != args.only_status) return;
   Solver<N> s(*tables, args, smem);
   s.run(agent);
 }

@@ -1,0 +1,64 @@
+"""Summarise an .ncu-rep (raw page + SASS source page joined with nvdisasm line info) - runs on CPU.
+
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-instantiation, default 10] [lib.so]
+"""
+import collections
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+rep = sys.argv[1]
+ninst = sys.argv[2] if len(sys.argv) > 2 else "10"
+lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                          "multi_agent_pkgs_b200", "libhdsm.so")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, vals = rows[0], rows[2]
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
+        "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct",
+        "lts__t_sector_hit_rate.pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "launch__grid_size"]
+for i, h in enumerate(hdr):
+    if h in want:
+        print(f"{h:70s} {vals[i]} {rows[1][i]}")
+sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(sass)))
+hdr, data = rows[1], rows[2:]
+ix = {h: i for i, h in enumerate(hdr)}
+tot = sum(int(r[ix["# Samples"]]) for r in data)
+print("static instructions", len(data), "samples", tot)
+stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+agg = {s: sum(int(r[ix[s]]) for r in data) for s in stalls}
+print("stalls:", ", ".join(f"{s[6:]} {100 * v / tot:.1f}%" for s, v in sorted(agg.items(), key=lambda x: -x[1])[:8]))
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
+cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+start = next(i for i, l in enumerate(dis) if l.startswith(f".text._ZN4hdsm17hdsm_solve_kernelILi{ninst}E"))
+end = next((i for i in range(start + 1, len(dis)) if dis[i].startswith("\t.section")), len(dis))
+cur, per = None, []
+for l in dis[start:end]:
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m:
+        cur = (m.group(1).split("/")[-1], int(m.group(2)))
+    elif re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
+        per.append(cur)
+if len(per) != len(data):
+    print("WARNING: disassembly / profile length mismatch", len(per), len(data))
+n = min(len(per), len(data))
+static, samp, execd = collections.Counter(), collections.Counter(), collections.Counter()
+for i in range(n):
+    static[per[i]] += 1
+    samp[per[i]] += int(data[i][ix["# Samples"]])
+    execd[per[i]] += int(data[i][ix["Instructions Executed"]])
+src = open(os.path.join(os.path.dirname(lib), "csrc", "hdsm_kernel.cuh")).read().split("\n")
+print("--- top source lines by stall samples")
+for k, v in samp.most_common(int(os.environ.get("TOP", "30"))):
+    s = src[k[1] - 1].strip()[:100] if k and k[0] == "hdsm_kernel.cuh" else ""
+    print(f"{str(k):30s} static {static[k]:5d} samples {100 * v / tot:5.1f}% exec {execd[k] / 1e6:8.1f}M | {s}")
