@@ -112,11 +112,18 @@ class Exchange:
         import torch.distributed as dist
         if self.even:
             dist.all_gather_into_tensor(self.table, pos_out.contiguous())
-        else:
+        else:  # ragged shards: pad every rank's block to the largest shard, gather, drop the padding
             sizes = shard_sizes(self.n_rob, self.world)
-            outs = [torch.empty((s, self.N + 1, 3), dtype=torch.float64, device=self.device) for s in sizes]
-            dist.all_gather(outs, pos_out.contiguous())
-            torch.cat(outs, out=self.table)
+            mx = max(sizes)
+            send = torch.zeros((mx, self.N + 1, 3), dtype=torch.float64, device=self.device)
+            send[: pos_out.shape[0]] = pos_out
+            recv = torch.empty((self.world * mx, self.N + 1, 3), dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(recv, send)
+            recv = recv.view(self.world, mx, self.N + 1, 3)
+            off = 0
+            for r, sz in enumerate(sizes):
+                self.table[off:off + sz] = recv[r, :sz]
+                off += sz
         return self.table
 
 
