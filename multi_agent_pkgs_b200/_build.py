@@ -29,6 +29,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ into multi_agent_pkgs_b200/libhdsm.so if it is missing or older than its sources."""
     if force or stale():
         cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+        if os.environ.get("HDSM_MINBLOCKS"):
+            cmd.insert(1, "-DHDSM_MINBLOCKS=" + os.environ["HDSM_MINBLOCKS"])
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

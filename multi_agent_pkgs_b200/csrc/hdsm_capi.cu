@@ -6,9 +6,11 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/hdsm.h"
 #include "hdsm_kernel.cuh"
@@ -67,6 +69,8 @@ struct hdsm_handle {
   unsigned char *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
   size_t in_cap = 0, out_cap = 0;
   int64_t launches = 0;
+  long long* d_prof = nullptr;  // HDSM_PROFILE=1: per-agent phase cycle counters (host path prints a summary)
+  int warps = 4;  // warps per agent (HDSM_WARPS=1 selects the single-warp kernel)
   std::string err;
   void* comm = nullptr;
   int n_ranks = 1;
@@ -87,21 +91,21 @@ int cuda_fail(hdsm_handle* h, cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);    \
   } while (0)
 
-template <int N>
+template <int N, int W>
 cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
   static int configured_for = -1;  // per instantiation; the smem attribute is per device function
   const int need = std::max(h->smem_bytes, h->smem_bytes_big);
   if (configured_for < need) {
-    cudaError_t e = cudaFuncSetAttribute(hdsm_solve_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    cudaError_t e = cudaFuncSetAttribute(hdsm_solve_kernel<N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
     if (e != cudaSuccess) return e;
     configured_for = need;
   }
   a.row_cap = h->row_cap, a.only_status = -1;
-  hdsm_solve_kernel<N><<<a.n_local, 32, h->smem_bytes, s>>>(h->dev_tables, a);
+  hdsm_solve_kernel<N, W><<<a.n_local, 32 * W, h->smem_bytes, s>>>(h->dev_tables, a);
   h->launches += 1;
   if (h->row_cap_big > 0) {  // agents whose rows did not fit the small pool
     a.row_cap = h->row_cap_big, a.only_status = HDSM_ROW_OVERFLOW;
-    hdsm_solve_kernel<N><<<a.n_local, 32, h->smem_bytes_big, s>>>(h->dev_tables, a);
+    hdsm_solve_kernel<N, W><<<a.n_local, 32 * W, h->smem_bytes_big, s>>>(h->dev_tables, a);
     h->launches += 1;
   }
   return cudaGetLastError();
@@ -111,7 +115,7 @@ cudaError_t dispatch(hdsm_handle* h, const KernelArgs& a, cudaStream_t s) {
   switch (h->prm.n_hor) {
 #define HDSM_CASE(n) \
   case n:            \
-    return launch<n>(h, a, s);
+    return h->warps == 1 ? launch<n, 1>(h, a, s) : launch<n, 4>(h, a, s);
     HDSM_CASE(5)
     HDSM_CASE(6)
     HDSM_CASE(7)
@@ -148,6 +152,7 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
     return HDSM_ERR_INVALID;
   }
   h->device = device, h->max_agents = max_agents, h->max_neighbours = max_neighbours;
+  if (const char* e = std::getenv("HDSM_WARPS")) h->warps = std::atoi(e) == 1 ? 1 : 4;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || device < 0 || device >= ndev) {  // no CPU fallback: fail loudly
@@ -190,6 +195,7 @@ void hdsm_destroy(hdsm_handle* h) {
   hdsm_comm_destroy(h);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->dev_tables);
+  cudaFree(h->d_prof);
   cudaFree(h->d_in);
   cudaFree(h->d_out);
   cudaFreeHost(h->h_in);
@@ -221,7 +227,7 @@ int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_i
   a.global_id = global_id, a.nbr_begin = nbr_begin, a.nbr_end = nbr_end, a.poly_rows = poly_rows, a.assign_in = assign_in;
   a.x0 = x0, a.ref = ref, a.poly_A = poly_A, a.poly_b = poly_b, a.prev = prev_self_pos, a.all_pos = all_pos;
   a.all_valid = all_valid, a.traj = traj, a.ctrl = ctrl, a.pos_out = pos_out, a.poly_used = poly_used;
-  a.assign_out = assign_out, a.res = res;
+  a.assign_out = assign_out, a.res = res, a.prof = h->d_prof;
   a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   CU(dispatch(h, a, s));
@@ -281,6 +287,10 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
     CU(cudaMallocHost(&h->h_out, out_bytes));
     h->out_cap = out_bytes;
   }
+  if (std::getenv("HDSM_PROFILE") && !h->d_prof) {
+    CU(cudaMalloc(&h->d_prof, (size_t)h->max_agents * 16 * 8));
+    CU(cudaMemset(h->d_prof, 0, (size_t)h->max_agents * 16 * 8));
+  }
   for (const Seg& s : in)
     if (s.bytes) std::memcpy(h->h_in + s.off, s.src, s.bytes);
   CU(cudaMemcpyAsync(h->d_in, h->h_in, in_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -294,6 +304,19 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
   if (rc != HDSM_OK) return rc;
   CU(cudaMemcpyAsync(h->h_out, h->d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  if (h->d_prof) {
+    std::vector<long long> hp((size_t)n_local * 16);
+    CU(cudaMemcpy(hp.data(), h->d_prof, hp.size() * 8, cudaMemcpyDeviceToHost));
+    double tot[12] = {0};
+    for (int i = 0; i < n_local; ++i)
+      for (int s = 0; s < 12; ++s) tot[s] += (double)hp[(size_t)i * 16 + s];
+    const char* names[12] = {"setup+planes", "static rows", "qp init", "pass1", "residual/rhs", "kkt assembly", "factor",
+                             "solves", "dense products", "other passes", "search", "-"};
+    double all = 0;
+    for (double t : tot) all += t;
+    std::fprintf(stderr, "[hdsm profile] warp-0 cycles per agent: %.0f\n", all / n_local);
+    for (int s = 0; s < 11; ++s) std::fprintf(stderr, "  %-16s %6.1f%%  %10.0f cycles/agent\n", names[s], 100 * tot[s] / all, tot[s] / n_local);
+  }
   std::memcpy(traj, h->h_out + o_traj, n * (N + 1) * 9 * 8);
   std::memcpy(ctrl, h->h_out + o_ctrl, n * N * 3 * 8);
   std::memcpy(res, h->h_out + o_res, n * sizeof(hdsm_result));

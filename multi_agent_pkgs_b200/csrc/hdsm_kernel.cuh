@@ -27,6 +27,9 @@ constexpr double kStepFrac = 0.97;
 constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still inside the 1e-6 KKT target
 constexpr int kStackCap = 48;          // >= 1 + N * ceil(log2 P) open nodes
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef HDSM_MINBLOCKS
+#define HDSM_MINBLOCKS 8  // resident 4-warp blocks per SM the register allocation aims for (64 registers)
+#endif
 
 struct KernelArgs {
   int n_local, n_rob, rmax, P;
@@ -39,6 +42,7 @@ struct KernelArgs {
   hdsm_result* res;
   int row_cap;     // rows (inter-agent + corridor) one block can hold in shared memory
   int only_status; // >= 0: solve only agents whose res[].status equals this (second, large-memory pass)
+  long long* prof; // optional [n_local][16] cycle counters per phase (HDSM_PROFILE=1), else null
   int max_iter, max_nodes, prune;
   double tol;
 };
@@ -48,7 +52,7 @@ struct KernelArgs {
 // time, follow.
 struct FixedLayout {
   int Ks, invd, diag0, bs, bl, DQ, TQ, FQ, qv, dq, dqc, qbar, Mk, Tk, Fk, p, dp, dpc, pbar, plo, phi, w, dw, dwc, g, bestw, s0,
-      viol, ints, var;
+      viol, red, ints, var;
 };
 HDSM_HD constexpr FixedLayout make_layout(int N) {
   const int NW = 3 * (N - 2), NQ3 = 3 * (3 * N - 2), K3 = 3 * (N + 1);
@@ -80,11 +84,12 @@ HDSM_HD constexpr FixedLayout make_layout(int N) {
   s.dwc = o, o += NW;
   s.g = o, o += NW;
   s.bestw = o, o += NW;
-  s.s0 = o, o += 10;
+  s.s0 = o, o += 12;   // x0 (9), c0, spare
+  s.red = o, o += 2 * 4 * 4;  // block reductions: 2 buffers x 4 warps x 4 values
   s.viol = o, o += N * kMaxP;
   s.ints = o;
   // int32 region: segment tables 4(N+2), bestsig N, fullsig N, prow_n 8, cur 16 B, stack, pair table u16
-  const int int_words = 4 * (N + 2) + 2 * N + kMaxP + 4 + kStackCap * 4 + (NW * (NW + 1) / 2 + 1) / 2 + 2;
+  const int int_words = 4 * (N + 2) + 2 * N + kMaxP + 4 + kStackCap * 4 + (NW * (NW + 1) / 2 + 1) / 2 + 2 + 8;
   o += (int_words + 1) / 2;
   s.var = o;
   return s;
@@ -136,14 +141,18 @@ __device__ __forceinline__ bool interagent_plane(const hdsm_params& P, const dou
   return true;
 }
 
-template <int N>
+// N: horizon.  W: warps cooperating on one agent (1 or 4).  Set-up, plane assembly and the search
+// bookkeeping run on warp 0; the interior-point iterations use all W warps.
+template <int N, int W>
 struct Solver {
   static constexpr int NZ = N - 2, NW = 3 * NZ, NQ = 3 * N - 2, NQ3 = 3 * NQ, K3 = 3 * (N + 1), LD = NW + 1;
+  static constexpr int NT = 32 * W;             // threads per agent
+  static constexpr int TPR = W >= 4 ? 4 : 1;    // threads sharing one row of the KKT matrix
+  static_assert(W == 1 || W == 4, "W must be 1 or 4");
 
   const Tables& T;
   const KernelArgs& A;
-  const int lane, grp, sub;
-  const unsigned gmask;
+  const int tid, lane, wid;
   static constexpr FixedLayout L = make_layout(N);
   // shared memory views: fixed-offset arrays are sm + constant, only the last five need registers
   double* const sm;
@@ -153,21 +162,22 @@ struct Solver {
                 *const Mk = sm + L.Mk, *const Tk = sm + L.Tk, *const Fk = sm + L.Fk, *const p = sm + L.p,
                 *const dp = sm + L.dp, *const dpc = sm + L.dpc, *const pbar = sm + L.pbar, *const plo = sm + L.plo,
                 *const phi = sm + L.phi, *const w = sm + L.w, *const dw = sm + L.dw, *const dwc = sm + L.dwc,
-                *const g = sm + L.g, *const bestw = sm + L.bestw, *const s0 = sm + L.s0, *const viol = sm + L.viol;
+                *const g = sm + L.g, *const bestw = sm + L.bestw, *const s0 = sm + L.s0, *const viol = sm + L.viol,
+                *const red = sm + L.red;
   int* const ip = reinterpret_cast<int*>(sm + L.ints);
   int *const segb = ip, *const sege = ip + 2 * (N + 2), *const bestsig = ip + 4 * (N + 2), *const fullsig = bestsig + N,
              *const prow_n = fullsig + N;  // segb/sege[2*slot + {0: inter-agent, 1: corridor}]
   unsigned char* const cur = reinterpret_cast<unsigned char*>(prow_n + kMaxP);  // current node's masks [N]
   unsigned char* const stack = cur + 16;  // kStackCap entries of 16 bytes: per-step candidate masks
-  unsigned short* const tab = reinterpret_cast<unsigned short*>(stack + kStackCap * 16);  // pairs (i << 8 | k)
+  int* const ctl = reinterpret_cast<int*>(stack + kStackCap * 16);  // block-wide control words (8)
+  unsigned short* const tab = reinterpret_cast<unsigned short*>(ctl + 8);  // pairs (i << 8 | k)
   double *poly, *rown, *rs, *rl;
   unsigned char* nid;  // per polytope row: id of the first row with the same normal
   double c0;
   int nkp, Peff, n_nbr_rows;
 
   __device__ Solver(const Tables& t, const KernelArgs& a, double* smem)
-      : T(t), A(a), lane(threadIdx.x), grp(threadIdx.x >> 2), sub(threadIdx.x & 3), gmask(0xFu << (threadIdx.x & ~3)),
-        sm(smem) {
+      : T(t), A(a), tid(threadIdx.x), lane(threadIdx.x & 31), wid(threadIdx.x >> 5), sm(smem) {
     const int rows = a.row_cap;
     poly = sm + L.var;
     rown = poly + a.P * a.rmax * 4;
@@ -180,7 +190,7 @@ struct Solver {
   // ---------------------------------------------------------------- small dense products
   // out[k][a] = (bar ? bar[k][a] : 0) + QP[a][k] . x[a*NZ ...]   (static + noinline: one copy, no `this`)
   __device__ __forceinline__ static void positions_of(const Tables& T, const double* x, const double* bar, double* out) {
-    for (int idx = threadIdx.x; idx < K3; idx += 32) {
+    for (int idx = threadIdx.x; idx < K3; idx += NT) {
       const int k = idx / 3, a = idx - 3 * k;
       double v = bar ? bar[idx] : 0.0;
 #pragma unroll
@@ -189,7 +199,7 @@ struct Solver {
     }
   }
   __device__ __forceinline__ static void quantities_of(const Tables& T, const double* x, const double* bar, double* out) {
-    for (int idx = threadIdx.x; idx < NQ3; idx += 32) {
+    for (int idx = threadIdx.x; idx < NQ3; idx += NT) {
       const int a = idx / NQ, q = idx - a * NQ;
       double v = bar ? bar[idx] : 0.0;
 #pragma unroll
@@ -206,14 +216,67 @@ struct Solver {
     return !(mx <= b - kPruneMargin);
   }
 
-  // rows acting on the position of `slot`: two segments (inter-agent, corridor), strided over the quad
+  // Position rows are processed by groups of `lps` adjacent lanes (a power of two), one group per
+  // variable position step, rows strided over the group: the 3x3 barrier blocks reduce inside the
+  // group with shuffles.  W = 1: 4 lanes per step at N = 10; W = 4: 16.
+  int lps, slot_of_thread, sub;
+  unsigned gmask;
+  __device__ __forceinline__ void init_groups() {
+    lps = 32;
+    while (lps * nkp > NT) lps >>= 1;
+    slot_of_thread = tid / lps, sub = tid % lps;
+    gmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (lane & ~(lps - 1)));
+  }
+  __device__ __forceinline__ double group_sum(double v) const {
+    for (int o = lps >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+  }
   template <class F>
-  __device__ __forceinline__ void for_slot_rows(int slot, F&& f) {
+  __device__ __forceinline__ void for_my_rows(F&& f) {
+    if (slot_of_thread >= nkp) return;
 #pragma unroll 1
     for (int sg = 0; sg < 2; ++sg) {
-      const int end = sege[2 * slot + sg];
+      const int end = sege[2 * slot_of_thread + sg];
 #pragma unroll 1
-      for (int i = segb[2 * slot + sg] + sub; i < end; i += 4) f(rown + 4 * i, rs[i], rl[i]);
+      for (int i = segb[2 * slot_of_thread + sg] + sub; i < end; i += lps) f(rown + 4 * i, rs[i], rl[i]);
+    }
+  }
+  long long tprof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = 0;
+  __device__ __forceinline__ void tick(int slot) {  // attribute the cycles since the last tick to `slot`
+    if (A.prof) {
+      const long long now = clock64();
+      tprof[slot] += now - tlast;
+      tlast = now;
+    }
+  }
+  __device__ __forceinline__ void bsync() const {
+    if (W > 1) __syncthreads();
+    else __syncwarp();
+  }
+  // Reduce four values over the block (bit i of MAXMASK: max instead of sum); result in every thread.
+  int red_buf = 0;
+  template <int MAXMASK>
+  __device__ __forceinline__ void reduce4(double (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (MAXMASK >> i & 1) ? warp_max(v[i]) : warp_sum(v[i]);
+    if (W > 1) {
+      double* buf = red + red_buf * 16;
+      red_buf ^= 1;
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) buf[wid * 4 + i] = v[i];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double r = buf[i];
+#pragma unroll
+        for (int w2 = 1; w2 < W; ++w2) r = (MAXMASK >> i & 1) ? fmax(r, buf[w2 * 4 + i]) : r + buf[w2 * 4 + i];
+        v[i] = r;
+      }
+    } else {
+      __syncwarp();
     }
   }
 
@@ -270,6 +333,7 @@ struct Solver {
       g[lane] = gi;
     }
     c0 = warp_sum(cpart);
+    if (lane == 0) s0[9] = c0;  // the other warps read it from shared memory
     for (int idx = lane; idx < K3; idx += 32) {
       const int k = idx / 3, a = idx - 3 * k;
       pbar[idx] = T.cP[a][k][0] * s0[a] + T.cP[a][k][1] * s0[3 + a] + T.cP[a][k][2] * s0[6 + a];
@@ -479,50 +543,51 @@ struct Solver {
     return side == 0 ? T.qhi[a][q] - qv[idx] : qv[idx] - T.qlo[a][q];
   }
 
-  // Cholesky of Ks (lower part, in place).  A pivot that lost all its digits to cancellation
-  // (<= 1e-13 of the original diagonal) marks a direction the barrier has pinned: the variable is
-  // frozen for this solve (inverse pivot 0) instead of aborting.  Only a non-positive / NaN original
-  // diagonal is a failure.  Work per step j: scale column j (one lane per row), then the trailing
-  // update spread over all 32 lanes through the pair table.
-  __device__ __forceinline__ static bool factor(double* Ks, double* invd, const double* diag0, const unsigned short* tab) {
-    const int lane = threadIdx.x;
+  // Cholesky of Ks (lower part, in place), all threads of the block.  A pivot that lost all its
+  // digits to cancellation (<= 1e-13 of the original diagonal) marks a direction the barrier has
+  // pinned: the variable is frozen for this solve (inverse pivot 0) instead of aborting.  Only a
+  // non-positive / NaN original diagonal is a failure.  Per step j: scale column j (one thread per
+  // row), then the trailing update spread over all threads through the pair table.
+  __device__ __forceinline__ bool factor() {
     bool ok = true;
 #pragma unroll 1
     for (int j = 0; j < NW; ++j) {
       const double djj = Ks[j * LD + j], dor = diag0[j];
       ok &= dor > 0.0;
       const double inv = djj > 1e-13 * dor ? rsqrt(djj) : 0.0;
-      if (lane > j && lane < NW) Ks[lane * LD + j] *= inv;
-      __syncwarp();
-      if (lane == j) Ks[j * LD + j] = djj * inv, invd[j] = inv;
+      if (tid > j && tid < NW) Ks[tid * LD + j] *= inv;
+      bsync();
+      if (tid == j) Ks[j * LD + j] = djj * inv, invd[j] = inv;
       const int T_j = (NW - 1 - j) * (NW - j) / 2;
 #pragma unroll 2
-      for (int t = lane; t < T_j; t += 32) {
+      for (int t = tid; t < T_j; t += NT) {
         const int ik = tab[t], i = ik >> 8, k = ik & 255;
         Ks[i * LD + k] -= Ks[i * LD + j] * Ks[k * LD + j];
       }
-      __syncwarp();
+      bsync();
     }
     return ok;
   }
-  // two triangular solves with the factor in Ks; rhs and result live one entry per lane
-  __device__ __forceinline__ static double solve(const double* Ks, const double* invd, double rhs) {
-    const int lane = threadIdx.x;
-    const double myinv = lane < NW ? invd[lane] : 0.0;
-    double acc = lane < NW ? rhs : 0.0, x = 0;
+  // two triangular solves with the factor in Ks, warp 0 only: v[NW] in shared memory is overwritten
+  __device__ __forceinline__ void solve_inplace(double* v) const {
+    if (wid == 0) {
+      const double myinv = lane < NW ? invd[lane] : 0.0;
+      double acc = lane < NW ? v[lane] : 0.0, x = 0;
 #pragma unroll 1
-    for (int j = 0; j < NW; ++j) {  // L y = rhs
-      const double yj = __shfl_sync(kFull, acc * myinv, j);
-      if (lane > j && lane < NW) acc -= Ks[lane * LD + j] * yj;
-      if (lane == j) acc = yj;
-    }
+      for (int j = 0; j < NW; ++j) {  // L y = rhs
+        const double yj = __shfl_sync(kFull, acc * myinv, j);
+        if (lane > j && lane < NW) acc -= Ks[lane * LD + j] * yj;
+        if (lane == j) acc = yj;
+      }
 #pragma unroll 1
-    for (int i = NW - 1; i >= 0; --i) {  // L' x = y
-      const double xi = __shfl_sync(kFull, acc * myinv, i);
-      if (lane < i) acc -= Ks[i * LD + lane] * xi;
-      if (lane == i) x = xi, acc = 0;
+      for (int i = NW - 1; i >= 0; --i) {  // L' x = y
+        const double xi = __shfl_sync(kFull, acc * myinv, i);
+        if (lane < i) acc -= Ks[i * LD + lane] * xi;
+        if (lane == i) x = xi, acc = 0;
+      }
+      if (lane < NW) v[lane] = x;
     }
-    return x;
+    bsync();
   }
 
   struct QpOut {
@@ -544,42 +609,81 @@ struct Solver {
     return r;
   }
 
+  // block (row, b) of the KKT matrix: acc[c] for c < NZ.
+  //   diag:  Hw[ax][rr][c] (first == true) + sum_{q in [q0, q1)} DQ[q] EQ[q][rr] EQ[q][c]
+  //   all:   sum_slots M_slot(ax, b) QP[ax][kp][rr] QP[b][kp][c]      (slots == true)
+  __device__ __forceinline__ void kkt_block(int ax, int rr, int b, bool first, int q0, int q1, bool slots, double (&acc)[NZ]) const {
+#pragma unroll
+    for (int c = 0; c < NZ; ++c) acc[c] = first ? T.Hw[ax][rr][c] : 0.0;
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+      const double f = DQ[ax * NQ + q] * T.EQ[ax][q][rr];
+#pragma unroll
+      for (int c = 0; c < NZ; ++c) acc[c] += f * T.EQ[ax][q][c];
+    }
+    if (slots) {
+      // symmetric 3x3 block stored as (00,01,02,11,12,22): entry (ax, b)
+      const int mi = ax == b ? (ax == 0 ? 0 : ax == 1 ? 3 : 5) : (ax + b == 1 ? 1 : ax + b == 2 ? 2 : 4);
+#pragma unroll 1
+      for (int slot = 0; slot < nkp; ++slot) {
+        const int kp = T.kp_of_slot[slot];
+        const double f = Mk[6 * slot + mi] * T.QP[ax][kp][rr];
+#pragma unroll
+        for (int c = 0; c < NZ; ++c) acc[c] += f * T.QP[b][kp][c];
+      }
+    }
+  }
+  __device__ __forceinline__ static double tpr_sum(double v) {
+    if (TPR > 1) {
+      v += __shfl_xor_sync(kFull, v, 1);
+      v += __shfl_xor_sync(kFull, v, 2);
+    }
+    return v;
+  }
+
   __device__ QpOut solve_qp() {
     QpOut out{HDSM_MAX_ITER, 0, INFINITY, INFINITY};
-    const double tol = A.tol;
-    int nbox = 0, npos = 0;
-    for (int idx = lane; idx < NQ3; idx += 32) {
+    const double tol = A.tol, c0v = s0[9];
+    init_groups();
+    int nrows = 0;
+    for (int idx = tid; idx < NQ3; idx += NT) {
       const int a = idx / NQ, q = idx - a * NQ;
-      nbox += T.qconst[a][q] ? 0 : 2;
+      nrows += T.qconst[a][q] ? 0 : 2;
     }
-    if (lane < 2 * nkp) npos = sege[lane] - segb[lane];
-    const int mtot = __reduce_add_sync(kFull, nbox + npos);
+    if (tid < 2 * nkp) nrows += sege[tid] - segb[tid];
+    double cnt4[4] = {(double)nrows, 0, 0, 0};
+    reduce4<0>(cnt4);
+    const int mtot = (int)cnt4[0];
     const double inv_m = 1.0 / (mtot > 0 ? mtot : 1);
-    const int ax = lane < NW ? lane / NZ : 0, rr = lane < NW ? lane - ax * NZ : 0;
+    // KKT row handled by this thread (TPR threads share a row)
+    const int row = tid / TPR, part = tid % TPR;
+    const bool rowact = row < NW;
+    const int ax = rowact ? row / NZ : 0, rr = rowact ? row - ax * NZ : 0;
     // start: unconstrained minimiser of the objective
-    if (lane < NW) {
+    if (tid < NW) {
+      const int a = tid / NZ, r = tid - a * NZ;
       double v = 0;
 #pragma unroll
-      for (int c = 0; c < NZ; ++c) v -= T.HwInv[ax][rr][c] * g[ax * NZ + c];
-      w[lane] = v;
+      for (int c = 0; c < NZ; ++c) v -= T.HwInv[a][r][c] * g[a * NZ + c];
+      w[tid] = v;
     }
-    const double gmax = warp_max(lane < NW ? fabs(g[lane]) : 0.0);
-    __syncwarp();
+    double gm4[4] = {tid < NW ? fabs(g[tid]) : 0.0, 0, 0, 0};
+    reduce4<1>(gm4);  // includes the barrier that publishes w
+    const double gmax = gm4[0];
     positions_of(T, w, pbar, p);
     quantities_of(T, w, qbar, qv);
-    __syncwarp();
-#pragma unroll 1
-    for (int slot = grp; slot < nkp; slot += 8) {
-      const int kp = T.kp_of_slot[slot];
+    bsync();
+    {
+      const int kp = slot_of_thread < nkp ? T.kp_of_slot[slot_of_thread] : 0;
       const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
-      for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+      for_my_rows([&](const double* r, double& s, double& l) {
         const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
         s = fmax(slk, 1.0);
         l = 1.0 / s;
       });
     }
 #pragma unroll 1
-    for (int idx = lane; idx < NQ3; idx += 32) {
+    for (int idx = tid; idx < NQ3; idx += NT) {
       const int a = idx / NQ, q = idx - a * NQ;
       if (T.qconst[a][q]) continue;
       const double sc = 0.05 * (T.qhi[a][q] - T.qlo[a][q]);
@@ -589,40 +693,42 @@ struct Solver {
         bs[2 * idx + side] = s, bl[2 * idx + side] = 1.0 / s;
       }
     }
-    __syncwarp();
+    bsync();
 
+    tick(2);
 #pragma unroll 1
     for (int it = 0;; ++it) {
+      const int kp = slot_of_thread < nkp ? T.kp_of_slot[slot_of_thread] : 0;
+      const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+      tick(8);
       // ---- pass 1: residuals and barrier blocks
-      double mu = 0, rcmax = 0, lamsl = 0, lamsum = 0;
-#pragma unroll 1
-      for (int slot = grp; slot < nkp; slot += 8) {
-        const int kp = T.kp_of_slot[slot];
-        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+      double acc4[4] = {0, 0, 0, 0};  // mu, rcmax, lam.slack, sum lam
+      {
         double m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, t0 = 0, t1 = 0, t2 = 0, f0 = 0, f1 = 0, f2 = 0;
-        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+        for_my_rows([&](const double* r, double& s, double& l) {
           const double nx = r[0], ny = r[1], nz = r[2];
           const double slk = r[3] - (nx * px + ny * py + nz * pz);
           const double rc = s - slk, d = l / s, t = d * rc;
-          mu += s * l, rcmax = fmax(rcmax, fabs(rc)), lamsl += l * slk, lamsum += l;
+          acc4[0] += s * l, acc4[1] = fmax(acc4[1], fabs(rc)), acc4[2] += l * slk, acc4[3] += l;
           const double dx = d * nx, dy = d * ny, dz = d * nz;
           m0 += dx * nx, m1 += dx * ny, m2 += dx * nz, m3 += dy * ny, m4 += dy * nz, m5 += dz * nz;
           t0 += t * nx, t1 += t * ny, t2 += t * nz;
           f0 += l * nx, f1 += l * ny, f2 += l * nz;
         });
-        m0 = quad_sum(gmask, m0), m1 = quad_sum(gmask, m1), m2 = quad_sum(gmask, m2), m3 = quad_sum(gmask, m3);
-        m4 = quad_sum(gmask, m4), m5 = quad_sum(gmask, m5);
-        t0 = quad_sum(gmask, t0), t1 = quad_sum(gmask, t1), t2 = quad_sum(gmask, t2);
-        f0 = quad_sum(gmask, f0), f1 = quad_sum(gmask, f1), f2 = quad_sum(gmask, f2);
-        if (sub == 0) {
-          double* M = Mk + 6 * slot;
-          M[0] = m0, M[1] = m1, M[2] = m2, M[3] = m3, M[4] = m4, M[5] = m5;
-          Tk[3 * slot] = t0, Tk[3 * slot + 1] = t1, Tk[3 * slot + 2] = t2;
-          Fk[3 * slot] = f0, Fk[3 * slot + 1] = f1, Fk[3 * slot + 2] = f2;
+        if (slot_of_thread < nkp) {
+          m0 = group_sum(m0), m1 = group_sum(m1), m2 = group_sum(m2), m3 = group_sum(m3), m4 = group_sum(m4);
+          m5 = group_sum(m5), t0 = group_sum(t0), t1 = group_sum(t1), t2 = group_sum(t2);
+          f0 = group_sum(f0), f1 = group_sum(f1), f2 = group_sum(f2);
+          if (sub == 0) {
+            double* M = Mk + 6 * slot_of_thread;
+            M[0] = m0, M[1] = m1, M[2] = m2, M[3] = m3, M[4] = m4, M[5] = m5;
+            Tk[3 * slot_of_thread] = t0, Tk[3 * slot_of_thread + 1] = t1, Tk[3 * slot_of_thread + 2] = t2;
+            Fk[3 * slot_of_thread] = f0, Fk[3 * slot_of_thread + 1] = f1, Fk[3 * slot_of_thread + 2] = f2;
+          }
         }
       }
 #pragma unroll 1
-      for (int idx = lane; idx < NQ3; idx += 32) {
+      for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         double dsum = 0, tsum = 0, fsum = 0;
         if (!T.qconst[a][q]) {
@@ -631,37 +737,41 @@ struct Solver {
           for (int side = 0; side < 2; ++side) {
             const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
             const double rc = s - slk, d = l / s, sg = side == 0 ? 1.0 : -1.0;
-            mu += s * l, rcmax = fmax(rcmax, fabs(rc) * irange), lamsl += l * slk, lamsum += l;
+            acc4[0] += s * l, acc4[1] = fmax(acc4[1], fabs(rc) * irange), acc4[2] += l * slk, acc4[3] += l;
             dsum += d, tsum += sg * d * rc, fsum += sg * l;
           }
         }
         DQ[idx] = dsum, TQ[idx] = tsum, FQ[idx] = fsum;
       }
       __syncwarp();
-      mu = warp_sum(mu) * inv_m, rcmax = warp_max(rcmax), lamsl = warp_sum(lamsl), lamsum = warp_sum(lamsum);
+      reduce4<2>(acc4);  // also the barrier that publishes Mk / Tk / Fk / DQ / TQ / FQ
+      const double mu = acc4[0] * inv_m, rcmax = acc4[1], lamsl = acc4[2], lamsum = acc4[3];
 
+      tick(3);
       // ---- smooth gradient, dual residual, objective, right-hand side of the predictor
-      double hg = 0, fi = 0, ti = 0, wi = 0;
-      if (lane < NW) {
-        wi = w[lane];
-        hg = g[lane];
-#pragma unroll
-        for (int c = 0; c < NZ; ++c) hg += T.Hw[ax][rr][c] * w[ax * NZ + c];
+      double hg = 0, fi = 0, ti = 0;
+      if (rowact) {
 #pragma unroll 1
-        for (int slot = 0; slot < nkp; ++slot) {
+        for (int c = part; c < NZ; c += TPR) hg += T.Hw[ax][rr][c] * w[ax * NZ + c];
+#pragma unroll 1
+        for (int slot = part; slot < nkp; slot += TPR) {
           const double qp = T.QP[ax][T.kp_of_slot[slot]][rr];
           fi += Fk[3 * slot + ax] * qp, ti += Tk[3 * slot + ax] * qp;
         }
 #pragma unroll 2
-        for (int q = 0; q < NQ; ++q) {
+        for (int q = part; q < NQ; q += TPR) {
           const double e = T.EQ[ax][q][rr];
           fi += FQ[ax * NQ + q] * e, ti += TQ[ax * NQ + q] * e;
         }
       }
-      const double rdmax = warp_max(fabs(hg + fi));
-      const double fmaxv = warp_max(fabs(fi));
-      const double wf = warp_sum(wi * fi);
-      const double obj = c0 + 0.5 * warp_sum(lane < NW ? wi * (hg + g[lane]) : 0.0);
+      hg = tpr_sum(hg), fi = tpr_sum(fi), ti = tpr_sum(ti);
+      if (rowact) hg += g[row];
+      const bool owner = rowact && part == 0;
+      const double wi = owner ? w[row] : 0.0;
+      double r4[4] = {owner ? fabs(hg + fi) : 0.0, owner ? fabs(fi) : 0.0, wi * fi, owner ? wi * (hg + g[row]) : 0.0};
+      reduce4<3>(r4);
+      const double rdmax = r4[0], fmaxv = r4[1], wf = r4[2];
+      const double obj = c0v + 0.5 * r4[3];
       const auto accept = [&](double tl) {
         return rdmax <= tl * (1 + gmax) && rcmax <= tl && mu <= 0.1 * tl * fmax(1.0, fabs(obj));
       };
@@ -682,101 +792,114 @@ struct Solver {
         return out;
       }
 
-      // ---- K = Hw + sum_slots QP' M QP + sum_q DQ EQ EQ'   (row `lane`, written to shared memory)
-      if (lane < NW) {
+      tick(4);
+      // ---- K = Hw + sum_slots QP' M QP + sum_q DQ EQ EQ'   (lower blocks, written to shared memory)
+      if (TPR == 1) {
+        if (rowact) {
 #pragma unroll 1
-        for (int b = 0; b < 3; ++b) {
-          double acc[NZ];
+          for (int b = 0; b < 3; ++b) {
+            double acc[NZ];
+            kkt_block(ax, rr, b, b == ax, 0, b == ax ? NQ : 0, true, acc);
 #pragma unroll
-          for (int c = 0; c < NZ; ++c) acc[c] = 0.0;
-          if (b == ax) {
+            for (int c = 0; c < NZ; ++c) Ks[row * LD + b * NZ + c] = acc[c];
+            if (b == ax) {
+              double dg = acc[0];
 #pragma unroll
-            for (int c = 0; c < NZ; ++c) acc[c] = T.Hw[ax][rr][c];
-#pragma unroll 1
-            for (int q = 0; q < NQ; ++q) {
-              const double f = DQ[ax * NQ + q] * T.EQ[ax][q][rr];
-#pragma unroll
-              for (int c = 0; c < NZ; ++c) acc[c] += f * T.EQ[ax][q][c];
+              for (int c = 1; c < NZ; ++c) dg = c == rr ? acc[c] : dg;
+              diag0[row] = dg;
             }
           }
-          // symmetric 3x3 block stored as (00,01,02,11,12,22): entry (ax, b)
-          const int mi = ax == b ? (ax == 0 ? 0 : ax == 1 ? 3 : 5) : (ax + b == 1 ? 1 : ax + b == 2 ? 2 : 4);
-#pragma unroll 1
-          for (int slot = 0; slot < nkp; ++slot) {
-            const int kp = T.kp_of_slot[slot];
-            const double f = Mk[6 * slot + mi] * T.QP[ax][kp][rr];
-#pragma unroll
-            for (int c = 0; c < NZ; ++c) acc[c] += f * T.QP[b][kp][c];
-          }
-#pragma unroll
-          for (int c = 0; c < NZ; ++c) Ks[lane * LD + b * NZ + c] = acc[c];
         }
-        diag0[lane] = Ks[lane * LD + lane];
+      } else {
+        // four threads per row: part b < ax -> off-diagonal block b; part ax -> diagonal block with the
+        // first half of the box terms and the position terms; part 3 -> second half of the box terms
+        double acc[NZ];
+        const bool diag_main = rowact && part == ax, diag_aux = rowact && part == 3;
+        const bool off = rowact && part < ax;
+        if (diag_main) kkt_block(ax, rr, ax, true, 0, NQ / 2, true, acc);
+        else if (diag_aux) kkt_block(ax, rr, ax, false, NQ / 2, NQ, false, acc);
+        else if (off) kkt_block(ax, rr, part, false, 0, 0, true, acc);
+        else {
+#pragma unroll
+          for (int c = 0; c < NZ; ++c) acc[c] = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < NZ; ++c) {
+          const double o = __shfl_sync(kFull, acc[c], (lane & ~3) | 3);
+          if (diag_main) acc[c] += o;
+        }
+        if (diag_main || off) {
+          const int b = diag_main ? ax : part;
+#pragma unroll
+          for (int c = 0; c < NZ; ++c) Ks[row * LD + b * NZ + c] = acc[c];
+        }
+        if (diag_main) {
+          double dg = acc[0];
+#pragma unroll
+          for (int c = 1; c < NZ; ++c) dg = c == rr ? acc[c] : dg;
+          diag0[row] = dg;
+        }
       }
-      __syncwarp();
-      if (!factor(Ks, invd, diag0, tab)) {
+      if (owner) dw[row] = -hg - ti;  // right-hand side of the predictor
+      bsync();
+      tick(5);
+      if (!factor()) {
         out.status = HDSM_NUMERICAL, out.iters = it;
         return out;
       }
 
+      tick(6);
       // ---- predictor
-      const double dwa = solve(Ks, invd, -hg - ti);
-      if (lane < NW) dw[lane] = dwa;
-      __syncwarp();
+      solve_inplace(dw);
+      tick(7);
       positions_of(T, dw, nullptr, dp);
       quantities_of(T, dw, nullptr, dq);
-      __syncwarp();
+      bsync();
+      const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
+      tick(8);
       // largest relative decrease of any s or lam along the step: alpha_max = 1 / rmax
-      double rmax = 0.0, s_sl = 0, s_x = 0, s_dd = 0;
+      double a4[4] = {0, 0, 0, 0};  // rmax, sum s.lam, sum (s dl + l ds), sum ds.dl
+      for_my_rows([&](const double* r, double& s, double& l) {
+        const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
+        const RowStep e = row_step(s, l, slk, r[0] * dx + r[1] * dy + r[2] * dz, 0.0);
+        a4[0] = fmax(a4[0], fmax(-e.ds * e.inv_s, -e.dl * e.inv_l));
+        a4[1] += s * l, a4[2] += s * e.dl + l * e.ds, a4[3] += e.ds * e.dl;
+      });
 #pragma unroll 1
-      for (int slot = grp; slot < nkp; slot += 8) {
-        const int kp = T.kp_of_slot[slot];
-        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
-        const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
-        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
-          const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
-          const RowStep e = row_step(s, l, slk, r[0] * dx + r[1] * dy + r[2] * dz, 0.0);
-          rmax = fmax(rmax, fmax(-e.ds * e.inv_s, -e.dl * e.inv_l));
-          s_sl += s * l, s_x += s * e.dl + l * e.ds, s_dd += e.ds * e.dl;
-        });
-      }
-#pragma unroll 1
-      for (int idx = lane; idx < NQ3; idx += 32) {
+      for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
           const RowStep e = row_step(s, l, slk, side == 0 ? dq[idx] : -dq[idx], 0.0);
-          rmax = fmax(rmax, fmax(-e.ds * e.inv_s, -e.dl * e.inv_l));
-          s_sl += s * l, s_x += s * e.dl + l * e.ds, s_dd += e.ds * e.dl;
+          a4[0] = fmax(a4[0], fmax(-e.ds * e.inv_s, -e.dl * e.inv_l));
+          a4[1] += s * l, a4[2] += s * e.dl + l * e.ds, a4[3] += e.ds * e.dl;
         }
       }
       __syncwarp();
-      rmax = warp_max(rmax), s_sl = warp_sum(s_sl), s_x = warp_sum(s_x), s_dd = warp_sum(s_dd);
-      double alpha = rmax > 1.0 ? 1.0 / rmax : 1.0;
-      const double mu_aff = fmax((s_sl + alpha * s_x + alpha * alpha * s_dd) * inv_m, 0.0);
+      reduce4<1>(a4);
+      const double alpha = a4[0] > 1.0 ? 1.0 / a4[0] : 1.0;
+      const double mu_aff = fmax((a4[1] + alpha * a4[2] + alpha * alpha * a4[3]) * inv_m, 0.0);
       const double ratio = mu > 0 ? mu_aff / mu : 0.0;
       const double smu = ratio * ratio * ratio * mu;
 
       // ---- corrector right-hand side
-#pragma unroll 1
-      for (int slot = grp; slot < nkp; slot += 8) {
-        const int kp = T.kp_of_slot[slot];
-        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
-        const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
+      {
         double t0 = 0, t1 = 0, t2 = 0;
-        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
+        for_my_rows([&](const double* r, double& s, double& l) {
           const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
           const RowStep e = row_step(s, l, slk, r[0] * dx + r[1] * dy + r[2] * dz, 0.0);
           const double t = (l * (s - slk) - (e.ds * e.dl - smu)) * e.inv_s;
           t0 += t * r[0], t1 += t * r[1], t2 += t * r[2];
         });
-        t0 = quad_sum(gmask, t0), t1 = quad_sum(gmask, t1), t2 = quad_sum(gmask, t2);
-        if (sub == 0) Tk[3 * slot] = t0, Tk[3 * slot + 1] = t1, Tk[3 * slot + 2] = t2;
+        if (slot_of_thread < nkp) {
+          t0 = group_sum(t0), t1 = group_sum(t1), t2 = group_sum(t2);
+          if (sub == 0) Tk[3 * slot_of_thread] = t0, Tk[3 * slot_of_thread + 1] = t1, Tk[3 * slot_of_thread + 2] = t2;
+        }
       }
 #pragma unroll 1
-      for (int idx = lane; idx < NQ3; idx += 32) {
+      for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         double tsum = 0;
         if (!T.qconst[a][q]) {
@@ -790,41 +913,38 @@ struct Solver {
         }
         TQ[idx] = tsum;
       }
-      __syncwarp();
+      bsync();
       double tc = 0;
-      if (lane < NW) {
+      if (rowact) {
 #pragma unroll 1
-        for (int slot = 0; slot < nkp; ++slot) tc += Tk[3 * slot + ax] * T.QP[ax][T.kp_of_slot[slot]][rr];
+        for (int slot = part; slot < nkp; slot += TPR) tc += Tk[3 * slot + ax] * T.QP[ax][T.kp_of_slot[slot]][rr];
 #pragma unroll 2
-        for (int q = 0; q < NQ; ++q) tc += TQ[ax * NQ + q] * T.EQ[ax][q][rr];
+        for (int q = part; q < NQ; q += TPR) tc += TQ[ax * NQ + q] * T.EQ[ax][q][rr];
       }
-      const double dwv = solve(Ks, invd, -hg - tc);
-      if (lane < NW) dwc[lane] = dwv;
-      __syncwarp();
+      tc = tpr_sum(tc);
+      if (owner) dwc[row] = -hg - tc;
+      bsync();
+      tick(9);
+      solve_inplace(dwc);
+      tick(7);
       positions_of(T, dwc, nullptr, dpc);
       quantities_of(T, dwc, nullptr, dqc);
-      __syncwarp();
+      bsync();
+      const double ex = dpc[3 * kp], ey = dpc[3 * kp + 1], ez = dpc[3 * kp + 2];
 
+      tick(8);
       // ---- step length of the combined direction
-      rmax = 0.0;
+      double m4[4] = {0, 0, 0, 0};
+      for_my_rows([&](const double* r, double& s, double& l) {
+        const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
+        const double dsa = -(s - slk) - (r[0] * dx + r[1] * dy + r[2] * dz);
+        const RowStep e0 = row_step(s, l, slk, r[0] * ex + r[1] * ey + r[2] * ez, 0.0);
+        const double dla = -l - l * dsa * e0.inv_s;
+        const double dl = -l - ((dsa * dla - smu) + l * e0.ds) * e0.inv_s;
+        m4[0] = fmax(m4[0], fmax(-e0.ds * e0.inv_s, -dl * e0.inv_l));
+      });
 #pragma unroll 1
-      for (int slot = grp; slot < nkp; slot += 8) {
-        const int kp = T.kp_of_slot[slot];
-        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
-        const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
-        const double ex = dpc[3 * kp], ey = dpc[3 * kp + 1], ez = dpc[3 * kp + 2];
-        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
-          const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
-          const double rc = s - slk;
-          const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
-          const RowStep e0 = row_step(s, l, slk, r[0] * ex + r[1] * ey + r[2] * ez, 0.0);
-          const double dla = -l - l * dsa * e0.inv_s;
-          const double dl = -l - ((dsa * dla - smu) + l * e0.ds) * e0.inv_s;
-          rmax = fmax(rmax, fmax(-e0.ds * e0.inv_s, -dl * e0.inv_l));
-        });
-      }
-#pragma unroll 1
-      for (int idx = lane; idx < NQ3; idx += 32) {
+      for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
 #pragma unroll 1
@@ -835,34 +955,27 @@ struct Solver {
           const RowStep e0 = row_step(s, l, slk, sg * dqc[idx], 0.0);
           const double dla = -l - l * dsa * e0.inv_s;
           const double dl = -l - ((dsa * dla - smu) + l * e0.ds) * e0.inv_s;
-          rmax = fmax(rmax, fmax(-e0.ds * e0.inv_s, -dl * e0.inv_l));
+          m4[0] = fmax(m4[0], fmax(-e0.ds * e0.inv_s, -dl * e0.inv_l));
         }
       }
       __syncwarp();
-      rmax = warp_max(rmax);
+      reduce4<1>(m4);
       // 0.97 of the way to the boundary: 0.995 leaves the blocking pair so far off the central path
       // that predictor and centring steps alternate without reducing mu on ~0.4% of the QPs
-      const double al = rmax > kStepFrac ? kStepFrac / rmax : 1.0;
+      const double al = m4[0] > kStepFrac ? kStepFrac / m4[0] : 1.0;
 
       // ---- update
+      for_my_rows([&](const double* r, double& s, double& l) {
+        const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
+        const double rc = s - slk, inv_s = 1.0 / s;
+        const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
+        const double dla = -l - l * dsa * inv_s;
+        const double ds = -rc - (r[0] * ex + r[1] * ey + r[2] * ez);
+        const double dl = -l - ((dsa * dla - smu) + l * ds) * inv_s;
+        s += al * ds, l += al * dl;
+      });
 #pragma unroll 1
-      for (int slot = grp; slot < nkp; slot += 8) {
-        const int kp = T.kp_of_slot[slot];
-        const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
-        const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
-        const double ex = dpc[3 * kp], ey = dpc[3 * kp + 1], ez = dpc[3 * kp + 2];
-        for_slot_rows(slot, [&](const double* r, double& s, double& l) {
-          const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
-          const double rc = s - slk, inv_s = 1.0 / s;
-          const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
-          const double dla = -l - l * dsa * inv_s;
-          const double ds = -rc - (r[0] * ex + r[1] * ey + r[2] * ez);
-          const double dl = -l - ((dsa * dla - smu) + l * ds) * inv_s;
-          s += al * ds, l += al * dl;
-        });
-      }
-#pragma unroll 1
-      for (int idx = lane; idx < NQ3; idx += 32) {
+      for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
 #pragma unroll 1
@@ -875,130 +988,153 @@ struct Solver {
           bs[2 * idx + side] = s + al * ds, bl[2 * idx + side] = l + al * dl;
         }
       }
-      bool finite = true;
-      if (lane < NW) {
-        const double v = w[lane] + al * dwv;
-        finite = isfinite(v);
-        w[lane] = v;
+      double fin4[4] = {0, 0, 0, 0};
+      if (tid < NW) {
+        const double v = w[tid] + al * dwc[tid];
+        fin4[0] = isfinite(v) ? 0.0 : 1.0;
+        w[tid] = v;
       }
-      __syncwarp();
-      if (!__all_sync(kFull, finite)) {
+      reduce4<1>(fin4);  // also publishes w
+      if (fin4[0] > 0.0) {
         out.status = HDSM_NUMERICAL, out.iters = it;
         return out;
       }
+      tick(9);
       positions_of(T, w, pbar, p);
       quantities_of(T, w, qbar, qv);
-      __syncwarp();
+      bsync();
     }
   }
 
   // ---------------------------------------------------------------- K3 + epilogue
+  // Warp 0 owns the search state (stack, incumbent, counters); the other warps only join solve_qp.
+  // ctl[0]: 1 = a node is ready to be solved, 0 = finished.
   __device__ void run(int agent) {
     hdsm_result R{HDSM_INFEASIBLE, 0, 0, 0, INFINITY, INFINITY};
-    int st = setup(agent);
-    if (st < 0) st = build_neighbour_rows(agent);
-    if (st < 0 && !root_sets(agent)) st = HDSM_INFEASIBLE;
+    int st = -1, top = 0, nodes = 0, iters = 0, maxrows = 0, fail = 0;
     double best = INFINITY, bestkkt = INFINITY;
-    int nodes = 0, iters = 0, maxrows = 0, fail = 0;
     bool exhausted = true, overflow = false;
-    if (st < 0) {
-      int top = 0;
-      if (lane < 16) stack[lane] = lane < N ? cur[lane] : 0;
-      top = 1;
-      __syncwarp();
-      while (top > 0) {
-        if (nodes >= A.max_nodes) {
-          exhausted = false;
-          break;
-        }
-        --top;
-        if (lane < 16) cur[lane] = stack[top * 16 + lane];
-        __syncwarp();
-        const int nstat = build_static_rows();
-        if (nstat < 0) {  // the row pool is too small for this agent: the large-memory pass redoes it
-          overflow = true;
-          break;
-        }
-        maxrows = max(maxrows, nstat + n_nbr_rows);
-        const QpOut q = solve_qp();
-        ++nodes;
-        iters += q.iters;
-        if (q.status != HDSM_OPTIMAL) {
-          if (q.status != HDSM_INFEASIBLE) fail = q.status;
-          continue;
-        }
-        if (q.obj >= best - kPruneRel * fmax(1.0, fabs(best))) continue;
-        // coverage of every segment (p_k, p_k+1) by one member of its candidate set
-        for (int idx = lane; idx < N * Peff; idx += 32) {
-          const int k = idx / Peff, j = idx - k * Peff;
-          double v = INFINITY;
-          if (cur[k] >> j & 1) {
-            v = -INFINITY;
-            const double ax_ = p[3 * k], ay = p[3 * k + 1], az = p[3 * k + 2];
-            const double bx = p[3 * k + 3], by = p[3 * k + 4], bz = p[3 * k + 5];
-            for (int r = 0; r < prow_n[j]; ++r) {
-              const double* c = poly + 4 * (j * A.rmax + r);
-              v = fmax(v, fmax(c[0] * ax_ + c[1] * ay + c[2] * az, c[0] * bx + c[1] * by + c[2] * bz) - c[3]);
-            }
-          }
-          viol[k * kMaxP + j] = v;
-        }
-        __syncwarp();
-        // branch on the uncovered step that is farthest from all of its candidates
-        int bk = -1;
-        double bkv = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < N; ++k) {
-          int fk = -1;
-          double vmin = INFINITY;
-#pragma unroll 1
-          for (int j = 0; j < Peff; ++j) {
-            const double v = viol[k * kMaxP + j];
-            vmin = fmin(vmin, v);
-            if (fk < 0 && v <= kContainTol) fk = j;
-          }
-          if (lane == 0) fullsig[k] = fk;
-          if (fk < 0 && (bk < 0 || vmin > bkv)) bk = k, bkv = vmin;
-        }
-        __syncwarp();
-        if (bk < 0) {  // node optimum is feasible for the mixed-integer problem: new incumbent
-          best = q.obj, bestkkt = q.kkt;
-          if (lane < NW) bestw[lane] = w[lane];
-          if (lane < N) bestsig[lane] = fullsig[lane];
-          __syncwarp();
-          continue;
-        }
-        // split the candidate set of step bk in two halves ordered by (violation, index)
-        int order[kMaxP], no = 0;
-        double vv[kMaxP];
-        for (int j = 0; j < Peff; ++j)
-          if (cur[bk] >> j & 1) order[no] = j, vv[no++] = viol[bk * kMaxP + j];
-        for (int x = 1; x < no; ++x)
-          for (int y = x; y > 0 && vv[y] < vv[y - 1]; --y) {
-            const double tv = vv[y];
-            vv[y] = vv[y - 1], vv[y - 1] = tv;
-            const int to = order[y];
-            order[y] = order[y - 1], order[y - 1] = to;
-          }
-        if (no <= 1) continue;
-        const int h = (no + 1) / 2;
-        unsigned lo_m = 0, hi_m = 0;
-        for (int x = 0; x < no; ++x) {
-          if (x < h) lo_m |= 1u << order[x];
-          else hi_m |= 1u << order[x];
-        }
-        if (top + 2 > kStackCap) {
-          exhausted = false;
-          break;
-        }
-        if (lane < 16) {
-          const unsigned char c = cur[lane];
-          stack[top * 16 + lane] = lane == bk ? (unsigned char)hi_m : c;
-          stack[(top + 1) * 16 + lane] = lane == bk ? (unsigned char)lo_m : c;  // least violated half first
-        }
-        top += 2;
+    if (wid == 0) {
+      if (A.prof) tlast = clock64();
+      st = setup(agent);
+      if (st < 0) st = build_neighbour_rows(agent);
+      if (st < 0 && !root_sets(agent)) st = HDSM_INFEASIBLE;
+      if (st < 0) {
+        if (lane < 16) stack[lane] = lane < N ? cur[lane] : 0;
+        top = 1;
         __syncwarp();
       }
+      tick(0);
+    }
+    for (;;) {
+      if (wid == 0) {
+        int cmd = 0;
+        if (st < 0 && !overflow) {
+          if (top > 0 && nodes >= A.max_nodes) {
+            exhausted = false;
+          } else if (top > 0) {
+            --top;
+            if (lane < 16) cur[lane] = stack[top * 16 + lane];
+            __syncwarp();
+            tick(10);
+            const int nstat = build_static_rows();
+            tick(1);
+            if (nstat < 0) {  // the row pool is too small for this agent: the large-memory pass redoes it
+              overflow = true;
+            } else {
+              maxrows = max(maxrows, nstat + n_nbr_rows);
+              cmd = 1;
+            }
+          }
+        }
+        if (lane == 0) ctl[0] = cmd;
+      }
+      bsync();
+      if (ctl[0] == 0) break;
+      if (A.prof) tlast = clock64();
+      const QpOut q = solve_qp();  // all warps; the result is uniform over the block
+      if (wid != 0) continue;
+      ++nodes;
+      iters += q.iters;
+      if (q.status != HDSM_OPTIMAL) {
+        if (q.status != HDSM_INFEASIBLE) fail = q.status;
+        continue;
+      }
+      if (q.obj >= best - kPruneRel * fmax(1.0, fabs(best))) continue;
+      // coverage of every segment (p_k, p_k+1) by one member of its candidate set
+      for (int idx = lane; idx < N * Peff; idx += 32) {
+        const int k = idx / Peff, j = idx - k * Peff;
+        double v = INFINITY;
+        if (cur[k] >> j & 1) {
+          v = -INFINITY;
+          const double ax_ = p[3 * k], ay = p[3 * k + 1], az = p[3 * k + 2];
+          const double bx = p[3 * k + 3], by = p[3 * k + 4], bz = p[3 * k + 5];
+          for (int r = 0; r < prow_n[j]; ++r) {
+            const double* c = poly + 4 * (j * A.rmax + r);
+            v = fmax(v, fmax(c[0] * ax_ + c[1] * ay + c[2] * az, c[0] * bx + c[1] * by + c[2] * bz) - c[3]);
+          }
+        }
+        viol[k * kMaxP + j] = v;
+      }
+      __syncwarp();
+      // branch on the uncovered step that is farthest from all of its candidates
+      int bk = -1;
+      double bkv = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < N; ++k) {
+        int fk = -1;
+        double vmin = INFINITY;
+#pragma unroll 1
+        for (int j = 0; j < Peff; ++j) {
+          const double v = viol[k * kMaxP + j];
+          vmin = fmin(vmin, v);
+          if (fk < 0 && v <= kContainTol) fk = j;
+        }
+        if (lane == 0) fullsig[k] = fk;
+        if (fk < 0 && (bk < 0 || vmin > bkv)) bk = k, bkv = vmin;
+      }
+      __syncwarp();
+      if (bk < 0) {  // node optimum is feasible for the mixed-integer problem: new incumbent
+        best = q.obj, bestkkt = q.kkt;
+        if (lane < NW) bestw[lane] = w[lane];
+        if (lane < N) bestsig[lane] = fullsig[lane];
+        __syncwarp();
+        continue;
+      }
+      // split the candidate set of step bk in two halves ordered by (violation, index)
+      int order[kMaxP], no = 0;
+      double vv[kMaxP];
+      for (int j = 0; j < Peff; ++j)
+        if (cur[bk] >> j & 1) order[no] = j, vv[no++] = viol[bk * kMaxP + j];
+      for (int x = 1; x < no; ++x)
+        for (int y = x; y > 0 && vv[y] < vv[y - 1]; --y) {
+          const double tv = vv[y];
+          vv[y] = vv[y - 1], vv[y - 1] = tv;
+          const int to = order[y];
+          order[y] = order[y - 1], order[y - 1] = to;
+        }
+      if (no <= 1) continue;
+      const int h = (no + 1) / 2;
+      unsigned lo_m = 0, hi_m = 0;
+      for (int x = 0; x < no; ++x) {
+        if (x < h) lo_m |= 1u << order[x];
+        else hi_m |= 1u << order[x];
+      }
+      if (top + 2 > kStackCap) {
+        exhausted = false;
+        top = 0;
+        continue;
+      }
+      if (lane < 16) {
+        const unsigned char c = cur[lane];
+        stack[top * 16 + lane] = lane == bk ? (unsigned char)hi_m : c;
+        stack[(top + 1) * 16 + lane] = lane == bk ? (unsigned char)lo_m : c;  // least violated half first
+      }
+      top += 2;
+      __syncwarp();
+    }
+    if (wid != 0) return;
+    if (st < 0) {
       R.nodes = nodes, R.iters = iters, R.rows = maxrows;
       if (overflow) {
         best = INFINITY;
@@ -1012,6 +1148,9 @@ struct Solver {
     } else {
       R.status = st;
     }
+    tick(10);
+    if (A.prof && lane == 0)
+      for (int i = 0; i < 12; ++i) A.prof[(size_t)agent * 16 + i] = tprof[i];
     write_outputs(agent, R, best < INFINITY);
   }
 
@@ -1062,13 +1201,13 @@ struct Solver {
   }
 };
 
-template <int N>
-__global__ void __launch_bounds__(32) hdsm_solve_kernel(const Tables* __restrict__ tables, const KernelArgs args) {
+template <int N, int W>
+__global__ void __launch_bounds__(32 * W, W == 4 ? HDSM_MINBLOCKS : 1) hdsm_solve_kernel(const Tables* __restrict__ tables, const KernelArgs args) {
   extern __shared__ double smem[];
   const int agent = blockIdx.x;
   if (agent >= args.n_local) return;
   if (args.only_status >= 0 && args.res[agent].status != args.only_status) return;
-  Solver<N> s(*tables, args, smem);
+  Solver<N, W> s(*tables, args, smem);
   s.run(agent);
 }
 
