@@ -31,6 +31,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
         if os.environ.get("HDSM_MINBLOCKS"):
             cmd.insert(1, "-DHDSM_MINBLOCKS=" + os.environ["HDSM_MINBLOCKS"])
+        if os.environ.get("HDSM_ENABLE_PROFILE"):
+            cmd.insert(1, "-DHDSM_ENABLE_PROFILE")
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

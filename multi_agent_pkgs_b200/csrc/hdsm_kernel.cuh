@@ -28,7 +28,7 @@ constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still
 constexpr int kStackCap = 48;          // >= 1 + N * ceil(log2 P) open nodes
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef HDSM_MINBLOCKS
-#define HDSM_MINBLOCKS 8  // resident 4-warp blocks per SM the register allocation aims for (64 registers)
+#define HDSM_MINBLOCKS 3  // resident 4-warp blocks per SM the register allocation aims for (168 registers, no spills)
 #endif
 
 struct KernelArgs {
@@ -94,9 +94,10 @@ HDSM_HD constexpr FixedLayout make_layout(int N) {
   s.var = o;
   return s;
 }
-// run-time part after FixedLayout::var: poly [P*rmax*4], rown [rows*4], rs [rows], rl [rows], nid [P*rmax bytes]
+// run-time part after FixedLayout::var: poly [P*rmax*4], bmin [P*rmax*P], rown [rows*4], rs [rows], rl [rows],
+// nid [P*rmax bytes]
 HDSM_HD inline int smem_doubles(int N, int P, int rmax, int row_cap) {
-  return make_layout(N).var + P * rmax * 4 + row_cap * 6 + (P * rmax + 7) / 8;
+  return make_layout(N).var + P * rmax * 4 + P * rmax * P + row_cap * 6 + (P * rmax + 7) / 8;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -171,7 +172,7 @@ struct Solver {
   unsigned char* const stack = cur + 16;  // kStackCap entries of 16 bytes: per-step candidate masks
   int* const ctl = reinterpret_cast<int*>(stack + kStackCap * 16);  // block-wide control words (8)
   unsigned short* const tab = reinterpret_cast<unsigned short*>(ctl + 8);  // pairs (i << 8 | k)
-  double *poly, *rown, *rs, *rl;
+  double *poly, *bmin, *rown, *rs, *rl;  // bmin[id][j]: tightest offset of normal `id` in polytope j (inf: absent)
   unsigned char* nid;  // per polytope row: id of the first row with the same normal
   double c0;
   int nkp, Peff, n_nbr_rows;
@@ -180,7 +181,8 @@ struct Solver {
       : T(t), A(a), tid(threadIdx.x), lane(threadIdx.x & 31), wid(threadIdx.x >> 5), sm(smem) {
     const int rows = a.row_cap;
     poly = sm + L.var;
-    rown = poly + a.P * a.rmax * 4;
+    bmin = poly + a.P * a.rmax * 4;
+    rown = bmin + a.P * a.rmax * a.P;
     rs = rown + rows * 4;
     rl = rs + rows;
     nid = reinterpret_cast<unsigned char*>(rl + rows);
@@ -241,6 +243,8 @@ struct Solver {
       for (int i = segb[2 * slot_of_thread + sg] + sub; i < end; i += lps) f(rown + 4 * i, rs[i], rl[i]);
     }
   }
+  // phase cycle counters: compiled in only with -DHDSM_ENABLE_PROFILE (HDSM_PROFILE=1 then prints them)
+#ifdef HDSM_ENABLE_PROFILE
   long long tprof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = 0;
   __device__ __forceinline__ void tick(int slot) {  // attribute the cycles since the last tick to `slot`
@@ -250,6 +254,18 @@ struct Solver {
       tlast = now;
     }
   }
+  __device__ __forceinline__ void tick_start() {
+    if (A.prof) tlast = clock64();
+  }
+  __device__ __forceinline__ void tick_flush(int agent) {
+    if (A.prof && lane == 0)
+      for (int i = 0; i < 12; ++i) A.prof[(size_t)agent * 16 + i] = tprof[i];
+  }
+#else
+  __device__ __forceinline__ void tick(int) {}
+  __device__ __forceinline__ void tick_start() {}
+  __device__ __forceinline__ void tick_flush(int) {}
+#endif
   __device__ __forceinline__ void bsync() const {
     if (W > 1) __syncthreads();
     else __syncwarp();
@@ -296,15 +312,33 @@ struct Solver {
     __syncwarp();
     Peff = 0;
     while (Peff < A.P && prow_n[Peff] > 0) ++Peff;  // P_eff = leading present polytopes (:913)
-    // id of a row's normal = flat index of the first row (over all polytopes) with bit-identical normal
-    for (int i = lane; i < A.P * A.rmax; i += 32) {
-      int id = i;
-      for (int i2 = 0; i2 < i; ++i2)
-        if (poly[4 * i2] == poly[4 * i] && poly[4 * i2 + 1] == poly[4 * i + 1] && poly[4 * i2 + 2] == poly[4 * i + 2]) {
-          id = i2;
-          break;
+    // id of a row's normal = flat index of the first valid row (over all polytopes) with a bit-identical
+    // normal; 255 marks padding rows.  bmin[id][j] = tightest offset of that normal in polytope j.
+    const int PR = A.P * A.rmax;
+    for (int i = lane; i < PR; i += 32) {
+      const int j = i / A.rmax, r = i - j * A.rmax;
+      int id = 255;
+      if (j < Peff && r < prow_n[j]) {
+        id = i;
+        for (int i2 = 0; i2 < i; ++i2) {
+          const int j2 = i2 / A.rmax;
+          if (i2 - j2 * A.rmax < prow_n[j2] && poly[4 * i2] == poly[4 * i] && poly[4 * i2 + 1] == poly[4 * i + 1] &&
+              poly[4 * i2 + 2] == poly[4 * i + 2]) {
+            id = i2;
+            break;
+          }
         }
+      }
       nid[i] = (unsigned char)id;
+    }
+    __syncwarp();
+    for (int t = lane; t < PR * A.P; t += 32) {
+      const int i = t / A.P, j = t - i * A.P;
+      double bm = INFINITY;
+      if (nid[i] == i && j < Peff)
+        for (int r2 = 0; r2 < prow_n[j]; ++r2)
+          if (nid[j * A.rmax + r2] == i) bm = fmin(bm, poly[4 * (j * A.rmax + r2) + 3]);
+      bmin[t] = bm;
     }
     // lower-triangle pairs ordered by column descending: the trailing update of Cholesky step j
     // touches exactly the first (NW-1-j)(NW-j)/2 entries
@@ -476,30 +510,18 @@ struct Solver {
     return !any_empty;
   }
 
-  // rows of a candidate set at lane `r`: the polytope's own row (singleton) or the union-hull row
-  // (normal shared bit-identically by every member, offset = max over members of their tightest)
-  __device__ __forceinline__ bool set_row(unsigned mask, int r, double n[3], double& b) const {
-    const int first = __ffs(mask) - 1;
-    if (r >= prow_n[first]) return false;
-    const double* a = poly + 4 * (first * A.rmax + r);
-    n[0] = a[0], n[1] = a[1], n[2] = a[2], b = a[3];
-    if ((mask & (mask - 1)) == 0) return true;
-    const int myid = nid[first * A.rmax + r];
-#pragma unroll 1
-    for (int r2 = 0; r2 < r; ++r2)  // duplicate normal inside `first`: handled by its first occurrence
-      if (nid[first * A.rmax + r2] == myid) return false;
+  // Row of a candidate set for the distinct normal whose first occurrence is flat row i: offset = max
+  // over the members of their tightest offset for that normal; absent in any member -> no row.  For a
+  // single polytope this is the polytope itself (duplicate normals collapse to the tightest one); for
+  // several it is the union hull used by the relaxation.
+  __device__ __forceinline__ bool hull_row(unsigned mask, int i, double n[3], double& b) const {
+    if (i >= A.P * A.rmax || nid[i] != i) return false;
     double bmax = -INFINITY;
 #pragma unroll 1
-    for (int j = first; j < Peff; ++j) {
-      if (!(mask >> j & 1)) continue;
-      double bmin = INFINITY;
-#pragma unroll 2
-      for (int r2 = 0; r2 < prow_n[j]; ++r2)
-        if (nid[j * A.rmax + r2] == myid) bmin = fmin(bmin, poly[4 * (j * A.rmax + r2) + 3]);
-      if (bmin == INFINITY) return false;
-      bmax = fmax(bmax, bmin);
-    }
-    b = bmax;
+    for (int j = 0; j < Peff; ++j)
+      if (mask >> j & 1) bmax = fmax(bmax, bmin[i * A.P + j]);
+    if (!(bmax < INFINITY)) return false;
+    n[0] = poly[4 * i], n[1] = poly[4 * i + 1], n[2] = poly[4 * i + 2], b = bmax;
     return true;
   }
 
@@ -508,28 +530,27 @@ struct Solver {
     int cnt = 0;
     const int stat_cap = A.row_cap - n_nbr_rows;
     const unsigned lt = (1u << lane) - 1;
-    double pn[3] = {0, 0, 0}, pb = 0;  // rows of the previous step's set, reused when the set repeats
-    bool pvalid = false;
-    int pk = -2;
+    const int rounds = (A.P * A.rmax + 31) / 32;
     for (int slot = 0; slot < nkp; ++slot) {
       const int kp = T.kp_of_slot[slot];
       segb[2 * slot + 1] = n_nbr_rows + cnt;
       for (int k = kp - 1; k <= kp; ++k) {
         if (k < 0 || k >= N) continue;
         if (k == kp && kp >= 1 && cur[kp - 1] == cur[kp]) continue;  // same rows already put on p_kp by step kp-1
-        if (!(pk >= 0 && cur[pk] == cur[k])) pvalid = set_row(cur[k], lane, pn, pb);
-        pk = k;
-        bool valid = pvalid;
-        if (valid && A.prune) valid = reachable(pn, pb, kp);
-        const unsigned m = __ballot_sync(kFull, valid);
-        if (valid) {
-          const int pos = cnt + __popc(m & lt);
-          if (pos < stat_cap) {
-            double* r = rown + 4 * (n_nbr_rows + pos);
-            r[0] = pn[0], r[1] = pn[1], r[2] = pn[2], r[3] = pb;
+        for (int rd = 0; rd < rounds; ++rd) {
+          double n[3], b;
+          bool valid = hull_row(cur[k], rd * 32 + lane, n, b);
+          if (valid && A.prune) valid = reachable(n, b, kp);
+          const unsigned m = __ballot_sync(kFull, valid);
+          if (valid) {
+            const int pos = cnt + __popc(m & lt);
+            if (pos < stat_cap) {
+              double* r = rown + 4 * (n_nbr_rows + pos);
+              r[0] = n[0], r[1] = n[1], r[2] = n[2], r[3] = b;
+            }
           }
+          cnt += __popc(m);
         }
-        cnt += __popc(m);
       }
       sege[2 * slot + 1] = n_nbr_rows + min(cnt, stat_cap);
     }
@@ -547,7 +568,20 @@ struct Solver {
   // digits to cancellation (<= 1e-13 of the original diagonal) marks a direction the barrier has
   // pinned: the variable is frozen for this solve (inverse pivot 0) instead of aborting.  Only a
   // non-positive / NaN original diagonal is a failure.  Per step j: scale column j (one thread per
-  // row), then the trailing update spread over all threads through the pair table.
+  // row), then the trailing update spread over all threads.  With four warps every thread keeps its
+  // <= PM (row, column) pairs in registers; with one warp the pairs come from the table.
+  // On exit the strict lower part holds L_ij / L_jj (forward solve) and the strict upper part
+  // L_ki / L_kk at (i, k) (backward solve), so neither solve has a multiply on its critical path.
+  static constexpr int PM = W == 1 ? 0 : (NW * (NW + 1) / 2 + NT - 1) / NT;
+  int pr_dst[PM > 0 ? PM : 1], pr_i[PM > 0 ? PM : 1], pr_k[PM > 0 ? PM : 1];
+  __device__ __forceinline__ void init_pairs() {
+#pragma unroll
+    for (int m = 0; m < PM; ++m) {
+      const int t = tid + m * NT;
+      const int ik = t < NW * (NW + 1) / 2 ? tab[t] : 0, i = ik >> 8, kk = ik & 255;
+      pr_dst[m] = i * LD + kk, pr_i[m] = i * LD, pr_k[m] = kk * LD;
+    }
+  }
   __device__ __forceinline__ bool factor() {
     bool ok = true;
 #pragma unroll 1
@@ -559,33 +593,49 @@ struct Solver {
       bsync();
       if (tid == j) Ks[j * LD + j] = djj * inv, invd[j] = inv;
       const int T_j = (NW - 1 - j) * (NW - j) / 2;
-#pragma unroll 2
-      for (int t = tid; t < T_j; t += NT) {
-        const int ik = tab[t], i = ik >> 8, k = ik & 255;
-        Ks[i * LD + k] -= Ks[i * LD + j] * Ks[k * LD + j];
+      if (W == 1) {
+#pragma unroll 3
+        for (int t = tid; t < T_j; t += NT) {
+          const int ik = tab[t], i = ik >> 8, kk = ik & 255;
+          Ks[i * LD + kk] -= Ks[i * LD + j] * Ks[kk * LD + j];
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < PM; ++m)
+          if (tid + m * NT < T_j) Ks[pr_dst[m]] -= Ks[pr_i[m] + j] * Ks[pr_k[m] + j];
       }
       bsync();
     }
+    // scaled copies for the two solves
+    for (int t = tid; t < NW * (NW + 1) / 2; t += NT) {
+      const int ik = tab[t], i = ik >> 8, kk = ik & 255;
+      if (i != kk) {
+        const double l = Ks[i * LD + kk];
+        Ks[i * LD + kk] = l * invd[kk];
+        Ks[kk * LD + i] = l * invd[i];
+      }
+    }
+    bsync();
     return ok;
   }
-  // two triangular solves with the factor in Ks, warp 0 only: v[NW] in shared memory is overwritten
+  // two triangular solves with the scaled factor, warp 0 only: v[NW] in shared memory is overwritten
   __device__ __forceinline__ void solve_inplace(double* v) const {
     if (wid == 0) {
       const double myinv = lane < NW ? invd[lane] : 0.0;
-      double acc = lane < NW ? v[lane] : 0.0, x = 0;
-#pragma unroll 1
-      for (int j = 0; j < NW; ++j) {  // L y = rhs
-        const double yj = __shfl_sync(kFull, acc * myinv, j);
-        if (lane > j && lane < NW) acc -= Ks[lane * LD + j] * yj;
-        if (lane == j) acc = yj;
+      const double* myrow = Ks + (lane < NW ? lane : 0) * LD;
+      double acc = lane < NW ? v[lane] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NW - 1; ++j) {  // L y = rhs, y = z / diag
+        const double zj = __shfl_sync(kFull, acc, j);
+        if (lane > j && lane < NW) acc -= myrow[j] * zj;
       }
-#pragma unroll 1
-      for (int i = NW - 1; i >= 0; --i) {  // L' x = y
-        const double xi = __shfl_sync(kFull, acc * myinv, i);
-        if (lane < i) acc -= Ks[i * LD + lane] * xi;
-        if (lane == i) x = xi, acc = 0;
+      acc *= myinv;
+#pragma unroll
+      for (int i = NW - 1; i > 0; --i) {  // L' x = y, x = u / diag
+        const double ui = __shfl_sync(kFull, acc, i);
+        if (lane < i) acc -= myrow[i] * ui;
       }
-      if (lane < NW) v[lane] = x;
+      if (lane < NW) v[lane] = acc * myinv;
     }
     bsync();
   }
@@ -645,6 +695,7 @@ struct Solver {
     QpOut out{HDSM_MAX_ITER, 0, INFINITY, INFINITY};
     const double tol = A.tol, c0v = s0[9];
     init_groups();
+    init_pairs();
     int nrows = 0;
     for (int idx = tid; idx < NQ3; idx += NT) {
       const int a = idx / NQ, q = idx - a * NQ;
@@ -687,7 +738,7 @@ struct Solver {
       const int a = idx / NQ, q = idx - a * NQ;
       if (T.qconst[a][q]) continue;
       const double sc = 0.05 * (T.qhi[a][q] - T.qlo[a][q]);
-#pragma unroll 1
+#pragma unroll
       for (int side = 0; side < 2; ++side) {
         const double s = fmax(box_slack(idx, side, a, q), sc);
         bs[2 * idx + side] = s, bl[2 * idx + side] = 1.0 / s;
@@ -716,9 +767,12 @@ struct Solver {
           f0 += l * nx, f1 += l * ny, f2 += l * nz;
         });
         if (slot_of_thread < nkp) {
-          m0 = group_sum(m0), m1 = group_sum(m1), m2 = group_sum(m2), m3 = group_sum(m3), m4 = group_sum(m4);
-          m5 = group_sum(m5), t0 = group_sum(t0), t1 = group_sum(t1), t2 = group_sum(t2);
-          f0 = group_sum(f0), f1 = group_sum(f1), f2 = group_sum(f2);
+          for (int o = lps >> 1; o > 0; o >>= 1) {  // twelve independent butterflies per step
+            m0 += __shfl_xor_sync(gmask, m0, o), m1 += __shfl_xor_sync(gmask, m1, o), m2 += __shfl_xor_sync(gmask, m2, o);
+            m3 += __shfl_xor_sync(gmask, m3, o), m4 += __shfl_xor_sync(gmask, m4, o), m5 += __shfl_xor_sync(gmask, m5, o);
+            t0 += __shfl_xor_sync(gmask, t0, o), t1 += __shfl_xor_sync(gmask, t1, o), t2 += __shfl_xor_sync(gmask, t2, o);
+            f0 += __shfl_xor_sync(gmask, f0, o), f1 += __shfl_xor_sync(gmask, f1, o), f2 += __shfl_xor_sync(gmask, f2, o);
+          }
           if (sub == 0) {
             double* M = Mk + 6 * slot_of_thread;
             M[0] = m0, M[1] = m1, M[2] = m2, M[3] = m3, M[4] = m4, M[5] = m5;
@@ -733,7 +787,7 @@ struct Solver {
         double dsum = 0, tsum = 0, fsum = 0;
         if (!T.qconst[a][q]) {
           const double irange = 1.0 / (T.qhi[a][q] - T.qlo[a][q]);
-#pragma unroll 1
+#pragma unroll
           for (int side = 0; side < 2; ++side) {
             const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
             const double rc = s - slk, d = l / s, sg = side == 0 ? 1.0 : -1.0;
@@ -869,7 +923,7 @@ struct Solver {
       for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
-#pragma unroll 1
+#pragma unroll
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
           const RowStep e = row_step(s, l, slk, side == 0 ? dq[idx] : -dq[idx], 0.0);
@@ -894,7 +948,8 @@ struct Solver {
           t0 += t * r[0], t1 += t * r[1], t2 += t * r[2];
         });
         if (slot_of_thread < nkp) {
-          t0 = group_sum(t0), t1 = group_sum(t1), t2 = group_sum(t2);
+          for (int o = lps >> 1; o > 0; o >>= 1)
+            t0 += __shfl_xor_sync(gmask, t0, o), t1 += __shfl_xor_sync(gmask, t1, o), t2 += __shfl_xor_sync(gmask, t2, o);
           if (sub == 0) Tk[3 * slot_of_thread] = t0, Tk[3 * slot_of_thread + 1] = t1, Tk[3 * slot_of_thread + 2] = t2;
         }
       }
@@ -903,7 +958,7 @@ struct Solver {
         const int a = idx / NQ, q = idx - a * NQ;
         double tsum = 0;
         if (!T.qconst[a][q]) {
-#pragma unroll 1
+#pragma unroll
           for (int side = 0; side < 2; ++side) {
             const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
             const RowStep e = row_step(s, l, slk, side == 0 ? dq[idx] : -dq[idx], 0.0);
@@ -947,7 +1002,7 @@ struct Solver {
       for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
-#pragma unroll 1
+#pragma unroll
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
           const double sg = side == 0 ? 1.0 : -1.0;
@@ -978,7 +1033,7 @@ struct Solver {
       for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         if (T.qconst[a][q]) continue;
-#pragma unroll 1
+#pragma unroll
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
           const double sg = side == 0 ? 1.0 : -1.0, inv_s = 1.0 / s;
@@ -1015,7 +1070,7 @@ struct Solver {
     double best = INFINITY, bestkkt = INFINITY;
     bool exhausted = true, overflow = false;
     if (wid == 0) {
-      if (A.prof) tlast = clock64();
+      tick_start();
       st = setup(agent);
       if (st < 0) st = build_neighbour_rows(agent);
       if (st < 0 && !root_sets(agent)) st = HDSM_INFEASIBLE;
@@ -1051,7 +1106,7 @@ struct Solver {
       }
       bsync();
       if (ctl[0] == 0) break;
-      if (A.prof) tlast = clock64();
+      tick_start();
       const QpOut q = solve_qp();  // all warps; the result is uniform over the block
       if (wid != 0) continue;
       ++nodes;
@@ -1149,8 +1204,7 @@ struct Solver {
       R.status = st;
     }
     tick(10);
-    if (A.prof && lane == 0)
-      for (int i = 0; i < 12; ++i) A.prof[(size_t)agent * 16 + i] = tprof[i];
+    tick_flush(agent);
     write_outputs(agent, R, best < INFINITY);
   }
 
