@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--swarms S]
 
 Workload (BASELINE.json configs[1]): 10-agent circular exchange over the forest map, horizon 10,
-replicated as S independent swarm instances per GPU (frozen closed-loop snapshots at steps
+replicated as S (default 4096) independent swarm instances per GPU (frozen closed-loop snapshots at steps
 {1, 6, 12, 18}, rotated between timed iterations; L2 flushed between iterations).  One "step" is one
 replanning step of every agent of every instance: inter-agent plane assembly, exact assignment
 search, interior-point solves, position pack - one kernel launch - plus, for N > 1, one NCCL
@@ -29,6 +29,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; the contract is ONE json line there
 
 from multi_agent_pkgs_b200 import scenarios as sc  # noqa: E402
 
@@ -286,6 +288,10 @@ def run_ours(args, rank, world, local_rank):
             peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
         kernel_ms = total_ms / args.steps
         achieved = balg * n_local / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per agent QP from the ncu --set full capture
+        if os.path.exists(tpath):
+            traffic = float(json.load(open(tpath))["dram_bytes_per_agent_qp"]) * n_local
         cpu_rate, cores, cpu_n, cpu_t = cpu_solve_rate(snaps, min_seconds=args.cpu_seconds, max_agents=20000)
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -294,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src,
+                             "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_solve": balg,
                              "note": "the solve is FP64-latency bound, not HBM bound (DESIGN.md section 5); "
                                      "traffic from ncu is in profiles/"},
@@ -320,7 +326,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--swarms", type=int, default=2048, help="independent 10-agent swarm instances per GPU")
+    ap.add_argument("--swarms", type=int, default=4096, help="independent 10-agent swarm instances per GPU")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()

@@ -29,7 +29,9 @@ for i, h in enumerate(hdr):
         print(f"{h:70s} {vals[i]} {rows[1][i]}")
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(sass)))
-hdr, data = rows[1], rows[2:]
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]  # one block per profiled launch
+end0 = starts[1] if len(starts) > 1 else len(rows)
+hdr, data = rows[starts[0] + 1], [r for r in rows[starts[0] + 2:end0] if len(r) == len(rows[starts[0] + 1])]
 ix = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ix["# Samples"]]) for r in data)
 print("static instructions", len(data), "samples", tot)
