@@ -28,7 +28,7 @@ constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still
 constexpr int kStackCap = 48;          // >= 1 + N * ceil(log2 P) open nodes
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef HDSM_MINBLOCKS
-#define HDSM_MINBLOCKS 3  // resident 4-warp blocks per SM the register allocation aims for (168 registers, no spills)
+#define HDSM_MINBLOCKS 4  // resident 4-warp blocks per SM the register allocation aims for (128 registers; 5 spills badly)
 #endif
 
 struct KernelArgs {
@@ -129,9 +129,14 @@ __device__ __forceinline__ bool interagent_plane(const hdsm_params& P, const dou
   const double nrm = sqrt(nx * nx + ny * ny + nz * nz);
   if (!(nrm > 0.0)) return false;
   const double ux = nx / nrm, uy = ny / nrm, uz = nz / nrm;
-  const double ang = M_PI_2 - fabs(acos(fmin(1.0, fmax(-1.0, uz))));
-  const double t = atan(P.drone_radius / P.drone_z_offset * tan(ang));
-  const double sd = hypot(P.drone_radius * cos(t), P.drone_z_offset * sin(t));
+  // Safety distance of the reference (:1159-1165): ang = pi/2 - |acos(uz)| = asin(uz),
+  // t = atan((r/h) tan(ang)), s = hypot(r cos t, h sin t).  With c = uz, rho = r/h:
+  // tan(ang) = c / sqrt(1 - c^2), tan(t) = rho c / sqrt(1 - c^2) and
+  //     s^2 = (r^2 + h^2 tan^2 t) / (1 + tan^2 t) = r^2 / (1 - c^2 (1 - rho^2)),
+  // the same number without the chain of six dependent FP64 transcendentals (agreement with the
+  // libm sequence to ~1e-15 relative; tests/test_gpu_parity.py checks the planes through the QPs).
+  const double rho = P.drone_radius / P.drone_z_offset, cz = fmin(1.0, fmax(-1.0, uz));
+  const double sd = P.drone_radius * rsqrt(1.0 - cz * cz * (1.0 - rho * rho));
   const double h = fmin(2.0 * sd, nrm) / 2.0;
   const double px = (pc[0] + po[0]) / 2 - h * ux, py = (pc[1] + po[1]) / 2 - h * uy, pz = (pc[2] + po[2]) / 2 - h * uz;
   // right = u x (0,0,1) + u x (0,1,0) = (uy - uz, -ux, ux);  up_final = u x (0,1,0) = (-uz, 0, ux)
@@ -564,14 +569,15 @@ struct Solver {
     return side == 0 ? T.qhi[a][q] - qv[idx] : qv[idx] - T.qlo[a][q];
   }
 
-  // Cholesky of Ks (lower part, in place), all threads of the block.  A pivot that lost all its
-  // digits to cancellation (<= 1e-13 of the original diagonal) marks a direction the barrier has
-  // pinned: the variable is frozen for this solve (inverse pivot 0) instead of aborting.  Only a
-  // non-positive / NaN original diagonal is a failure.  Per step j: scale column j (one thread per
-  // row), then the trailing update spread over all threads.  With four warps every thread keeps its
-  // <= PM (row, column) pairs in registers; with one warp the pairs come from the table.
-  // On exit the strict lower part holds L_ij / L_jj (forward solve) and the strict upper part
-  // L_ki / L_kk at (i, k) (backward solve), so neither solve has a multiply on its critical path.
+  // LDL^T of Ks (lower part, in place), all threads of the block, one barrier per pivot.  Column j is
+  // kept unscaled (c_ij = L_ij d_j) while the trailing matrix is updated with c_ij c_kj / d_j, so no
+  // separate scaling pass (and no second barrier) is needed inside the loop.  A pivot that lost all its
+  // digits to cancellation (<= 1e-13 of the original diagonal) marks a direction the barrier function
+  // has pinned: the variable is frozen for this solve (1/d := 0) instead of aborting.  Only a
+  // non-positive / NaN original diagonal is a failure.  With four warps every thread keeps its <= PM
+  // (row, column) pairs in registers; with one warp the pairs come from the table.
+  // On exit both triangles hold the unit factor L_ik (at (i,k) and (k,i)) and invd[j] = 1/d_j, so the
+  // two solves have no multiply or divide on their critical path.
   static constexpr int PM = W == 1 ? 0 : (NW * (NW + 1) / 2 + NT - 1) / NT;
   int pr_dst[PM > 0 ? PM : 1], pr_i[PM > 0 ? PM : 1], pr_k[PM > 0 ? PM : 1];
   __device__ __forceinline__ void init_pairs() {
@@ -588,54 +594,52 @@ struct Solver {
     for (int j = 0; j < NW; ++j) {
       const double djj = Ks[j * LD + j], dor = diag0[j];
       ok &= dor > 0.0;
-      const double inv = djj > 1e-13 * dor ? rsqrt(djj) : 0.0;
-      if (tid > j && tid < NW) Ks[tid * LD + j] *= inv;
-      bsync();
-      if (tid == j) Ks[j * LD + j] = djj * inv, invd[j] = inv;
+      const double inv = djj > 1e-13 * dor ? 1.0 / djj : 0.0;
+      if (tid == j) invd[j] = inv;
       const int T_j = (NW - 1 - j) * (NW - j) / 2;
       if (W == 1) {
 #pragma unroll 3
         for (int t = tid; t < T_j; t += NT) {
           const int ik = tab[t], i = ik >> 8, kk = ik & 255;
-          Ks[i * LD + kk] -= Ks[i * LD + j] * Ks[kk * LD + j];
+          Ks[i * LD + kk] -= Ks[i * LD + j] * inv * Ks[kk * LD + j];
         }
       } else {
 #pragma unroll
         for (int m = 0; m < PM; ++m)
-          if (tid + m * NT < T_j) Ks[pr_dst[m]] -= Ks[pr_i[m] + j] * Ks[pr_k[m] + j];
+          if (tid + m * NT < T_j) Ks[pr_dst[m]] -= Ks[pr_i[m] + j] * inv * Ks[pr_k[m] + j];
       }
       bsync();
     }
-    // scaled copies for the two solves
+    // unit factor in both triangles for the two solves
     for (int t = tid; t < NW * (NW + 1) / 2; t += NT) {
       const int ik = tab[t], i = ik >> 8, kk = ik & 255;
       if (i != kk) {
-        const double l = Ks[i * LD + kk];
-        Ks[i * LD + kk] = l * invd[kk];
-        Ks[kk * LD + i] = l * invd[i];
+        const double l = Ks[i * LD + kk] * invd[kk];
+        Ks[i * LD + kk] = l;
+        Ks[kk * LD + i] = l;
       }
     }
     bsync();
     return ok;
   }
-  // two triangular solves with the scaled factor, warp 0 only: v[NW] in shared memory is overwritten
+  // K x = v with K = L D L^T (unit L in both triangles), warp 0 only: v[NW] in shared memory is overwritten
   __device__ __forceinline__ void solve_inplace(double* v) const {
     if (wid == 0) {
       const double myinv = lane < NW ? invd[lane] : 0.0;
       const double* myrow = Ks + (lane < NW ? lane : 0) * LD;
       double acc = lane < NW ? v[lane] : 0.0;
-#pragma unroll
-      for (int j = 0; j < NW - 1; ++j) {  // L y = rhs, y = z / diag
+#pragma unroll 6
+      for (int j = 0; j < NW - 1; ++j) {  // L z = rhs
         const double zj = __shfl_sync(kFull, acc, j);
         if (lane > j && lane < NW) acc -= myrow[j] * zj;
       }
-      acc *= myinv;
-#pragma unroll
-      for (int i = NW - 1; i > 0; --i) {  // L' x = y, x = u / diag
-        const double ui = __shfl_sync(kFull, acc, i);
-        if (lane < i) acc -= myrow[i] * ui;
+      acc *= myinv;  // y = D^-1 z
+#pragma unroll 6
+      for (int i = NW - 1; i > 0; --i) {  // L' x = y
+        const double xi = __shfl_sync(kFull, acc, i);
+        if (lane < i) acc -= myrow[i] * xi;
       }
-      if (lane < NW) v[lane] = acc * myinv;
+      if (lane < NW) v[lane] = acc;
     }
     bsync();
   }
