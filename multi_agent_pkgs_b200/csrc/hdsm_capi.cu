@@ -62,8 +62,9 @@ struct hdsm_handle {
   Tables host_tables{};
   Tables* dev_tables = nullptr;
   int device = 0, max_agents = 0, max_neighbours = 0;
-  int row_cap = 0, smem_bytes = 0;          // first pass: typical row count, many blocks per SM
-  int row_cap_big = 0, smem_bytes_big = 0;  // second pass for ROW_OVERFLOW agents: worst case (0 = not needed)
+  // row-pool tiers: pass t re-solves the agents that overflowed pass t-1 with a larger pool (fewer
+  // resident blocks per SM); the last tier is the worst case or what one SM can hold
+  int n_tiers = 0, row_cap[3] = {0, 0, 0}, smem_bytes[3] = {0, 0, 0};
   cudaStream_t stream = nullptr;
   // staging for the host-pointer entry point
   unsigned char *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
@@ -94,18 +95,15 @@ int cuda_fail(hdsm_handle* h, cudaError_t e, const char* what) {
 template <int N, int W>
 cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
   static int configured_for = -1;  // per instantiation; the smem attribute is per device function
-  const int need = std::max(h->smem_bytes, h->smem_bytes_big);
+  const int need = h->smem_bytes[h->n_tiers - 1];
   if (configured_for < need) {
     cudaError_t e = cudaFuncSetAttribute(hdsm_solve_kernel<N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
     if (e != cudaSuccess) return e;
     configured_for = need;
   }
-  a.row_cap = h->row_cap, a.only_status = -1;
-  hdsm_solve_kernel<N, W><<<a.n_local, 32 * W, h->smem_bytes, s>>>(h->dev_tables, a);
-  h->launches += 1;
-  if (h->row_cap_big > 0) {  // agents whose rows did not fit the small pool
-    a.row_cap = h->row_cap_big, a.only_status = HDSM_ROW_OVERFLOW;
-    hdsm_solve_kernel<N, W><<<a.n_local, 32 * W, h->smem_bytes_big, s>>>(h->dev_tables, a);
+  for (int t = 0; t < h->n_tiers; ++t) {  // t > 0: only agents whose rows did not fit the previous pool
+    a.row_cap = h->row_cap[t], a.only_status = t == 0 ? -1 : HDSM_ROW_OVERFLOW;
+    hdsm_solve_kernel<N, W><<<a.n_local, 32 * W, h->smem_bytes[t], s>>>(h->dev_tables, a);
     h->launches += 1;
   }
   return cudaGetLastError();
@@ -178,12 +176,16 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   const long fit = std::max(16L, (long)(smem_max - smem_doubles(N, P, rmax, 0) * 8 - 1024) / 48);
-  const long small = h->prm.prune ? 96 : worst;
-  h->row_cap = (int)std::min(std::min(worst, small), fit);
-  h->smem_bytes = smem_doubles(N, P, rmax, h->row_cap) * 8;
-  if (worst > h->row_cap) {
-    h->row_cap_big = (int)std::min(worst, fit);
-    h->smem_bytes_big = smem_doubles(N, P, rmax, h->row_cap_big) * 8;
+  const long tiers[3] = {h->prm.prune ? 96 : worst, 384, worst};
+  long prev = 0;
+  for (long t : tiers) {
+    const long cap = std::min(std::min(t, worst), fit);
+    if (cap <= prev) continue;
+    h->row_cap[h->n_tiers] = (int)cap;
+    h->smem_bytes[h->n_tiers] = smem_doubles(N, P, rmax, (int)cap) * 8;
+    ++h->n_tiers;
+    prev = cap;
+    if (cap >= std::min(worst, fit)) break;
   }
   *out = h;
   return HDSM_OK;
@@ -206,7 +208,7 @@ void hdsm_destroy(hdsm_handle* h) {
 
 const char* hdsm_last_error(const hdsm_handle* h) { return h ? h->err.c_str() : "null handle"; }
 int64_t hdsm_launch_count(const hdsm_handle* h) { return h ? h->launches : 0; }
-int hdsm_smem_bytes(const hdsm_handle* h) { return h ? h->smem_bytes : 0; }
+int hdsm_smem_bytes(const hdsm_handle* h) { return h ? h->smem_bytes[0] : 0; }
 
 int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
                             const int32_t* nbr_end, const double* x0, const double* ref, const double* poly_A,

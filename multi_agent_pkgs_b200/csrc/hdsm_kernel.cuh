@@ -425,13 +425,79 @@ struct Solver {
   }
 
   // ---------------------------------------------------------------- K1: inter-agent rows, packed by position step
+  // Quick-reject radius of the plane test for own point ps (previous plan, step k+1) against the
+  // reachable box of p_kp: |x - ps| <= rho for every reachable x, the plane keeps distance
+  // |n|/2 - smax from ps along u and n_f.u = 1, so the row is inactive if nfmax*rho < |n|/2 - smax - margin.
+  __device__ __forceinline__ double reject_thr2(const double ps[3], int kp) const {
+    const hdsm_params& P = T.prm;
+    const double smax = fmax(P.drone_radius, P.drone_z_offset);
+    const double nfmax = 1.0 + 3.0 * fabs(P.tilt);  // |n_f| <= |u| + tilt (|right| + |up|)
+    double rho2 = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double d = fmax(fabs(plo[3 * kp + a] - ps[a]), fabs(phi[3 * kp + a] - ps[a]));
+      rho2 += d * d;
+    }
+    const double thr = 2.0 * (nfmax * sqrt(rho2) + smax + 1e-3);
+    return thr * thr;
+  }
+
+  // K1 phase A, all warps: compact list of the neighbours that come close enough at any step to give a
+  // row that can be active (with 4095 candidates only a few dozen do).  Each warp scans a quarter of
+  // the candidate range and appends to its own sub-list (u16 offsets from nbr_begin, kept in the
+  // not-yet-used slack array); ctl[2 + w] = entries of warp w, or -1 if its sub-list overflowed.
+  __device__ void scan_neighbours(int agent) {
+    const int gid = A.global_id[agent];
+    const int nb0 = A.nbr_begin ? A.nbr_begin[agent] : 0, nb1 = A.nbr_end ? A.nbr_end[agent] : A.n_rob;
+    const double* prev = A.prev + (size_t)agent * K3;
+    double* thr2k = viol;  // scratch: viol is first written after the first QP
+    if (tid < N) {
+      const double ps[3] = {prev[3 * (tid + 1)], prev[3 * (tid + 1) + 1], prev[3 * (tid + 1) + 2]};
+      thr2k[tid] = fmax(reject_thr2(ps, tid), reject_thr2(ps, tid + 1));
+    }
+    for (int i = tid; i < K3; i += NT) dp[i] = prev[i];  // own previous positions (dp is scratch here)
+    bsync();
+    unsigned short* list = reinterpret_cast<unsigned short*>(rs) + wid * A.row_cap;
+    const int n = nb1 - nb0, chunk = (n + W - 1) / W;
+    const int j_beg = nb0 + wid * chunk, j_end = min(nb1, j_beg + chunk);
+    const unsigned lt = (1u << lane) - 1;
+    int cnt = 0;
+    if (n <= 65535) {
+      for (int j0 = j_beg; j0 < j_end; j0 += 32) {
+        const int j = j0 + lane;
+        bool near = j < j_end && j != gid && A.all_valid[j] != 0;
+        if (near && A.prune) {
+          const double* q = A.all_pos + (size_t)j * K3;
+          near = false;
+#pragma unroll 2
+          for (int kk = 0; kk < N; ++kk) {
+            const double dx = q[3 * kk + 3] - dp[3 * kk + 3], dy = q[3 * kk + 4] - dp[3 * kk + 4], dz = q[3 * kk + 5] - dp[3 * kk + 5];
+            near |= dx * dx + dy * dy + dz * dz <= thr2k[kk];
+          }
+        }
+        const unsigned m = __ballot_sync(kFull, near);
+        if (near) {
+          const int pos = cnt + __popc(m & lt);
+          if (pos < A.row_cap) list[pos] = (unsigned short)(j - nb0);
+        }
+        cnt += __popc(m);
+      }
+    } else {
+      cnt = A.row_cap + 1;  // offsets do not fit 16 bits: phase B scans the whole range
+    }
+    if (lane == 0) ctl[2 + wid] = cnt <= A.row_cap ? cnt : -1;
+    bsync();
+  }
+
+  // K1 phase B, warp 0: planes of the listed neighbours, packed by position step
   __device__ int build_neighbour_rows(int agent) {
     const hdsm_params& P = T.prm;
     const int gid = A.global_id[agent];
     const int nb0 = A.nbr_begin ? A.nbr_begin[agent] : 0, nb1 = A.nbr_end ? A.nbr_end[agent] : A.n_rob;
     const double* prev = A.prev + (size_t)agent * K3;
-    const double smax = fmax(P.drone_radius, P.drone_z_offset);
-    const double nfmax = 1.0 + 3.0 * fabs(P.tilt);  // |n_f| <= |u| + tilt (|right| + |up|)
+    bool use_list = true;
+    for (int w2 = 0; w2 < W; ++w2) use_list &= ctl[2 + w2] >= 0;
+    const unsigned short* lists = reinterpret_cast<const unsigned short*>(rs);
     int cnt = 0, status = -1;
     const unsigned lt = (1u << lane) - 1;
     for (int kp = 0; kp <= N; ++kp) {
@@ -440,19 +506,8 @@ struct Solver {
       for (int k = kp - 1; k <= kp; ++k) {
         if (k < 0 || k >= N) continue;
         const double ps[3] = {prev[3 * (k + 1)], prev[3 * (k + 1) + 1], prev[3 * (k + 1) + 2]};
-        // quick reject: |x - ps| <= rho for every reachable x, and the plane keeps distance
-        // |n|/2 - smax from ps along u, n_f.u = 1  =>  inactive if nfmax*rho < |n|/2 - smax - margin
-        double rho2 = 0;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const double d = fmax(fabs(plo[3 * kp + a] - ps[a]), fabs(phi[3 * kp + a] - ps[a]));
-          rho2 += d * d;
-        }
-        const double thr = 2.0 * (nfmax * sqrt(rho2) + smax + 1e-3);
-        const double thr2 = thr * thr;
-        for (int j0 = nb0; j0 < nb1; j0 += 32) {
-          const int j = j0 + lane;
-          bool valid = j < nb1 && j != gid && A.all_valid[j] != 0;
+        const double thr2 = reject_thr2(ps, kp);
+        const auto process = [&](int j, bool valid) {
           double nf[3] = {0, 0, 0}, b = 0;
           if (valid) {
             const double* q = A.all_pos + ((size_t)j * (N + 1) + k + 1) * 3;
@@ -479,6 +534,20 @@ struct Solver {
             }
           }
           cnt += __popc(m);
+        };
+        if (use_list) {
+          for (int w2 = 0; w2 < W; ++w2) {
+            const int nl = ctl[2 + w2];
+            for (int i0 = 0; i0 < nl; i0 += 32) {
+              const int i = i0 + lane;
+              process(i < nl ? nb0 + lists[w2 * A.row_cap + i] : 0, i < nl);
+            }
+          }
+        } else {
+          for (int j0 = nb0; j0 < nb1; j0 += 32) {
+            const int j = j0 + lane;
+            process(j, j < nb1 && j != gid && A.all_valid[j] != 0);
+          }
         }
       }
       if (slot >= 0) sege[2 * slot] = cnt;
@@ -1076,6 +1145,11 @@ struct Solver {
     if (wid == 0) {
       tick_start();
       st = setup(agent);
+      if (lane == 0) ctl[1] = st;
+    }
+    bsync();
+    if (ctl[1] < 0) scan_neighbours(agent);  // uniform over the block
+    if (wid == 0) {
       if (st < 0) st = build_neighbour_rows(agent);
       if (st < 0 && !root_sets(agent)) st = HDSM_INFEASIBLE;
       if (st < 0) {

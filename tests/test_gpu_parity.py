@@ -219,3 +219,49 @@ def test_many_neighbours_config4_slice():
     assert gap.max() <= OBJ_RTOL
     _check_properties(b, out, np.nonzero(ok)[0][:16])
     pl.close()
+
+
+def test_sharded_swarm_closed_loop_single_rank():
+    """The harness path (device pointers, packed positions, table exchange) over a few closed-loop
+    steps equals the host-pointer path driven by the C port."""
+    import torch
+    from oracle import c_oracle as co
+    from multi_agent_pkgs_b200.swarm import ShardedSwarm
+    sw_a = sc.config2_circle(n_swarms=2, seed=51)
+    sw_b = sc.config2_circle(n_swarms=2, seed=51)
+    sh = ShardedSwarm(sw_a, world=1, rank=0, device="cuda:0", max_nodes=400)
+    for step in range(4):
+        res = sh.step()
+        b = sw_b.make_batch()
+        ref = co.solve_batch(b, max_nodes=400)
+        assert np.array_equal(res["status"], ref["res"]["status"]), step
+        ok = ref["res"]["status"] == OPTIMAL
+        gap = np.abs(res["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1, np.abs(ref["res"]["obj"][ok]))
+        assert gap.max() <= OBJ_RTOL
+        sw_b.advance(ref["traj"], ref["ctrl"], ok)
+        # the exchanged table holds every agent's new positions (or the shifted old plan on failure)
+        table = sh.exchange.table.cpu().numpy()
+        assert np.abs(table[ok] - ref["traj"][ok][:, :, :3]).max() <= POS_ATOL
+    assert sh.planner.launch_count >= 4
+
+
+def test_config5_slice_many_neighbours():
+    """512 agents of a 1024-agent random swarm (every agent sees 1023 candidates): quick-reject and
+    exact pruning keep the row pool small; results equal the C port's."""
+    from oracle import c_oracle as co
+    sw = sc.config5_random(n_rob=1024, side=100.0)
+    b = sw.make_batch()
+    ref = co.solve_batch(b, max_nodes=64)
+    sw.advance(ref["traj"], ref["ctrl"], ref["res"]["status"] == 0)
+    b = sw.make_batch().take(np.arange(0, 1024, 2))
+    ref = co.solve_batch(b, max_nodes=64)
+    pl = TrajectoryPlanner(b.params, max_agents=b.n, max_neighbours=1024, max_nodes=64)
+    out = pl.solve_batch(b)
+    assert np.array_equal(out["res"]["status"], ref["res"]["status"])
+    ok = ref["res"]["status"] == OPTIMAL
+    assert ok.sum() > 400
+    gap = np.abs(out["res"]["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1, np.abs(ref["res"]["obj"][ok]))
+    assert gap.max() <= OBJ_RTOL
+    assert out["res"]["rows"].max() < 450
+    _check_properties(b, out, np.nonzero(ok)[0][:8])
+    pl.close()
