@@ -1,0 +1,70 @@
+// TEST INFRASTRUCTURE - stand-in for the Eigen-based geometry headers of the reference.
+//
+// The reference's corridor generator (convex_decomp_util/src/convex_decomp.cpp) only needs small
+// fixed-size integer / double vectors and a container of (point, normal) pairs from
+// decomp_geometry/polyhedron.h and decomp_basis/data_type.h, which in the reference are Eigen aliases.
+// Eigen is not installed in this image, so this header supplies just those types with the same names
+// and the handful of operations the generator uses (element access with () and [], +, -, unary -,
+// dot).  With it on the include path the reference's own convex_decomp.cpp compiles UNMODIFIED from
+// /root/reference into oracle/_ref/ (see oracle/Makefile target `ref`), which is what pins the C
+// restatement in oracle/corridor_oracle.c and the CUDA kernel.  Nothing of the product includes this.
+#ifndef HDSM_REF_SHIM_POLYHEDRON_H_
+#define HDSM_REF_SHIM_POLYHEDRON_H_
+
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <utility>
+#include <vector>
+
+typedef double decimal_t;
+
+template <class S, int N>
+struct ShimVec {
+  S v[N];
+  ShimVec() {}
+  ShimVec(S a, S b) { static_assert(N == 2, "size"); v[0] = a, v[1] = b; }
+  ShimVec(S a, S b, S c) { static_assert(N == 3, "size"); v[0] = a, v[1] = b, v[2] = c; }
+  ShimVec(S a, S b, S c, S d) { static_assert(N == 4, "size"); v[0] = a, v[1] = b, v[2] = c, v[3] = d; }
+  S& operator()(int i) { return v[i]; }
+  const S& operator()(int i) const { return v[i]; }
+  S& operator[](int i) { return v[i]; }
+  const S& operator[](int i) const { return v[i]; }
+  ShimVec operator+(const ShimVec& o) const { ShimVec r; for (int i = 0; i < N; ++i) r.v[i] = v[i] + o.v[i]; return r; }
+  ShimVec operator-(const ShimVec& o) const { ShimVec r; for (int i = 0; i < N; ++i) r.v[i] = v[i] - o.v[i]; return r; }
+  ShimVec operator-() const { ShimVec r; for (int i = 0; i < N; ++i) r.v[i] = -v[i]; return r; }
+  S dot(const ShimVec& o) const { S s = v[0] * o.v[0]; for (int i = 1; i < N; ++i) s += v[i] * o.v[i]; return s; }
+};
+
+template <int N> using Veci = ShimVec<int, N>;
+template <int N> using Vecf = ShimVec<decimal_t, N>;
+typedef Veci<2> Vec2i;
+typedef Veci<3> Vec3i;
+typedef Vecf<2> Vec2f;
+typedef Vecf<3> Vec3f;
+template <class T> using vec_E = std::vector<T>;
+
+template <int Dim>
+struct Hyperplane {
+  Hyperplane() {}
+  Hyperplane(const Vecf<Dim>& p, const Vecf<Dim>& n) : p_(p), n_(n) {}
+  Vecf<Dim> p_, n_;
+};
+typedef Hyperplane<3> Hyperplane3D;
+
+template <int Dim>
+struct Polyhedron {
+  Polyhedron() {}
+  Polyhedron(const vec_E<Hyperplane<Dim>>& vs) : vs_(vs) {}
+  vec_E<std::pair<Vecf<Dim>, Vecf<Dim>>> cal_normals() const {
+    vec_E<std::pair<Vecf<Dim>, Vecf<Dim>>> ns(vs_.size());
+    for (size_t i = 0; i < vs_.size(); i++) ns[i] = std::make_pair(vs_[i].p_, vs_[i].n_);
+    return ns;
+  }
+  vec_E<Hyperplane<Dim>> hyperplanes() const { return vs_; }
+  vec_E<Hyperplane<Dim>> vs_;
+};
+typedef Polyhedron<3> Polyhedron3D;
+
+#endif
