@@ -29,6 +29,7 @@
 #ifndef HDSM_H_
 #define HDSM_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -151,6 +152,68 @@ int hdsm_comm_unique_id(uint8_t id_out[128]);
 int hdsm_comm_init(hdsm_handle* h, int n_ranks, int rank, const uint8_t id[128]);
 int hdsm_allgather_positions(hdsm_handle* h, const double* send, double* recv, int n_local, void* stream);
 void hdsm_comm_destroy(hdsm_handle* h);
+
+/* ---- safe-corridor generation ----------------------------------
+ * hdsm_corridor_batch replaces Agent::GenerateSafeCorridor (agent_class.cpp:1236-1447) together with
+ * convex_decomp_lib::GetPolyOcta3D (convex_decomp_util/src/convex_decomp.cpp:5-376), the call at
+ * agent_class.cpp:163, for a batch of agents; its outputs are exactly hdsm_solve_batch's poly_A / poly_b
+ * / poly_rows inputs (the conversion at :1428-1437).  One warp per agent; see csrc/hdsm_corridor.cu. */
+#define HDSM_COR_SQUEEZED 1      /* a seed voxel was squeezed between occupied voxels: the reference switches to
+                                    GetPolyOcta3DNew there (:1385-1395), this library used GetPolyOcta3D */
+#define HDSM_COR_ROW_OVERFLOW 2  /* a polytope had more rows than max_rows_per_poly: generation stopped */
+#define HDSM_COR_SEED_OUTSIDE 4  /* a seed fell outside the voxel grid: generation stopped */
+#define HDSM_COR_LIST_OVERFLOW 8 /* internal cell list overflow (cannot happen for n_it_decomp <= 90) */
+
+typedef struct hdsm_corridor_params {
+  int32_t poly_hor;          /* poly_hor: polytopes per agent P, 1..HDSM_MAX_POLY (:1302) */
+  int32_t n_it_decomp;       /* n_it_decomp: face-growth iterations of GetPolyOcta3D, <= 90 */
+  int32_t max_rows_per_poly; /* row stride Rmax of the polytope arrays, 18..32 (<= 12 chamfers + 6 faces) */
+  int32_t n_traj;            /* points of the previous plan traj_curr_ (N + 1); 0 = none */
+  int32_t max_path;          /* row stride of `path` */
+  int32_t reserved;
+  double voxel_size;         /* VoxelGrid::GetVoxSize() */
+} hdsm_corridor_params;
+
+typedef struct hdsm_corridor hdsm_corridor;
+
+/* max_grids voxel grids of at most grid_stride voxels each (int8, x fastest, then y, then z, as
+ * voxel_grid_util lays them out; 0 free, 100 occupied, -1 unknown, 1..99 potential field = free). */
+int hdsm_corridor_create(const hdsm_corridor_params* params, int max_agents, int max_grids, size_t grid_stride,
+                         int device, hdsm_corridor** out);
+void hdsm_corridor_destroy(hdsm_corridor* h);
+const char* hdsm_corridor_last_error(const hdsm_corridor* h);
+int64_t hdsm_corridor_launch_count(const hdsm_corridor* h);
+int hdsm_corridor_smem_bytes(const hdsm_corridor* h);
+
+/* One corridor update for n agents; HOST pointers; synchronous.
+ *
+ *  grids       [n_grids][grid_stride]   voxel_grid_ (copied and OccupyUnknown'ed on the fly, :1292-1301)
+ *  grid_index  [n] or NULL              grid of each agent (NULL: agent i uses grid i)
+ *  dims        [n][3]                   GetDim()  (x, y, z)
+ *  origins     [n][3]                   GetOrigin()
+ *  pos         [n][3]                   state_curr_[0..2] (:1288)
+ *  path        [n][max_path][3]         path_curr_ (:1284-1287), n_path[n] points each
+ *  prev_n      [n] or NULL              poly_const_vec_.size() of the previous step (NULL: first step)
+ *  prev_A/b/rows/seeds                  previous poly_const_vec_ / poly_seeds_, layouts as the outputs
+ *  prev_used   [n][P]                   poly_used_idx_ of the last optimisation (hdsm_solve_batch's poly_used)
+ *  prev_traj   [n][n_traj][3]           positions of traj_curr_ (:1252-1259)
+ *  poly_A      [n][P][Rmax][3], poly_b [n][P][Rmax], poly_rows [n][P] (0 = absent), seeds [n][P][3]
+ *  flags       [n]                      HDSM_COR_* bits
+ * Outputs must not alias the prev_* inputs. */
+int hdsm_corridor_batch(hdsm_corridor* h, int n, int n_grids, const int8_t* grids, const int32_t* grid_index,
+                        const int32_t* dims, const double* origins, const double* pos, const double* path,
+                        const int32_t* n_path, const int32_t* prev_n, const double* prev_A, const double* prev_b,
+                        const int32_t* prev_rows, const double* prev_seeds, const uint8_t* prev_used,
+                        const double* prev_traj, double* poly_A, double* poly_b, int32_t* poly_rows, double* seeds,
+                        int32_t* flags);
+
+/* Same with DEVICE pointers, enqueued on `stream` (NULL = the handle's stream), no host synchronisation. */
+int hdsm_corridor_batch_device(hdsm_corridor* h, int n, const int8_t* grids, const int32_t* grid_index,
+                               const int32_t* dims, const double* origins, const double* pos, const double* path,
+                               const int32_t* n_path, const int32_t* prev_n, const double* prev_A,
+                               const double* prev_b, const int32_t* prev_rows, const double* prev_seeds,
+                               const uint8_t* prev_used, const double* prev_traj, double* poly_A, double* poly_b,
+                               int32_t* poly_rows, double* seeds, int32_t* flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -359,7 +359,8 @@ int cor_safe_corridor(const cor_params* P, const int8_t* grid, const int32_t dim
 
   /* OccupyUnknown on a private copy of the grid (:1289-1305) */
   const size_t nvox = (size_t)dim[0] * dim[1] * dim[2];
-  int8_t* data = (int8_t*)malloc(nvox);
+  int8_t* data = (int8_t*)malloc(2 * nvox);
+  int8_t* work = data + nvox;
   for (size_t i = 0; i < nvox; ++i) data[i] = grid[i] == COR_UNKNOWN ? COR_OCC : grid[i];
   const double vs = P->voxel, samp = vs / 10;
   double cur[3] = {pos[0], pos[1], pos[2]};
@@ -405,9 +406,10 @@ int cor_safe_corridor(const cor_params* P, const int8_t* grid, const int32_t dim
       if (in_lo && in_hi && vox(data, dim, lo) == COR_OCC && vox(data, dim, hi) == COR_OCC) flags |= COR_FLAG_SQUEEZED;
     }
     double pts[3 * COR_MAX_PLANES], nrm[3 * COR_MAX_PLANES];
-    /* marks of earlier polytopes (-1, -2, ...) are neither == conv nor >= OCC, so one copy serves all
-     * (the reference takes a fresh copy per polytope, :1405) */
-    const int np = cor_poly_octa(sv, data, dim, P->n_it, vs, -(n_poly + 1), origin, pts, nrm);
+    /* a fresh copy of the grid per polytope, like the reference (:1405): the seed voxel is marked even
+     * when it is occupied, so marks left behind would read as free space to the next polytope */
+    memcpy(work, data, nvox);
+    const int np = cor_poly_octa(sv, work, dim, P->n_it, vs, -(n_poly + 1), origin, pts, nrm);
     if (np > R) {
       flags |= COR_FLAG_ROWS;
       break;

@@ -1,0 +1,130 @@
+"""Parity of the CUDA corridor generator (hdsm_corridor_batch, csrc/hdsm_corridor.cu) through the C ABI.
+
+Bar: BIT-EXACT.  Normals are small integers; points, offsets b = p . n and seeds are doubles computed
+in the reference's evaluation order without FMA contraction, so every output array must equal the
+checker's array exactly:
+  * against tests/golden/corridor_ref.npz - GetPolyOcta3D outputs of the reference's own code;
+  * against oracle/corridor_oracle.c (cor_safe_corridor) on scenario batches, first and follow-up steps.
+"""
+import numpy as np
+import pytest
+
+from multi_agent_pkgs_b200 import corridor as cr, scenarios as sc
+from oracle import corridor as oc
+from test_corridor_oracle import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(cb):
+    G = cb.grids.shape[0]
+    return cr.SafeCorridorGenerator(cb.poly_hor, cb.n_it, cb.voxel, cb.n, G, int(cb.grids[0].size), cb.prev_traj.shape[1],
+                                    cb.path.shape[1], rmax=cb.rmax)
+
+
+def _assert_equal(out, ref):
+    for k in ("poly_rows", "flags", "poly_A", "poly_b", "seeds"):
+        assert np.array_equal(out[k], ref[k]), k
+
+
+def test_single_polytopes_match_reference_golden():
+    """One GetPolyOcta3D per agent, seeded at the golden seed voxel (poly_hor = 1, a 1 m path)."""
+    by_cfg = {}
+    for c in golden_cases():
+        by_cfg.setdefault((c["n_it"], c["res"]), []).append(c)
+    checked = 0
+    for (n_it, res), cases in by_cfg.items():
+        stride = max(c["grid"].size for c in cases)
+        n = len(cases)
+        grids = np.zeros((n, stride), np.int8)
+        dims, origins, pos = np.zeros((n, 3), np.int32), np.zeros((n, 3)), np.zeros((n, 3))
+        path, n_path = np.zeros((n, 2, 3)), np.ones(n, np.int32)
+        for i, c in enumerate(cases):
+            g = c["grid"]
+            grids[i, :g.size] = g.ravel()
+            dims[i] = (g.shape[2], g.shape[1], g.shape[0])
+            origins[i] = c["origin"]
+            pos[i] = (np.array(c["seed"]) + 0.5) * res + c["origin"]
+            path[i, 0] = pos[i] + np.array([0.7, 0.0, 0.0])
+        gen = cr.SafeCorridorGenerator(1, n_it, res, n, n, stride, 0, 2, rmax=18)
+        cb = cr.CorridorBatch(1, n_it, 18, res, grids[:, None, None, :], None, dims, origins, pos, path, n_path,
+                              np.zeros((n, 0, 3)))
+        out = gen.generate(cb)
+        gen.close()
+        for i, c in enumerate(cases):
+            r = len(c["pts"])
+            assert out["poly_rows"][i, 0] == r, (i, out["poly_rows"][i], r, out["flags"][i])
+            assert np.array_equal(out["poly_A"][i, 0, :r], c["nrm"])
+            b = (c["pts"][:, 0] * c["nrm"][:, 0] + c["pts"][:, 1] * c["nrm"][:, 1]) + c["pts"][:, 2] * c["nrm"][:, 2]
+            assert np.array_equal(out["poly_b"][i, 0, :r], b)
+            checked += 1
+    assert checked >= 64
+
+
+@pytest.mark.parametrize("n_it", [42, 60])
+def test_scenario_batch_matches_c_restatement(n_it):
+    sw = sc.config2_circle(n_swarms=6)
+    for i in range(sw.n):
+        sw.state[i, :2] = sw.world.push_free(0.45 * sw.state[i, :2] + 0.55 * sw.goal[i, :2], 0.3)
+    cb = cr.corridor_batch(sw, n_it=n_it)
+    gen = _gen(cb)
+    out = gen.generate(cb)
+    ref = oc.c_safe_corridor(cb)
+    _assert_equal(out, ref)
+    assert gen.launch_count == 1
+    # follow-up step: previous polytopes, used flags and previous plan decide what is kept
+    rng = np.random.default_rng(5)
+    used = (rng.random((cb.n, cb.poly_hor)) < 0.5).astype(np.uint8)
+    N = sw.params["n_hor"]
+    traj = cb.pos[:, None, :] + np.linspace(0, 1, N + 1)[None, :, None] * (cb.path[:, 0] - cb.pos)[:, None, :] * \
+        rng.uniform(0.0, 0.4, (cb.n, 1, 1))
+    sw.state[:, :3] = traj[:, 1]
+    cb2 = cr.corridor_batch(sw, n_it=n_it).with_previous(out, used, traj)
+    out2 = gen.generate(cb2)
+    ref2 = oc.c_safe_corridor(cb2)
+    _assert_equal(out2, ref2)
+    assert (out2["poly_rows"] > 0).any()
+    gen.close()
+
+
+def test_shared_grid_and_empty_map():
+    """Agents sharing one grid through grid_index; an empty map gives the 4.5 m cube."""
+    sw = sc.config1_single_agent()
+    cb = cr.corridor_batch(sw)
+    n = 5
+    cb5 = cr.CorridorBatch(cb.poly_hor, cb.n_it, cb.rmax, cb.voxel, cb.grids, np.zeros(n, np.int32), np.repeat(cb.dims, n, 0),
+                           np.repeat(cb.origins, n, 0), np.repeat(cb.pos, n, 0) + np.arange(n)[:, None] * 0.31,
+                           np.repeat(cb.path, n, 0), np.repeat(cb.n_path, n), np.zeros((n, 11, 3)))
+    gen = cr.SafeCorridorGenerator(cb.poly_hor, cb.n_it, cb.voxel, n, 1, int(cb.grids[0].size), 11, cb.path.shape[1])
+    out = gen.generate(cb5)
+    cb5_own = cr.CorridorBatch(cb.poly_hor, cb.n_it, cb.rmax, cb.voxel, np.repeat(cb.grids, n, 0), None, cb5.dims, cb5.origins,
+                               cb5.pos, cb5.path, cb5.n_path, cb5.prev_traj)
+    _assert_equal(out, oc.c_safe_corridor(cb5_own))
+    r = out["poly_rows"][0, 0]
+    assert r == 6
+    A, b = out["poly_A"][0, 0, :6], out["poly_b"][0, 0, :6]
+    ext = b[1] + b[3]  # +x and -x faces: 15 voxels of 0.3 m
+    assert abs(ext - 4.5) < 1e-9
+    gen.close()
+
+
+def test_corridor_feeds_the_optimisation():
+    """Corridor rows go straight into hdsm_solve_batch: the agents get OPTIMAL plans inside them."""
+    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
+    sw = sc.config2_circle(n_swarms=2)
+    cb = cr.corridor_batch(sw)
+    gen = _gen(cb)
+    out = gen.generate(cb)
+    gen.close()
+    b = sw.make_batch()
+    b.poly_A, b.poly_b, b.poly_rows = out["poly_A"], out["poly_b"], out["poly_rows"]
+    pl = TrajectoryPlanner(sw.params, max_agents=b.n, max_neighbours=10)
+    res = pl.solve_batch(b)
+    pl.close()
+    from oracle import c_oracle as co
+    ref = co.solve_batch(b)
+    assert np.array_equal(res["res"]["status"], ref["res"]["status"])
+    ok = ref["res"]["status"] == 0
+    assert ok.mean() > 0.8
+    gap = np.abs(res["res"]["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1.0, np.abs(ref["res"]["obj"][ok]))
+    assert gap.max() <= 1e-6
