@@ -170,6 +170,86 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------
+# secondary measurement: the corridor producer of the path, reported under "corridor"
+# ----------------------------------------------------------------------------------------------
+def corridor_measure(n_agents=4096, steps=10, local_rank=0, cpu=True):
+    """Throughput of hdsm_corridor_batch_device / hdsm_corridor_batch next to the CPU checkers.
+    Workload: agents of the config-2 circle swap pulled into the forest, one 66 x 66 x 20 int8 local voxel
+    grid per agent (357 MB for 4096 agents: larger than L2), poly_hor 4, n_it_decomp 42; tiled from 240
+    distinct agents.  L2 flushed between timed launches."""
+    import torch
+    from multi_agent_pkgs_b200 import corridor as cr
+    sw = sc.config2_circle(n_swarms=DISTINCT_SWARMS)
+    for i in range(sw.n):
+        sw.state[i, :2] = sw.world.push_free(0.45 * sw.state[i, :2] + 0.55 * sw.goal[i, :2], 0.3)
+    base = cr.corridor_batch(sw)
+    reps = -(-n_agents // base.n)
+
+    def tile(a):
+        return np.ascontiguousarray(np.concatenate([a] * reps)[:n_agents])
+    cb = cr.CorridorBatch(base.poly_hor, base.n_it, base.rmax, base.voxel, tile(base.grids), None, tile(base.dims),
+                          tile(base.origins), tile(base.pos), tile(base.path), tile(base.n_path), tile(base.prev_traj))
+    dev = torch.device(f"cuda:{local_rank}")
+    gen = cr.SafeCorridorGenerator(cb.poly_hor, cb.n_it, cb.voxel, cb.n, cb.n, int(cb.grids[0].size), cb.prev_traj.shape[1],
+                                   cb.path.shape[1], device=local_rank)
+    db = cr.DeviceCorridorBatch(cb, dev)
+    stream = torch.cuda.current_stream(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        gen.generate_device(db.t, cb.n, stream.cuda_stream)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        gen.generate_device(db.t, cb.n, stream.cuda_stream)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    rows = db.t["poly_rows"].cpu().numpy()
+    npoly = int((rows > 0).sum())
+    gen.generate(cb)
+    t0 = time.perf_counter()
+    out = gen.generate(cb)
+    e2e = time.perf_counter() - t0
+    launches = gen.launch_count
+    smem = gen.smem_bytes
+    gen.close()
+    balg = cr.corridor_algorithmic_bytes(cb, rows)
+    line = {"workload": f"{cb.n} agents, one 66x66x20 int8 local grid each, poly_hor {cb.poly_hor}, n_it_decomp {cb.n_it}",
+            "metric": "corridor updates/sec (agents/s)", "value": cb.n / (ms * 1e-3), "kernel_ms": ms,
+            "polytopes_per_s": npoly / (ms * 1e-3), "dtype": "int8 grid -> f64 rows",
+            "e2e": {"value": cb.n / e2e, "unit": "agents/s", "h2d_bytes_per_step": cb.input_bytes(),
+                    "d2h_bytes_per_step": int(sum(out[k].nbytes for k in out))},
+            "gpu_launches": int(launches), "algorithmic_bytes_per_agent": balg, "smem_bytes_per_block": smem,
+            "squeezed_seed_agents": int((out["flags"] & 1 != 0).sum())}
+    if cpu:
+        from oracle import corridor as oc
+        t0 = time.perf_counter()
+        ref = oc.c_safe_corridor(cb)
+        t_cpu = time.perf_counter() - t0
+        line["bit_exact_vs_cpu_port"] = bool(all(np.array_equal(out[k], ref[k]) for k in out))
+        line["cpu_baseline"] = {"value": cb.n / t_cpu, "unit": "agents/s", "cores": oc.max_threads(), "kind": "port",
+                                "sample": f"all {cb.n} agents once, C restatement on all host threads"}
+        if oc.have_ref():  # the reference's own GetPolyOcta3D (compiled unmodified), one thread, same seeds
+            t_ref, cnt = 0.0, 0
+            for i in range(min(base.n, 120)):
+                g = base.grids[i].copy()
+                g[g == -1] = 100
+                for p in range(base.poly_hor):
+                    if ref["poly_rows"][i, p] == 0:
+                        continue
+                    sv = np.round((ref["seeds"][i, p] - base.origins[i]) / base.voxel - 0.5).astype(np.int32)
+                    t0 = time.perf_counter()
+                    oc.ref_poly(g, sv, base.n_it, base.voxel, -(p + 1), base.origins[i])
+                    t_ref += time.perf_counter() - t0
+                    cnt += 1
+            line["cpu_reference"] = {"value": cnt / t_ref, "unit": "polytopes/s", "cores": 1, "kind": "reference",
+                                     "sample": f"{cnt} GetPolyOcta3D calls of oracle/_ref (the reference's own code) on the same seeds"}
+    return line, balg * cb.n / (ms * 1e-3) / 1e9
+
+
 def config_dict(args, world):
     return {"workload": f"config2: 10-agent circular exchange, forest map, N=10, {args.swarms} independent swarm "
                         f"instances per GPU ({args.swarms * 10} agent QPs per GPU per step)",
@@ -293,6 +373,12 @@ def run_ours(args, rank, world, local_rank):
         if os.path.exists(tpath):
             traffic = float(json.load(open(tpath))["dram_bytes_per_agent_qp"]) * n_local
         cpu_rate, cores, cpu_n, cpu_t = cpu_solve_rate(snaps, min_seconds=args.cpu_seconds, max_agents=20000)
+        corridor = None
+        if args.corridor_agents > 0:
+            torch.cuda.set_stream(torch.cuda.default_stream(dev))
+            corridor, cor_gbs = corridor_measure(args.corridor_agents, 10, local_rank)
+            corridor["roofline"] = {"bound": "hbm", "achieved": cor_gbs, "peak": peak, "unit": "GB/s", "frac": cor_gbs / peak,
+                                    "traffic": None, "note": "serial list logic in shared memory: latency bound, not HBM bound"}
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -312,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
                     ("optimal", "infeasible", "max_iter", "numerical", "node_limit", "row_overflow"), stat)},
                     "max_kkt_residual": kkt, "ipm_iters_per_solve": iters / max(1, stat.sum()),
                     "qp_relaxations_per_solve": nodes / max(1, stat.sum())},
-                "smem_bytes_per_block": pl.smem_bytes}
+                "smem_bytes_per_block": pl.smem_bytes, "corridor": corridor}
         print(json.dumps(line), flush=True)
     pl.close()
     if dist:
@@ -329,6 +415,8 @@ def main():
     ap.add_argument("--swarms", type=int, default=4096, help="independent 10-agent swarm instances per GPU")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--corridor-agents", type=int, default=4096,
+                    help="agents of the secondary corridor-generation measurement (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -131,6 +131,18 @@ class SafeCorridorGenerator:
             raise RuntimeError(f"hdsm_corridor_batch failed ({rc}): {self.L.hdsm_corridor_last_error(self.h).decode()}")
         return out
 
+    def generate_device(self, t, n, stream_ptr=0):
+        """hdsm_corridor_batch_device on a DeviceCorridorBatch's tensors `t`; stream ordered, no sync."""
+        def dp(k):
+            v = t.get(k)
+            return None if v is None else C.c_void_p(v.data_ptr())
+        rc = self.L.hdsm_corridor_batch_device(
+            self.h, C.c_int(n), dp("grids"), dp("grid_index"), dp("dims"), dp("origins"), dp("pos"), dp("path"), dp("n_path"),
+            dp("prev_n"), dp("prev_A"), dp("prev_b"), dp("prev_rows"), dp("prev_seeds"), dp("prev_used"), dp("prev_traj"),
+            dp("poly_A"), dp("poly_b"), dp("poly_rows"), dp("seeds"), dp("flags"), C.c_void_p(stream_ptr))
+        if rc != 0:
+            raise RuntimeError(f"hdsm_corridor_batch_device failed ({rc}): {self.L.hdsm_corridor_last_error(self.h).decode()}")
+
     def close(self):
         if self.h is not None:
             self.L.hdsm_corridor_destroy(self.h)
@@ -141,6 +153,42 @@ class SafeCorridorGenerator:
             self.close()
         except Exception:
             pass
+
+
+class DeviceCorridorBatch:
+    """A CorridorBatch as contiguous torch tensors on `device`, plus the output tensors."""
+
+    IN_KEYS = ("grids", "grid_index", "dims", "origins", "pos", "path", "n_path", "prev_n", "prev_A", "prev_b",
+               "prev_rows", "prev_seeds", "prev_used", "prev_traj")
+
+    def __init__(self, cb: CorridorBatch, device):
+        import torch
+        self.n = cb.n
+        self.t = {}
+        for k in self.IN_KEYS:
+            a = getattr(cb, k)
+            if a is None or (k == "prev_traj" and cb.prev_n is None):
+                continue
+            a = np.ascontiguousarray(a.reshape(a.shape[0], -1) if k == "grids" else a)
+            self.t[k] = torch.from_numpy(a).to(device)
+        n, PH, R = cb.n, cb.poly_hor, cb.rmax
+        f64 = torch.float64
+        self.t["poly_A"] = torch.zeros((n, PH, R, 3), dtype=f64, device=device)
+        self.t["poly_b"] = torch.zeros((n, PH, R), dtype=f64, device=device)
+        self.t["poly_rows"] = torch.zeros((n, PH), dtype=torch.int32, device=device)
+        self.t["seeds"] = torch.zeros((n, PH, 3), dtype=f64, device=device)
+        self.t["flags"] = torch.zeros(n, dtype=torch.int32, device=device)
+
+
+def corridor_algorithmic_bytes(cb: CorridorBatch, poly_rows) -> float:
+    """Compulsory HBM traffic of one corridor update, bytes per agent: the occupancy rows a polytope can
+    look at ((2g + 3)^2 rows of 32 voxels around its seed, g = ceil(n_it / 6)), the path, the kept
+    polytopes read once, and every output written once."""
+    g = (cb.n_it + 5) // 6
+    new_polys = (np.asarray(poly_rows) > 0).sum(1) - (0 if cb.prev_n is None else 0)
+    window = (2 * g + 3) ** 2 * 32
+    out_bytes = cb.poly_hor * (cb.rmax * 32 + 4 + 24) + 4
+    return float(np.mean(new_polys * window + cb.n_path * 24 + 24 + 36 + out_bytes))
 
 
 # --------------------------------------------------------------------------------------
