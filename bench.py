@@ -194,7 +194,8 @@ def corridor_measure(n_agents=4096, steps=10, local_rank=0, cpu=True):
     gen = cr.SafeCorridorGenerator(cb.poly_hor, cb.n_it, cb.voxel, cb.n, cb.n, int(cb.grids[0].size), cb.prev_traj.shape[1],
                                    cb.path.shape[1], device=local_rank)
     db = cr.DeviceCorridorBatch(cb, dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(device=dev)  # a real stream: NULL would select the handle's own stream, unseen by the events
+    torch.cuda.set_stream(stream)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     for _ in range(3):
         gen.generate_device(db.t, cb.n, stream.cuda_stream)
@@ -375,7 +376,6 @@ def run_ours(args, rank, world, local_rank):
         cpu_rate, cores, cpu_n, cpu_t = cpu_solve_rate(snaps, min_seconds=args.cpu_seconds, max_agents=20000)
         corridor = None
         if args.corridor_agents > 0:
-            torch.cuda.set_stream(torch.cuda.default_stream(dev))
             corridor, cor_gbs = corridor_measure(args.corridor_agents, 10, local_rank)
             corridor["roofline"] = {"bound": "hbm", "achieved": cor_gbs, "peak": peak, "unit": "GB/s", "frac": cor_gbs / peak,
                                     "traffic": None, "note": "serial list logic in shared memory: latency bound, not HBM bound"}

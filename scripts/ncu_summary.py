@@ -1,6 +1,6 @@
 """Summarise an .ncu-rep (raw page + SASS source page joined with nvdisasm line info) - runs on CPU.
 
-    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-instantiation, default 10] [lib.so]
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-instantiation, default 10 | corridor] [lib.so]
 """
 import collections
 import csv
@@ -40,9 +40,13 @@ agg = {s: sum(int(r[ix[s]]) for r in data) for s in stalls}
 print("stalls:", ", ".join(f"{s[6:]} {100 * v / tot:.1f}%" for s, v in sorted(agg.items(), key=lambda x: -x[1])[:8]))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
-start = next(i for i, l in enumerate(dis) if l.startswith(f".text._ZN4hdsm17hdsm_solve_kernelILi{ninst}E"))
+sym = ".text._ZN8hdsm_cor15corridor_kernel" if ninst == "corridor" else f".text._ZN4hdsm17hdsm_solve_kernelILi{ninst}E"
+srcname = "hdsm_corridor.cu" if ninst == "corridor" else "hdsm_kernel.cuh"
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):  # one cubin per .cu file
+    dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+    if any(l.startswith(sym) for l in dis):
+        break
+start = next(i for i, l in enumerate(dis) if l.startswith(sym))
 end = next((i for i in range(start + 1, len(dis)) if dis[i].startswith("\t.section")), len(dis))
 cur, per = None, []
 for l in dis[start:end]:
@@ -59,8 +63,8 @@ for i in range(n):
     static[per[i]] += 1
     samp[per[i]] += int(data[i][ix["# Samples"]])
     execd[per[i]] += int(data[i][ix["Instructions Executed"]])
-src = open(os.path.join(os.path.dirname(lib), "csrc", "hdsm_kernel.cuh")).read().split("\n")
+src = open(os.path.join(os.path.dirname(lib), "csrc", srcname)).read().split("\n")
 print("--- top source lines by stall samples")
 for k, v in samp.most_common(int(os.environ.get("TOP", "30"))):
-    s = src[k[1] - 1].strip()[:100] if k and k[0] == "hdsm_kernel.cuh" else ""
+    s = src[k[1] - 1].strip()[:100] if k and k[0] == srcname else ""
     print(f"{str(k):30s} static {static[k]:5d} samples {100 * v / tot:5.1f}% exec {execd[k] / 1e6:8.1f}M | {s}")
