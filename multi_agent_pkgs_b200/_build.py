@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "libhdsm.so")
 SOURCES = ["hdsm_capi.cu", "hdsm_corridor.cu"]
 DEPS = ["hdsm_capi.cu", "hdsm_corridor.cu", "hdsm_kernel.cuh", "hdsm_tables.h", os.path.join("..", "..", "include", "hdsm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-diag-suppress", "68", "-shared", "-Xcompiler", "-fPIC"]
+              "-diag-suppress", "68", "-shared", "-Xcompiler", "-fPIC,-pthread"]
 
 
 def _nvcc():

@@ -200,6 +200,33 @@ def test_large_batch_is_batch_invariant():
     pl.close()
 
 
+def test_chunked_host_pipeline_is_batch_invariant():
+    """hdsm_solve_batch pipelines batches above 4096 agents in chunks over two streams (staging, H2D,
+    kernels and D2H overlapped): every replica of every agent must come back bit-identical to the
+    single-chunk solve, whatever chunk it fell into (9 840 agents -> 2 chunks of 4 920)."""
+    sw = sc.config2_circle(n_swarms=8, seed=43)
+    from oracle import c_oracle as co
+    for _ in range(4):
+        b = sw.make_batch()
+        ref = co.solve_batch(b, max_nodes=64)
+        sw.advance(ref["traj"], ref["ctrl"], ref["res"]["status"] == 0)
+    b = sw.make_batch()
+    reps = 123  # 9 840 agents: two chunks of 4 920
+    big = b.take(np.tile(np.arange(b.n), reps))
+    pl = TrajectoryPlanner(b.params, max_agents=big.n, max_neighbours=10, max_nodes=64)
+    small = pl.solve_batch(b)
+    for _ in range(2):  # twice: the arenas are reused
+        out = pl.solve_batch(big)
+        for key in ("traj", "ctrl", "assign", "poly_used"):
+            got = out[key].reshape(reps, b.n, *out[key].shape[1:])
+            assert np.array_equal(got, np.broadcast_to(small[key], got.shape)), key
+        for f in ("status", "iters", "nodes", "rows"):
+            assert np.array_equal(out["res"][f].reshape(reps, b.n), np.broadcast_to(small["res"][f], (reps, b.n))), f
+        assert np.array_equal(out["res"]["obj"].reshape(reps, b.n), np.broadcast_to(small["res"]["obj"], (reps, b.n)), equal_nan=True)
+    assert (small["res"]["status"] == OPTIMAL).mean() > 0.5
+    pl.close()
+
+
 def test_many_neighbours_config4_slice():
     """256-agent circle a few steps in: every agent sees 255 candidates, pruning keeps the rows small."""
     from oracle import c_oracle as co
