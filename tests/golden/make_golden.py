@@ -89,3 +89,17 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def export_lp_files():
+    """Gurobi-readable LP files of a few golden instances (tests/golden/lp/): `gurobi_cl Threads=1
+    ResultFile=x.sol <file>.lp` on a licensed machine confirms `obj` / `traj` of <file>.expected.json."""
+    from oracle import export_lp
+    from multi_agent_pkgs_b200.scenarios import Batch
+    os.makedirs(os.path.join(HERE, "lp"), exist_ok=True)
+    for name, want in (("config1_step1", 0), ("config2_step8", 3), ("config3_step12", 2), ("dense24_step8", 5)):
+        b = Batch.load(os.path.join(HERE, name + "_in.npz"))
+        exp = dict(np.load(os.path.join(HERE, name + "_exp.npz")))
+        ok = np.flatnonzero(exp["status"] == 0)
+        i = int(ok[min(want, len(ok) - 1)])
+        export_lp.export_agent(b, i, os.path.join(HERE, "lp", f"{name}_agent{i}"), exp)
