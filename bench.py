@@ -176,7 +176,7 @@ def run_reference(args, rank, world):
 def corridor_measure(n_agents=4096, steps=10, local_rank=0, cpu=True):
     """Throughput of hdsm_corridor_batch_device / hdsm_corridor_batch next to the CPU checkers.
     Workload: agents of the config-2 circle swap pulled into the forest, one 66 x 66 x 20 int8 local voxel
-    grid per agent (357 MB for 4096 agents: larger than L2), poly_hor 4, n_it_decomp 42; tiled from 240
+    grid per agent (1.4 GB for the default 16 384 agents = 9 waves of one-warp blocks), poly_hor 4, n_it_decomp 42; tiled from 240
     distinct agents.  L2 flushed between timed launches."""
     import torch
     from multi_agent_pkgs_b200 import corridor as cr
@@ -415,7 +415,7 @@ def main():
     ap.add_argument("--swarms", type=int, default=4096, help="independent 10-agent swarm instances per GPU")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--corridor-agents", type=int, default=4096,
+    ap.add_argument("--corridor-agents", type=int, default=16384,
                     help="agents of the secondary corridor-generation measurement (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

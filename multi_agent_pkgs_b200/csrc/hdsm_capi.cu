@@ -75,6 +75,10 @@ struct hdsm_handle {
   unsigned char *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
   size_t in_cap = 0, out_cap = 0;
   int64_t launches = 0;
+  // longest-first dispatch: order[slot] of the previous call per pipeline chunk (valid while n matches)
+  int32_t* d_order = nullptr;
+  int order_n[kMaxChunks] = {};
+  bool use_order = true;
   long long* d_prof = nullptr;  // HDSM_PROFILE=1: per-agent phase cycle counters (host path prints a summary)
   int warps = 4;  // warps per agent (HDSM_WARPS=1 selects the single-warp kernel)
   std::string err;
@@ -175,6 +179,7 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   }
   h->device = device, h->max_agents = max_agents, h->max_neighbours = max_neighbours;
   if (const char* e = std::getenv("HDSM_WARPS")) h->warps = std::atoi(e) == 1 ? 1 : 4;
+  if (const char* e = std::getenv("HDSM_NO_ORDER")) h->use_order = std::atoi(e) == 0;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || device < 0 || device >= ndev) {  // no CPU fallback: fail loudly
@@ -196,6 +201,7 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   if ((e = cudaMalloc(&h->dev_tables, sizeof(Tables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
   if ((e = cudaMemcpy(h->dev_tables, &h->host_tables, sizeof(Tables), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail(e, "copy tables");
+  if ((e = cudaMalloc(&h->d_order, sizeof(int32_t) * (size_t)max_agents)) != cudaSuccess) return bail(e, "cudaMalloc order");
   // Shared-memory budget.  Worst case per agent: 2 planes per neighbour and variable position step
   // plus two polytopes' rows per step.  Exact pruning usually leaves a few dozen rows, so the first
   // pass runs with a small row pool (more resident blocks per SM); agents that overflow it are
@@ -231,6 +237,7 @@ void hdsm_destroy(hdsm_handle* h) {
     if (h->ev_chunk[c]) cudaEventDestroy(h->ev_chunk[c]), cudaEventDestroy(h->ev_begin[c]);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   cudaFree(h->dev_tables);
+  cudaFree(h->d_order);
   cudaFree(h->d_prof);
   cudaFree(h->d_in);
   cudaFree(h->d_out);
@@ -244,19 +251,23 @@ const char* hdsm_last_error(const hdsm_handle* h) { return h ? h->err.c_str() : 
 int64_t hdsm_launch_count(const hdsm_handle* h) { return h ? h->launches : 0; }
 int hdsm_smem_bytes(const hdsm_handle* h) { return h ? h->smem_bytes[0] : 0; }
 
-int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
-                            const int32_t* nbr_end, const double* x0, const double* ref, const double* poly_A,
-                            const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,
-                            const double* all_pos, const uint8_t* all_valid, int n_rob, const int32_t* assign_in,
-                            double* traj, double* ctrl, uint8_t* poly_used, int32_t* assign_out, hdsm_result* res,
-                            double* pos_out, void* stream) {
+// `slot` / `order_offset`: which pipeline chunk of the handle this call is (the public device entry point is
+// slot 0); the dispatch order computed after the previous call of the same slot and size is used, then
+// recomputed from this call's iteration counts.
+static int solve_device(hdsm_handle* h, int slot, size_t order_offset, int n_local, const int32_t* global_id,
+                        const int32_t* nbr_begin, const int32_t* nbr_end, const double* x0, const double* ref,
+                        const double* poly_A, const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,
+                        const double* all_pos, const uint8_t* all_valid, int n_rob, const int32_t* assign_in, double* traj,
+                        double* ctrl, uint8_t* poly_used, int32_t* assign_out, hdsm_result* res, double* pos_out,
+                        void* stream) {
   if (!h) return HDSM_ERR_INVALID;
   if (n_local == 0) return HDSM_OK;
   if (n_local < 0 || n_rob < 0 || !global_id || !x0 || !ref || !poly_A || !poly_b || !poly_rows || !prev_self_pos ||
       !traj || !ctrl || !poly_used || !assign_out || !res || (n_rob > 0 && (!all_pos || !all_valid)) ||
       ((nbr_begin == nullptr) != (nbr_end == nullptr)))
     return fail(h, HDSM_ERR_INVALID, "hdsm_solve_batch: null or inconsistent argument");
-  if (n_local > h->max_agents) return fail(h, HDSM_ERR_CAPACITY, "n_local exceeds max_agents of the handle");
+  if (n_local > h->max_agents || order_offset + n_local > (size_t)h->max_agents)
+    return fail(h, HDSM_ERR_CAPACITY, "n_local exceeds max_agents of the handle");
   CU(cudaSetDevice(h->device));
   KernelArgs a{};
   a.n_local = n_local, a.n_rob = n_rob, a.rmax = h->prm.max_rows_per_poly, a.P = h->prm.poly_hor;
@@ -265,9 +276,27 @@ int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_i
   a.all_valid = all_valid, a.traj = traj, a.ctrl = ctrl, a.pos_out = pos_out, a.poly_used = poly_used;
   a.assign_out = assign_out, a.res = res, a.prof = h->d_prof;
   a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
+  const bool ordered = h->use_order && n_local >= 1024;  // below ~2 waves of blocks the order cannot matter
+  a.order = ordered && h->order_n[slot] == n_local ? h->d_order + order_offset : nullptr;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   CU(dispatch(h, a, s));
+  if (ordered) {
+    hdsm_order_kernel<<<1, 1024, 0, s>>>(res, n_local, h->d_order + order_offset);
+    h->launches += 1;
+    h->order_n[slot] = n_local;
+    CU(cudaGetLastError());
+  }
   return HDSM_OK;
+}
+
+int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
+                            const int32_t* nbr_end, const double* x0, const double* ref, const double* poly_A,
+                            const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,
+                            const double* all_pos, const uint8_t* all_valid, int n_rob, const int32_t* assign_in,
+                            double* traj, double* ctrl, uint8_t* poly_used, int32_t* assign_out, hdsm_result* res,
+                            double* pos_out, void* stream) {
+  return solve_device(h, 0, 0, n_local, global_id, nbr_begin, nbr_end, x0, ref, poly_A, poly_b, poly_rows, prev_self_pos,
+                      all_pos, all_valid, n_rob, assign_in, traj, ctrl, poly_used, assign_out, res, pos_out, stream);
 }
 
 int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
@@ -369,8 +398,8 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
       CU(cudaMemcpyAsync(h->d_in + o, h->h_in + o, bytes, cudaMemcpyHostToDevice, s));
     }
     if (trace) CU(cudaEventRecord(h->ev_begin[c], s));
-    int rc = hdsm_solve_batch_device(
-        h, (int)cnt, (const int32_t*)dp(0, first), (const int32_t*)dp(1, first), (const int32_t*)dp(2, first),
+    int rc = solve_device(
+        h, c, first, (int)cnt, (const int32_t*)dp(0, first), (const int32_t*)dp(1, first), (const int32_t*)dp(2, first),
         (const double*)dp(5, first), (const double*)dp(6, first), (const double*)dp(7, first), (const double*)dp(8, first),
         (const int32_t*)dp(3, first), (const double*)dp(9, first), (const double*)dp(10, 0), (const uint8_t*)dp(11, 0), n_rob,
         (const int32_t*)dp(4, first), (double*)(h->d_out + o_traj + first * outs[0].stride),

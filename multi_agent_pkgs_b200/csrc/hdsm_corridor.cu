@@ -36,7 +36,6 @@ constexpr int kOccVal = 100;   // CVX_DCMP_OCC / ENV_BUILDER_OCC
 constexpr int kUnknown = -1;   // ENV_BUILDER_UNK (OccupyUnknown turns it into occupied, voxel_grid.cpp:234-240)
 constexpr int kCentre = 16;    // local coordinate of the seed inside the 32^3 window
 constexpr int kDq = 128, kDqStart = 32;  // deque storage: <= 31 pushes at either end per layer
-constexpr int kMaxPlanes = 18;
 
 // face tables (convex_decomp.cpp:15-43): outward axis/sign, the two in-face growth axes (directions 2, 3
 // are their negatives), the box edge met in each in-face direction, the face across it and which of that
@@ -62,26 +61,27 @@ struct Args {
   int32_t *poly_rows, *flags;
 };
 
-// fixed part of the per-warp shared memory; cells[6][cell_cap], layer[layer_cap] (u16) and
-// rows[P][Rmax][4] (double) follow
+// fixed part of the per-warp shared memory; occ[span^2], mark[span^2] (u32), cells[6][cell_cap],
+// layer[layer_cap] (u16) and rows[P][Rmax][4] (double) follow
 struct Fixed {
-  unsigned occ[1024];   // bit x of word (y + 32 z): occupied or outside the grid
-  unsigned mark[1024];  // voxels of the convex set being grown
   double edge_pos[12][3];
+  double et_pos[4][3];
   int edge_slope[12], edge_dir[12], edge_fixed[12], edge_steps[12];
   int et_slope[4], et_dir[4], et_fixed[4], et_steps[4];
-  double et_pos[4][3];
   int lim[6][4], alive[6], tip[6], ncell[6];
   int lm[4], ext[4], app[4];
-  int dq_lo[8], dq_hi[8];  // 0..3: in-face front lines ("ring"); 4..7: their part above the set ("top")
+  int top_lo[4], top_hi[4], top_buf[4];  // final state of the four "top" lines of a layer (written once per layer)
   int valid;
-  unsigned short dq[8][kDq];
-  unsigned short tmpr[kDq];
+  unsigned short ring[4][kDq];    // in-face front lines, stored minus (advances so far) * step
+  unsigned short top[4][2][kDq];  // their part above the set, double buffered (a failed advance keeps the old one)
 };
 
 __device__ __forceinline__ int coord(unsigned c, int a) { return (c >> (5 * a)) & 31; }
-__device__ __forceinline__ bool bit(const unsigned* bm, unsigned c) { return (bm[c >> 5] >> (c & 31)) & 1u; }
 __device__ __forceinline__ unsigned pack(int x, int y, int z) { return (unsigned)(x | (y << 5) | (z << 10)); }
+// four 8-bit counters packed in one 32-bit register: uniform over the warp, indexed dynamically with one
+// shift and one mask (64-bit variable shifts cost several instructions each)
+__device__ __forceinline__ int get8(unsigned v, int q) { return (int)((v >> (8 * q)) & 0xffu); }
+__device__ __forceinline__ unsigned set8(unsigned v, int q, int x) { return (v & ~(0xffu << (8 * q))) | ((unsigned)(x & 0xff) << (8 * q)); }
 
 // exact arithmetic helpers: never contracted into FMAs
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
@@ -92,57 +92,64 @@ __device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, 
 struct Agent {
   const Args& A;
   Fixed& S;
+  unsigned* occ;          // [span^2] bit x of word (y - wlo) + span (z - wlo): occupied or outside the grid
+  unsigned* mark;         // [span^2] voxels of the convex set being grown
   unsigned short* cells;  // [6][cell_cap]
   unsigned short* layer;  // [layer_cap]
   double* rows;           // [P][Rmax][4]: (A0, A1, A2, b) of the polytopes decided so far
   const int lane;
   int dim[3], w0[3];
+  int wlo, span;          // staged rows of the window: y, z in [wlo, wlo + span)
   double origin[3];
   const int8_t* grid;
   int flags = 0;
 
   __device__ Agent(const Args& a, Fixed& s, unsigned char* dyn, int agent) : A(a), S(s), lane(threadIdx.x & 31) {
-    cells = reinterpret_cast<unsigned short*>(dyn);
+    const int g = (a.prm.n_it_decomp + 5) / 6 + 1;  // layers a face can gain, plus the cells looked at beyond
+    wlo = max(0, kCentre - g);
+    span = min(31, kCentre + g) - wlo + 1;
+    occ = reinterpret_cast<unsigned*>(dyn);
+    mark = occ + span * span;
+    cells = reinterpret_cast<unsigned short*>(mark + span * span);
     layer = cells + 6 * a.cell_cap;
-    size_t off = (size_t)(6 * a.cell_cap + a.layer_cap) * sizeof(unsigned short);
+    size_t off = (size_t)2 * span * span * sizeof(unsigned) + (size_t)(6 * a.cell_cap + a.layer_cap) * sizeof(unsigned short);
     off = (off + 7) & ~size_t(7);
     rows = reinterpret_cast<double*>(dyn + off);
     for (int k = 0; k < 3; ++k) dim[k] = a.dims[3 * agent + k], origin[k] = a.origins[3 * agent + k];
     grid = a.grids + (size_t)(a.grid_index ? a.grid_index[agent] : agent) * a.grid_stride;
   }
 
+  __device__ __forceinline__ int word_of(unsigned c) const { return (int)((c >> 5) & 31) - wlo + span * ((int)(c >> 10) - wlo); }
+  __device__ __forceinline__ bool bit(const unsigned* bm, unsigned c) const { return (bm[word_of(c)] >> (c & 31)) & 1u; }
+
   // ---------------------------------------------------------------- occupancy window
   __device__ void stage_window(const int seed[3]) {
     for (int k = 0; k < 3; ++k) w0[k] = seed[k] - kCentre;
-    for (int i = lane; i < 1024; i += 32) S.occ[i] = kFull, S.mark[i] = 0u;
-    __syncwarp();
-    const int g = (A.prm.n_it_decomp + 5) / 6 + 1;  // layers a face can gain, plus the cells looked at beyond
-    const int lo = max(0, kCentre - g), hi = min(31, kCentre + g), span = hi - lo + 1;
+    for (int i = lane; i < span * span; i += 32) mark[i] = 0u;
     const int gx = w0[0] + lane;
     const bool x_in = gx >= 0 && gx < dim[0];
     for (int r0 = 0; r0 < span * span; r0 += 4) {
       int v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {  // four independent coalesced row loads in flight
-        const int r = r0 + u, z = lo + r / span, y = lo + r % span;
-        const int gy = w0[1] + y, gz = w0[2] + z;
+        const int r = r0 + u, gy = w0[1] + wlo + r % span, gz = w0[2] + wlo + r / span;
         const bool in = r < span * span && x_in && gy >= 0 && gy < dim[1] && gz >= 0 && gz < dim[2];
         v[u] = in ? (int)__ldg(grid + gx + (size_t)gy * dim[0] + (size_t)gz * dim[0] * dim[1]) : kOccVal;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int r = r0 + u;
         const unsigned m = __ballot_sync(kFull, v[u] >= kOccVal || v[u] == kUnknown);
-        if (lane == 0 && r < span * span) S.occ[(lo + r % span) + 32 * (lo + r / span)] = m;
+        if (lane == 0 && r0 + u < span * span) occ[r0 + u] = m;
       }
     }
     __syncwarp();
   }
 
   // ---------------------------------------------------------------- GetPolyOcta3D
-  // returns the number of hyperplanes written to pts / nrm (lane 0's registers are authoritative; every
-  // lane receives the same values through shared memory), or -1 if a list outgrew its buffer
-  __device__ int poly_octa(const int seed[3], double (*pts)[3], double (*nrm)[3]) {
+  // Grows the convex set around `seed`; the hyperplanes are written as rows (A = normal, b = point . normal,
+  // agent_class.cpp:1428-1437) of polytope slot `slot` in shared memory.  Returns their number, or -1 if a
+  // list outgrew its buffer.
+  __device__ int poly_octa(const int seed[3], int slot) {
     const double res = A.prm.voxel_size;
     const unsigned lt = (1u << lane) - 1u;
     stage_window(seed);
@@ -155,7 +162,7 @@ struct Agent {
         const int l0 = cAxS[f][0] * seed[cAxA[f][0]], l1 = cAxS[f][1] * seed[cAxA[f][1]];
         S.lim[f][0] = l0, S.lim[f][1] = l1, S.lim[f][2] = -l0, S.lim[f][3] = -l1;
       }
-      S.mark[sc >> 5] |= 1u << (sc & 31);
+      mark[word_of(sc)] |= 1u << (sc & 31);
     }
     __syncwarp();
     bool overflow = false;
@@ -204,7 +211,7 @@ struct Agent {
             t = (unsigned)((int)cf[i] + ostep);
             const int ta[3] = {w0[0] + coord(t, 0), w0[1] + coord(t, 1), w0[2] + coord(t, 2)};
             ok = ta[0] >= 1 && ta[1] >= 1 && ta[2] >= 1 && ta[0] < dim[0] - 1 && ta[1] < dim[1] - 1 && ta[2] < dim[2] - 1 &&
-                 !bit(S.occ, t) && s0 * ta[a0] <= lm0 && s1 * ta[a1] <= lm1 && -s0 * ta[a0] <= lm2 && -s1 * ta[a1] <= lm3;
+                 !bit(occ, t) && s0 * ta[a0] <= lm0 && s1 * ta[a1] <= lm1 && -s0 * ta[a0] <= lm2 && -s1 * ta[a1] <= lm3;
           }
           const unsigned m = __ballot_sync(kFull, ok);
           if (m) {
@@ -215,38 +222,49 @@ struct Agent {
       }
       if (s2 < 0) continue;
 
-      // in-layer growth from s2: the four front lines advance in turn until none can (:119-209).  A
-      // line that failed once can never advance later (its failing cell stays in it; limits, marks and
-      // occupancy do not change during the layer), so closed lines are skipped instead of re-tested.
-      if (lane < 8) S.dq[lane][kDqStart] = (unsigned short)s2, S.dq_lo[lane] = kDqStart, S.dq_hi[lane] = kDqStart + 1;
-      if (lane < 4) S.ext[lane] = s2;
+      // In-layer growth from s2: the four front lines advance in turn until none can (:119-209).  A line that
+      // failed once can never advance later (its failing cell stays in it; limits, marks and occupancy do not
+      // change during the layer), so closed lines are skipped instead of re-tested.  All bookkeeping of the
+      // eight deques is warp-uniform register state: RLO / RHI and TLO / THI hold the [lo, hi) bounds of the ring
+      // and top lines (one byte per direction), CNT how often a ring line advanced (its cells are stored minus
+      // CNT * step, so an advance moves no data), ext0..3 the front of each top line the last time it was
+      // non-empty (border_limit_tmp), BUF the live buffer of each top line.
+      if (lane < 4) S.ring[lane][kDqStart] = (unsigned short)s2, S.top[lane][0][kDqStart] = (unsigned short)s2;
       if (lane == 0) layer[0] = (unsigned short)s2;
       __syncwarp();
+      unsigned RLO = 0x20202020u, RHI = 0x21212121u, TLO = 0x20202020u, THI = 0x21212121u;  // kDqStart = 32
+      unsigned ext0 = (unsigned)s2, ext1 = ext0, ext2 = ext0, ext3 = ext0;
+      unsigned CNT = 0, BUF = 0, open = 15u;
       int nlayer = 1;
-      unsigned open = 15u;
+      const auto set_ext = [&](int q, unsigned v) {
+        ext0 = q == 0 ? v : ext0, ext1 = q == 1 ? v : ext1, ext2 = q == 2 ? v : ext2, ext3 = q == 3 ? v : ext3;
+      };
 #pragma unroll 1
       for (int k = 0; open; ++k) {
         const int j = k & 3;
         if (!((open >> j) & 1u)) continue;
         const int a = cAxA[f][j & 1], s = (j < 2 ? 1 : -1) * cAxS[f][j & 1];
         const int step = s * (1 << (5 * a));
-        const int lo = S.dq_lo[j], len = S.dq_hi[j] - lo, limit = S.lm[j];
-        unsigned short* ring = S.dq[j];
+        const int lo = get8(RLO, j), len = get8(RHI, j) - lo, limit = S.lm[j];
+        const int shift = get8(CNT, j) * step;
+        const unsigned short* ring = S.ring[j];
+        unsigned short* alt = S.top[j][((BUF >> j) & 1u) ^ 1u];
         int nr = 0;
-        bool ok = true;
+        bool ok = true, first_real = false, last_real = false;
+        unsigned front_real = 0;
 #pragma unroll 1
         for (int base = 0; base < len; base += 32) {
           const int i = base + lane;
           bool fail = false, real = false;
           unsigned t = 0;
           if (i < len) {
-            const unsigned c = ring[lo + i];
+            const unsigned c = (unsigned)((int)ring[lo + i] + shift) & 0xffffu;
             if (s * (w0[a] + coord(c, a) + s) > limit) {  // tested before packing: the moved coordinate may leave 0..31
               fail = true;
             } else {
               t = (unsigned)((int)c + step);
-              if (bit(S.mark, (unsigned)((int)t - ostep))) {  // above the set: must be free
-                if (bit(S.occ, t)) fail = true;
+              if (bit(mark, (unsigned)((int)t - ostep))) {  // above the set: must be free
+                if (bit(occ, t)) fail = true;
                 else real = true;
               }
             }
@@ -256,8 +274,14 @@ struct Agent {
             ok = false;
             break;
           }
-          if (real) S.tmpr[nr + __popc(rm & lt)] = (unsigned short)t;
-          nr += __popc(rm);
+          if (rm) {
+            if (nr == 0) front_real = __shfl_sync(kFull, t, __ffs(rm) - 1);
+            if (base == 0) first_real = rm & 1u;
+            if (base + 32 >= len) last_real = (rm >> ((len - 1) & 31)) & 1u;
+            const int pos = nr + __popc(rm & lt);
+            if (real && nlayer + pos < A.layer_cap) alt[kDqStart + pos] = (unsigned short)t, layer[nlayer + pos] = (unsigned short)t;
+            nr += __popc(rm);
+          }
         }
         if (!ok) {
           open &= ~(1u << j);
@@ -267,39 +291,51 @@ struct Agent {
           overflow = true;
           break;
         }
-        for (int i = lane; i < len; i += 32) ring[lo + i] = (unsigned short)((int)ring[lo + i] + step);
-        __syncwarp();
-        for (int i = lane; i < nr; i += 32) {
-          const unsigned short v = S.tmpr[i];
-          S.dq[4 + j][kDqStart + i] = v;
-          layer[nlayer + i] = v;
-        }
+        // the advance succeeded: ring j moves by one step, its top line is replaced, the neighbours grow
+        const unsigned first = (unsigned)((int)ring[lo] + shift + step) & 0xffffu;
+        const unsigned last = (unsigned)((int)ring[lo + len - 1] + shift + step) & 0xffffu;
+        CNT += 1u << (8 * j);
+        BUF ^= 1u << j;
         nlayer += nr;
-        __syncwarp();
+        TLO = set8(TLO, j, kDqStart), THI = set8(THI, j, kDqStart + nr);
+        if (nr > 0) set_ext(j, front_real);
+        const int jb = (j + 3) & 3, ja = (j + 1) & 3;
+        const int sb = (jb < 2 ? 1 : -1) * cAxS[f][jb & 1] * (1 << (5 * cAxA[f][jb & 1]));
+        const int sa = (ja < 2 ? 1 : -1) * cAxS[f][ja & 1] * (1 << (5 * cAxA[f][ja & 1]));
+        const int hb = get8(RHI, jb), la = get8(RLO, ja) - 1;
+        RHI += 1u << (8 * jb), RLO -= 1u << (8 * ja);
+        const bool push_tb = nr > 0 && first_real, push_ta = nr > 0 && last_real;
+        const int thb = get8(THI, jb), tla = get8(TLO, ja) - 1;
+        if (push_tb) {
+          if (thb == get8(TLO, jb)) set_ext(jb, first);  // the line was empty: its front changes
+          THI += 1u << (8 * jb);
+        }
+        if (push_ta) {
+          TLO -= 1u << (8 * ja);
+          set_ext(ja, last);
+        }
         if (lane == 0) {
-          S.dq_lo[4 + j] = kDqStart, S.dq_hi[4 + j] = kDqStart + nr;
-          const unsigned short first = ring[lo], last = ring[lo + len - 1];
-          const int jb = (j + 3) & 3, ja = (j + 1) & 3;
-          S.dq[jb][S.dq_hi[jb]++] = first;
-          S.dq[ja][--S.dq_lo[ja]] = last;
-          if (nr > 0) {
-            if (first == S.tmpr[0]) S.dq[4 + jb][S.dq_hi[4 + jb]++] = first;
-            if (last == S.tmpr[nr - 1]) S.dq[4 + ja][--S.dq_lo[4 + ja]] = last;
-          }
-          for (int q = 0; q < 4; ++q)
-            if (S.dq_hi[4 + q] > S.dq_lo[4 + q]) S.ext[q] = S.dq[4 + q][S.dq_lo[4 + q]];
+          S.ring[jb][hb] = (unsigned short)((int)first - get8(CNT, jb) * sb);
+          S.ring[ja][la] = (unsigned short)((int)last - get8(CNT, ja) * sa);
+          if (push_tb) S.top[jb][(BUF >> jb) & 1u][thb] = (unsigned short)first;
+          if (push_ta) S.top[ja][(BUF >> ja) & 1u][tla] = (unsigned short)last;
         }
         __syncwarp();
       }
       if (overflow) break;
+      if (lane < 4) {
+        S.top_lo[lane] = get8(TLO, lane), S.top_hi[lane] = get8(THI, lane), S.top_buf[lane] = (BUF >> lane) & 1u;
+        S.ext[lane] = (int)(lane == 0 ? ext0 : lane == 1 ? ext1 : lane == 2 ? ext2 : ext3);
+      }
+      __syncwarp();
 
       // chamfer bookkeeping of the four edges around the face (:217-301), lane 0
       if (lane == 0) {
         int valid = 1;
         for (int j = 0; j < 4 && valid; ++j) {
-          if (S.dq_hi[4 + j] > S.dq_lo[4 + j]) {
+          if (S.top_hi[j] > S.top_lo[j]) {
             const int a = cAxA[f][j & 1], s = (j < 2 ? 1 : -1) * cAxS[f][j & 1];
-            const unsigned fr = S.dq[4 + j][S.dq_lo[4 + j]];
+            const unsigned fr = S.top[j][S.top_buf[j]][S.top_lo[j]];
             const int dist = S.lim[f][j] - s * (w0[a] + coord(fr, a));
             int sl = S.et_slope[j], dr = S.et_dir[j], fx = S.et_fixed[j], st = S.et_steps[j];
             if (sl == 0) {
@@ -358,8 +394,8 @@ struct Agent {
           S.edge_slope[e] = S.et_slope[j], S.edge_dir[e] = S.et_dir[j], S.edge_fixed[e] = S.et_fixed[j], S.edge_steps[e] = S.et_steps[j];
           for (int c = 0; c < 3; ++c) S.edge_pos[e][c] = S.et_pos[j][c];
           int app = 0;
-          if (S.et_slope[j] == 0 && S.dq_hi[4 + j] > S.dq_lo[4 + j]) {
-            const unsigned fr = S.dq[4 + j][S.dq_lo[4 + j]];
+          if (S.et_slope[j] == 0 && S.top_hi[j] > S.top_lo[j]) {
+            const unsigned fr = S.top[j][S.top_buf[j]][S.top_lo[j]];
             if (S.lim[f][j] - s * (w0[a] + coord(fr, a)) == 0) {
               app = 1;  // the face across gains this line of cells and one unit of limit
               S.lim[cAcross[f][j]][cAcrossLim[f][j]] += 1;
@@ -375,18 +411,19 @@ struct Agent {
         for (int i = lane; i < nlayer; i += 32) {
           const unsigned c = layer[i];
           cf[i] = (unsigned short)c;
-          atomicOr(&S.mark[c >> 5], 1u << (c & 31));
+          atomicOr(&mark[word_of(c)], 1u << (c & 31));
         }
       }
       __syncwarp();
       for (int j = 0; j < 4; ++j) {
         if (!S.app[j]) continue;
-        const int g = cAcross[f][j], lo = S.dq_lo[4 + j], cnt = S.dq_hi[4 + j] - lo, n0 = S.ncell[g];
+        const int g = cAcross[f][j], lo = S.top_lo[j], cnt = S.top_hi[j] - lo, n0 = S.ncell[g];
         if (n0 + cnt > A.cell_cap) {
           overflow = true;
           break;
         }
-        for (int i = lane; i < cnt; i += 32) cells[g * A.cell_cap + n0 + i] = S.dq[4 + j][lo + i];
+        const unsigned short* tp = S.top[j][S.top_buf[j]];
+        for (int i = lane; i < cnt; i += 32) cells[g * A.cell_cap + n0 + i] = tp[lo + i];
         __syncwarp();
         if (lane == 0) S.ncell[g] = n0 + cnt;
         __syncwarp();
@@ -394,28 +431,35 @@ struct Agent {
     }
     if (overflow) return -1;
 
-    // hyperplanes (:343-375): chamfers in edge order, then the six faces
-    int np = 0;
-    for (int e = 0; e < 12; ++e) {
-      const int sl = S.edge_slope[e];
-      if (sl <= 0) continue;
-      const int f1 = cEdgeFaces[e][0], f2 = cEdgeFaces[e][1];
-      const int steep = S.edge_dir[e] == f1 ? f1 : f2, flat = S.edge_dir[e] == f1 ? f2 : f1;
-      for (int c = 0; c < 3; ++c) {
-        nrm[np][c] = (double)(sl * (c == cOutAxis[steep] ? cOutSign[steep] : 0) + (c == cOutAxis[flat] ? cOutSign[flat] : 0));
-        pts[np][c] = add(S.edge_pos[e][c], origin[c]);
+    // hyperplanes (:343-375): chamfers in edge order, then the six faces; one lane per plane
+    const int R = A.prm.max_rows_per_poly;
+    const bool cham = lane < 12 && S.edge_slope[lane < 12 ? lane : 0] > 0;
+    const unsigned cm = __ballot_sync(kFull, cham);
+    const int ncham = __popc(cm), np = ncham + 6;
+    if (np <= R && (cham || (lane >= 12 && lane < 18))) {
+      double n3[3], p3[3];
+      int row;
+      if (cham) {
+        const int e = lane, sl = S.edge_slope[e], f1 = cEdgeFaces[e][0], f2 = cEdgeFaces[e][1];
+        const int steep = S.edge_dir[e] == f1 ? f1 : f2, flat = S.edge_dir[e] == f1 ? f2 : f1;
+        for (int c = 0; c < 3; ++c) {
+          n3[c] = (double)(sl * (c == cOutAxis[steep] ? cOutSign[steep] : 0) + (c == cOutAxis[flat] ? cOutSign[flat] : 0));
+          p3[c] = add(S.edge_pos[e][c], origin[c]);
+        }
+        row = __popc(cm & lt);
+      } else {
+        const int f = lane - 12;
+        const unsigned tp = (unsigned)S.tip[f];
+        for (int c = 0; c < 3; ++c) {
+          const double o = (double)(c == cOutAxis[f] ? cOutSign[f] : 0);
+          p3[c] = add(add(add(mul((double)(w0[c] + coord(tp, c)), res), dvd(mul(o, res), 2.0)), dvd(res, 2.0)), origin[c]);
+          n3[c] = o;
+        }
+        row = ncham + f;
       }
-      ++np;
-    }
-    for (int f = 0; f < 6; ++f) {
-      const unsigned tp = (unsigned)S.tip[f];
-      for (int c = 0; c < 3; ++c) {
-        const double o = (double)(c == cOutAxis[f] ? cOutSign[f] : 0);
-        const double p = add(add(mul((double)(w0[c] + coord(tp, c)), res), dvd(mul(o, res), 2.0)), dvd(res, 2.0));
-        pts[np][c] = add(p, origin[c]);
-        nrm[np][c] = o;
-      }
-      ++np;
+      double* r = rows + (size_t)(slot * R + row) * 4;
+      r[0] = n3[0], r[1] = n3[1], r[2] = n3[2];
+      r[3] = add(add(mul(p3[0], n3[0]), mul(p3[1], n3[1])), mul(p3[2], n3[2]));
     }
     __syncwarp();
     return np;
@@ -537,8 +581,7 @@ struct Agent {
         flags |= HDSM_COR_SEED_OUTSIDE;
         break;
       }
-      double pts[kMaxPlanes][3], nrm[kMaxPlanes][3];
-      const int np = poly_octa(sv, pts, nrm);
+      const int np = poly_octa(sv, n_poly);
       if (np < 0) {
         flags |= HDSM_COR_LIST_OVERFLOW;
         break;
@@ -548,22 +591,12 @@ struct Agent {
       for (int c = 0; c < 3; ++c) {
         const bool in_lo = sv[c] - 1 >= 0, in_hi = sv[c] + 1 < dim[c];
         const unsigned ctr = pack(kCentre, kCentre, kCentre);
-        if (in_lo && in_hi && bit(S.occ, ctr - (1u << (5 * c))) && bit(S.occ, ctr + (1u << (5 * c)))) flags |= HDSM_COR_SQUEEZED;
+        if (in_lo && in_hi && bit(occ, ctr - (1u << (5 * c))) && bit(occ, ctr + (1u << (5 * c)))) flags |= HDSM_COR_SQUEEZED;
       }
       if (np > R) {
         flags |= HDSM_COR_ROW_OVERFLOW;
         break;
       }
-      if (lane < np) {  // A = normal, b = point . normal (:1428-1437)
-        double* r = rows + (size_t)(n_poly * R + lane) * 4;
-        double n3[3], p3[3];
-        for (int i = 0; i < kMaxPlanes; ++i)  // select without dynamic indexing of a register array
-          if (i == lane)
-            for (int c = 0; c < 3; ++c) n3[c] = nrm[i][c], p3[c] = pts[i][c];
-        r[0] = n3[0], r[1] = n3[1], r[2] = n3[2];
-        r[3] = add(add(mul(p3[0], n3[0]), mul(p3[1], n3[1])), mul(p3[2], n3[2]));
-      }
-      __syncwarp();
       for (int c = 0; c < 3; ++c) seed_of[n_poly][c] = sw[c];
       nrows_of[n_poly] = np;
       store_poly(agent, n_poly, np, sw);
@@ -583,7 +616,9 @@ __global__ void __launch_bounds__(32) corridor_kernel(const Args args) {
 }
 
 inline size_t smem_bytes(const hdsm_corridor_params& p, int cell_cap, int layer_cap) {
-  size_t dyn = (size_t)(6 * cell_cap + layer_cap) * sizeof(unsigned short);
+  const int g = (p.n_it_decomp + 5) / 6 + 1, wlo = kCentre - g > 0 ? kCentre - g : 0;
+  const int span = (kCentre + g < 31 ? kCentre + g : 31) - wlo + 1;
+  size_t dyn = (size_t)2 * span * span * sizeof(unsigned) + (size_t)(6 * cell_cap + layer_cap) * sizeof(unsigned short);
   dyn = (dyn + 7) & ~size_t(7);
   dyn += (size_t)p.poly_hor * p.max_rows_per_poly * 4 * sizeof(double);
   return ((sizeof(Fixed) + 15) & ~size_t(15)) + dyn;

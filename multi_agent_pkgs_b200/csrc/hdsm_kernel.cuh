@@ -40,6 +40,7 @@ struct KernelArgs {
   uint8_t* poly_used;
   int32_t* assign_out;
   hdsm_result* res;
+  const int32_t* order;  // optional dispatch order: block b solves agent order[b] (longest expected first)
   int row_cap;     // rows (inter-agent + corridor) one block can hold in shared memory
   int only_status; // >= 0: solve only agents whose res[].status equals this (second, large-memory pass)
   long long* prof; // optional [n_local][16] cycle counters per phase (HDSM_PROFILE=1), else null
@@ -1336,11 +1337,46 @@ struct Solver {
 template <int N, int W>
 __global__ void __launch_bounds__(32 * W, W == 4 ? HDSM_MINBLOCKS : 1) hdsm_solve_kernel(const Tables* __restrict__ tables, const KernelArgs args) {
   extern __shared__ double smem[];
-  const int agent = blockIdx.x;
-  if (agent >= args.n_local) return;
+  if ((int)blockIdx.x >= args.n_local) return;
+  const int agent = args.order ? args.order[blockIdx.x] : (int)blockIdx.x;
   if (args.only_status >= 0 && args.res[agent].status != args.only_status) return;
   Solver<N, W> s(*tables, args, smem);
   s.run(agent);
+}
+
+// Dispatch order for the next call on the same slots: agents sorted by the interior-point iterations they
+// needed this time, most expensive first (counting sort, one block).  A few agents need 100x the median
+// work (deep branch and bound); started last they leave the GPU almost idle while they finish, started
+// first they overlap with everybody else.  Hardness persists from one replanning step to the next, so last
+// step's count is the predictor.  Only the order of execution changes, never a result.
+__global__ void __launch_bounds__(1024) hdsm_order_kernel(const hdsm_result* __restrict__ res, int n, int32_t* __restrict__ order) {
+  __shared__ int hist[1024];
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x;
+  hist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) atomicAdd(&hist[1023 - min(max(res[i].iters, 0), 1023)], 1);
+  __syncthreads();
+  const int v = hist[tid];  // exclusive prefix sum over the 1024 bins
+  int incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if ((tid & 31) >= o) incl += t;
+  }
+  if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = wsum[tid];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, w, o);
+      if (tid >= o) w += t;
+    }
+    wsum[tid] = w;
+  }
+  __syncthreads();
+  hist[tid] = incl - v + (tid >= 32 ? wsum[(tid >> 5) - 1] : 0);
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) order[atomicAdd(&hist[1023 - min(max(res[i].iters, 0), 1023)], 1)] = i;
 }
 
 }  // namespace hdsm

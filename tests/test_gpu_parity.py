@@ -227,6 +227,35 @@ def test_chunked_host_pipeline_is_batch_invariant():
     pl.close()
 
 
+def test_longest_first_dispatch_changes_no_result():
+    """From the second call on a handle, blocks are dispatched in the order of the previous call's iteration
+    counts (hdsm_order_kernel).  Every output must stay bit-identical to the natural-order first call, on
+    the device path and on the chunked host path, also when the batch changes between calls."""
+    sw = sc.config2_circle(n_swarms=12, seed=47)
+    from oracle import c_oracle as co
+    batches = []
+    for step in range(6):
+        b = sw.make_batch()
+        if step >= 3:
+            batches.append(b.take(np.tile(np.arange(b.n), 20)))  # 2400 agents: above the ordering threshold
+        ref = co.solve_batch(b, max_nodes=64)
+        sw.advance(ref["traj"], ref["ctrl"], ref["res"]["status"] == 0)
+    first = []
+    for b in batches:  # a fresh handle per batch: natural order
+        pl = TrajectoryPlanner(b.params, max_agents=b.n, max_neighbours=10, max_nodes=64)
+        first.append(pl.solve_batch(b))
+        pl.close()
+    pl = TrajectoryPlanner(batches[0].params, max_agents=batches[0].n, max_neighbours=10, max_nodes=64)
+    for rnd in range(2):
+        for b, want in zip(batches, first):  # order comes from the previous (different) batch
+            got = pl.solve_batch(b)
+            for key in ("traj", "ctrl", "assign", "poly_used"):
+                assert np.array_equal(got[key], want[key]), (rnd, key)
+            assert np.array_equal(got["res"], want["res"])
+    assert pl.launch_count > 0
+    pl.close()
+
+
 def test_many_neighbours_config4_slice():
     """256-agent circle a few steps in: every agent sees 255 candidates, pruning keeps the rows small."""
     from oracle import c_oracle as co
