@@ -81,13 +81,14 @@ def ref_poly(grid, seed, n_it, res, conv, origin, use_new=False):
     return pts[:n].copy(), nrm[:n].copy(), out
 
 
-def c_poly(grid, seed, n_it, res, conv, origin):
-    """Same from the C restatement (cor_poly_octa)."""
+def c_poly(grid, seed, n_it, res, conv, origin, use_new=False):
+    """Same from the C restatement (cor_poly_octa, or cor_poly_octa_new if use_new)."""
     L = _lib("c")
-    L.cor_poly_octa.restype = C.c_int
+    fn = L.cor_poly_octa_new if use_new else L.cor_poly_octa
+    fn.restype = C.c_int
     grid, dim, seed, origin, pts, nrm = _poly(None, grid, seed, n_it, res, conv, origin)
     out = grid.copy()
-    n = L.cor_poly_octa(_p(seed), _p(out), _p(dim), C.c_int(n_it), C.c_double(res), C.c_int(conv), _p(origin), _p(pts), _p(nrm))
+    n = fn(_p(seed), _p(out), _p(dim), C.c_int(n_it), C.c_double(res), C.c_int(conv), _p(origin), _p(pts), _p(nrm))
     return pts[:n].copy(), nrm[:n].copy(), out
 
 

@@ -40,25 +40,35 @@ def random_grid(rng, kind, dx, dy, dz):
     return g
 
 
-def main(n_cases=64, seed=2026):
+def main(n_cases=112, n_original=64, seed=2026):
+    """Cases 0..63: GetPolyOcta3D; cases 64..111: GetPolyOcta3DNew (convex_decomp.cpp:590-1162), two thirds of
+    them with the seed squeezed between two occupied voxels as in agent_class.cpp:1385-1395."""
     assert oc.build_ref() and oc.have_ref(), "the reference checkout is needed to regenerate this fixture"
     rng = np.random.default_rng(seed)
     out = {}
     k = 0
     while k < n_cases:
+        use_new = k >= n_original
         dx, dy, dz = (int(v) for v in (rng.integers(12, 44), rng.integers(12, 44), rng.integers(8, 20)))
         g = random_grid(rng, k % 4, dx, dy, dz)
         free = np.argwhere(g < 100)
         if len(free) == 0:
             continue
         z, y, x = (int(v) for v in free[rng.integers(len(free))])
+        if use_new and k % 3 != 0:
+            ax = int(rng.integers(3))
+            for sgn in (-1, 1):
+                c = [x, y, z]
+                c[ax] += sgn
+                if 0 <= c[0] < dx and 0 <= c[1] < dy and 0 <= c[2] < dz:
+                    g[c[2], c[1], c[0]] = 100
         n_it = int(rng.choice([6, 17, 42, 42, 60, 90]))
         res = float(rng.choice([0.3, 0.2, 0.25]))
         conv = -int(rng.integers(1, 5))
         origin = np.round(rng.uniform(-20, 20, 3) / res) * res
-        pts, nrm, marked = oc.ref_poly(g, (x, y, z), n_it, res, conv, origin)
+        pts, nrm, marked = oc.ref_poly(g, (x, y, z), n_it, res, conv, origin, use_new=use_new)
         out[f"grid{k}"] = g
-        out[f"call{k}"] = np.array([x, y, z, n_it, conv], np.int32)
+        out[f"call{k}"] = np.array([x, y, z, n_it, conv, int(use_new)], np.int32)
         out[f"fp{k}"] = np.array([res, *origin])
         out[f"pts{k}"] = pts
         out[f"nrm{k}"] = nrm

@@ -19,26 +19,25 @@ from oracle import corridor as oc
 def golden_cases():
     z = np.load(os.path.join(GOLDEN, "corridor_ref.npz"))
     for k in range(int(z["n_cases"])):
-        x, y, zz, n_it, conv = (int(v) for v in z[f"call{k}"])
+        x, y, zz, n_it, conv, use_new = (int(v) for v in z[f"call{k}"])
         fp = z[f"fp{k}"]
-        yield dict(grid=z[f"grid{k}"], seed=(x, y, zz), n_it=n_it, conv=conv, res=float(fp[0]), origin=fp[1:4],
+        yield dict(grid=z[f"grid{k}"], seed=(x, y, zz), n_it=n_it, conv=conv, res=float(fp[0]), origin=fp[1:4], use_new=bool(use_new),
                    pts=z[f"pts{k}"], nrm=z[f"nrm{k}"], marks=z[f"marks{k}"])
 
 
 def test_c_restatement_matches_reference_golden():
     n = 0
     for c in golden_cases():
-        pts, nrm, marked = oc.c_poly(c["grid"], c["seed"], c["n_it"], c["res"], c["conv"], c["origin"])
+        pts, nrm, marked = oc.c_poly(c["grid"], c["seed"], c["n_it"], c["res"], c["conv"], c["origin"], use_new=c["use_new"])
         assert pts.shape == c["pts"].shape
         assert np.array_equal(pts, c["pts"]) and np.array_equal(nrm, c["nrm"])  # bit-exact, same order
         assert np.array_equal(np.flatnonzero(marked.ravel() == c["conv"]), c["marks"])
         n += 1
-    assert n >= 64
+    assert n >= 112
 
 
 def test_golden_planes_bound_the_marked_voxels():
-    """The six face planes (the last six rows) bound every marked voxel, and the seed voxel's centre
-    satisfies all rows.  (Chamfer rows may cut marked voxels in the reference: a chamfer is fitted to the
+    """The six face planes (the last six rows) bound every marked voxel and the seed voxel's centre.  (Chamfer rows may cut marked voxels in the reference: a chamfer is fitted to the
     staircase of layer ends, convex_decomp.cpp:217-301, not to the voxel corners.)"""
     for c in golden_cases():
         g = c["grid"]
@@ -49,7 +48,7 @@ def test_golden_planes_bound_the_marked_voxels():
         ctr = (np.stack([xc, yc, zc], 1) + 0.5) * c["res"] + c["origin"]
         assert (ctr @ c["nrm"][-6:].T - b[None, -6:]).max() <= -0.5 * c["res"] + 1e-9
         seed = (np.array(c["seed"]) + 0.5) * c["res"] + c["origin"]
-        assert (c["nrm"] @ seed - b).max() <= 1e-9
+        assert (c["nrm"][-6:] @ seed - b[-6:]).max() <= 1e-9
         assert 6 <= len(b) <= 18
 
 
@@ -62,7 +61,7 @@ def test_c_restatement_matches_reference_live():
     random_grid = mod.random_grid
     rng = np.random.default_rng(77)
     done = 0
-    while done < 300:
+    while done < 400:
         dx, dy, dz = (int(v) for v in (rng.integers(12, 70), rng.integers(12, 70), rng.integers(8, 24)))
         g = random_grid(rng, done % 4, dx, dy, dz)
         free = np.argwhere(g < 100)
@@ -71,9 +70,17 @@ def test_c_restatement_matches_reference_live():
         z, y, x = (int(v) for v in free[rng.integers(len(free))])
         n_it, res, conv = int(rng.choice([6, 17, 42, 60, 90])), float(rng.choice([0.3, 0.2])), -int(rng.integers(1, 5))
         origin = rng.uniform(-20, 20, 3)
-        a = oc.ref_poly(g, (x, y, z), n_it, res, conv, origin)
-        b = oc.c_poly(g, (x, y, z), n_it, res, conv, origin)
-        assert all(np.array_equal(u, v) for u, v in zip(a, b)), (done, (dx, dy, dz), (x, y, z), n_it)
+        use_new = done % 2 == 1  # GetPolyOcta3D and GetPolyOcta3DNew alternate; every fourth seed is squeezed
+        if done % 4 == 3:
+            ax = int(rng.integers(3))
+            for sgn in (-1, 1):
+                c = [x, y, z]
+                c[ax] += sgn
+                if 0 <= c[0] < dx and 0 <= c[1] < dy and 0 <= c[2] < dz:
+                    g[c[2], c[1], c[0]] = 100
+        a = oc.ref_poly(g, (x, y, z), n_it, res, conv, origin, use_new=use_new)
+        b = oc.c_poly(g, (x, y, z), n_it, res, conv, origin, use_new=use_new)
+        assert all(np.array_equal(u, v) for u, v in zip(a, b)), (done, use_new, (dx, dy, dz), (x, y, z), n_it)
         done += 1
 
 
@@ -117,7 +124,7 @@ def test_safe_corridor_polytopes_match_reference_per_seed(forest_batch):
     one polytope to the next (an occupied seed voxel is marked, i.e. freed, in the working copy)."""
     sw, cb = forest_batch
     out = oc.c_safe_corridor(cb)
-    checked = 0
+    checked = n_new = 0
     for i in range(cb.n):
         g = cb.grids[i].copy()
         g[g == cr.UNKNOWN] = cr.OCC
@@ -126,11 +133,20 @@ def test_safe_corridor_polytopes_match_reference_per_seed(forest_batch):
             if r == 0:
                 continue
             sv = np.round((out["seeds"][i, p] - cb.origins[i]) / cb.voxel - 0.5).astype(int)
-            pts, nrm, _ = oc.ref_poly(g, sv, cb.n_it, cb.voxel, -(p + 1), cb.origins[i])
+            squeezed = False  # agent_class.cpp:1385-1395 (IsOccupied is false outside the grid)
+            for ax in range(3):
+                lo, hi = sv.copy(), sv.copy()
+                lo[ax] -= 1
+                hi[ax] += 1
+                if lo[ax] >= 0 and hi[ax] < g.shape[2 - ax]:
+                    squeezed |= g[lo[2], lo[1], lo[0]] == cr.OCC and g[hi[2], hi[1], hi[0]] == cr.OCC
+            n_new += squeezed
+            assert bool(out["flags"][i] & oc.FLAG_SQUEEZED) >= squeezed
+            pts, nrm, _ = oc.ref_poly(g, sv, cb.n_it, cb.voxel, -(p + 1), cb.origins[i], use_new=squeezed)
             b = (pts[:, 0] * nrm[:, 0] + pts[:, 1] * nrm[:, 1]) + pts[:, 2] * nrm[:, 2]
             assert len(b) == r and np.array_equal(nrm, out["poly_A"][i, p, :r]) and np.array_equal(b, out["poly_b"][i, p, :r])
             checked += 1
-    assert checked >= 3 * cb.n
+    assert checked >= 3 * cb.n and n_new >= 1
 
 
 def test_safe_corridor_keeps_previous_polytopes(forest_batch):
