@@ -155,11 +155,12 @@ void hdsm_comm_destroy(hdsm_handle* h);
 
 /* ---- safe-corridor generation ----------------------------------
  * hdsm_corridor_batch replaces Agent::GenerateSafeCorridor (agent_class.cpp:1236-1447) together with
- * convex_decomp_lib::GetPolyOcta3D (convex_decomp_util/src/convex_decomp.cpp:5-376), the call at
+ * convex_decomp_lib::GetPolyOcta3D and GetPolyOcta3DNew (convex_decomp_util/src/convex_decomp.cpp:5-376,
+ * :590-1162 with FindCorners :378-561), the call at
  * agent_class.cpp:163, for a batch of agents; its outputs are exactly hdsm_solve_batch's poly_A / poly_b
  * / poly_rows inputs (the conversion at :1428-1437).  One warp per agent; see csrc/hdsm_corridor.cu. */
-#define HDSM_COR_SQUEEZED 1      /* a seed voxel was squeezed between occupied voxels: the reference switches to
-                                    GetPolyOcta3DNew there (:1385-1395), this library used GetPolyOcta3D */
+#define HDSM_COR_SQUEEZED 1      /* informational: a seed voxel was squeezed between occupied voxels and its polytope
+                                    was grown with GetPolyOcta3DNew, as the reference does (:1385-1395) */
 #define HDSM_COR_ROW_OVERFLOW 2  /* a polytope had more rows than max_rows_per_poly: generation stopped */
 #define HDSM_COR_SEED_OUTSIDE 4  /* a seed fell outside the voxel grid: generation stopped */
 #define HDSM_COR_LIST_OVERFLOW 8 /* internal cell list overflow (cannot happen for n_it_decomp <= 90) */
@@ -170,7 +171,7 @@ typedef struct hdsm_corridor_params {
   int32_t max_rows_per_poly; /* row stride Rmax of the polytope arrays, 18..32 (<= 12 chamfers + 6 faces) */
   int32_t n_traj;            /* points of the previous plan traj_curr_ (N + 1); 0 = none */
   int32_t max_path;          /* row stride of `path` */
-  int32_t reserved;
+  int32_t use_cvx_new;       /* use_cvx_new: 1 = always GetPolyOcta3DNew (:1383); 0 = only for squeezed seeds (:1385-1395) */
   double voxel_size;         /* VoxelGrid::GetVoxSize() */
 } hdsm_corridor_params;
 

@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's safe-corridor step, on top of the C ABI (include/hdsm.h).
 
 Reference: Agent::GenerateSafeCorridor (multi_agent_planner/src/agent_class.cpp:1236-1447) calling
-convex_decomp_lib::GetPolyOcta3D (convex_decomp_util/src/convex_decomp.cpp:5-376), SURVEY.md 8(f) row 1.
+convex_decomp_lib::GetPolyOcta3D / GetPolyOcta3DNew (convex_decomp_util/src/convex_decomp.cpp:5-376, :590-1162),
+SURVEY.md 8(f) row 1.
 `SafeCorridorGenerator.generate` is `hdsm_corridor_batch`; its outputs (`poly_A`, `poly_b`, `poly_rows`) are
 `hdsm_solve_batch`'s polytope inputs, `seeds` are the reference's `poly_seeds_`.
 
@@ -23,13 +24,13 @@ import numpy as np
 from . import _lib
 from .scenarios import Forest, plan_path
 
-FLAG_SQUEEZED, FLAG_ROW_OVERFLOW, FLAG_SEED_OUTSIDE, FLAG_LIST_OVERFLOW = 1, 2, 4, 8
+FLAG_SQUEEZED, FLAG_ROW_OVERFLOW, FLAG_SEED_OUTSIDE, FLAG_LIST_OVERFLOW = 1, 2, 4, 8  # SQUEEZED is informational
 OCC, FREE, UNKNOWN = 100, 0, -1
 
 
 class HdsmCorridorParams(C.Structure):
     _fields_ = [("poly_hor", C.c_int32), ("n_it_decomp", C.c_int32), ("max_rows_per_poly", C.c_int32),
-                ("n_traj", C.c_int32), ("max_path", C.c_int32), ("reserved", C.c_int32), ("voxel_size", C.c_double)]
+                ("n_traj", C.c_int32), ("max_path", C.c_int32), ("use_cvx_new", C.c_int32), ("voxel_size", C.c_double)]
 
 
 @dataclass
@@ -53,6 +54,7 @@ class CorridorBatch:
     prev_rows: Optional[np.ndarray] = None
     prev_seeds: Optional[np.ndarray] = None  # [n][P][3]
     prev_used: Optional[np.ndarray] = None   # [n][P] uint8
+    use_cvx_new: bool = False                # use_cvx_new_ (agent_class.cpp:1383)
 
     @property
     def n(self):
@@ -85,7 +87,7 @@ class SafeCorridorGenerator:
     """hdsm_corridor_create / hdsm_corridor_batch / hdsm_corridor_destroy."""
 
     def __init__(self, poly_hor, n_it_decomp, voxel_size, max_agents, max_grids, grid_stride, n_traj, max_path,
-                 rmax=18, device=0):
+                 rmax=18, device=0, use_cvx_new=False):
         self.L = _lib.load()
         L = self.L
         L.hdsm_corridor_create.restype = C.c_int
@@ -94,7 +96,7 @@ class SafeCorridorGenerator:
         L.hdsm_corridor_last_error.restype = C.c_char_p
         L.hdsm_corridor_launch_count.restype = C.c_int64
         L.hdsm_corridor_smem_bytes.restype = C.c_int
-        self.prm = HdsmCorridorParams(poly_hor, n_it_decomp, rmax, n_traj, max_path, 0, voxel_size)
+        self.prm = HdsmCorridorParams(poly_hor, n_it_decomp, rmax, n_traj, max_path, int(use_cvx_new), voxel_size)
         self.h = C.c_void_p()
         rc = L.hdsm_corridor_create(C.byref(self.prm), C.c_int(max_agents), C.c_int(max_grids), C.c_size_t(grid_stride),
                                     C.c_int(device), C.byref(self.h))

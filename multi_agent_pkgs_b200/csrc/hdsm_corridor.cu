@@ -3,6 +3,7 @@
 // Replaces, per agent and per replanning step:
 //   Agent::GenerateSafeCorridor            multi_agent_planner/src/agent_class.cpp:1236-1447
 //   convex_decomp_lib::GetPolyOcta3D       convex_decomp_util/src/convex_decomp.cpp:5-376
+//   convex_decomp_lib::GetPolyOcta3DNew    convex_decomp_util/src/convex_decomp.cpp:590-1162 (+ FindCorners :378-561)
 // and writes the polytope rows straight into the [n][P][Rmax][3] / [n][P][Rmax] / [n][P] arrays that
 // hdsm_solve_batch_device consumes (agent_class.cpp:1428-1437), so corridor -> optimisation needs no
 // host round trip.
@@ -72,8 +73,13 @@ struct Fixed {
   int lm[4], ext[4], app[4];
   int top_lo[4], top_hi[4], top_buf[4];  // final state of the four "top" lines of a layer (written once per layer)
   int valid;
-  unsigned short ring[4][kDq];    // in-face front lines, stored minus (advances so far) * step
-  unsigned short top[4][2][kDq];  // their part above the set, double buffered (a failed advance keeps the old one)
+  // GetPolyOcta3DNew: limits / edge slopes / line ends of a trial layer (FindCorners), chamfers just started
+  int lm2[4], sl2[4], ov_slope[4], ov_dir[4], ov_fixed[4], ov_steps[4];
+  int t_lo[4], t_hi[4], t_buf[4], t_ext[4], started[4], fin[4];
+  int soft, expand, trial_found;
+  unsigned short ring[4][kDq];     // in-face front lines, stored minus (advances so far) * step
+  unsigned short top[4][2][kDq];   // their part above the set, double buffered (a failed advance keeps the old one)
+  unsigned short ttop[4][2][kDq];  // the same for a trial layer, so that the layer under decision survives
 };
 
 __device__ __forceinline__ int coord(unsigned c, int a) { return (c >> (5 * a)) & 31; }
@@ -94,6 +100,7 @@ struct Agent {
   Fixed& S;
   unsigned* occ;          // [span^2] bit x of word (y - wlo) + span (z - wlo): occupied or outside the grid
   unsigned* mark;         // [span^2] voxels of the convex set being grown
+  unsigned* posb;         // [span^2] voxel value > 0 after OccupyUnknown, or outside the grid (GetVoxel(...) > 0, :187-209)
   unsigned short* cells;  // [6][cell_cap]
   unsigned short* layer;  // [layer_cap]
   double* rows;           // [P][Rmax][4]: (A0, A1, A2, b) of the polytopes decided so far
@@ -110,9 +117,10 @@ struct Agent {
     span = min(31, kCentre + g) - wlo + 1;
     occ = reinterpret_cast<unsigned*>(dyn);
     mark = occ + span * span;
-    cells = reinterpret_cast<unsigned short*>(mark + span * span);
+    posb = mark + span * span;
+    cells = reinterpret_cast<unsigned short*>(posb + span * span);
     layer = cells + 6 * a.cell_cap;
-    size_t off = (size_t)2 * span * span * sizeof(unsigned) + (size_t)(6 * a.cell_cap + a.layer_cap) * sizeof(unsigned short);
+    size_t off = (size_t)3 * span * span * sizeof(unsigned) + (size_t)(6 * a.cell_cap + a.layer_cap) * sizeof(unsigned short);
     off = (off + 7) & ~size_t(7);
     rows = reinterpret_cast<double*>(dyn + off);
     for (int k = 0; k < 3; ++k) dim[k] = a.dims[3 * agent + k], origin[k] = a.origins[3 * agent + k];
@@ -139,20 +147,236 @@ struct Agent {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned m = __ballot_sync(kFull, v[u] >= kOccVal || v[u] == kUnknown);
-        if (lane == 0 && r0 + u < span * span) occ[r0 + u] = m;
+        const unsigned m2 = __ballot_sync(kFull, v[u] > 0 || v[u] == kUnknown);
+        if (lane == 0 && r0 + u < span * span) occ[r0 + u] = m, posb[r0 + u] = m2;
       }
     }
     __syncwarp();
   }
 
-  // ---------------------------------------------------------------- GetPolyOcta3D
+  // ---------------------------------------------------------------- pieces shared by GetPolyOcta3D / ...New / FindCorners
+  struct Lines {  // warp-uniform result of growing the four front lines of one layer
+    unsigned TLO, THI, BUF, ext0, ext1, ext2, ext3;
+    int nlayer;
+    bool overflow;
+  };
+
+  __device__ __forceinline__ static int dir_axis(int f, int j) { return cAxA[f][j & 1]; }
+  __device__ __forceinline__ static int dir_sign(int f, int j) { return (j < 2 ? 1 : -1) * cAxS[f][j & 1]; }
+  __device__ __forceinline__ int along(unsigned c, int f, int j) const {  // cell . in-face direction j, grid coordinates
+    const int a = dir_axis(f, j);
+    return dir_sign(f, j) * (w0[a] + coord(c, a));
+  }
+
+  // limits of the next layer of face f: the face's own (lim4), pulled in where a chamfer is running (:70-91).
+  // ovmask bit j: the state of the edge in direction j comes from S.ov_* instead of the box (corners_list_tmp).
+  // Lanes 0..3 write out_lm[j]; when `keep` they also copy the edge state into S.et_* (corners_tmp), else only
+  // its slope into S.sl2.
+  __device__ void layer_limits(int f, const int* lim4, unsigned ovmask, int* out_lm, bool keep) {
+    if (lane < 4) {
+      const int j = lane, e = cEdge[f][j];
+      const bool ov = (ovmask >> j) & 1u;
+      int l = lim4[j];
+      const int sl = ov ? S.ov_slope[j] : S.edge_slope[e], dr = ov ? S.ov_dir[j] : S.edge_dir[e];
+      const int fx = ov ? S.ov_fixed[j] : S.edge_fixed[e], st = ov ? S.ov_steps[j] : S.edge_steps[e];
+      if (sl > 0) {
+        if (fx) {
+          if (dr != f) {
+            if (st >= sl) l -= 1;
+          } else {
+            l -= sl;
+          }
+        } else if (dr == f) {
+          l -= sl;
+        }
+      }
+      out_lm[j] = l;
+      if (keep) {
+        S.et_slope[j] = sl, S.et_dir[j] = dr, S.et_fixed[j] = fx, S.et_steps[j] = st;
+        for (int a = 0; a < 3; ++a) S.et_pos[j][a] = S.edge_pos[e][a];
+      } else {
+        S.sl2[j] = sl;
+      }
+    }
+    __syncwarp();
+  }
+
+  // first cell of the list whose outward neighbour is a free voxel in [1, dim - margin) within the limits
+  // (:97-117; margin 1 in GetPolyOcta3D, 0 in GetPolyOcta3DNew and FindCorners); -1 if none
+  __device__ int find_seed2d(const unsigned short* cf, int n, int f, const int* lm, int margin) const {
+    const int ostep = cOutSign[f] * (1 << (5 * cOutAxis[f]));
+    const int a0 = cAxA[f][0], s0 = cAxS[f][0], a1 = cAxA[f][1], s1 = cAxS[f][1];
+    const int lm0 = lm[0], lm1 = lm[1], lm2 = lm[2], lm3 = lm[3];
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      bool ok = false;
+      unsigned t = 0;
+      if (i < n) {
+        t = (unsigned)((int)(cf[i] & 0x7fffu) + ostep);
+        const int ta[3] = {w0[0] + coord(t, 0), w0[1] + coord(t, 1), w0[2] + coord(t, 2)};
+        ok = ta[0] >= 1 && ta[1] >= 1 && ta[2] >= 1 && ta[0] < dim[0] - margin && ta[1] < dim[1] - margin &&
+             ta[2] < dim[2] - margin && !bit(occ, t) && s0 * ta[a0] <= lm0 && s1 * ta[a1] <= lm1 && -s0 * ta[a0] <= lm2 &&
+             -s1 * ta[a1] <= lm3;
+      }
+      const unsigned m = __ballot_sync(kFull, ok);
+      if (m) return (int)__shfl_sync(kFull, t, __ffs(m) - 1);
+    }
+    return -1;
+  }
+
+  // In-layer growth from s2: the four front lines advance in turn until none can (:119-209).  A line that
+  // failed once can never advance later (its failing cell stays in it; limits, marks and occupancy do not
+  // change during the layer), so closed lines are skipped instead of re-tested.  All bookkeeping of the
+  // eight deques is warp-uniform register state: RLO / RHI and TLO / THI hold the [lo, hi) bounds of the ring
+  // and top lines (one byte per direction), CNT how often a ring line advanced (its cells are stored minus
+  // CNT * step, so an advance moves no data), ext0..3 the front of each top line the last time it was
+  // non-empty (border_limit_tmp), BUF the live buffer of each top line.  `tp` is the top-line storage
+  // ([4][2][kDq]); the cells of the layer are appended to `layer` when lay is set (border_real_tmp).
+  __device__ Lines grow_lines(int f, int s2, const int* lm, unsigned short (*tp)[2][kDq], bool lay) {
+    const unsigned lt = (1u << lane) - 1u;
+    const int ostep = cOutSign[f] * (1 << (5 * cOutAxis[f]));
+    if (lane < 4) S.ring[lane][kDqStart] = (unsigned short)s2, tp[lane][0][kDqStart] = (unsigned short)s2;
+    if (lay && lane == 0) layer[0] = (unsigned short)s2;
+    __syncwarp();
+    unsigned RLO = 0x20202020u, RHI = 0x21212121u;  // kDqStart = 32
+    Lines L{0x20202020u, 0x21212121u, 0u, (unsigned)s2, (unsigned)s2, (unsigned)s2, (unsigned)s2, 1, false};
+    unsigned CNT = 0, open = 15u;
+    const auto set_ext = [&](int q, unsigned v) {
+      L.ext0 = q == 0 ? v : L.ext0, L.ext1 = q == 1 ? v : L.ext1, L.ext2 = q == 2 ? v : L.ext2, L.ext3 = q == 3 ? v : L.ext3;
+    };
+#pragma unroll 1
+    for (int k = 0; open; ++k) {
+      const int j = k & 3;
+      if (!((open >> j) & 1u)) continue;
+      const int a = dir_axis(f, j), s = dir_sign(f, j);
+      const int step = s * (1 << (5 * a));
+      const int lo = get8(RLO, j), len = get8(RHI, j) - lo, limit = lm[j];
+      const int shift = get8(CNT, j) * step;
+      const unsigned short* ring = S.ring[j];
+      unsigned short* alt = tp[j][((L.BUF >> j) & 1u) ^ 1u];
+      int nr = 0;
+      bool ok = true, first_real = false, last_real = false;
+      unsigned front_real = 0;
+#pragma unroll 1
+      for (int base = 0; base < len; base += 32) {
+        const int i = base + lane;
+        bool fail = false, real = false;
+        unsigned t = 0;
+        if (i < len) {
+          const unsigned c = (unsigned)((int)ring[lo + i] + shift) & 0xffffu;
+          if (s * (w0[a] + coord(c, a) + s) > limit) {  // tested before packing: the moved coordinate may leave 0..31
+            fail = true;
+          } else {
+            t = (unsigned)((int)c + step);
+            if (bit(mark, (unsigned)((int)t - ostep))) {  // above the set: must be free
+              if (bit(occ, t)) fail = true;
+              else real = true;
+            }
+          }
+        }
+        const unsigned fm = __ballot_sync(kFull, fail), rm = __ballot_sync(kFull, real);
+        if (fm) {
+          ok = false;
+          break;
+        }
+        if (rm) {
+          if (nr == 0) front_real = __shfl_sync(kFull, t, __ffs(rm) - 1);
+          if (base == 0) first_real = rm & 1u;
+          if (base + 32 >= len) last_real = (rm >> ((len - 1) & 31)) & 1u;
+          const int pos = nr + __popc(rm & lt);
+          if (real) {
+            alt[kDqStart + pos] = (unsigned short)t;
+            if (lay && L.nlayer + pos < A.layer_cap) layer[L.nlayer + pos] = (unsigned short)t;
+          }
+          nr += __popc(rm);
+        }
+      }
+      if (!ok) {
+        open &= ~(1u << j);
+        continue;
+      }
+      if (lay && L.nlayer + nr > A.layer_cap) {
+        L.overflow = true;
+        break;
+      }
+      // the advance succeeded: ring j moves by one step, its top line is replaced, the neighbours grow
+      const unsigned first = (unsigned)((int)ring[lo] + shift + step) & 0xffffu;
+      const unsigned last = (unsigned)((int)ring[lo + len - 1] + shift + step) & 0xffffu;
+      CNT += 1u << (8 * j);
+      L.BUF ^= 1u << j;
+      L.nlayer += nr;
+      L.TLO = set8(L.TLO, j, kDqStart), L.THI = set8(L.THI, j, kDqStart + nr);
+      if (nr > 0) set_ext(j, front_real);
+      const int jb = (j + 3) & 3, ja = (j + 1) & 3;
+      const int sb = dir_sign(f, jb) * (1 << (5 * dir_axis(f, jb))), sa = dir_sign(f, ja) * (1 << (5 * dir_axis(f, ja)));
+      const int hb = get8(RHI, jb), la = get8(RLO, ja) - 1;
+      RHI += 1u << (8 * jb), RLO -= 1u << (8 * ja);
+      const bool push_tb = nr > 0 && first_real, push_ta = nr > 0 && last_real;
+      const int thb = get8(L.THI, jb), tla = get8(L.TLO, ja) - 1;
+      if (push_tb) {
+        if (thb == get8(L.TLO, jb)) set_ext(jb, first);  // the line was empty: its front changes
+        L.THI += 1u << (8 * jb);
+      }
+      if (push_ta) {
+        L.TLO -= 1u << (8 * ja);
+        set_ext(ja, last);
+      }
+      if (lane == 0) {
+        S.ring[jb][hb] = (unsigned short)((int)first - get8(CNT, jb) * sb);
+        S.ring[ja][la] = (unsigned short)((int)last - get8(CNT, ja) * sa);
+        if (push_tb) tp[jb][(L.BUF >> jb) & 1u][thb] = (unsigned short)first;
+        if (push_ta) tp[ja][(L.BUF >> ja) & 1u][tla] = (unsigned short)last;
+      }
+      __syncwarp();
+    }
+    return L;
+  }
+
+  // FindCorners (:378-561): trial of the next layer of face f on the lists cf[0..n) / limits lim4; S.fin[j] = the
+  // slope edge j would have afterwards (only "a chamfer starts" is evaluated); returns false when the face is
+  // closed or the trial layer would shrink to less than half the area.
+  __device__ bool find_corners(int f, const unsigned short* cf, int n, const int* lim4, unsigned ovmask) {
+    if (!S.alive[f]) return false;
+    layer_limits(f, lim4, ovmask, S.lm2, false);
+    if (lane < 4) S.fin[lane] = S.sl2[lane];
+    __syncwarp();
+    const int s2 = find_seed2d(cf, n, f, S.lm2, 0);
+    if (s2 < 0) return true;
+    const Lines T = grow_lines(f, s2, S.lm2, S.ttop, false);
+    bool ok = true;
+    {
+      const double area = fabs(fabs((double)S.lm2[0]) - fabs((double)S.lm2[2])) * fabs(fabs((double)S.lm2[1]) - fabs((double)S.lm2[3]));
+      const double narea = fabs(fabs((double)along(T.ext0, f, 0)) - fabs((double)along(T.ext2, f, 2))) *
+                           fabs(fabs((double)along(T.ext1, f, 1)) - fabs((double)along(T.ext3, f, 3)));
+      if (narea < area / 2) ok = false;
+    }
+    if (lane < 4) {
+      const int j = lane, lo = get8(T.TLO, j), hi = get8(T.THI, j);
+      if (hi > lo && S.sl2[j] == 0) {
+        const int dist = lim4[j] - along(S.ttop[j][(T.BUF >> j) & 1u][lo], f, j);
+        if (dist > 0) S.fin[j] = dist;
+      }
+    }
+    __syncwarp();
+    return ok;
+  }
+
+  // SideIsEmpty (:197-209) over a list: non-empty and every neighbour in direction `istep` holds a value <= 0
+  __device__ bool side_is_empty(const unsigned short* v, int n, int istep) const {
+    if (n == 0) return false;
+    bool any = false;
+    for (int i = lane; i < n; i += 32) any |= bit(posb, (unsigned)((int)(v[i] & 0x7fffu) + istep));
+    return !__any_sync(kFull, any);
+  }
+
+  // ---------------------------------------------------------------- GetPolyOcta3D / GetPolyOcta3DNew
   // Grows the convex set around `seed`; the hyperplanes are written as rows (A = normal, b = point . normal,
   // agent_class.cpp:1428-1437) of polytope slot `slot` in shared memory.  Returns their number, or -1 if a
-  // list outgrew its buffer.
-  __device__ int poly_octa(const int seed[3], int slot) {
+  // list outgrew its buffer.  use_new selects GetPolyOcta3DNew (convex_decomp.cpp:590-1162).
+  __device__ int poly_octa(const int seed[3], int slot, bool use_new) {
     const double res = A.prm.voxel_size;
     const unsigned lt = (1u << lane) - 1u;
-    stage_window(seed);
     const unsigned sc = pack(kCentre, kCentre, kCentre);
     if (lane == 0) {
       for (int e = 0; e < 12; ++e) S.edge_slope[e] = 0, S.edge_dir[e] = -1, S.edge_fixed[e] = 0, S.edge_steps[e] = 0;
@@ -173,185 +397,58 @@ struct Agent {
       if (!S.alive[f]) continue;
       const int oa = cOutAxis[f], os = cOutSign[f];
       const int ostep = os * (1 << (5 * oa));
-      // limits of this layer: the face's own, pulled in where a chamfer is running (:70-91)
-      if (lane < 4) {
-        const int j = lane, e = cEdge[f][j];
-        int l = S.lim[f][j];
-        const int sl = S.edge_slope[e], dr = S.edge_dir[e], fx = S.edge_fixed[e], st = S.edge_steps[e];
-        if (sl > 0) {
-          if (fx) {
-            if (dr != f) {
-              if (st >= sl) l -= 1;
-            } else {
-              l -= sl;
-            }
-          } else if (dr == f) {
-            l -= sl;
-          }
-        }
-        S.lm[j] = l;
-        S.et_slope[j] = sl, S.et_dir[j] = dr, S.et_fixed[j] = fx, S.et_steps[j] = st;
-        for (int a = 0; a < 3; ++a) S.et_pos[j][a] = S.edge_pos[e][a];
-      }
-      __syncwarp();
-      const int a0 = cAxA[f][0], s0 = cAxS[f][0], a1 = cAxA[f][1], s1 = cAxS[f][1];
-      const int lm0 = S.lm[0], lm1 = S.lm[1], lm2 = S.lm[2], lm3 = S.lm[3];
-
-      // first cell of the face whose outward neighbour is a free interior voxel within the limits (:97-117)
-      int s2 = -1;
-      {
-        const unsigned short* cf = cells + f * A.cell_cap;
-        const int n = S.ncell[f];
-#pragma unroll 1
-        for (int base = 0; base < n; base += 32) {
-          const int i = base + lane;
-          bool ok = false;
-          unsigned t = 0;
-          if (i < n) {
-            t = (unsigned)((int)cf[i] + ostep);
-            const int ta[3] = {w0[0] + coord(t, 0), w0[1] + coord(t, 1), w0[2] + coord(t, 2)};
-            ok = ta[0] >= 1 && ta[1] >= 1 && ta[2] >= 1 && ta[0] < dim[0] - 1 && ta[1] < dim[1] - 1 && ta[2] < dim[2] - 1 &&
-                 !bit(occ, t) && s0 * ta[a0] <= lm0 && s1 * ta[a1] <= lm1 && -s0 * ta[a0] <= lm2 && -s1 * ta[a1] <= lm3;
-          }
-          const unsigned m = __ballot_sync(kFull, ok);
-          if (m) {
-            s2 = (int)__shfl_sync(kFull, t, __ffs(m) - 1);
-            break;
-          }
-        }
-      }
+      layer_limits(f, S.lim[f], 0u, S.lm, true);
+      const int s2 = find_seed2d(cells + f * A.cell_cap, S.ncell[f], f, S.lm, use_new ? 0 : 1);
       if (s2 < 0) continue;
-
-      // In-layer growth from s2: the four front lines advance in turn until none can (:119-209).  A line that
-      // failed once can never advance later (its failing cell stays in it; limits, marks and occupancy do not
-      // change during the layer), so closed lines are skipped instead of re-tested.  All bookkeeping of the
-      // eight deques is warp-uniform register state: RLO / RHI and TLO / THI hold the [lo, hi) bounds of the ring
-      // and top lines (one byte per direction), CNT how often a ring line advanced (its cells are stored minus
-      // CNT * step, so an advance moves no data), ext0..3 the front of each top line the last time it was
-      // non-empty (border_limit_tmp), BUF the live buffer of each top line.
-      if (lane < 4) S.ring[lane][kDqStart] = (unsigned short)s2, S.top[lane][0][kDqStart] = (unsigned short)s2;
-      if (lane == 0) layer[0] = (unsigned short)s2;
-      __syncwarp();
-      unsigned RLO = 0x20202020u, RHI = 0x21212121u, TLO = 0x20202020u, THI = 0x21212121u;  // kDqStart = 32
-      unsigned ext0 = (unsigned)s2, ext1 = ext0, ext2 = ext0, ext3 = ext0;
-      unsigned CNT = 0, BUF = 0, open = 15u;
-      int nlayer = 1;
-      const auto set_ext = [&](int q, unsigned v) {
-        ext0 = q == 0 ? v : ext0, ext1 = q == 1 ? v : ext1, ext2 = q == 2 ? v : ext2, ext3 = q == 3 ? v : ext3;
-      };
-#pragma unroll 1
-      for (int k = 0; open; ++k) {
-        const int j = k & 3;
-        if (!((open >> j) & 1u)) continue;
-        const int a = cAxA[f][j & 1], s = (j < 2 ? 1 : -1) * cAxS[f][j & 1];
-        const int step = s * (1 << (5 * a));
-        const int lo = get8(RLO, j), len = get8(RHI, j) - lo, limit = S.lm[j];
-        const int shift = get8(CNT, j) * step;
-        const unsigned short* ring = S.ring[j];
-        unsigned short* alt = S.top[j][((BUF >> j) & 1u) ^ 1u];
-        int nr = 0;
-        bool ok = true, first_real = false, last_real = false;
-        unsigned front_real = 0;
-#pragma unroll 1
-        for (int base = 0; base < len; base += 32) {
-          const int i = base + lane;
-          bool fail = false, real = false;
-          unsigned t = 0;
-          if (i < len) {
-            const unsigned c = (unsigned)((int)ring[lo + i] + shift) & 0xffffu;
-            if (s * (w0[a] + coord(c, a) + s) > limit) {  // tested before packing: the moved coordinate may leave 0..31
-              fail = true;
-            } else {
-              t = (unsigned)((int)c + step);
-              if (bit(mark, (unsigned)((int)t - ostep))) {  // above the set: must be free
-                if (bit(occ, t)) fail = true;
-                else real = true;
-              }
-            }
-          }
-          const unsigned fm = __ballot_sync(kFull, fail), rm = __ballot_sync(kFull, real);
-          if (fm) {
-            ok = false;
-            break;
-          }
-          if (rm) {
-            if (nr == 0) front_real = __shfl_sync(kFull, t, __ffs(rm) - 1);
-            if (base == 0) first_real = rm & 1u;
-            if (base + 32 >= len) last_real = (rm >> ((len - 1) & 31)) & 1u;
-            const int pos = nr + __popc(rm & lt);
-            if (real && nlayer + pos < A.layer_cap) alt[kDqStart + pos] = (unsigned short)t, layer[nlayer + pos] = (unsigned short)t;
-            nr += __popc(rm);
-          }
-        }
-        if (!ok) {
-          open &= ~(1u << j);
-          continue;
-        }
-        if (nlayer + nr > A.layer_cap) {
-          overflow = true;
-          break;
-        }
-        // the advance succeeded: ring j moves by one step, its top line is replaced, the neighbours grow
-        const unsigned first = (unsigned)((int)ring[lo] + shift + step) & 0xffffu;
-        const unsigned last = (unsigned)((int)ring[lo + len - 1] + shift + step) & 0xffffu;
-        CNT += 1u << (8 * j);
-        BUF ^= 1u << j;
-        nlayer += nr;
-        TLO = set8(TLO, j, kDqStart), THI = set8(THI, j, kDqStart + nr);
-        if (nr > 0) set_ext(j, front_real);
-        const int jb = (j + 3) & 3, ja = (j + 1) & 3;
-        const int sb = (jb < 2 ? 1 : -1) * cAxS[f][jb & 1] * (1 << (5 * cAxA[f][jb & 1]));
-        const int sa = (ja < 2 ? 1 : -1) * cAxS[f][ja & 1] * (1 << (5 * cAxA[f][ja & 1]));
-        const int hb = get8(RHI, jb), la = get8(RLO, ja) - 1;
-        RHI += 1u << (8 * jb), RLO -= 1u << (8 * ja);
-        const bool push_tb = nr > 0 && first_real, push_ta = nr > 0 && last_real;
-        const int thb = get8(THI, jb), tla = get8(TLO, ja) - 1;
-        if (push_tb) {
-          if (thb == get8(TLO, jb)) set_ext(jb, first);  // the line was empty: its front changes
-          THI += 1u << (8 * jb);
-        }
-        if (push_ta) {
-          TLO -= 1u << (8 * ja);
-          set_ext(ja, last);
-        }
-        if (lane == 0) {
-          S.ring[jb][hb] = (unsigned short)((int)first - get8(CNT, jb) * sb);
-          S.ring[ja][la] = (unsigned short)((int)last - get8(CNT, ja) * sa);
-          if (push_tb) S.top[jb][(BUF >> jb) & 1u][thb] = (unsigned short)first;
-          if (push_ta) S.top[ja][(BUF >> ja) & 1u][tla] = (unsigned short)last;
-        }
-        __syncwarp();
+      const Lines L = grow_lines(f, s2, S.lm, S.top, true);
+      if (L.overflow) {
+        overflow = true;
+        break;
       }
-      if (overflow) break;
+      const int nlayer = L.nlayer;
       if (lane < 4) {
-        S.top_lo[lane] = get8(TLO, lane), S.top_hi[lane] = get8(THI, lane), S.top_buf[lane] = (BUF >> lane) & 1u;
-        S.ext[lane] = (int)(lane == 0 ? ext0 : lane == 1 ? ext1 : lane == 2 ? ext2 : ext3);
+        S.top_lo[lane] = get8(L.TLO, lane), S.top_hi[lane] = get8(L.THI, lane), S.top_buf[lane] = (L.BUF >> lane) & 1u;
+        S.ext[lane] = (int)(lane == 0 ? L.ext0 : lane == 1 ? L.ext1 : lane == 2 ? L.ext2 : L.ext3);
       }
       __syncwarp();
 
-      // chamfer bookkeeping of the four edges around the face (:217-301), lane 0
+      // chamfer bookkeeping of the four edges around the face (:217-301; New: :228-327), lane 0
       if (lane == 0) {
-        int valid = 1;
+        int valid = 1, soft = 1;
+        if (use_new) {  // a layer that shrinks the face to less than half its area is refused (:214-226)
+          const double area = fabs(fabs((double)S.lm[0]) - fabs((double)S.lm[2])) * fabs(fabs((double)S.lm[1]) - fabs((double)S.lm[3]));
+          const double narea = fabs(fabs((double)along(L.ext0, f, 0)) - fabs((double)along(L.ext2, f, 2))) *
+                               fabs(fabs((double)along(L.ext1, f, 1)) - fabs((double)along(L.ext3, f, 3)));
+          if (narea < area / 2) soft = 0;
+        }
+        for (int j = 0; j < 4; ++j) S.started[j] = 0;
         for (int j = 0; j < 4 && valid; ++j) {
+          bool stop = false;
           if (S.top_hi[j] > S.top_lo[j]) {
-            const int a = cAxA[f][j & 1], s = (j < 2 ? 1 : -1) * cAxS[f][j & 1];
             const unsigned fr = S.top[j][S.top_buf[j]][S.top_lo[j]];
-            const int dist = S.lim[f][j] - s * (w0[a] + coord(fr, a));
+            const int dist = S.lim[f][j] - along(fr, f, j);
             int sl = S.et_slope[j], dr = S.et_dir[j], fx = S.et_fixed[j], st = S.et_steps[j];
             if (sl == 0) {
               if (dist > 0) {
                 const int g = cAcross[f][j], ga = cOutAxis[g], gs = cOutSign[g];
-                for (int c = 0; c < 3; ++c) {  // cell*res - out*res/2 + out_across*res/2 + res/2, left to right (:226-241)
+                for (int c = 0; c < 3; ++c) {  // cell*res - out*res/2 + out_across*res/2 + res/2 [+ res/2], left to right
                   const double cell = (double)(w0[c] + coord(fr, c));
                   const double o1 = (double)(c == oa ? os : 0), o2 = (double)(c == ga ? gs : 0);
-                  S.et_pos[j][c] = add(add(sub(mul(cell, res), dvd(mul(o1, res), 2.0)), dvd(mul(o2, res), 2.0)), dvd(res, 2.0));
+                  double v = add(add(sub(mul(cell, res), dvd(mul(o1, res), 2.0)), dvd(mul(o2, res), 2.0)), dvd(res, 2.0));
+                  if (use_new) v = add(v, dvd(res, 2.0));  // (:243-251)
+                  S.et_pos[j][c] = v;
                 }
                 sl = dist, st = dist;
                 if (dist > 1) dr = f;
+                S.started[j] = dist > 1 ? 2 : 1;
+                if (use_new && it < 6) soft = 0;  // no chamfers during the first round (:264-266)
               }
             } else if (fx) {
               if (dr == f || dr == -1) {
-                if (dist > sl) valid = 0;
+                if (dist > sl) {
+                  if (use_new) stop = true;  // New leaves the loop here WITHOUT invalidating the layer (:269-271)
+                  else valid = 0;
+                }
               } else if (st >= sl) {
                 if (dist > 1) valid = 0;
                 else st = 1;
@@ -372,14 +469,100 @@ struct Agent {
                 else valid = 0;
               }
             }
-            S.et_slope[j] = sl, S.et_dir[j] = dr, S.et_fixed[j] = fx, S.et_steps[j] = st;
+            if (stop) break;  // corners_tmp[j..3] keep their copies
+            if (valid) S.et_slope[j] = sl, S.et_dir[j] = dr, S.et_fixed[j] = fx, S.et_steps[j] = st;
           }
         }
         S.valid = valid;
+        S.soft = soft;
         if (!valid) S.alive[f] = 0;
       }
       __syncwarp();
-      if (!S.valid) continue;
+      if (!S.valid || !S.soft) continue;
+
+      if (use_new) {
+        // is there anything to chamfer around?  (:330-366)
+        bool expand = true;
+        unsigned any_started = 0;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int stj = S.started[j];
+          if (!stj) continue;
+          any_started |= 1u << j;
+          const bool first = side_is_empty(S.top[j][S.top_buf[j]] + S.top_lo[j], S.top_hi[j] - S.top_lo[j], ostep);
+          bool second = true;
+          if (stj == 1) {  // cells of the face across that lie on its limit towards this face
+            const int g = cAcross[f][j], q = cAcrossLim[f][j], limg = S.lim[g][q];
+            const int gstep = cOutSign[g] * (1 << (5 * cOutAxis[g]));
+            const unsigned short* cg = cells + g * A.cell_cap;
+            bool have = false, pos = false;
+            for (int i = lane; i < S.ncell[g]; i += 32) {
+              const unsigned c = cg[i];
+              if (along(c, g, q) == limg) have = true, pos |= bit(posb, (unsigned)((int)c + gstep));
+            }
+            second = __any_sync(kFull, have) && !__any_sync(kFull, pos);
+          }
+          expand = !(first && second);
+          if (!expand) {
+            if (lane == 0) S.alive[f] = 0;
+            break;
+          }
+        }
+        __syncwarp();
+        if (expand && any_started) {
+          // trial: mark the layer, look one layer further on this face, unmark (:369-413)
+          for (int i = lane; i < nlayer; i += 32) {
+            const unsigned c = layer[i];
+            const unsigned b = 1u << (c & 31);
+            const unsigned old = atomicOr(&mark[word_of(c)], b);
+            if (old & b) layer[i] = (unsigned short)(c | 0x8000u);  // was already part of the set
+          }
+          if (lane < 4) {
+            S.t_ext[lane] = along((unsigned)S.ext[lane], f, lane);  // borders_tmp[idx].limits
+            S.ov_slope[lane] = S.et_slope[lane], S.ov_dir[lane] = S.et_dir[lane], S.ov_fixed[lane] = S.et_fixed[lane];
+            S.ov_steps[lane] = S.et_steps[lane];
+          }
+          __syncwarp();
+          unsigned ovmask = 0;  // corners_list_tmp takes corners_tmp only where no chamfer has just started
+          for (int j = 0; j < 4; ++j)
+            if (!S.started[j]) ovmask |= 1u << j;
+          const bool vfinal = find_corners(f, layer, nlayer, S.t_ext, ovmask);
+          int fin[4];
+          for (int j = 0; j < 4; ++j) fin[j] = S.fin[j];
+          __syncwarp();
+          for (int i = lane; i < nlayer; i += 32) {
+            const unsigned c = layer[i];
+            if (c & 0x8000u) layer[i] = (unsigned short)(c & 0x7fffu);
+            else atomicAnd(&mark[word_of(c)], ~(1u << (c & 31)));
+          }
+          __syncwarp();
+          if (vfinal) {
+            for (int j = 0; j < 4; ++j)
+              if (S.started[j] == 2 && fin[j] < S.et_slope[j]) {
+                expand = false;
+                if (lane == 0) S.alive[f] = 0;
+                break;
+              }
+            if (expand) {
+#pragma unroll 1
+              for (int j = 0; j < 4; ++j) {
+                if (S.started[j] != 1) continue;
+                const int g = cAcross[f][j];
+                // borders_tmp[g] equals borders[g] (only face f was replaced); corners_list is the box's own
+                const bool v2 = find_corners(g, cells + g * A.cell_cap, S.ncell[g], S.lim[g], 0u);
+                const int fin2 = S.fin[cAcrossLim[f][j]];
+                __syncwarp();
+                if (v2 && fin2 == 0 && fin[j] == 0) {
+                  expand = false;
+                  break;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if (!expand) continue;
+      }
 
       // commit the layer (:311-339)
       if (nlayer > A.cell_cap) {
@@ -388,15 +571,14 @@ struct Agent {
       }
       if (lane == 0) {
         for (int j = 0; j < 4; ++j) {
-          const int a = cAxA[f][j & 1], s = (j < 2 ? 1 : -1) * cAxS[f][j & 1];
           const int e = cEdge[f][j];
-          S.lim[f][j] = s * (w0[a] + coord((unsigned)S.ext[j], a));
+          S.lim[f][j] = along((unsigned)S.ext[j], f, j);
           S.edge_slope[e] = S.et_slope[j], S.edge_dir[e] = S.et_dir[j], S.edge_fixed[e] = S.et_fixed[j], S.edge_steps[e] = S.et_steps[j];
           for (int c = 0; c < 3; ++c) S.edge_pos[e][c] = S.et_pos[j][c];
           int app = 0;
           if (S.et_slope[j] == 0 && S.top_hi[j] > S.top_lo[j]) {
             const unsigned fr = S.top[j][S.top_buf[j]][S.top_lo[j]];
-            if (S.lim[f][j] - s * (w0[a] + coord(fr, a)) == 0) {
+            if (S.lim[f][j] - along(fr, f, j) == 0) {
               app = 1;  // the face across gains this line of cells and one unit of limit
               S.lim[cAcross[f][j]][cAcrossLim[f][j]] += 1;
             }
@@ -581,17 +763,20 @@ struct Agent {
         flags |= HDSM_COR_SEED_OUTSIDE;
         break;
       }
-      const int np = poly_octa(sv, n_poly);
-      if (np < 0) {
-        flags |= HDSM_COR_LIST_OVERFLOW;
-        break;
-      }
-      // squeezed seed: the reference switches to GetPolyOcta3DNew here (:1385-1395); IsOccupied is false
-      // outside the grid, the window bitmap says "occupied" there, hence the explicit range test
+      stage_window(sv);
+      // squeezed seed: the reference switches to GetPolyOcta3DNew (:1385-1395); IsOccupied is false outside the
+      // grid, the window bitmap says "occupied" there, hence the explicit range test
+      bool squeezed = false;
       for (int c = 0; c < 3; ++c) {
         const bool in_lo = sv[c] - 1 >= 0, in_hi = sv[c] + 1 < dim[c];
         const unsigned ctr = pack(kCentre, kCentre, kCentre);
-        if (in_lo && in_hi && bit(occ, ctr - (1u << (5 * c))) && bit(occ, ctr + (1u << (5 * c)))) flags |= HDSM_COR_SQUEEZED;
+        if (in_lo && in_hi && bit(occ, ctr - (1u << (5 * c))) && bit(occ, ctr + (1u << (5 * c)))) squeezed = true;
+      }
+      if (squeezed) flags |= HDSM_COR_SQUEEZED;
+      const int np = poly_octa(sv, n_poly, squeezed || A.prm.use_cvx_new != 0);
+      if (np < 0) {
+        flags |= HDSM_COR_LIST_OVERFLOW;
+        break;
       }
       if (np > R) {
         flags |= HDSM_COR_ROW_OVERFLOW;
@@ -618,7 +803,7 @@ __global__ void __launch_bounds__(32) corridor_kernel(const Args args) {
 inline size_t smem_bytes(const hdsm_corridor_params& p, int cell_cap, int layer_cap) {
   const int g = (p.n_it_decomp + 5) / 6 + 1, wlo = kCentre - g > 0 ? kCentre - g : 0;
   const int span = (kCentre + g < 31 ? kCentre + g : 31) - wlo + 1;
-  size_t dyn = (size_t)2 * span * span * sizeof(unsigned) + (size_t)(6 * cell_cap + layer_cap) * sizeof(unsigned short);
+  size_t dyn = (size_t)3 * span * span * sizeof(unsigned) + (size_t)(6 * cell_cap + layer_cap) * sizeof(unsigned short);
   dyn = (dyn + 7) & ~size_t(7);
   dyn += (size_t)p.poly_hor * p.max_rows_per_poly * 4 * sizeof(double);
   return ((sizeof(Fixed) + 15) & ~size_t(15)) + dyn;

@@ -99,7 +99,7 @@ def max_threads():
 def c_safe_corridor(cb, n_threads=None):
     """GenerateSafeCorridor for a CorridorBatch (multi_agent_pkgs_b200.corridor.CorridorBatch layout)."""
     L = _lib("c")
-    P = CorParams(cb.poly_hor, cb.n_it, cb.rmax, cb.prev_traj.shape[1], cb.path.shape[1], 0, cb.voxel)
+    P = CorParams(cb.poly_hor, cb.n_it, cb.rmax, cb.prev_traj.shape[1], cb.path.shape[1], int(getattr(cb, "use_cvx_new", False)), cb.voxel)
     n, PH, R = cb.n, cb.poly_hor, cb.rmax
     out = dict(poly_A=np.zeros((n, PH, R, 3)), poly_b=np.zeros((n, PH, R)), poly_rows=np.zeros((n, PH), np.int32),
                seeds=np.zeros((n, PH, 3)), flags=np.zeros(n, np.int32))

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 def _gen(cb):
     G = cb.grids.shape[0]
     return cr.SafeCorridorGenerator(cb.poly_hor, cb.n_it, cb.voxel, cb.n, G, int(cb.grids[0].size), cb.prev_traj.shape[1],
-                                    cb.path.shape[1], rmax=cb.rmax)
+                                    cb.path.shape[1], rmax=cb.rmax, use_cvx_new=cb.use_cvx_new)
 
 
 def _assert_equal(out, ref):
@@ -28,12 +28,13 @@ def _assert_equal(out, ref):
 
 
 def test_single_polytopes_match_reference_golden():
-    """One GetPolyOcta3D per agent, seeded at the golden seed voxel (poly_hor = 1, a 1 m path)."""
+    """One GetPolyOcta3D / GetPolyOcta3DNew per agent, seeded at the golden seed voxel (poly_hor = 1, a 0.7 m
+    path).  The New cases run with use_cvx_new = 1, like the reference with that parameter set."""
     by_cfg = {}
     for c in golden_cases():
-        by_cfg.setdefault((c["n_it"], c["res"]), []).append(c)
-    checked = 0
-    for (n_it, res), cases in by_cfg.items():
+        by_cfg.setdefault((c["n_it"], c["res"], c["use_new"]), []).append(c)
+    checked = n_new = 0
+    for (n_it, res, use_new), cases in by_cfg.items():
         stride = max(c["grid"].size for c in cases)
         n = len(cases)
         grids = np.zeros((n, stride), np.int8)
@@ -46,7 +47,7 @@ def test_single_polytopes_match_reference_golden():
             origins[i] = c["origin"]
             pos[i] = (np.array(c["seed"]) + 0.5) * res + c["origin"]
             path[i, 0] = pos[i] + np.array([0.7, 0.0, 0.0])
-        gen = cr.SafeCorridorGenerator(1, n_it, res, n, n, stride, 0, 2, rmax=18)
+        gen = cr.SafeCorridorGenerator(1, n_it, res, n, n, stride, 0, 2, rmax=18, use_cvx_new=use_new)
         cb = cr.CorridorBatch(1, n_it, 18, res, grids[:, None, None, :], None, dims, origins, pos, path, n_path,
                               np.zeros((n, 0, 3)))
         out = gen.generate(cb)
@@ -58,7 +59,8 @@ def test_single_polytopes_match_reference_golden():
             b = (c["pts"][:, 0] * c["nrm"][:, 0] + c["pts"][:, 1] * c["nrm"][:, 1]) + c["pts"][:, 2] * c["nrm"][:, 2]
             assert np.array_equal(out["poly_b"][i, 0, :r], b)
             checked += 1
-    assert checked >= 64
+            n_new += use_new
+    assert checked >= 112 and n_new >= 48
 
 
 @pytest.mark.parametrize("n_it", [42, 60])
@@ -85,6 +87,23 @@ def test_scenario_batch_matches_c_restatement(n_it):
     _assert_equal(out2, ref2)
     assert (out2["poly_rows"] > 0).any()
     gen.close()
+
+
+def test_squeezed_seeds_take_the_new_method():
+    """Agents pulled next to the columns: squeezed seeds (flag bit 0) are grown with GetPolyOcta3DNew by the
+    kernel and by the checker alike; also the all-New mode (use_cvx_new = 1)."""
+    sw = sc.config2_circle(n_swarms=24)
+    for i in range(sw.n):
+        sw.state[i, :2] = sw.world.push_free(0.45 * sw.state[i, :2] + 0.55 * sw.goal[i, :2], 0.3)
+    for use_new in (False, True):
+        cb = cr.corridor_batch(sw)
+        cb.use_cvx_new = use_new
+        gen = _gen(cb)
+        out = gen.generate(cb)
+        gen.close()
+        _assert_equal(out, oc.c_safe_corridor(cb))
+        assert (out["flags"] & cr.FLAG_SQUEEZED).any()
+        assert (out["flags"] & ~cr.FLAG_SQUEEZED == 0).all()
 
 
 def test_shared_grid_and_empty_map():
