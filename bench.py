@@ -29,8 +29,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout; the contract is ONE json line there
+# The contract is ONE json line on stdout, but libraries write there too (NCCL prints its version banner to
+# stdout at every debug level above NONE).  File descriptor 1 is therefore pointed at stderr for the whole
+# run and the result line is written to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 from multi_agent_pkgs_b200 import scenarios as sc  # noqa: E402
 
@@ -170,7 +177,7 @@ def run_reference(args, rank, world):
                                        f"C port of the oracle on all host threads, Gurobi not available"},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -402,7 +409,7 @@ def run_ours(args, rank, world, local_rank):
                     "max_kkt_residual": kkt, "ipm_iters_per_solve": iters / max(1, stat.sum()),
                     "qp_relaxations_per_solve": nodes / max(1, stat.sum())},
                 "smem_bytes_per_block": pl.smem_bytes, "corridor": corridor}
-        print(json.dumps(line), flush=True)
+        emit(line)
     pl.close()
     if dist:
         dist.barrier()

@@ -10,4 +10,4 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 line, gbs = bench.corridor_measure(n, steps)
 line["achieved_gbs"] = gbs
-print(json.dumps(line))
+bench.emit(line)
