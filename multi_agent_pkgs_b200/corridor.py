@@ -263,3 +263,35 @@ def corridor_batch(sw, poly_hor=None, n_it=42, rmax=18, voxel=0.3, max_path=16, 
     prev_traj = np.zeros((n, N + 1, 3))
     return CorridorBatch(P, n_it, rmax, voxel, np.stack(grids), None, dims, origins,
                          np.ascontiguousarray(sw.state[ids, :3]), path, n_path, prev_traj)
+
+
+class CorridorLoop:
+    """Closed loop of the two replaced calls for a scenarios.Swarm (agent_class.cpp:163-174): every step the
+    corridor generator gets the previous step's polytopes, seeds, `poly_used_idx_` and plan, and its rows replace
+    the synthetic polytopes of `Swarm.make_batch`.  `generate(cb)` is SafeCorridorGenerator.generate or a checker
+    with the same signature."""
+
+    def __init__(self, sw, n_it=42, max_path=16):
+        self.sw, self.n_it, self.max_path = sw, n_it, max_path
+        self.prev_out = None
+        self.prev_used = None
+
+    def corridor_inputs(self) -> CorridorBatch:
+        cb = corridor_batch(self.sw, n_it=self.n_it, max_path=self.max_path)
+        if self.prev_out is not None:
+            traj = self.sw.traj[:, :, :3] if self.sw.traj is not None else cb.prev_traj
+            cb.with_previous(self.prev_out, self.prev_used, np.ascontiguousarray(traj))
+        return cb
+
+    def solver_inputs(self, out):
+        b = self.sw.make_batch()
+        b.poly_A, b.poly_b, b.poly_rows = out["poly_A"].copy(), out["poly_b"].copy(), out["poly_rows"].copy()
+        return b
+
+    def advance(self, out, solved, ok):
+        """`solved`: dict(traj, ctrl, poly_used) of this step; failed agents keep poly_used_idx_ (:997-1019)."""
+        used = np.ascontiguousarray(solved["poly_used"], np.uint8).copy()
+        if self.prev_used is not None:
+            used[~ok] = self.prev_used[~ok]
+        self.prev_out, self.prev_used = out, used
+        self.sw.advance(solved["traj"], solved["ctrl"], ok)

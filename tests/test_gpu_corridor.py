@@ -147,3 +147,47 @@ def test_corridor_feeds_the_optimisation():
     assert ok.mean() > 0.8
     gap = np.abs(res["res"]["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1.0, np.abs(ref["res"]["obj"][ok]))
     assert gap.max() <= 1e-6
+
+
+def test_closed_loop_corridor_then_optimisation():
+    """Ten replanning steps of 20 agents through both replaced calls on the GPU; every step the corridor rows
+    must equal the checker's bit for bit (kept polytopes, used flags and previous plans now come from real
+    solves) and the optimisation must agree with the C port on those rows."""
+    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
+    from oracle import c_oracle as co
+    sw = sc.config2_circle(n_swarms=2, seed=9)
+    for i in range(sw.n):
+        sw.state[i, :2] = sw.world.push_free(0.6 * sw.state[i, :2] + 0.4 * sw.goal[i, :2], 0.3)
+    loop = cr.CorridorLoop(sw)
+    cb = loop.corridor_inputs()
+    gen = _gen(cb)
+    pl = TrajectoryPlanner(sw.params, max_agents=sw.n, max_neighbours=10, max_nodes=5000)  # exact search on both sides
+    kept = solved_ok = 0
+    for step in range(10):
+        cb = loop.corridor_inputs()
+        out = gen.generate(cb)
+        _assert_equal(out, oc.c_safe_corridor(cb))
+        assert (out["flags"] & ~cr.FLAG_SQUEEZED == 0).all() and (out["poly_rows"][:, 0] >= 6).all()
+        if cb.prev_n is not None:  # kept polytopes come first, unchanged
+            for i in range(cb.n):
+                keep = [p for p in range(cb.prev_n[i]) if cb.prev_used[i, p]]
+                last = cb.prev_n[i] - 1
+                r = cb.prev_rows[i, last]
+                inside = (cb.prev_A[i, last, :r] @ cb.prev_traj[i].T - cb.prev_b[i, last, :r, None]).max() <= 0
+                src = [last] if inside else keep
+                for slot, p in enumerate(src):
+                    assert np.array_equal(out["poly_A"][i, slot], cb.prev_A[i, p]) and np.array_equal(out["seeds"][i, slot], cb.prev_seeds[i, p])
+                    kept += 1
+        b = loop.solver_inputs(out)
+        res = pl.solve_batch(b)
+        ref = co.solve_batch(b, max_nodes=5000)
+        assert np.array_equal(res["res"]["status"], ref["res"]["status"])
+        ok = ref["res"]["status"] == 0
+        if ok.any():
+            gap = np.abs(res["res"]["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1.0, np.abs(ref["res"]["obj"][ok]))
+            assert gap.max() <= 1e-6
+        solved_ok += int(ok.sum())
+        loop.advance(out, res, ok)
+    assert kept > 50 and solved_ok > 100
+    gen.close()
+    pl.close()
