@@ -25,7 +25,7 @@ constexpr double kContainTol = 1e-7;   // segment-in-polytope test on a node opt
 constexpr double kPruneRel = 1e-7;     // bound pruning, relative
 constexpr double kStepFrac = 0.97;
 constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still inside the 1e-6 KKT target
-constexpr int kStackCap = 48;          // >= 1 + N * ceil(log2 P) open nodes
+constexpr int kStackCap = 96;          // >= 1 + N * (P - 1) open nodes (a branching can push up to P sets)
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef HDSM_MINBLOCKS
 #define HDSM_MINBLOCKS 4  // resident 4-warp blocks per SM the register allocation aims for (128 registers; 5 spills badly)
@@ -1248,24 +1248,49 @@ struct Solver {
           order[y] = order[y - 1], order[y - 1] = to;
         }
       if (no <= 1) continue;
+      // Split the candidates of step bk, ordered by violation, in two halves (least violated explored
+      // first).  A half whose hull still contains the segment of the node optimum would be solved to the very
+      // same point and then split again on the same step: that solve is skipped, the half is split right away.
+      int wx0[2 * kMaxP], wx1[2 * kMaxP], nw = 0;
       const int h = (no + 1) / 2;
-      unsigned lo_m = 0, hi_m = 0;
-      for (int x = 0; x < no; ++x) {
-        if (x < h) lo_m |= 1u << order[x];
-        else hi_m |= 1u << order[x];
+      wx0[nw] = 0, wx1[nw++] = h;  // last in, first out: the upper half is pushed on the search stack first
+      wx0[nw] = h, wx1[nw++] = no;
+      bool full = false;
+      const double sax = p[3 * bk], say = p[3 * bk + 1], saz = p[3 * bk + 2];
+      const double sbx = p[3 * bk + 3], sby = p[3 * bk + 4], sbz = p[3 * bk + 5];
+#pragma unroll 1
+      while (nw > 0) {
+        const int x0 = wx0[--nw], x1 = wx1[nw];
+        unsigned m = 0;
+        for (int x = x0; x < x1; ++x) m |= 1u << order[x];
+        bool contains = false;
+        if (x1 - x0 > 1) {
+          bool out = false;
+          for (int i = lane; i < A.P * A.rmax; i += 32) {
+            double n[3], b;
+            if (hull_row(m, i, n, b))
+              out |= fmax(n[0] * sax + n[1] * say + n[2] * saz, n[0] * sbx + n[1] * sby + n[2] * sbz) - b > kContainTol;
+          }
+          contains = !__any_sync(kFull, out);
+        }
+        if (contains) {
+          const int hh = (x1 - x0 + 1) / 2;
+          wx0[nw] = x0, wx1[nw++] = x0 + hh;
+          wx0[nw] = x0 + hh, wx1[nw++] = x1;
+          continue;
+        }
+        if (top + 1 > kStackCap) {
+          full = true;
+          break;
+        }
+        if (lane < 16) stack[top * 16 + lane] = lane == bk ? (unsigned char)m : cur[lane];
+        ++top;
+        __syncwarp();
       }
-      if (top + 2 > kStackCap) {
+      if (full) {
         exhausted = false;
         top = 0;
-        continue;
       }
-      if (lane < 16) {
-        const unsigned char c = cur[lane];
-        stack[top * 16 + lane] = lane == bk ? (unsigned char)hi_m : c;
-        stack[(top + 1) * 16 + lane] = lane == bk ? (unsigned char)lo_m : c;  // least violated half first
-      }
-      top += 2;
-      __syncwarp();
     }
     if (wid != 0) return;
     if (st < 0) {

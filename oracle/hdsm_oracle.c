@@ -882,20 +882,40 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
       continue;
     }
     if (no <= 1) continue;
-    int h = (no + 1) / 2;
-    unsigned lo_m = 0, hi_m = 0;
-    for (int x = 0; x < no; x++) {
-      if (x < h) lo_m |= 1u << order[x];
-      else hi_m |= 1u << order[x];
+    /* Split the candidates of step bk, ordered by violation, in two halves (least violated explored first).
+     * A half whose hull still contains the segment of the node optimum would be solved to the very same point
+     * and then split again on the same step: that solve is skipped and the half is split right away. */
+    struct { int x0, x1; } work[2 * MAXP];
+    int nw = 0, overflow = 0;
+    const int h = (no + 1) / 2;
+    work[nw].x0 = 0, work[nw++].x1 = h;   /* processed last-in first-out: the upper half is pushed first */
+    work[nw].x0 = h, work[nw++].x1 = no;
+    while (nw > 0 && !overflow) {
+      const int x0 = work[--nw].x0, x1 = work[nw].x1;
+      unsigned m = 0;
+      for (int x = x0; x < x1; x++) m |= 1u << order[x];
+      int contains = 0;
+      if (x1 - x0 > 1) {
+        set_rows(pA, pb_, prow_n, rmax, m, &rs);
+        contains = seg_violation(&rs.A[0][0], rs.b, rs.n, p[bk], p[bk + 1]) <= 1e-7; /* the coverage tolerance */
+      }
+      if (contains) {
+        const int hh = (x1 - x0 + 1) / 2;
+        work[nw].x0 = x0, work[nw++].x1 = x0 + hh;
+        work[nw].x0 = x0 + hh, work[nw++].x1 = x1;
+        continue;
+      }
+      if (top + 1 > cap) {
+        overflow = 1;
+        break;
+      }
+      memcpy(stack[top], sets, sizeof(sets));
+      stack[top++][bk] = m;
     }
-    if (top + 2 > cap) {
+    if (overflow) {
       exhausted = 0;
       break;
     }
-    memcpy(stack[top], sets, sizeof(sets));
-    stack[top++][bk] = hi_m;
-    memcpy(stack[top], sets, sizeof(sets));
-    stack[top++][bk] = lo_m; /* least-violated half explored first */
   }
   res->nodes = nodes, res->iters = iters, res->rows = maxrows;
   if (best < INFINITY) {
