@@ -27,6 +27,7 @@ constexpr double kStepFrac = 0.97;
 constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still inside the 1e-6 KKT target
 constexpr int kStackCap = 96;          // >= 1 + N * (P - 1) open nodes (a branching can push up to P sets)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kCutoff = 6;             // internal QP status: the dual bound reached the incumbent, solve abandoned
 #ifndef HDSM_MINBLOCKS
 #define HDSM_MINBLOCKS 4  // resident 4-warp blocks per SM the register allocation aims for (128 registers; 5 spills badly)
 #endif
@@ -767,7 +768,7 @@ struct Solver {
 
   __device__ QpOut solve_qp() {
     QpOut out{HDSM_MAX_ITER, 0, INFINITY, INFINITY};
-    const double tol = A.tol, c0v = s0[9];
+    const double tol = A.tol, c0v = s0[9], cutoff = s0[10];
     init_groups();
     init_pairs();
     int nrows = 0;
@@ -895,6 +896,7 @@ struct Solver {
       hg = tpr_sum(hg), fi = tpr_sum(fi), ti = tpr_sum(ti);
       if (rowact) hg += g[row];
       const bool owner = rowact && part == 0;
+      if (owner && cutoff < INFINITY) dwc[row] = g[row] + fi;  // v = g + C'lam for the dual bound below (dwc is free here)
       const double wi = owner ? w[row] : 0.0;
       double r4[4] = {owner ? fabs(hg + fi) : 0.0, owner ? fabs(fi) : 0.0, wi * fi, owner ? wi * (hg + g[row]) : 0.0};
       reduce4<3>(r4);
@@ -907,6 +909,23 @@ struct Solver {
         out.status = HDSM_OPTIMAL, out.iters = it, out.obj = obj;
         out.kkt = fmax(rdmax / (1 + gmax), fmax(rcmax, mu / fmax(1.0, fabs(obj))));  // scaled as in SURVEY 8(d)
         return out;
+      }
+      // Lagrangian dual bound (weak duality, any lam >= 0): min_w L(w, lam) = c0 - 1/2 v'Hw^-1 v - d'lam with
+      // v = g + C'lam (published in dwc by the reduction above) and d'lam = lam'(d - Cw) + w'C'lam.  Once it
+      // reaches the incumbent this relaxation cannot improve it: the solve is abandoned.
+      if (cutoff < INFINITY) {
+        double q4[4] = {0, 0, 0, 0};
+        if (owner) {
+          double hv = 0;
+#pragma unroll
+          for (int c = 0; c < NZ; ++c) hv += T.HwInv[ax][rr][c] * dwc[ax * NZ + c];
+          q4[0] = dwc[row] * hv;
+        }
+        reduce4<0>(q4);
+        if (c0v - 0.5 * q4[0] - (lamsl + wf) >= cutoff) {
+          out.status = kCutoff, out.iters = it;
+          return out;
+        }
       }
       if (mtot > 0 && lamsum > 0 && it >= 3) {  // Farkas certificate: lam >= 0, C'lam ~ 0, d'lam < 0
         const double dlam = (lamsl + wf) / lamsum;
@@ -1181,7 +1200,10 @@ struct Solver {
             }
           }
         }
-        if (lane == 0) ctl[0] = cmd;
+        if (lane == 0) {
+          ctl[0] = cmd;
+          s0[10] = best < INFINITY ? best - kPruneRel * fmax(1.0, fabs(best)) : INFINITY;  // cutoff of the dual bound
+        }
       }
       bsync();
       if (ctl[0] == 0) break;
@@ -1191,7 +1213,7 @@ struct Solver {
       ++nodes;
       iters += q.iters;
       if (q.status != HDSM_OPTIMAL) {
-        if (q.status != HDSM_INFEASIBLE) fail = q.status;
+        if (q.status != HDSM_INFEASIBLE && q.status != kCutoff) fail = q.status;
         continue;
       }
       if (q.obj >= best - kPruneRel * fmax(1.0, fabs(best))) continue;

@@ -37,7 +37,8 @@
 #define STEP_FRAC 0.97
 #define LOOSE_TOL 1e-6 /* accepted when the iteration limit is reached: still inside the 1e-6 KKT target */
 
-enum { ORC_OPTIMAL = 0, ORC_INFEASIBLE = 1, ORC_MAX_ITER = 2, ORC_NUMERICAL = 3, ORC_NODE_LIMIT = 4 };
+enum { ORC_OPTIMAL = 0, ORC_INFEASIBLE = 1, ORC_MAX_ITER = 2, ORC_NUMERICAL = 3, ORC_NODE_LIMIT = 4,
+       ORC_CUTOFF = 6 /* internal: the dual bound of a relaxation reached the incumbent, solve abandoned */ };
 
 typedef struct {
   int32_t n_hor, poly_hor, rk4, max_iter, max_nodes, prune;
@@ -316,6 +317,7 @@ typedef struct {
   prow_t *rows;               /* IPM position rows (variable kp only) */
   double *s, *lam;
   int m, cap;
+  double cutoff;              /* a relaxation whose dual bound reaches this value cannot improve the incumbent */
 } prob_t;
 
 static void setup_problem(prob_t *pb, const double x0[9], const double *ref /*[N][6]*/) {
@@ -500,7 +502,7 @@ static void solve_qp(prob_t *pb, qp_out *out) {
       }
     mu /= mtot > 0 ? mtot : 1;
     /* gradient of the smooth part and dual residual */
-    double hg[MAXNW], rdmax = 0, fmaxv = 0, wf = 0;
+    double hg[MAXNW], fv[MAXNW], rdmax = 0, fmaxv = 0, wf = 0;
     for (int a = 0; a < 3; a++)
       for (int r = 0; r < nz; r++) {
         double v = pb->g[a * nz + r];
@@ -510,6 +512,7 @@ static void solve_qp(prob_t *pb, qp_out *out) {
         for (int k = 0; k <= N; k++) f += Fk[k][a] * T->QP[a][k][r];
         for (int q = 0; q < nq; q++) f += FQ[a][q] * T->EQ[a][q][r];
         rdmax = fmax(rdmax, fabs(v + f)), fmaxv = fmax(fmaxv, fabs(f)), wf += w[a * nz + r] * f;
+        fv[a * nz + r] = pb->g[a * nz + r] + f;
       }
     double obj = pb->c0;
     for (int i = 0; i < nw; i++) obj += 0.5 * w[i] * (hg[i] + pb->g[i]);
@@ -526,6 +529,21 @@ static void solve_qp(prob_t *pb, qp_out *out) {
       double dl = (lamsl + wf) / lamsum;
       if (fmaxv / lamsum < 1e-9 * fmax(1.0, -dl * 1e3) && dl < -1e-7 && it >= 3) {
         out->status = ORC_INFEASIBLE, out->iters = it, out->obj = INFINITY;
+        return;
+      }
+    }
+    /* Lagrangian dual bound (weak duality, any lam >= 0): min_w L(w, lam) = c0 - 1/2 v'Hw^-1 v - d'lam with
+     * v = g + C'lam and d'lam = lam'(d - Cw) + w'C'lam.  Once it reaches the incumbent the node cannot win. */
+    if (pb->cutoff < INFINITY) {
+      double quad = 0;
+      for (int a = 0; a < 3; a++)
+        for (int r = 0; r < nz; r++) {
+          double hv = 0;
+          for (int c = 0; c < nz; c++) hv += T->HwInv[a][r][c] * fv[a * nz + c];
+          quad += fv[a * nz + r] * hv;
+        }
+      if (pb->c0 - 0.5 * quad - (lamsl + wf) >= pb->cutoff) {
+        out->status = ORC_CUTOFF, out->iters = it, out->obj = INFINITY;
         return;
       }
     }
@@ -827,6 +845,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
     }
     if (pb.m > maxrows) maxrows = pb.m;
     qp_out q;
+    pb.cutoff = best < INFINITY && !getenv("ORC_NO_CUTOFF") ? best - 1e-7 * fmax(1.0, fabs(best)) : INFINITY;
     solve_qp(&pb, &q);
     nodes++;
     iters += q.iters;
@@ -836,7 +855,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
       fprintf(stderr, " rows %d status %d it %d obj %.6f best %.6f\n", pb.m, q.status, q.iters, q.obj, best);
     }
     if (q.status != ORC_OPTIMAL) {
-      if (q.status != ORC_INFEASIBLE) anyfail = q.status;
+      if (q.status != ORC_INFEASIBLE && q.status != ORC_CUTOFF) anyfail = q.status;
       continue;
     }
     if (q.obj >= best - 1e-7 * fmax(1.0, fabs(best))) continue;
