@@ -499,7 +499,24 @@ struct Solver {
     const double* prev = A.prev + (size_t)agent * K3;
     bool use_list = true;
     for (int w2 = 0; w2 < W; ++w2) use_list &= ctl[2 + w2] >= 0;
-    const unsigned short* lists = reinterpret_cast<const unsigned short*>(rs);
+    unsigned short* lists = reinterpret_cast<unsigned short*>(rs);
+    // The W sub-lists are packed into one: every round below costs a full plane computation for all 32 lanes,
+    // and with a dozen neighbours four quarter-full rounds per step are four times the work of one.
+    int n_list = 0;
+    if (use_list) {
+      n_list = ctl[2];
+      for (int w2 = 1; w2 < W; ++w2) {
+        const int nl = ctl[2 + w2];
+        for (int i0 = 0; i0 < nl; i0 += 32) {  // destination never lies behind the source: read, then write
+          const int i = i0 + lane;
+          const unsigned short v = i < nl ? lists[w2 * A.row_cap + i] : (unsigned short)0;
+          __syncwarp();
+          if (i < nl) lists[n_list + i] = v;
+          __syncwarp();
+        }
+        n_list += nl;
+      }
+    }
     int cnt = 0, status = -1;
     const unsigned lt = (1u << lane) - 1;
     for (int kp = 0; kp <= N; ++kp) {
@@ -538,12 +555,9 @@ struct Solver {
           cnt += __popc(m);
         };
         if (use_list) {
-          for (int w2 = 0; w2 < W; ++w2) {
-            const int nl = ctl[2 + w2];
-            for (int i0 = 0; i0 < nl; i0 += 32) {
-              const int i = i0 + lane;
-              process(i < nl ? nb0 + lists[w2 * A.row_cap + i] : 0, i < nl);
-            }
+          for (int i0 = 0; i0 < n_list; i0 += 32) {
+            const int i = i0 + lane;
+            process(i < n_list ? nb0 + lists[i] : 0, i < n_list);
           }
         } else {
           for (int j0 = nb0; j0 < nb1; j0 += 32) {
