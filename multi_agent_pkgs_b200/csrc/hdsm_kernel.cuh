@@ -304,25 +304,30 @@ struct Solver {
   }
 
   // ---------------------------------------------------------------- per-agent set-up
-  // returns 0 ok, else an HDSM_* status
-  __device__ int setup(int agent) {
-    const hdsm_params& P = T.prm;
-    if (lane < 9) s0[lane] = A.x0[(size_t)agent * 9 + lane];  // x0 = (p, v, a): s0^a = (x0[a], x0[3+a], x0[6+a])
-    for (int i = lane; i < A.P * A.rmax; i += 32) {
-      const size_t base = (size_t)agent * A.P * A.rmax + i;
+  // block-wide part of the set-up: inputs into shared memory, normal ids, per-polytope offsets, pair table
+  __device__ void load_and_index(int agent) {
+    if (tid < 9) s0[tid] = A.x0[(size_t)agent * 9 + tid];  // x0 = (p, v, a): s0^a = (x0[a], x0[3+a], x0[6+a])
+    const int PR = A.P * A.rmax;
+    for (int i = tid; i < PR; i += NT) {
+      const size_t base = (size_t)agent * PR + i;
       poly[4 * i + 0] = A.poly_A[base * 3 + 0];
       poly[4 * i + 1] = A.poly_A[base * 3 + 1];
       poly[4 * i + 2] = A.poly_A[base * 3 + 2];
       poly[4 * i + 3] = A.poly_b[base];
     }
-    if (lane < kMaxP) prow_n[lane] = lane < A.P ? A.poly_rows[(size_t)agent * A.P + lane] : 0;
-    __syncwarp();
+    if (tid < kMaxP) prow_n[tid] = tid < A.P ? A.poly_rows[(size_t)agent * A.P + tid] : 0;
+    // lower-triangle pairs ordered by column descending: the trailing update of Cholesky step j
+    // touches exactly the first (NW-1-j)(NW-j)/2 entries
+    for (int t = tid; t < NW * NW; t += NT) {
+      const int k = t / NW, i = t - k * NW;
+      if (i >= k) tab[(NW - 1 - k) * (NW - k) / 2 + (i - k)] = (unsigned short)((i << 8) | k);
+    }
+    bsync();
     Peff = 0;
     while (Peff < A.P && prow_n[Peff] > 0) ++Peff;  // P_eff = leading present polytopes (:913)
     // id of a row's normal = flat index of the first valid row (over all polytopes) with a bit-identical
     // normal; 255 marks padding rows.  bmin[id][j] = tightest offset of that normal in polytope j.
-    const int PR = A.P * A.rmax;
-    for (int i = lane; i < PR; i += 32) {
+    for (int i = tid; i < PR; i += NT) {
       const int j = i / A.rmax, r = i - j * A.rmax;
       int id = 255;
       if (j < Peff && r < prow_n[j]) {
@@ -338,8 +343,8 @@ struct Solver {
       }
       nid[i] = (unsigned char)id;
     }
-    __syncwarp();
-    for (int t = lane; t < PR * A.P; t += 32) {
+    bsync();
+    for (int t = tid; t < PR * A.P; t += NT) {
       const int i = t / A.P, j = t - i * A.P;
       double bm = INFINITY;
       if (nid[i] == i && j < Peff)
@@ -347,12 +352,12 @@ struct Solver {
           if (nid[j * A.rmax + r2] == i) bm = fmin(bm, poly[4 * (j * A.rmax + r2) + 3]);
       bmin[t] = bm;
     }
-    // lower-triangle pairs ordered by column descending: the trailing update of Cholesky step j
-    // touches exactly the first (NW-1-j)(NW-j)/2 entries
-    for (int k = NW - 1; k >= 0; --k) {
-      const int base = (NW - 1 - k) * (NW - k) / 2;
-      for (int i = k + lane; i < NW; i += 32) tab[base + (i - k)] = (unsigned short)((i << 8) | k);
-    }
+    bsync();
+  }
+
+  // warp-0 part: objective, reachable boxes, constant checks; returns -1 ok, else an HDSM_* status
+  __device__ int setup(int agent) {
+    const hdsm_params& P = T.prm;
     const double* ref = A.ref + (size_t)agent * N * 6;
     // gradient and constant of the condensed objective (:870-883, :2098)
     double gi = 0, cpart = 0;
@@ -1176,8 +1181,9 @@ struct Solver {
     int st = -1, top = 0, nodes = 0, iters = 0, maxrows = 0, fail = 0;
     double best = INFINITY, bestkkt = INFINITY;
     bool exhausted = true, overflow = false;
+    if (wid == 0) tick_start();
+    load_and_index(agent);
     if (wid == 0) {
-      tick_start();
       st = setup(agent);
       if (lane == 0) ctl[1] = st;
     }
