@@ -224,15 +224,54 @@ def corridor_measure(n_agents=4096, steps=10, local_rank=0, cpu=True):
     t0 = time.perf_counter()
     out = gen.generate(cb)
     e2e = time.perf_counter() - t0
+    # steady state: the reference keeps the polytopes the last optimisation used (:1252-1281) and only grows
+    # the missing ones, so a replanning step in flight costs far less than the cold start timed above.  Five
+    # closed-loop steps of the distinct agents (corridor and optimisation on the GPU) give a batch with
+    # previous polytopes / used flags / plans; it is tiled and timed the same way.
+    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
+    loop = cr.CorridorLoop(sw)
+    g1 = cr.SafeCorridorGenerator(base.poly_hor, base.n_it, base.voxel, base.n, base.n, int(base.grids[0].size),
+                                  base.prev_traj.shape[1], base.path.shape[1], device=local_rank)
+    pl1 = TrajectoryPlanner(sw.params, max_agents=sw.n, max_neighbours=10, device=local_rank, max_nodes=MAX_NODES)
+    for _ in range(5):
+        o1 = g1.generate(loop.corridor_inputs())
+        r1 = pl1.solve_batch(loop.solver_inputs(o1))
+        st = r1["res"]["status"]
+        loop.advance(o1, r1, (st == 0) | ((st == 4) & np.isfinite(r1["res"]["obj"])))
+    sb = loop.corridor_inputs()
+    g1.close()
+    pl1.close()
+    cbs = cr.CorridorBatch(sb.poly_hor, sb.n_it, sb.rmax, sb.voxel, tile(sb.grids), None, tile(sb.dims), tile(sb.origins),
+                           tile(sb.pos), tile(sb.path), tile(sb.n_path), tile(sb.prev_traj), tile(sb.prev_n), tile(sb.prev_A),
+                           tile(sb.prev_b), tile(sb.prev_rows), tile(sb.prev_seeds), tile(sb.prev_used))
+    dbs = cr.DeviceCorridorBatch(cbs, dev)
+    for _ in range(3):
+        gen.generate_device(dbs.t, cbs.n, stream.cuda_stream)
+    torch.cuda.synchronize()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        ev2[k][0].record(stream)
+        gen.generate_device(dbs.t, cbs.n, stream.cuda_stream)
+        ev2[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms_steady = float(np.mean([a.elapsed_time(b) for a, b in ev2]))
+    kept = int(cbs.prev_n.sum()) if cbs.prev_n is not None else 0
+    new_steady = int((dbs.t["poly_rows"].cpu().numpy() > 0).sum()) - 0
     launches = gen.launch_count
     smem = gen.smem_bytes
     gen.close()
     balg = cr.corridor_algorithmic_bytes(cb, rows)
-    line = {"workload": f"{cb.n} agents, one 66x66x20 int8 local grid each, poly_hor {cb.poly_hor}, n_it_decomp {cb.n_it}",
+    line = {"workload": f"{cb.n} agents, one 66x66x20 int8 local grid each, poly_hor {cb.poly_hor}, n_it_decomp {cb.n_it}; "
+                        f"value = cold start (all {cb.poly_hor} polytopes grown), steady_state = a step in flight",
             "metric": "corridor updates/sec (agents/s)", "value": cb.n / (ms * 1e-3), "kernel_ms": ms,
             "polytopes_per_s": npoly / (ms * 1e-3), "dtype": "int8 grid -> f64 rows",
             "e2e": {"value": cb.n / e2e, "unit": "agents/s", "h2d_bytes_per_step": cb.input_bytes(),
                     "d2h_bytes_per_step": int(sum(out[k].nbytes for k in out))},
+            "steady_state": {"value": cbs.n / (ms_steady * 1e-3), "unit": "agents/s", "kernel_ms": ms_steady,
+                             "polytopes_out": new_steady, "polytopes_in": kept,
+                             "note": "closed-loop step 5: previous polytopes, used flags and plans supplied; "
+                                     "only the missing polytopes are grown"},
             "gpu_launches": int(launches), "algorithmic_bytes_per_agent": balg, "smem_bytes_per_block": smem,
             "squeezed_seed_agents": int((out["flags"] & 1 != 0).sum())}
     if cpu:
