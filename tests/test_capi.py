@@ -68,3 +68,27 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle-free", ""), f
+
+
+def test_corridor_structs_and_argument_checks():
+    """hdsm_corridor_params layout, and hdsm_corridor_create rejecting what the kernel cannot do (window of
+    32^3 voxels: n_it_decomp <= 90; row stride 18..32; poly_hor 1..8)."""
+    from multi_agent_pkgs_b200.corridor import HdsmCorridorParams
+    assert C.sizeof(HdsmCorridorParams) == 6 * 4 + 8
+    L = _lib.load()
+    L.hdsm_corridor_create.restype = C.c_int
+    h = C.c_void_p()
+
+    def create(poly_hor=4, n_it=42, rmax=18, n_traj=11, max_path=16, new=0, voxel=0.3, agents=4, grids=4, stride=1000):
+        p = HdsmCorridorParams(poly_hor, n_it, rmax, n_traj, max_path, new, voxel)
+        return L.hdsm_corridor_create(C.byref(p), C.c_int(agents), C.c_int(grids), C.c_size_t(stride), C.c_int(0), C.byref(h))
+
+    for bad in (dict(n_it=91), dict(rmax=17), dict(rmax=33), dict(poly_hor=0), dict(poly_hor=9), dict(voxel=0.0),
+                dict(max_path=0), dict(agents=0), dict(grids=0), dict(stride=0)):
+        assert create(**bad) == -1, bad  # HDSM_ERR_INVALID
+    assert L.hdsm_corridor_create(None, 1, 1, C.c_size_t(8), 0, C.byref(h)) == -1
+    if not has_gpu():
+        assert create() == -2  # HDSM_ERR_CUDA: no CPU fallback
+        from multi_agent_pkgs_b200.corridor import SafeCorridorGenerator
+        with pytest.raises(RuntimeError):
+            SafeCorridorGenerator(4, 42, 0.3, 4, 4, 1000, 11, 16)

@@ -191,3 +191,81 @@ def test_closed_loop_corridor_then_optimisation():
     assert kept > 50 and solved_ok > 100
     gen.close()
     pl.close()
+
+
+def _free_batch(n, dims=(40, 40, 16), voxel=0.3, n_it=42, poly_hor=3, max_path=4, n_traj=0):
+    g = np.zeros((n, dims[2], dims[1], dims[0]), np.int8)
+    d = np.tile(np.array(dims, np.int32), (n, 1))
+    o = np.zeros((n, 3))
+    pos = np.tile((np.array(dims) / 2 + 0.5) * voxel, (n, 1))
+    path = np.zeros((n, max_path, 3))
+    path[:, 0] = pos + np.array([1.0, 0.2, 0.0])
+    return cr.CorridorBatch(poly_hor, n_it, 18, voxel, g, None, d, o, pos, path, np.ones(n, np.int32), np.zeros((n, n_traj, 3)))
+
+
+def test_edge_cases_match_the_checker():
+    """Empty path, a path that leaves the grid, the largest supported n_it_decomp on a big free grid, another
+    voxel size, previous polytopes of which none survives, obstacles right at the grid boundary."""
+    # (a) empty path: nothing is grown, outputs are zero, no flag
+    cb = _free_batch(3)
+    cb.n_path[:] = 0
+    gen = _gen(cb)
+    out = gen.generate(cb)
+    _assert_equal(out, oc.c_safe_corridor(cb))
+    assert (out["poly_rows"] == 0).all() and (out["flags"] == 0).all()
+    # (b) the path leaves the grid: polytopes up to there, then HDSM_COR_SEED_OUTSIDE
+    cb = _free_batch(3, poly_hor=8)
+    cb.path[:, 0] = cb.pos + np.array([30.0, 0.0, 0.0])
+    gen.close()
+    gen = _gen(cb)
+    out = gen.generate(cb)
+    _assert_equal(out, oc.c_safe_corridor(cb))
+    assert (out["flags"] & cr.FLAG_SEED_OUTSIDE).all() and (out["poly_rows"][:, 0] == 6).all() and (out["poly_rows"][:, 7] == 0).all()
+    gen.close()
+    # (c) n_it_decomp = 90 on a free 70^3 grid: 15 layers per face, the whole 32^3 window in use
+    cb = _free_batch(2, dims=(70, 70, 70), n_it=90, poly_hor=2)
+    gen = _gen(cb)
+    out = gen.generate(cb)
+    _assert_equal(out, oc.c_safe_corridor(cb))
+    b = out["poly_b"][0, 0, :6]
+    assert abs((b[1] + b[3]) - 31 * 0.3) < 1e-9  # 15 + 1 + 15 voxels wide
+    gen.close()
+    # (d) voxel 0.2, n_it 60, columns touching the grid boundary
+    cb = _free_batch(4, dims=(36, 30, 12), voxel=0.2, n_it=60, poly_hor=3)
+    cb.grids[:, :, :, 0] = 100
+    cb.grids[:, :, -1, :] = 100
+    cb.grids[:, :, 10:14, 22:24] = 100
+    cb.grids[:, :3] = -1
+    gen = _gen(cb)
+    out = gen.generate(cb)
+    _assert_equal(out, oc.c_safe_corridor(cb))
+    assert (out["poly_rows"][:, 0] >= 6).all()
+    # (e) previous polytopes, none used and the plan outside the last one: all are dropped and regrown
+    N1 = 5
+    cb2 = _free_batch(4, dims=(36, 30, 12), voxel=0.2, n_it=60, poly_hor=3, n_traj=N1)
+    cb2.grids = cb.grids
+    far = np.repeat(cb2.pos[:, None, :] + np.array([100.0, 0.0, 0.0]), N1, 1)
+    cb2.with_previous(out, np.zeros((4, 3), np.uint8), far)
+    gen.close()
+    gen = _gen(cb2)
+    out2 = gen.generate(cb2)
+    _assert_equal(out2, oc.c_safe_corridor(cb2))
+    for k in ("poly_A", "poly_b", "poly_rows", "seeds"):
+        assert np.array_equal(out2[k], out[k]), k
+    gen.close()
+
+
+def test_corridor_error_codes():
+    cb = _free_batch(4)
+    gen = cr.SafeCorridorGenerator(cb.poly_hor, cb.n_it, cb.voxel, 2, 2, int(cb.grids[0].size), 0, cb.path.shape[1])
+    with pytest.raises(RuntimeError, match="capacity"):
+        gen.generate(cb)  # 4 agents on a handle made for 2
+    small = _free_batch(2)
+    small.grid_index = np.array([0, 5], np.int32)
+    with pytest.raises(RuntimeError, match="grid_index"):
+        gen.generate(small)
+    small.grid_index = None
+    small.dims[1] = (400, 400, 400)
+    with pytest.raises(RuntimeError, match="grid_stride"):
+        gen.generate(small)
+    gen.close()
