@@ -131,7 +131,9 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
 /* Same with DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL = the handle's stream), no
  * host synchronisation.  pos_out [n_local][N+1][3] (may be NULL) receives the packed positions of
  * the new plans - the send buffer of the trajectory exchange, written by the solver's epilogue;
- * agents without a usable result get their previous plan shifted by one step (:1004-1013). */
+ * agents without a usable result get their previous plan shifted by one step (:1004-1013).
+ * Calls on one handle must be ordered with respect to each other (same stream, or synchronised): the handle
+ * keeps a device-side dispatch order (most expensive agents of the previous call first) between calls. */
 int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_id, const int32_t* nbr_begin,
                             const int32_t* nbr_end, const double* x0, const double* ref, const double* poly_A,
                             const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,

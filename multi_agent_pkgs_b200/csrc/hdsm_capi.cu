@@ -79,6 +79,7 @@ struct hdsm_handle {
   int32_t* d_order = nullptr;
   int order_n[kMaxChunks] = {};
   bool use_order = true;
+  int smem_configured = -1;
   long long* d_prof = nullptr;  // HDSM_PROFILE=1: per-agent phase cycle counters (host path prints a summary)
   int warps = 4;  // warps per agent (HDSM_WARPS=1 selects the single-warp kernel)
   std::string err;
@@ -103,12 +104,13 @@ int cuda_fail(hdsm_handle* h, cudaError_t e, const char* what) {
 
 template <int N, int W>
 cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
-  static int configured_for = -1;  // per instantiation; the smem attribute is per device function
+  // the dynamic shared-memory limit is an attribute of the kernel on the current device: set once per handle
+  // (a handle has one horizon and one device), not once per process
   const int need = h->smem_bytes[h->n_tiers - 1];
-  if (configured_for < need) {
+  if (h->smem_configured < need) {
     cudaError_t e = cudaFuncSetAttribute(hdsm_solve_kernel<N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
     if (e != cudaSuccess) return e;
-    configured_for = need;
+    h->smem_configured = need;
   }
   for (int t = 0; t < h->n_tiers; ++t) {  // t > 0: only agents whose rows did not fit the previous pool
     a.row_cap = h->row_cap[t], a.only_status = t == 0 ? -1 : HDSM_ROW_OVERFLOW;
