@@ -845,7 +845,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
     }
     if (pb.m > maxrows) maxrows = pb.m;
     qp_out q;
-    pb.cutoff = best < INFINITY && !getenv("ORC_NO_CUTOFF") ? best - 1e-7 * fmax(1.0, fabs(best)) : INFINITY;
+    pb.cutoff = best < INFINITY ? best - 1e-7 * fmax(1.0, fabs(best)) : INFINITY;
     solve_qp(&pb, &q);
     nodes++;
     iters += q.iters;
