@@ -23,10 +23,12 @@
 // evaluation order so that no FMA contraction can change a bit.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 
 #include "../../include/hdsm.h"
 
@@ -818,8 +820,9 @@ struct hdsm_corridor {
   hdsm_corridor_params prm{};
   int device = 0, max_agents = 0, max_grids = 0, cell_cap = 0, layer_cap = 0;
   size_t grid_stride = 0, smem = 0;
-  cudaStream_t stream = nullptr;
-  unsigned char *d_in = nullptr, *d_out = nullptr, *h_out = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second lane of the chunked host-pointer pipeline
+  cudaEvent_t ev_shared = nullptr, ev_chunk[8] = {};
+  unsigned char *d_in = nullptr, *h_in = nullptr, *d_out = nullptr, *h_out = nullptr;
   size_t in_cap = 0, out_cap = 0;
   int64_t launches = 0;
   std::string err;
@@ -836,6 +839,24 @@ int cfail(hdsm_corridor* h, int code, const std::string& msg) {
     if (e_ != cudaSuccess) return cfail(h, HDSM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// memcpy between caller memory and the pinned arenas, large blocks split over a few threads
+void staged_copy(void* dst, const void* src, size_t bytes) {
+  constexpr size_t kPerThread = size_t(4) << 20;
+  const int nt = (int)std::min<size_t>(6, bytes / kPerThread);
+  if (nt < 2) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::thread th[6];
+  const size_t part = ((bytes / nt) + 63) & ~size_t(63);
+  for (int t = 1; t < nt; ++t) {
+    const size_t o = (size_t)t * part, len = t == nt - 1 ? bytes - o : part;
+    th[t] = std::thread([=] { memcpy((char*)dst + o, (const char*)src + o, len); });
+  }
+  memcpy(dst, src, part);
+  for (int t = 1; t < nt; ++t) th[t].join();
+}
 }  // namespace
 
 extern "C" {
@@ -857,9 +878,12 @@ int hdsm_corridor_create(const hdsm_corridor_params* p, int max_agents, int max_
   h->smem = hdsm_cor::smem_bytes(*p, h->cell_cap, h->layer_cap);
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_shared, cudaEventDisableTiming);
+  for (int c = 0; c < 8 && e == cudaSuccess; ++c) e = cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(hdsm_cor::corridor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e != cudaSuccess) {
-    delete h;
+    hdsm_corridor_destroy(h);
     return HDSM_ERR_CUDA;
   }
   *out = h;
@@ -869,10 +893,17 @@ int hdsm_corridor_create(const hdsm_corridor_params* p, int max_agents, int max_
 void hdsm_corridor_destroy(hdsm_corridor* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->d_in) cudaFree(h->d_in);
+  if (h->h_in) cudaFreeHost(h->h_in);
   if (h->d_out) cudaFree(h->d_out);
   if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->ev_shared) cudaEventDestroy(h->ev_shared);
+  for (int c = 0; c < 8; ++c)
+    if (h->ev_chunk[c]) cudaEventDestroy(h->ev_chunk[c]);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
 }
 
@@ -950,8 +981,10 @@ int hdsm_corridor_batch(hdsm_corridor* h, int n, int n_grids, const int8_t* grid
   const int i_pu = put(pv ? prev_used : nullptr, N * PH), i_pt = put(pv ? prev_traj : nullptr, N * h->prm.n_traj * 24);
   if (off > h->in_cap) {
     if (h->d_in) cudaFree(h->d_in);
-    h->d_in = nullptr, h->in_cap = 0;
+    if (h->h_in) cudaFreeHost(h->h_in);
+    h->d_in = h->h_in = nullptr, h->in_cap = 0;
     CCU(cudaMalloc(&h->d_in, off));
+    CCU(cudaMallocHost(&h->h_in, off));
     h->in_cap = off;
   }
   const size_t o_A = 0, o_b = o_A + al256(N * PH * R * 24), o_r = o_b + al256(N * PH * R * 8), o_s = o_r + al256(N * PH * 4);
@@ -964,23 +997,61 @@ int hdsm_corridor_batch(hdsm_corridor* h, int n, int n_grids, const int8_t* grid
     CCU(cudaMallocHost(&h->h_out, out_bytes));
     h->out_cap = out_bytes;
   }
-  for (int k = 0; k < ni; ++k)
-    if (in[k].bytes) CCU(cudaMemcpyAsync(h->d_in + in[k].off, in[k].src, in[k].bytes, cudaMemcpyHostToDevice, h->stream));
-  const auto dp = [&](int k) -> const void* { return in[k].bytes ? h->d_in + in[k].off : nullptr; };
-  const int rc = hdsm_corridor_batch_device(
-      h, n, (const int8_t*)dp(i_grid), (const int32_t*)dp(i_gi), (const int32_t*)dp(i_dim), (const double*)dp(i_org),
-      (const double*)dp(i_pos), (const double*)dp(i_path), (const int32_t*)dp(i_np), (const int32_t*)dp(i_pn),
-      (const double*)dp(i_pA), (const double*)dp(i_pb), (const int32_t*)dp(i_pr), (const double*)dp(i_ps),
-      (const uint8_t*)dp(i_pu), (const double*)dp(i_pt), (double*)(h->d_out + o_A), (double*)(h->d_out + o_b),
-      (int32_t*)(h->d_out + o_r), (double*)(h->d_out + o_s), (int32_t*)(h->d_out + o_f), h->stream);
-  if (rc != HDSM_OK) return rc;
-  CCU(cudaMemcpyAsync(h->h_out, h->d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
-  CCU(cudaStreamSynchronize(h->stream));
-  memcpy(poly_A, h->h_out + o_A, N * PH * R * 24);
-  memcpy(poly_b, h->h_out + o_b, N * PH * R * 8);
-  memcpy(poly_rows, h->h_out + o_r, N * PH * 4);
-  memcpy(seeds, h->h_out + o_s, N * PH * 24);
-  memcpy(flags, h->h_out + o_f, N * 4);
+  // Chunked pipeline over two streams (the voxel grids are 87 KB per agent: the copies cost more than the
+  // kernel): chunk c+1 is staged into the pinned arena by a few host threads and copied while chunk c runs;
+  // results come back per chunk.  Grids shared through grid_index are staged once, ahead of all chunks.
+  const size_t stride_in[16] = {h->grid_stride, 4, 12, 24, 24, (size_t)h->prm.max_path * 24, 4, 4, PH * R * 24, PH * R * 8,
+                                PH * 4, PH * 24, PH, (size_t)h->prm.n_traj * 24};  // bytes per agent, in the order of put()
+  struct Out {
+    void* dst;
+    size_t off, stride;
+  };
+  const Out outs[] = {{poly_A, o_A, PH * R * 24}, {poly_b, o_b, PH * R * 8}, {poly_rows, o_r, PH * 4}, {seeds, o_s, PH * 24}, {flags, o_f, 4}};
+  const bool shared_grids = grid_index != nullptr;
+  int n_chunks = n >= 2048 ? 4 : 1;
+  const int per = (n + n_chunks - 1) / n_chunks;
+  if (shared_grids) {
+    staged_copy(h->h_in + in[i_grid].off, in[i_grid].src, in[i_grid].bytes);
+    CCU(cudaMemcpyAsync(h->d_in + in[i_grid].off, h->h_in + in[i_grid].off, in[i_grid].bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  CCU(cudaEventRecord(h->ev_shared, h->stream));
+  CCU(cudaStreamWaitEvent(h->stream2, h->ev_shared, 0));
+  const auto dp = [&](int k, size_t first) -> const void* {
+    if (!in[k].bytes) return nullptr;
+    return h->d_in + in[k].off + ((k == i_grid && shared_grids) ? 0 : first * stride_in[k]);
+  };
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t first = (size_t)c * per;
+    if (first >= N) break;
+    const size_t cnt = std::min<size_t>(per, N - first);
+    cudaStream_t st = (c & 1) ? h->stream2 : h->stream;
+    for (int k = 0; k < ni; ++k) {
+      if (!in[k].bytes || (k == i_grid && shared_grids)) continue;
+      const size_t o = in[k].off + first * stride_in[k], bytes = cnt * stride_in[k];
+      staged_copy(h->h_in + o, (const char*)in[k].src + first * stride_in[k], bytes);
+      CCU(cudaMemcpyAsync(h->d_in + o, h->h_in + o, bytes, cudaMemcpyHostToDevice, st));
+    }
+    const int rc = hdsm_corridor_batch_device(
+        h, (int)cnt, (const int8_t*)dp(i_grid, first), (const int32_t*)dp(i_gi, first), (const int32_t*)dp(i_dim, first),
+        (const double*)dp(i_org, first), (const double*)dp(i_pos, first), (const double*)dp(i_path, first),
+        (const int32_t*)dp(i_np, first), (const int32_t*)dp(i_pn, first), (const double*)dp(i_pA, first),
+        (const double*)dp(i_pb, first), (const int32_t*)dp(i_pr, first), (const double*)dp(i_ps, first),
+        (const uint8_t*)dp(i_pu, first), (const double*)dp(i_pt, first), (double*)(h->d_out + o_A + first * outs[0].stride),
+        (double*)(h->d_out + o_b + first * outs[1].stride), (int32_t*)(h->d_out + o_r + first * outs[2].stride),
+        (double*)(h->d_out + o_s + first * outs[3].stride), (int32_t*)(h->d_out + o_f + first * outs[4].stride), st);
+    if (rc != HDSM_OK) return rc;
+    for (const Out& o : outs)
+      CCU(cudaMemcpyAsync(h->h_out + o.off + first * o.stride, h->d_out + o.off + first * o.stride, cnt * o.stride,
+                          cudaMemcpyDeviceToHost, st));
+    CCU(cudaEventRecord(h->ev_chunk[c], st));
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t first = (size_t)c * per;
+    if (first >= N) break;
+    const size_t cnt = std::min<size_t>(per, N - first);
+    CCU(cudaEventSynchronize(h->ev_chunk[c]));
+    for (const Out& o : outs) memcpy((char*)o.dst + first * o.stride, h->h_out + o.off + first * o.stride, cnt * o.stride);
+  }
   return HDSM_OK;
 }
 

@@ -269,3 +269,37 @@ def test_corridor_error_codes():
     with pytest.raises(RuntimeError, match="grid_stride"):
         gen.generate(small)
     gen.close()
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_chunked_host_pipeline_matches_the_checker(shared):
+    """Batches of 2048 agents and more go through hdsm_corridor_batch in four chunks over two streams (pinned
+    staging, H2D, kernel and D2H overlapped): 2 520 agents, per-agent grids and grids shared through grid_index,
+    with previous polytopes - every output equal to the checker's."""
+    sw = sc.config2_circle(n_swarms=2, seed=13)
+    for i in range(sw.n):
+        sw.state[i, :2] = sw.world.push_free(0.5 * sw.state[i, :2] + 0.5 * sw.goal[i, :2], 0.3)
+    base = cr.corridor_batch(sw)
+    first = oc.c_safe_corridor(base)
+    rng = np.random.default_rng(3)
+    N = sw.params["n_hor"]
+    base.with_previous(first, (rng.random((base.n, base.poly_hor)) < 0.6).astype(np.uint8),
+                       np.repeat(base.pos[:, None, :], N + 1, 1) + rng.normal(0, 0.3, (base.n, N + 1, 3)))
+    reps = 126
+
+    def tile(a):
+        return np.ascontiguousarray(np.concatenate([a] * reps))
+    grids = base.grids if shared else tile(base.grids)
+    gi = np.tile(np.arange(base.n, dtype=np.int32), reps) if shared else None
+    cb = cr.CorridorBatch(base.poly_hor, base.n_it, base.rmax, base.voxel, grids, gi, tile(base.dims), tile(base.origins),
+                          tile(base.pos), tile(base.path), tile(base.n_path), tile(base.prev_traj), tile(base.prev_n),
+                          tile(base.prev_A), tile(base.prev_b), tile(base.prev_rows), tile(base.prev_seeds), tile(base.prev_used))
+    gen = _gen(cb)
+    for _ in range(2):  # twice: the arenas are reused
+        out = gen.generate(cb)
+        small = oc.c_safe_corridor(base)
+        for k in ("poly_rows", "flags", "poly_A", "poly_b", "seeds"):
+            got = out[k].reshape(reps, base.n, *out[k].shape[1:])
+            assert np.array_equal(got, np.broadcast_to(small[k], got.shape)), k
+    assert gen.launch_count == 8
+    gen.close()
