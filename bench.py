@@ -461,8 +461,12 @@ def run_ours(args, rank, world, local_rank):
         achieved = balg * n_local / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per agent QP from the ncu --set full capture
+        pipes = None
         if os.path.exists(tpath):
-            traffic = float(json.load(open(tpath))["dram_bytes_per_agent_qp"]) * n_local
+            tj = json.load(open(tpath))
+            traffic = float(tj["dram_bytes_per_agent_qp"]) * n_local
+            pipes = {k: tj[k] for k in ("fp64_pipe_pct", "issue_active_pct", "warps_active_pct", "stall_barrier_pct",
+                                        "stall_wait_pct") if k in tj}
         cpu_rate, cores, cpu_n, cpu_t = cpu_solve_rate(snaps, min_seconds=args.cpu_seconds, max_agents=20000)
         corridor = None
         if args.corridor_agents > 0:
@@ -477,9 +481,10 @@ def run_ours(args, rank, world, local_rank):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_solve": balg,
-                             "note": "the solve is FP64-latency bound, not HBM bound (DESIGN.md section 5); "
-                                     "traffic from ncu is in profiles/"},
+                             "algorithmic_bytes_per_solve": balg, "ncu": pipes,
+                             "note": "the solve is FP64-latency bound, not HBM bound (DESIGN.md section 5); traffic and "
+                                     "the pipe / stall figures under `ncu` come from the --set full capture in profiles/ "
+                                     "(profiles/traffic.json), not from this run"},
                 "cpu_baseline": {"value": cpu_rate, "unit": "solves/s", "cores": cores, "kind": "port",
                                  "sample": f"{cpu_n} agent QPs of the same snapshots in {cpu_t:.1f}s, C port of the "
                                            f"oracle on all host threads (Gurobi not available)"},
