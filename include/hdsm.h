@@ -218,6 +218,59 @@ int hdsm_corridor_batch_device(hdsm_corridor* h, int n, const int8_t* grids, con
                                const uint8_t* prev_used, const double* prev_traj, double* poly_A, double* poly_b,
                                int32_t* poly_rows, double* seeds, int32_t* flags, void* stream);
 
+/* ---- reference-trajectory generation ----------------------------
+ * hdsm_reftraj_batch replaces Agent::GenerateReferenceTrajectory (agent_class.cpp:1449-1553, the call at
+ * :166) with SamplePath (:1591-1663), KeepOnlyFreeReference (:1665-1687), ComputePathVelocity (:1689-1801),
+ * GetVelocityLimit (:1803-1817) and the ray casts of path_finding_util::IsLineClear (path_tools.cpp:148-180,
+ * voxel_grid_util/src/raycast.cpp:21-186).  One warp per agent; see csrc/hdsm_reftraj.cu. */
+typedef struct hdsm_reftraj_params {
+  int32_t n_hor;            /* n_hor: N; the reference trajectory has N + 1 points */
+  int32_t max_path;         /* row stride of `path`, <= 32 */
+  int32_t n_traj;           /* points per plan in traj / all_pos (N + 1), 0 = no neighbour sweep */
+  int32_t reserved;
+  double dt;                /* dt */
+  double path_vel_min, path_vel_max, path_vel_dec; /* agent_agile_config.yaml:16-20 */
+  double sens_dist, sens_pot, sens_other_agents;   /* :1793, :1813-1815 */
+  double voxel_size;        /* VoxelGrid::GetVoxSize() */
+} hdsm_reftraj_params;
+
+typedef struct hdsm_reftraj hdsm_reftraj;
+
+int hdsm_reftraj_create(const hdsm_reftraj_params* params, int max_agents, int max_grids, size_t grid_stride, int device,
+                        hdsm_reftraj** out);
+void hdsm_reftraj_destroy(hdsm_reftraj* h);
+const char* hdsm_reftraj_last_error(const hdsm_reftraj* h);
+int64_t hdsm_reftraj_launch_count(const hdsm_reftraj* h);
+
+/* One reference-trajectory update for n agents; HOST pointers; synchronous.
+ *
+ *  grids / grid_index / dims / origins   voxel_grid_ as for hdsm_corridor_batch (potential-field values 1..99 matter here)
+ *  path        [n][max_path][3]          path_curr_ (:1451-1454), n_path[n] >= 1 points each
+ *  prev_ref    [n][N+1][3]               positions of traj_ref_curr_ of the previous step (:1459-1470)
+ *  have_prev   [n]                       traj_ref_curr_.size() > 0 && !reset_path_
+ *  increment   [n]                       increment_traj_ref_
+ *  traj        [n][n_traj][3]            positions of traj_curr_ (:1757-1760)
+ *  global_id / nbr_begin / nbr_end       as for hdsm_solve_batch
+ *  all_pos     [n_rob][n_traj][3]        last received plans of all agents (traj_other_agents_, :1769-1776)
+ *  all_valid   [n_rob]
+ *  ref         [n][N+1][6]               traj_ref_curr_: positions and the velocity reference (:1528-1546)
+ *  path_vel    [n]                       path_vel_
+ */
+int hdsm_reftraj_batch(hdsm_reftraj* h, int n, int n_grids, const int8_t* grids, const int32_t* grid_index,
+                       const int32_t* dims, const double* origins, const double* path, const int32_t* n_path,
+                       const double* prev_ref, const uint8_t* have_prev, const uint8_t* increment, const double* traj,
+                       const int32_t* global_id, const int32_t* nbr_begin, const int32_t* nbr_end, const double* all_pos,
+                       const uint8_t* all_valid, int n_rob, double* ref, double* path_vel);
+
+/* Same with DEVICE pointers on `stream`.  ref_solver [n][N][6] (may be NULL) receives the first N points in
+ * the layout of hdsm_solve_batch_device's `ref` input, so that the two chain without a copy. */
+int hdsm_reftraj_batch_device(hdsm_reftraj* h, int n, const int8_t* grids, const int32_t* grid_index, const int32_t* dims,
+                              const double* origins, const double* path, const int32_t* n_path, const double* prev_ref,
+                              const uint8_t* have_prev, const uint8_t* increment, const double* traj,
+                              const int32_t* global_id, const int32_t* nbr_begin, const int32_t* nbr_end,
+                              const double* all_pos, const uint8_t* all_valid, int n_rob, double* ref, double* ref_solver,
+                              double* path_vel, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,9 @@ EXPORTS = ["hdsm_version", "hdsm_create", "hdsm_destroy", "hdsm_last_error", "hd
            "hdsm_solve_batch_device", "hdsm_launch_count", "hdsm_smem_bytes", "hdsm_comm_unique_id",
            "hdsm_comm_init", "hdsm_allgather_positions", "hdsm_comm_destroy",
            "hdsm_corridor_create", "hdsm_corridor_destroy", "hdsm_corridor_last_error", "hdsm_corridor_launch_count",
-           "hdsm_corridor_smem_bytes", "hdsm_corridor_batch", "hdsm_corridor_batch_device"]
+           "hdsm_corridor_smem_bytes", "hdsm_corridor_batch", "hdsm_corridor_batch_device",
+           "hdsm_reftraj_create", "hdsm_reftraj_destroy", "hdsm_reftraj_last_error", "hdsm_reftraj_launch_count",
+           "hdsm_reftraj_batch", "hdsm_reftraj_batch_device"]
 
 
 class HdsmParams(C.Structure):

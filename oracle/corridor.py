@@ -41,7 +41,9 @@ def build_ref(force=False):
     src = os.path.join(REFERENCE, "convex_decomp_util", "src", "convex_decomp.cpp")
     if not os.path.exists(src):
         return _REF_SO if os.path.exists(_REF_SO) else None
-    if force or not os.path.exists(_REF_SO) or os.path.getmtime(_REF_SO) < os.path.getmtime(os.path.join(_HERE, "ref_wrap.cpp")):
+    voxel_so = os.path.join(_HERE, "_ref", "libref_voxel.so")
+    if force or not os.path.exists(_REF_SO) or not os.path.exists(voxel_so) or \
+            os.path.getmtime(_REF_SO) < os.path.getmtime(os.path.join(_HERE, "ref_wrap.cpp")):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "ref", f"REFERENCE={REFERENCE}"])
     return _REF_SO
 
