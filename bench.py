@@ -336,6 +336,71 @@ def corridor_measure(n_agents=4096, steps=10, local_rank=0, cpu=True):
     return line, balg * cb.n / (ms * 1e-3) / 1e9
 
 
+def reftraj_measure(n_agents=16384, steps=10, local_rank=0):
+    """Secondary measurement of the reference-trajectory producer: hdsm_reftraj_batch_device on
+    agents of the config-2 swarms inside the forest (66 x 66 x 20 grids with a potential field, 10 neighbours each
+    with plans), tiled from 240 distinct agents; the C port of the checker on all host threads beside it."""
+    import torch
+    from multi_agent_pkgs_b200 import reftraj as rtj
+    sw = sc.config2_circle(n_swarms=DISTINCT_SWARMS)
+    for i in range(sw.n):
+        sw.state[i, :2] = sw.world.push_free(0.45 * sw.state[i, :2] + 0.55 * sw.goal[i, :2], 0.3)
+    base = rtj.reftraj_batch(sw)
+    base.all_valid[:] = 1
+    reps = -(-n_agents // base.n)
+    n_rob = base.all_pos.shape[0]
+    off = np.repeat(np.arange(reps, dtype=np.int32) * n_rob, base.n)[:n_agents]
+
+    def tile(a):
+        return np.ascontiguousarray(np.concatenate([a] * reps)[:n_agents])
+    rb = rtj.RefTrajBatch(base.n_hor, base.dt, base.voxel, tile(base.grids), None, tile(base.dims), tile(base.origins),
+                          tile(base.path), tile(base.n_path), tile(base.prev_ref), tile(base.have_prev), tile(base.increment),
+                          tile(base.traj), tile(base.global_id) + off, tile(base.nbr_begin) + off, tile(base.nbr_end) + off,
+                          np.ascontiguousarray(np.concatenate([base.all_pos] * reps)), np.tile(base.all_valid, reps))
+    dev = torch.device(f"cuda:{local_rank}")
+    gen = rtj.ReferenceTrajectoryGenerator(rb, device=local_rank)
+    t = {}
+    for k in ("grids", "dims", "origins", "path", "n_path", "prev_ref", "have_prev", "increment", "traj", "global_id", "nbr_begin",
+              "nbr_end", "all_pos", "all_valid"):
+        a = getattr(rb, k)
+        t[k] = torch.from_numpy(np.ascontiguousarray(a.reshape(a.shape[0], -1) if k == "grids" else a)).to(dev)
+    N1 = rb.n_hor + 1
+    t["ref"] = torch.zeros((rb.n, N1, 6), dtype=torch.float64, device=dev)
+    t["ref_solver"] = torch.zeros((rb.n, rb.n_hor, 6), dtype=torch.float64, device=dev)
+    t["path_vel"] = torch.zeros(rb.n, dtype=torch.float64, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        gen.generate_device(t, rb.n, rb.all_pos.shape[0], stream.cuda_stream)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        gen.generate_device(t, rb.n, rb.all_pos.shape[0], stream.cuda_stream)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    got_ref, got_vel = t["ref"].cpu().numpy(), t["path_vel"].cpu().numpy()
+    solver_rows_equal = bool(np.array_equal(t["ref_solver"].cpu().numpy(), got_ref[:, :rb.n_hor]))
+    gen.close()
+    from oracle import reftraj as ort
+    t0 = time.perf_counter()
+    want = ort.c_generate(rb)
+    t_cpu = time.perf_counter() - t0
+    # compulsory traffic per agent: path, previous reference, own plan, neighbours' plans, outputs (the voxels a
+    # ray touches are a few hundred bytes out of an 87 KB grid and are left out)
+    balg = float(np.mean(rb.n_path * 24 + N1 * 24 + N1 * 24 + (rb.nbr_end - rb.nbr_begin) * N1 * 24 + N1 * 48 + rb.n_hor * 48 + 8))
+    return {"workload": f"{rb.n} agents, 66x66x20 grids with potential field, {int((rb.nbr_end - rb.nbr_begin)[0])} neighbour plans each",
+            "metric": "reference trajectories/sec (agents/s)", "value": rb.n / (ms * 1e-3), "kernel_ms": ms, "dtype": "f64",
+            "max_rel_path_vel_diff_vs_cpu_port": float(np.abs(got_vel / want["path_vel"] - 1).max()),
+            "max_abs_ref_diff_vs_cpu_port": float(np.abs(got_ref - want["ref"]).max()), "solver_layout_rows_equal": solver_rows_equal,
+            "algorithmic_bytes_per_agent": balg,
+            "cpu_baseline": {"value": rb.n / t_cpu, "unit": "agents/s", "cores": ort.max_threads(), "kind": "port",
+                             "sample": f"all {rb.n} agents once, C restatement on all host threads"}}
+
+
 def config_dict(args, world):
     return {"workload": f"config2: 10-agent circular exchange, forest map, N=10, {args.swarms} independent swarm "
                         f"instances per GPU ({args.swarms * 10} agent QPs per GPU per step)",
@@ -473,6 +538,12 @@ def run_ours(args, rank, world, local_rank):
             corridor, cor_gbs = corridor_measure(args.corridor_agents, 10, local_rank)
             corridor["roofline"] = {"bound": "hbm", "achieved": cor_gbs, "peak": peak, "unit": "GB/s", "frac": cor_gbs / peak,
                                     "traffic": None, "note": "serial list logic in shared memory: latency bound, not HBM bound"}
+        reftraj = None
+        if args.corridor_agents > 0:
+            reftraj = reftraj_measure(args.corridor_agents, 10, local_rank)
+            rt_gbs = reftraj["algorithmic_bytes_per_agent"] * reftraj["value"] / 1e9
+            reftraj["roofline"] = {"bound": "hbm", "achieved": rt_gbs, "peak": peak, "unit": "GB/s", "frac": rt_gbs / peak,
+                                   "traffic": None, "note": "serial voxel traversal and pow/exp per visited voxel: latency bound"}
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -493,7 +564,7 @@ def run_ours(args, rank, world, local_rank):
                     ("optimal", "infeasible", "max_iter", "numerical", "node_limit", "row_overflow"), stat)},
                     "max_kkt_residual": kkt, "ipm_iters_per_solve": iters / max(1, stat.sum()),
                     "qp_relaxations_per_solve": nodes / max(1, stat.sum())},
-                "smem_bytes_per_block": pl.smem_bytes, "corridor": corridor}
+                "smem_bytes_per_block": pl.smem_bytes, "corridor": corridor, "reference_trajectory": reftraj}
         emit(line)
     pl.close()
     if dist:

@@ -106,6 +106,19 @@ class ReferenceTrajectoryGenerator:
             raise RuntimeError(f"hdsm_reftraj_batch failed ({rc}): {self.L.hdsm_reftraj_last_error(self.h).decode()}")
         return dict(ref=ref, path_vel=vel)
 
+    def generate_device(self, t, n, n_rob, stream_ptr=0):
+        """hdsm_reftraj_batch_device on a dict of torch tensors (keys as RefTrajBatch fields plus the outputs
+        ref, path_vel and optionally ref_solver); stream ordered, no synchronisation."""
+        def dp(k):
+            v = t.get(k)
+            return None if v is None else C.c_void_p(v.data_ptr())
+        rc = self.L.hdsm_reftraj_batch_device(
+            self.h, C.c_int(n), dp("grids"), dp("grid_index"), dp("dims"), dp("origins"), dp("path"), dp("n_path"), dp("prev_ref"),
+            dp("have_prev"), dp("increment"), dp("traj"), dp("global_id"), dp("nbr_begin"), dp("nbr_end"), dp("all_pos"),
+            dp("all_valid"), C.c_int(n_rob), dp("ref"), dp("ref_solver"), dp("path_vel"), C.c_void_p(stream_ptr))
+        if rc != 0:
+            raise RuntimeError(f"hdsm_reftraj_batch_device failed ({rc}): {self.L.hdsm_reftraj_last_error(self.h).decode()}")
+
     def close(self):
         if self.h is not None:
             self.L.hdsm_reftraj_destroy(self.h)
