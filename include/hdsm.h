@@ -159,7 +159,7 @@ void hdsm_comm_destroy(hdsm_handle* h);
  * hdsm_corridor_batch replaces Agent::GenerateSafeCorridor (agent_class.cpp:1236-1447) together with
  * convex_decomp_lib::GetPolyOcta3D and GetPolyOcta3DNew (convex_decomp_util/src/convex_decomp.cpp:5-376,
  * :590-1162 with FindCorners :378-561), the call at
- * agent_class.cpp:163, for a batch of agents; its outputs are exactly hdsm_solve_batch's poly_A / poly_b
+ * agent_class.cpp:165, for a batch of agents; its outputs are exactly hdsm_solve_batch's poly_A / poly_b
  * / poly_rows inputs (the conversion at :1428-1437).  One warp per agent; see csrc/hdsm_corridor.cu. */
 #define HDSM_COR_SQUEEZED 1      /* informational: a seed voxel was squeezed between occupied voxels and its polytope
                                     was grown with GetPolyOcta3DNew, as the reference does (:1385-1395) */
@@ -220,8 +220,8 @@ int hdsm_corridor_batch_device(hdsm_corridor* h, int n, const int8_t* grids, con
 
 /* ---- reference-trajectory generation ----------------------------
  * hdsm_reftraj_batch replaces Agent::GenerateReferenceTrajectory (agent_class.cpp:1449-1553, the call at
- * :166) with SamplePath (:1591-1663), KeepOnlyFreeReference (:1665-1687), ComputePathVelocity (:1689-1801),
- * GetVelocityLimit (:1803-1817) and the ray casts of path_finding_util::IsLineClear (path_tools.cpp:148-180,
+ * :171) with SamplePath (:1591-1663), KeepOnlyFreeReference (:1665-1693), ComputePathVelocity (:1695-1803),
+ * GetVelocityLimit (:1805-1817) and the ray casts of path_finding_util::IsLineClear (path_tools.cpp:148-180,
  * voxel_grid_util/src/raycast.cpp:21-186).  One warp per agent; see csrc/hdsm_reftraj.cu. */
 typedef struct hdsm_reftraj_params {
   int32_t n_hor;            /* n_hor: N; the reference trajectory has N + 1 points */

@@ -266,7 +266,7 @@ def corridor_batch(sw, poly_hor=None, n_it=42, rmax=18, voxel=0.3, max_path=16, 
 
 
 class CorridorLoop:
-    """Closed loop of the two replaced calls for a scenarios.Swarm (agent_class.cpp:163-174): every step the
+    """Closed loop of the two replaced calls for a scenarios.Swarm (agent_class.cpp:165-174): every step the
     corridor generator gets the previous step's polytopes, seeds, `poly_used_idx_` and plan, and its rows replace
     the synthetic polytopes of `Swarm.make_batch`.  `generate(cb)` is SafeCorridorGenerator.generate or a checker
     with the same signature."""

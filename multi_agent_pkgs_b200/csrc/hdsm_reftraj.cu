@@ -3,9 +3,9 @@
 // Replaces, per agent and per replanning step (multi_agent_planner/src/agent_class.cpp):
 //   Agent::GenerateReferenceTrajectory   :1449-1553   start point on the path, sampling, velocity reference
 //   Agent::SamplePath                    :1591-1663
-//   Agent::KeepOnlyFreeReference         :1665-1687
-//   Agent::ComputePathVelocity           :1689-1801   ray casts through the potential field + neighbour sweep
-//   Agent::GetVelocityLimit              :1803-1817
+//   Agent::KeepOnlyFreeReference         :1665-1693
+//   Agent::ComputePathVelocity           :1695-1803   ray casts through the potential field + neighbour sweep
+//   Agent::GetVelocityLimit              :1805-1817
 //   voxel_grid_util::Raycast             voxel_grid_util/src/raycast.cpp:21-186 (via path_finding_util::IsLineClear)
 // and writes `ref` in the layout hdsm_solve_batch_device reads ([n][N][6]) next to the full [n][N+1][6]
 // trajectory the next step starts from.
@@ -62,7 +62,7 @@ struct Grid {
   }
 };
 
-// GetVelocityLimit (:1803-1817)
+// GetVelocityLimit (:1805-1817)
 __device__ __forceinline__ double velocity_limit(const hdsm_reftraj_params& P, double occ, double dist) {
   occ = fmin(fmax(occ, 0.0), 100.0);
   const double alpha = sub(1.0, mul(pow(dvd(occ, 100.0), P.sens_pot), dvd(1.0, exp(mul(P.sens_dist, dist)))));
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(32) reftraj_kernel(const Args A) {
   for (int i = lane; i < (ns - 1) * 3; i += 32) ps[1 + i / 3][i % 3] = path[3 * start_idx + i];
   __syncwarp();
 
-  // ---- ComputePathVelocity (:1689-1801)
+  // ---- ComputePathVelocity (:1695-1803)
   double vel = P.path_vel_max;
   if (ns >= 2) {
     double vmin = P.path_vel_max;  // per lane, reduced at the end
@@ -193,13 +193,13 @@ __global__ void __launch_bounds__(32) reftraj_kernel(const Args A) {
       bool too_long;
       const bool hit = raycast(G, s, e, maxd, col, &too_long, [](int, double, double, double) {});
       if (too_long) break;
-      if (!hit) {  // clear: every visited point and the start limit the speed (:1712-1735)
+      if (!hit) {  // clear: every visited point and the start limit the speed (:1721-1748)
         int total = 0;
         const auto visit = [&](int k, double x, double y, double z) {
           if ((k & 31) == lane) {
             double val = (double)G.get((int)x, (int)y, (int)z);
             if (val == -1) val = 100;
-            // world-frame path start minus local-frame point, times the voxel size, as in the reference (:1726)
+            // world-frame path start minus local-frame point, times the voxel size, as in the reference (:1735)
             const double dist = mul(norm3(sub(ps[0][0], x), sub(ps[0][1], y), sub(ps[0][2], z)), P.voxel_size);
             vmin = fmin(vmin, velocity_limit(P, val, dist));
           }
@@ -207,13 +207,13 @@ __global__ void __launch_bounds__(32) reftraj_kernel(const Args A) {
         };
         raycast(G, s, e, maxd, col, &too_long, visit);
         visit(total, s[0], s[1], s[2]);  // visited_points.push_back(start)
-      } else {  // collision: its voxel and its distance in voxel units (:1737-1749), then stop
+      } else {  // collision: its voxel and its distance in voxel units (:1749-1766), then stop
         const int val = (int)(signed char)G.get((int)col[0], (int)col[1], (int)col[2]);
         vmin = fmin(vmin, velocity_limit(P, (double)val, norm3(sub(s[0], col[0]), sub(s[1], col[1]), sub(s[2], col[2]))));
         break;
       }
     }
-    // other agents as obstacles whose weight decays along the horizon (:1756-1798): neighbours on lanes
+    // other agents as obstacles whose weight decays along the horizon (:1769-1801): neighbours on lanes
     const int self = A.global_id[agent];
     const int nb0 = A.nbr_begin ? A.nbr_begin[agent] : 0, nb1 = A.nbr_end ? A.nbr_end[agent] : A.n_rob;
     const double* traj = A.traj + (size_t)agent * P.n_traj * 3;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(32) reftraj_kernel(const Args A) {
     }
   }
   __syncwarp();
-  // ---- KeepOnlyFreeReference (:1665-1687): from the first unknown / occupied sample on, repeat the last free one
+  // ---- KeepOnlyFreeReference (:1665-1693): from the first unknown / occupied sample on, repeat the last free one
   {
     bool bad = false;
     if (lane >= 1 && lane < np) {

@@ -1,7 +1,7 @@
 """Host-side mirror of the reference's reference-trajectory step, on top of the C ABI (include/hdsm.h).
 
 Reference: Agent::GenerateReferenceTrajectory (multi_agent_planner/src/agent_class.cpp:1449-1553) with
-SamplePath (:1591-1663), KeepOnlyFreeReference (:1665-1687), ComputePathVelocity (:1689-1801) and the ray
+SamplePath (:1591-1663), KeepOnlyFreeReference (:1665-1693), ComputePathVelocity (:1695-1803) and the ray
 casts of voxel_grid_util::Raycast (voxel_grid_util/src/raycast.cpp:21-186); SURVEY.md 8(f) row 2.
 `ReferenceTrajectoryGenerator.generate` is `hdsm_reftraj_batch`; its `ref` output is `traj_ref_curr_`, whose
 first N rows are `hdsm_solve_batch`'s `ref` input.

@@ -5,17 +5,17 @@
  * Restates, in plain C:
  *   rt_raycast          voxel_grid_util::Raycast               voxel_grid_util/src/raycast.cpp:21-186
  *                       (the core of path_finding_util::IsLineClear, path_tools.cpp:148-180)
- *   rt_velocity_limit   Agent::GetVelocityLimit                multi_agent_planner/src/agent_class.cpp:1803-1817
- *   rt_path_velocity    Agent::ComputePathVelocity             :1689-1801
+ *   rt_velocity_limit   Agent::GetVelocityLimit                multi_agent_planner/src/agent_class.cpp:1805-1817
+ *   rt_path_velocity    Agent::ComputePathVelocity             :1695-1803
  *   rt_generate         Agent::GenerateReferenceTrajectory     :1449-1553  (+ IsOnSegment :1864-1884,
- *                       SamplePath :1591-1663, KeepOnlyFreeReference :1665-1687)
+ *                       SamplePath :1591-1663, KeepOnlyFreeReference :1665-1693)
  *
  * Parity: rt_raycast is PINNED - tests/test_reftraj_oracle.py compares its visited points and collision
  * point bit for bit with the reference's own Raycast (raycast.cpp and voxel_grid.cpp compiled unmodified
  * into oracle/_ref/libref_voxel.so).  The rest lives in agent_class.cpp (ROS2 + Gurobi headers: not
  * compilable) and follows it by reading, including its frame mix-up in ComputePathVelocity (the distance of a
- * visited voxel is taken between the path start in WORLD metres and the voxel in LOCAL voxel units, :1726)
- * and the collision distance left in voxel units (:1741).  pow / exp come from libm here and from CUDA's
+ * visited voxel is taken between the path start in WORLD metres and the voxel in LOCAL voxel units, :1735)
+ * and the collision distance left in voxel units (:1755).  pow / exp come from libm here and from CUDA's
  * math library in the kernel: parity of the velocity is to 1e-12 relative, not bit for bit.
  */
 #include <math.h>
@@ -108,7 +108,7 @@ int rt_raycast(const int8_t* data, const int32_t dim_in[3], const double start[3
   return n;
 }
 
-double rt_velocity_limit(const reftraj_params* P, double occ_val, double dist_start) { /* :1803-1817 */
+double rt_velocity_limit(const reftraj_params* P, double occ_val, double dist_start) { /* :1805-1817 */
   if (occ_val < 0) occ_val = 0;
   if (occ_val > 100) occ_val = 100;
   const double alpha = (1 - pow(occ_val / 100, P->sens_pot) * (1 / exp(P->sens_dist * dist_start)));
@@ -117,7 +117,7 @@ double rt_velocity_limit(const reftraj_params* P, double occ_val, double dist_st
 
 static double norm3(double x, double y, double z) { return sqrt((x * x + y * y) + z * z); }
 
-/* ComputePathVelocity (:1689-1801).  path [n_path][3] world metres (path[0] = the sampling start);
+/* ComputePathVelocity (:1695-1803).  path [n_path][3] world metres (path[0] = the sampling start);
  * traj [n_traj][3] own plan positions; all_pos [n_rob][n_traj][3], all_valid [n_rob]; self = own id. */
 double rt_path_velocity(const reftraj_params* P, const int8_t* data, const int32_t dim[3], const double origin[3],
                         const double* path, int n_path, const double* traj, const double* all_pos, const uint8_t* all_valid,
@@ -134,7 +134,7 @@ double rt_path_velocity(const reftraj_params* P, const int8_t* data, const int32
     const double maxd = norm3(s[0] - e[0], s[1] - e[1], s[2] - e[2]);
     int nv = rt_raycast(data, dim, s, e, maxd, visited, RT_MAX_VISITED - 1, col);
     if (nv < 0) break;
-    if (col[0] == -1) { /* clear: every visited voxel and the start limit the speed (:1712-1735) */
+    if (col[0] == -1) { /* clear: every visited voxel and the start limit the speed (:1721-1748) */
       if (nv > RT_MAX_VISITED - 1) nv = RT_MAX_VISITED - 1;
       visited[3 * nv] = s[0], visited[3 * nv + 1] = s[1], visited[3 * nv + 2] = s[2];
       ++nv;
@@ -142,12 +142,12 @@ double rt_path_velocity(const reftraj_params* P, const int8_t* data, const int32
         const double* pt = visited + 3 * k;
         double val = (double)vg_get(data, idim, (int)pt[0], (int)pt[1], (int)pt[2]);
         if (val == -1) val = 100;
-        /* world-frame path start minus local-frame voxel, as in the reference (:1726) */
+        /* world-frame path start minus local-frame voxel, as in the reference (:1735) */
         const double dist = norm3(path[0] - pt[0], path[1] - pt[1], path[2] - pt[2]) * P->voxel;
         const double v = rt_velocity_limit(P, val, dist);
         if (v < vel) vel = v;
       }
-    } else { /* collision: its voxel and its distance in voxel units (:1737-1749), then stop */
+    } else { /* collision: its voxel and its distance in voxel units (:1749-1766), then stop */
       const int8_t val = (int8_t)vg_get(data, idim, (int)col[0], (int)col[1], (int)col[2]);
       const double v = rt_velocity_limit(P, (double)val, norm3(s[0] - col[0], s[1] - col[1], s[2] - col[2]));
       if (v < vel) vel = v;
@@ -155,7 +155,7 @@ double rt_path_velocity(const reftraj_params* P, const int8_t* data, const int32
     }
   }
   free(visited);
-  /* other agents as obstacles whose weight decays along the horizon (:1756-1798) */
+  /* other agents as obstacles whose weight decays along the horizon (:1769-1801) */
   for (int i = 0; i < P->n_traj; ++i) {
     const double* me = traj + 3 * i;
     for (int j = nbr_begin; j < nbr_end; ++j) {
@@ -239,7 +239,7 @@ void rt_generate(const reftraj_params* P, const int8_t* data, const int32_t dim[
       }
     }
   }
-  /* KeepOnlyFreeReference (:1665-1687): from the first unknown / occupied sample on, repeat the last free one */
+  /* KeepOnlyFreeReference (:1665-1693): from the first unknown / occupied sample on, repeat the last free one */
   for (int i = 1; i < np; ++i) {
     const double* pt = pts + 3 * i;
     const int v = vg_get(data, idim, (int)((pt[0] - origin[0]) / P->voxel), (int)((pt[1] - origin[1]) / P->voxel),

@@ -65,7 +65,7 @@ def test_reference_trajectory_properties(forest):
             if np.linalg.norm(d) > 1e-2:
                 assert np.allclose(ref[i, k, 3:], vel[i] * d / np.linalg.norm(d), rtol=0, atol=1e-9)
         assert np.array_equal(ref[i, N, 3:], ref[i, N - 1, 3:])
-        for k in range(N + 1):                                                 # samples lie in free voxels (:1665-1687)
+        for k in range(N + 1):                                                 # samples lie in free voxels (:1665-1693)
             c = ((ref[i, k, :3] - rb.origins[i]) / rb.voxel).astype(int)
             assert rb.grids[i][c[2], c[1], c[0]] not in (100, -1)
 
