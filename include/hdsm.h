@@ -271,6 +271,34 @@ int hdsm_reftraj_batch_device(hdsm_reftraj* h, int n, const int8_t* grids, const
                               const double* all_pos, const uint8_t* all_valid, int n_rob, double* ref, double* ref_solver,
                               double* path_vel, void* stream);
 
+/* ---- local-map post-processing -----------------------------------
+ * hdsm_map_batch replaces the grid post-processing every map update runs before the grid is published to the
+ * planner (mapping_util/src/map_builder.cpp:207-216): MapBuilder::SetUncertainToUnknown (:331-365),
+ * VoxelGrid::InflateObstacles and VoxelGrid::CreatePotentialField (voxel_grid_util/src/voxel_grid.cpp:251-298,
+ * stencils from CreateMask :192-226).  One thread block per grid, the grid held twice in shared memory; see
+ * csrc/hdsm_map.cu.  The crop / merge / ray-cast clearing of map_builder.cpp:80-205 is not part of it. */
+typedef struct hdsm_map_params {
+  double voxel_size;      /* VoxelGrid::GetVoxSize() */
+  double inflation_dist;  /* inflation_dist (mapping_util/config: 0.3) */
+  double potential_dist;  /* potential_dist (1.5); 0 = no potential field */
+  int32_t potential_pow;  /* potential_pow (4) */
+  int32_t reserved;
+} hdsm_map_params;
+
+typedef struct hdsm_map hdsm_map;
+
+/* grid_stride: voxels per grid slot; two copies must fit into shared memory (grid_stride <= 116 000). */
+int hdsm_map_create(const hdsm_map_params* params, int max_grids, size_t grid_stride, int device, hdsm_map** out);
+void hdsm_map_destroy(hdsm_map* h);
+const char* hdsm_map_last_error(const hdsm_map* h);
+int64_t hdsm_map_launch_count(const hdsm_map* h);
+
+/* grids_in / grids_out [n_grids][grid_stride] int8 (x fastest; 0 free, 100 occupied, -1 unknown), dims [n_grids][3].
+ * HOST pointers, synchronous; the _device twin takes device pointers and a stream.  in and out may not alias. */
+int hdsm_map_batch(hdsm_map* h, int n_grids, const int8_t* grids_in, const int32_t* dims, int8_t* grids_out);
+int hdsm_map_batch_device(hdsm_map* h, int n_grids, const int8_t* grids_in, const int32_t* dims, int8_t* grids_out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

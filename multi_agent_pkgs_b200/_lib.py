@@ -17,7 +17,9 @@ EXPORTS = ["hdsm_version", "hdsm_create", "hdsm_destroy", "hdsm_last_error", "hd
            "hdsm_corridor_create", "hdsm_corridor_destroy", "hdsm_corridor_last_error", "hdsm_corridor_launch_count",
            "hdsm_corridor_smem_bytes", "hdsm_corridor_batch", "hdsm_corridor_batch_device",
            "hdsm_reftraj_create", "hdsm_reftraj_destroy", "hdsm_reftraj_last_error", "hdsm_reftraj_launch_count",
-           "hdsm_reftraj_batch", "hdsm_reftraj_batch_device"]
+           "hdsm_reftraj_batch", "hdsm_reftraj_batch_device",
+           "hdsm_map_create", "hdsm_map_destroy", "hdsm_map_last_error", "hdsm_map_launch_count", "hdsm_map_batch",
+           "hdsm_map_batch_device"]
 
 
 class HdsmParams(C.Structure):

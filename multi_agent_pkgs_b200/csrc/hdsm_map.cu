@@ -1,0 +1,282 @@
+// Local-map post-processing for sm_100a: one thread block per voxel grid, SURVEY.md section 8(f) row 4.
+//
+// Replaces, per agent and per map update, the sequence of mapping_util/src/map_builder.cpp:207-216:
+//   MapBuilder::SetUncertainToUnknown   map_builder.cpp:331-365            unknown space grows by the inflation cube
+//   VoxelGrid::InflateObstacles         voxel_grid_util/src/voxel_grid.cpp:251-277
+//   VoxelGrid::CreatePotentialField     voxel_grid.cpp:279-298
+// (stencils from VoxelGrid::CreateMask, voxel_grid.cpp:192-226).  The output grid is what
+// hdsm_corridor_batch and hdsm_reftraj_batch read.
+//
+// Design.  A local grid (66 x 66 x 20 int8 = 87 KB) fits twice into the 227 KB of shared memory of one SM: the
+// block loads it once with 16-byte accesses, runs the three stencil passes ping-ponging between the two
+// copies, and writes the result once - HBM sees exactly one read and one write per voxel.  The reference
+// scatters from every occupied voxel; here every voxel gathers, which needs no atomics and is exact because
+// none of the three passes feeds on its own output (the potential stencil's only value of 100 is its centre).
+// The potential pass walks the stencil in order of decreasing value and stops at the first occupied hit.
+// The stencils are computed on the host when the handle is created, with the reference's formula.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/hdsm.h"
+
+namespace hdsm_mp {
+
+constexpr int kOcc = 100, kUnk = -1;
+constexpr int kThreads = 512;
+
+struct Args {
+  int n_grids, cube, n_inf, n_pot;
+  size_t stride;
+  const int8_t* in;
+  int8_t* out;
+  const int32_t* dims;
+  const int8_t* inf_off;  // [n_inf][4] (dx, dy, dz, -)
+  const int8_t* pot_off;  // [n_pot][4] (dx, dy, dz, value), value descending
+};
+
+__global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
+  extern __shared__ __align__(16) int8_t smem[];
+  const int g = blockIdx.x;
+  if (g >= A.n_grids) return;
+  const int dx = A.dims[3 * g], dy = A.dims[3 * g + 1], dz = A.dims[3 * g + 2];
+  const int nvox = dx * dy * dz;
+  const size_t half = (A.stride + 15) & ~size_t(15);
+  int8_t* P = smem;         // ping
+  int8_t* Q = smem + half;  // pong
+  const int8_t* src = A.in + (size_t)g * A.stride;
+  int8_t* dst = A.out + (size_t)g * A.stride;
+  const int tid = threadIdx.x;
+  // ---- load (16-byte accesses where the grid start allows it)
+  if ((reinterpret_cast<size_t>(src) & 15) == 0) {
+    const int n16 = nvox / 16;
+    for (int i = tid; i < n16; i += kThreads) reinterpret_cast<int4*>(P)[i] = __ldg(reinterpret_cast<const int4*>(src) + i);
+    for (int i = n16 * 16 + tid; i < nvox; i += kThreads) P[i] = src[i];
+  } else {
+    for (int i = tid; i < nvox; i += kThreads) P[i] = src[i];
+  }
+  __syncthreads();
+  // ---- SetUncertainToUnknown: P -> Q.  A voxel that is not occupied turns unknown when an unknown voxel of the
+  // interior [c, dim - c) lies within the cube of half-width c around it.
+  const int c = A.cube;
+  for (int i = tid; i < nvox; i += kThreads) {
+    const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
+    int8_t v = P[i];
+    if (v != kOcc && v != kUnk && c > 0) {
+      bool hit = false;
+      for (int zz = max(z - c, c); zz <= min(z + c, dz - c - 1) && !hit; ++zz)
+        for (int yy = max(y - c, c); yy <= min(y + c, dy - c - 1) && !hit; ++yy)
+          for (int xx = max(x - c, c); xx <= min(x + c, dx - c - 1); ++xx)
+            if (P[xx + yy * dx + zz * dx * dy] == kUnk) {
+              hit = true;
+              break;
+            }
+      if (hit) v = kUnk;
+    }
+    Q[i] = v;
+  }
+  __syncthreads();
+  // ---- InflateObstacles: Q -> P.  A voxel becomes occupied when an occupied voxel (before the pass) has it in
+  // its stencil: gather over the mirrored stencil.
+  for (int i = tid; i < nvox; i += kThreads) {
+    const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
+    int8_t v = Q[i];
+    if (v != kOcc) {
+      for (int m = 0; m < A.n_inf; ++m) {
+        const int xx = x - A.inf_off[4 * m], yy = y - A.inf_off[4 * m + 1], zz = z - A.inf_off[4 * m + 2];
+        if (xx >= 0 && yy >= 0 && zz >= 0 && xx < dx && yy < dy && zz < dz && Q[xx + yy * dx + zz * dx * dy] == kOcc) {
+          v = kOcc;
+          break;
+        }
+      }
+    }
+    P[i] = v;
+  }
+  __syncthreads();
+  // ---- CreatePotentialField: P -> Q.  Known voxels take the largest stencil value any occupied voxel offers;
+  // the stencil is sorted by value, so the first occupied hit decides and values not above the own one end the walk.
+  for (int i = tid; i < nvox; i += kThreads) {
+    const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
+    int8_t v = P[i];
+    if (v != kUnk && v != kOcc) {
+      for (int m = 0; m < A.n_pot; ++m) {
+        const int8_t val = A.pot_off[4 * m + 3];
+        if (val <= v) break;
+        const int xx = x - A.pot_off[4 * m], yy = y - A.pot_off[4 * m + 1], zz = z - A.pot_off[4 * m + 2];
+        if (xx >= 0 && yy >= 0 && zz >= 0 && xx < dx && yy < dy && zz < dz && P[xx + yy * dx + zz * dx * dy] == kOcc) {
+          v = val;
+          break;
+        }
+      }
+    }
+    Q[i] = v;
+  }
+  __syncthreads();
+  // ---- store
+  if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
+    const int n16 = nvox / 16;
+    for (int i = tid; i < n16; i += kThreads) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(Q)[i];
+    for (int i = n16 * 16 + tid; i < nvox; i += kThreads) dst[i] = Q[i];
+  } else {
+    for (int i = tid; i < nvox; i += kThreads) dst[i] = Q[i];
+  }
+}
+
+// VoxelGrid::CreateMask (voxel_grid.cpp:192-226) on the host
+struct MaskEntry {
+  int x, y, z;
+  int8_t v;
+};
+inline std::vector<MaskEntry> create_mask(double vox, double mask_dist, double power) {
+  std::vector<MaskEntry> m;
+  if (!(mask_dist > 0)) return m;
+  const int rn = (int)std::ceil(mask_dist / vox);
+  for (int x = -rn; x <= rn; ++x)
+    for (int y = -rn; y <= rn; ++y)
+      for (int z = -rn; z <= rn; ++z) {
+        const double d = std::hypot(std::hypot((double)x, (double)y), (double)z);
+        if (std::abs(d - 1) * vox >= mask_dist) continue;
+        const double h = 100.0 * std::pow((1 - (double)std::hypot(std::hypot((double)x, (double)y), (double)z) / (rn + 1)), power);
+        if (h > 1e-3) m.push_back(MaskEntry{x, y, z, (int8_t)h});
+      }
+  return m;
+}
+
+}  // namespace hdsm_mp
+
+struct hdsm_map {
+  hdsm_map_params prm{};
+  int device = 0, max_grids = 0, cube = 0, n_inf = 0, n_pot = 0;
+  size_t grid_stride = 0, smem = 0;
+  cudaStream_t stream = nullptr;
+  int8_t *d_inf = nullptr, *d_pot = nullptr;
+  unsigned char *d_buf = nullptr;
+  size_t buf_cap = 0;
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+int mfail(hdsm_map* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define MCU(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) return mfail(h, HDSM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+}  // namespace
+
+extern "C" {
+
+void hdsm_map_destroy(hdsm_map* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_inf);
+  cudaFree(h->d_pot);
+  cudaFree(h->d_buf);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride, int device, hdsm_map** out) {
+  if (!p || !out || max_grids < 1 || grid_stride < 1) return HDSM_ERR_INVALID;
+  if (!(p->voxel_size > 0) || p->inflation_dist < 0 || p->potential_dist < 0 || p->potential_pow < 0) return HDSM_ERR_INVALID;
+  const size_t smem = 2 * ((grid_stride + 15) & ~size_t(15));
+  if (smem > 227 * 1024) return HDSM_ERR_INVALID;  // both copies of a grid must fit into one SM's shared memory
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return HDSM_ERR_CUDA;  // no CPU fallback
+  hdsm_map* h = new (std::nothrow) hdsm_map();
+  if (!h) return HDSM_ERR_INVALID;
+  h->prm = *p, h->device = device, h->max_grids = max_grids, h->grid_stride = grid_stride, h->smem = smem;
+  h->cube = (int)std::ceil(p->inflation_dist / p->voxel_size);
+  // stencils: inflation (values unused), potential (entries of value 0 change nothing: dropped; sorted by value)
+  std::vector<hdsm_mp::MaskEntry> inf = hdsm_mp::create_mask(p->voxel_size, p->inflation_dist, 1);
+  std::vector<hdsm_mp::MaskEntry> pot = hdsm_mp::create_mask(p->voxel_size, p->potential_dist, (double)p->potential_pow);
+  pot.erase(std::remove_if(pot.begin(), pot.end(), [](const hdsm_mp::MaskEntry& e) { return e.v <= 0; }), pot.end());
+  std::stable_sort(pot.begin(), pot.end(), [](const hdsm_mp::MaskEntry& a, const hdsm_mp::MaskEntry& b) { return a.v > b.v; });
+  for (const auto& e : pot)
+    if (e.v >= 100 && (e.x || e.y || e.z)) {  // would make the pass feed on itself
+      delete h;
+      return HDSM_ERR_INVALID;
+    }
+  const auto pack = [](const std::vector<hdsm_mp::MaskEntry>& m) {
+    std::vector<int8_t> v(4 * m.size() + 4, 0);
+    for (size_t i = 0; i < m.size(); ++i) v[4 * i] = (int8_t)m[i].x, v[4 * i + 1] = (int8_t)m[i].y, v[4 * i + 2] = (int8_t)m[i].z, v[4 * i + 3] = m[i].v;
+    return v;
+  };
+  const std::vector<int8_t> hi = pack(inf), hp = pack(pot);
+  h->n_inf = (int)inf.size(), h->n_pot = (int)pot.size();
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_inf, hi.size());
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_pot, hp.size());
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_inf, hi.data(), hi.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_pot, hp.data(), hp.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hdsm_mp::map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    hdsm_map_destroy(h);
+    return HDSM_ERR_CUDA;
+  }
+  *out = h;
+  return HDSM_OK;
+}
+
+const char* hdsm_map_last_error(const hdsm_map* h) { return h ? h->err.c_str() : "null handle"; }
+int64_t hdsm_map_launch_count(const hdsm_map* h) { return h ? h->launches : 0; }
+
+int hdsm_map_batch_device(hdsm_map* h, int n_grids, const int8_t* grids_in, const int32_t* dims, int8_t* grids_out, void* stream) {
+  if (!h) return HDSM_ERR_INVALID;
+  if (n_grids < 0 || !grids_in || !dims || !grids_out) return mfail(h, HDSM_ERR_INVALID, "null argument");
+  if (n_grids > h->max_grids) return mfail(h, HDSM_ERR_CAPACITY, "n_grids exceeds max_grids");
+  if (n_grids == 0) return HDSM_OK;
+  MCU(cudaSetDevice(h->device));
+  hdsm_mp::Args a{};
+  a.n_grids = n_grids, a.cube = h->cube, a.n_inf = h->n_inf, a.n_pot = h->n_pot, a.stride = h->grid_stride;
+  a.in = grids_in, a.out = grids_out, a.dims = dims, a.inf_off = h->d_inf, a.pot_off = h->d_pot;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  hdsm_mp::map_kernel<<<n_grids, hdsm_mp::kThreads, h->smem, s>>>(a);
+  h->launches += 1;
+  MCU(cudaGetLastError());
+  return HDSM_OK;
+}
+
+int hdsm_map_batch(hdsm_map* h, int n_grids, const int8_t* grids_in, const int32_t* dims, int8_t* grids_out) {
+  if (!h) return HDSM_ERR_INVALID;
+  if (n_grids < 0 || !grids_in || !dims || !grids_out) return mfail(h, HDSM_ERR_INVALID, "null argument");
+  if (n_grids > h->max_grids) return mfail(h, HDSM_ERR_CAPACITY, "n_grids exceeds max_grids");
+  if (n_grids == 0) return HDSM_OK;
+  for (int i = 0; i < n_grids; ++i) {
+    const int32_t* d = dims + 3 * i;
+    if (d[0] < 1 || d[1] < 1 || d[2] < 1 || (size_t)d[0] * d[1] * d[2] > h->grid_stride)
+      return mfail(h, HDSM_ERR_INVALID, "grid dimensions exceed grid_stride");
+  }
+  MCU(cudaSetDevice(h->device));
+  const size_t gb = (size_t)n_grids * h->grid_stride, db = ((size_t)n_grids * 12 + 255) & ~size_t(255);
+  const size_t need = 2 * ((gb + 255) & ~size_t(255)) + db;
+  if (need > h->buf_cap) {
+    cudaFree(h->d_buf);
+    h->d_buf = nullptr, h->buf_cap = 0;
+    MCU(cudaMalloc(&h->d_buf, need));
+    h->buf_cap = need;
+  }
+  int8_t* d_in = reinterpret_cast<int8_t*>(h->d_buf);
+  int8_t* d_out = d_in + ((gb + 255) & ~size_t(255));
+  int32_t* d_dims = reinterpret_cast<int32_t*>(d_out + ((gb + 255) & ~size_t(255)));
+  MCU(cudaMemcpyAsync(d_in, grids_in, gb, cudaMemcpyHostToDevice, h->stream));
+  MCU(cudaMemcpyAsync(d_dims, dims, (size_t)n_grids * 12, cudaMemcpyHostToDevice, h->stream));
+  const int rc = hdsm_map_batch_device(h, n_grids, d_in, d_dims, d_out, h->stream);
+  if (rc != HDSM_OK) return rc;
+  MCU(cudaMemcpyAsync(grids_out, d_out, gb, cudaMemcpyDeviceToHost, h->stream));
+  MCU(cudaStreamSynchronize(h->stream));
+  return HDSM_OK;
+}
+
+}  // extern "C"
