@@ -38,6 +38,11 @@ struct Args {
   const int32_t* dims;
   const int8_t* inf_off;  // [n_inf][4] (dx, dy, dz, -)
   const int8_t* pot_off;  // [n_pot][4] (dx, dy, dz, value), value descending
+  // row form of the potential stencil: for every (dy, dz) the values at |dx| = 0..7, pairs sorted by their best value
+  int n_pair, rn;
+  size_t bits_bytes;                    // shared memory set aside for the occupancy bit rows
+  const int2* pair_yz;                  // (dy, dz) and best value packed: x = dy | dz << 8 | best << 16, y unused
+  const unsigned long long* pair_vals;  // eight int8 values, |dx| = 0..7
 };
 
 __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
@@ -49,9 +54,13 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   const size_t half = (A.stride + 15) & ~size_t(15);
   int8_t* P = smem;         // ping
   int8_t* Q = smem + half;  // pong
+  int* st_inf = reinterpret_cast<int*>(smem + 2 * half);  // stencils: one packed int (dx, dy, dz, value) per entry
+  int* st_pot = st_inf + A.n_inf;
   const int8_t* src = A.in + (size_t)g * A.stride;
   int8_t* dst = A.out + (size_t)g * A.stride;
   const int tid = threadIdx.x;
+  for (int m = tid; m < A.n_inf; m += kThreads) st_inf[m] = reinterpret_cast<const int*>(A.inf_off)[m];
+  for (int m = tid; m < A.n_pot; m += kThreads) st_pot[m] = reinterpret_cast<const int*>(A.pot_off)[m];
   // ---- load (16-byte accesses where the grid start allows it)
   if ((reinterpret_cast<size_t>(src) & 15) == 0) {
     const int n16 = nvox / 16;
@@ -88,8 +97,9 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
     int8_t v = Q[i];
     if (v != kOcc) {
       for (int m = 0; m < A.n_inf; ++m) {
-        const int xx = x - A.inf_off[4 * m], yy = y - A.inf_off[4 * m + 1], zz = z - A.inf_off[4 * m + 2];
-        if (xx >= 0 && yy >= 0 && zz >= 0 && xx < dx && yy < dy && zz < dz && Q[xx + yy * dx + zz * dx * dy] == kOcc) {
+        const int e = st_inf[m];
+        const int xx = x - (int)(signed char)(e & 0xff), yy = y - (int)(signed char)((e >> 8) & 0xff), zz = z - (int)(signed char)((e >> 16) & 0xff);
+        if ((unsigned)xx < (unsigned)dx && (unsigned)yy < (unsigned)dy && (unsigned)zz < (unsigned)dz && Q[xx + yy * dx + zz * dx * dy] == kOcc) {
           v = kOcc;
           break;
         }
@@ -98,23 +108,68 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
     P[i] = v;
   }
   __syncthreads();
-  // ---- CreatePotentialField: P -> Q.  Known voxels take the largest stencil value any occupied voxel offers;
-  // the stencil is sorted by value, so the first occupied hit decides and values not above the own one end the walk.
-  for (int i = tid; i < nvox; i += kThreads) {
-    const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
-    int8_t v = P[i];
-    if (v != kUnk && v != kOcc) {
-      for (int m = 0; m < A.n_pot; ++m) {
-        const int8_t val = A.pot_off[4 * m + 3];
-        if (val <= v) break;
-        const int xx = x - A.pot_off[4 * m], yy = y - A.pot_off[4 * m + 1], zz = z - A.pot_off[4 * m + 2];
-        if (xx >= 0 && yy >= 0 && zz >= 0 && xx < dx && yy < dy && zz < dz && P[xx + yy * dx + zz * dx * dy] == kOcc) {
-          v = val;
-          break;
+  // ---- CreatePotentialField: P -> Q.  Known voxels take the largest stencil value any occupied voxel offers.
+  // Row form: occupancy is packed one bit per voxel along x (bit x + 8 of the row, so that a window never starts
+  // below bit 0); for a stencil row (dy, dz) the nearest occupied voxel along x is a count-leading / find-first on
+  // an 11-bit window, and because the value only falls with |dx| that one voxel decides the row.  Rows are
+  // visited in order of their best value and the walk stops once no row can beat what the voxel already has.
+  const int nw = (dx + 16 + 31) / 32 + 1;  // words per row, one spare
+  unsigned* bits = reinterpret_cast<unsigned*>(st_pot + A.n_pot);
+  const bool rows_ok = A.n_pair > 0 && A.rn <= 7 && (size_t)nw * dy * dz * 4 <= A.bits_bytes;
+  if (rows_ok) {
+    const int warp = tid >> 5, lane = tid & 31, nwarp = kThreads / 32;
+    for (int r = warp; r < dy * dz; r += nwarp)
+      for (int w = 0; w < nw; ++w) {
+        const int x = w * 32 + lane - 8;
+        const unsigned m = __ballot_sync(0xffffffffu, x >= 0 && x < dx && P[x + r * dx] == kOcc);
+        if (lane == 0) bits[r * nw + w] = m;
+      }
+    __syncthreads();
+    const int rn = A.rn;
+    const unsigned wmask = (1u << (2 * rn + 1)) - 1u, lmask = (1u << (rn + 1)) - 1u;
+    for (int i = tid; i < nvox; i += kThreads) {
+      const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
+      int v = P[i];
+      if (v != kUnk && v != kOcc) {
+        const int bp = x - rn + 8, wi = bp >> 5, sh = bp & 31;
+        for (int m = 0; m < A.n_pair; ++m) {
+          const int e = A.pair_yz[m].x;
+          if (((e >> 16) & 0xff) <= v) break;
+          const int yy = y + (int)(signed char)(e & 0xff), zz = z + (int)(signed char)((e >> 8) & 0xff);
+          if ((unsigned)yy >= (unsigned)dy || (unsigned)zz >= (unsigned)dz) continue;
+          const unsigned* row = bits + (yy + zz * dy) * nw + wi;
+          const unsigned win = (unsigned)((((unsigned long long)row[1] << 32) | row[0]) >> sh) & wmask;
+          if (!win) continue;
+          const unsigned right = win >> rn, left = win & lmask;
+          int d = 99;
+          if (right) d = __ffs(right) - 1;
+          if (left) d = min(d, rn - (31 - __clz(left)));
+          const int val = (int)(signed char)((A.pair_vals[m] >> (8 * d)) & 0xff);
+          v = max(v, val);
         }
       }
+      Q[i] = (int8_t)v;
     }
-    Q[i] = v;
+  } else {
+    // scan form: the stencil is sorted by value, so the first occupied hit decides and values not above the own
+    // one end the walk
+    for (int i = tid; i < nvox; i += kThreads) {
+      const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
+      int8_t v = P[i];
+      if (v != kUnk && v != kOcc) {
+        for (int m = 0; m < A.n_pot; ++m) {
+          const int e = st_pot[m];
+          const int8_t val = (int8_t)(e >> 24);
+          if (val <= v) break;
+          const int xx = x - (int)(signed char)(e & 0xff), yy = y - (int)(signed char)((e >> 8) & 0xff), zz = z - (int)(signed char)((e >> 16) & 0xff);
+          if ((unsigned)xx < (unsigned)dx && (unsigned)yy < (unsigned)dy && (unsigned)zz < (unsigned)dz && P[xx + yy * dx + zz * dx * dy] == kOcc) {
+            v = val;
+            break;
+          }
+        }
+      }
+      Q[i] = v;
+    }
   }
   __syncthreads();
   // ---- store
@@ -155,6 +210,10 @@ struct hdsm_map {
   size_t grid_stride = 0, smem = 0;
   cudaStream_t stream = nullptr;
   int8_t *d_inf = nullptr, *d_pot = nullptr;
+  int2* d_pair = nullptr;
+  unsigned long long* d_pvals = nullptr;
+  int n_pair = 0, rn = 0;
+  size_t bits_bytes = 0;
   unsigned char *d_buf = nullptr;
   size_t buf_cap = 0;
   int64_t launches = 0;
@@ -181,6 +240,8 @@ void hdsm_map_destroy(hdsm_map* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_inf);
   cudaFree(h->d_pot);
+  cudaFree(h->d_pair);
+  cudaFree(h->d_pvals);
   cudaFree(h->d_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -189,8 +250,8 @@ void hdsm_map_destroy(hdsm_map* h) {
 int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride, int device, hdsm_map** out) {
   if (!p || !out || max_grids < 1 || grid_stride < 1) return HDSM_ERR_INVALID;
   if (!(p->voxel_size > 0) || p->inflation_dist < 0 || p->potential_dist < 0 || p->potential_pow < 0) return HDSM_ERR_INVALID;
-  const size_t smem = 2 * ((grid_stride + 15) & ~size_t(15));
-  if (smem > 227 * 1024) return HDSM_ERR_INVALID;  // both copies of a grid must fit into one SM's shared memory
+  size_t smem = 2 * ((grid_stride + 15) & ~size_t(15));
+  if (smem > 220 * 1024) return HDSM_ERR_INVALID;  // both copies of a grid (and the stencils) must fit into one SM's shared memory
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return HDSM_ERR_CUDA;  // no CPU fallback
   hdsm_map* h = new (std::nothrow) hdsm_map();
@@ -214,12 +275,52 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
   };
   const std::vector<int8_t> hi = pack(inf), hp = pack(pot);
   h->n_inf = (int)inf.size(), h->n_pot = (int)pot.size();
+  smem += 4 * (size_t)(h->n_inf + h->n_pot);
+  if (smem > 227 * 1024) {
+    delete h;
+    return HDSM_ERR_INVALID;
+  }
+  // row form of the potential stencil (used when the radius is at most 7 voxels and the bit rows fit)
+  std::vector<int2> pair_yz;
+  std::vector<unsigned long long> pair_vals;
+  h->rn = p->potential_dist > 0 ? (int)std::ceil(p->potential_dist / p->voxel_size) : 0;
+  if (h->rn >= 1 && h->rn <= 7) {
+    struct Row {
+      int dy, dz, best;
+      unsigned long long vals;
+    };
+    std::vector<Row> rows;
+    for (int dy = -h->rn; dy <= h->rn; ++dy)
+      for (int dz = -h->rn; dz <= h->rn; ++dz) {
+        Row r{dy, dz, 0, 0ull};
+        for (const auto& e : pot)
+          if (e.y == dy && e.z == dz && e.x >= 0) {
+            r.vals |= (unsigned long long)(unsigned char)e.v << (8 * e.x);
+            r.best = std::max(r.best, (int)e.v);
+          }
+        if (r.best > 0) rows.push_back(r);
+      }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.best > b.best; });
+    for (const Row& r : rows) {
+      pair_yz.push_back(make_int2((r.dy & 0xff) | ((r.dz & 0xff) << 8) | (r.best << 16), 0));
+      pair_vals.push_back(r.vals);
+    }
+    h->n_pair = (int)rows.size();
+    const size_t room = 227 * 1024 - smem;  // whatever shared memory is left holds the bit rows
+    h->bits_bytes = room & ~size_t(15);
+    smem += h->bits_bytes;
+  }
+  h->smem = smem;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_inf, hi.size());
   if (e == cudaSuccess) e = cudaMalloc(&h->d_pot, hp.size());
   if (e == cudaSuccess) e = cudaMemcpy(h->d_inf, hi.data(), hi.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_pot, hp.data(), hp.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h->n_pair) e = cudaMalloc(&h->d_pair, pair_yz.size() * sizeof(int2));
+  if (e == cudaSuccess && h->n_pair) e = cudaMalloc(&h->d_pvals, pair_vals.size() * 8);
+  if (e == cudaSuccess && h->n_pair) e = cudaMemcpy(h->d_pair, pair_yz.data(), pair_yz.size() * sizeof(int2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h->n_pair) e = cudaMemcpy(h->d_pvals, pair_vals.data(), pair_vals.size() * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(hdsm_mp::map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     hdsm_map_destroy(h);
@@ -241,6 +342,7 @@ int hdsm_map_batch_device(hdsm_map* h, int n_grids, const int8_t* grids_in, cons
   hdsm_mp::Args a{};
   a.n_grids = n_grids, a.cube = h->cube, a.n_inf = h->n_inf, a.n_pot = h->n_pot, a.stride = h->grid_stride;
   a.in = grids_in, a.out = grids_out, a.dims = dims, a.inf_off = h->d_inf, a.pot_off = h->d_pot;
+  a.n_pair = h->n_pair, a.rn = h->rn, a.pair_yz = h->d_pair, a.pair_vals = h->d_pvals, a.bits_bytes = h->bits_bytes;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   hdsm_mp::map_kernel<<<n_grids, hdsm_mp::kThreads, h->smem, s>>>(a);
   h->launches += 1;

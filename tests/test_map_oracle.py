@@ -43,7 +43,7 @@ def test_process_properties():
     out = om.c_process(grids, 0.3, 0.3, 1.5, 4)
     assert ((grids == 100) <= (out == 100)).all()                    # occupied stays occupied
     assert (out == 100).sum() > 5 * (grids == 100).sum()             # and grows by the inflation stencil
-    assert ((grids == -1) <= (out == -1)).all()                      # unknown stays unknown
+    assert ((grids == -1) <= ((out == -1) | (out == 100))).all()     # unknown stays unknown unless an obstacle inflates into it
     known_free = (out != 100) & (out != -1)
     assert out[known_free].min() >= 0 and out[known_free].max() < 100 and (out[known_free] > 0).any()
     again = om.c_process(out, 0.3, 0.0, 0.0, 4)                      # no inflation, no potential: identity
