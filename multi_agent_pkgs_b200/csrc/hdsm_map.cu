@@ -114,7 +114,10 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   // an 11-bit window, and because the value only falls with |dx| that one voxel decides the row.  Rows are
   // visited in order of their best value and the walk stops once no row can beat what the voxel already has.
   const int nw = (dx + 16 + 31) / 32 + 1;  // words per row, one spare
-  unsigned* bits = reinterpret_cast<unsigned*>(st_pot + A.n_pot);
+  int* pr_yz = st_inf + ((A.n_inf + A.n_pot + 1) & ~1);  // the row table in shared memory (8-byte aligned): (dy | dz << 8 | best << 16), then the value words
+  unsigned long long* pr_val = reinterpret_cast<unsigned long long*>(pr_yz + ((A.n_pair + 1) & ~1));
+  unsigned* bits = reinterpret_cast<unsigned*>(pr_val + A.n_pair);
+  for (int m = tid; m < A.n_pair; m += kThreads) pr_yz[m] = A.pair_yz[m].x, pr_val[m] = A.pair_vals[m];
   const bool rows_ok = A.n_pair > 0 && A.rn <= 7 && (size_t)nw * dy * dz * 4 <= A.bits_bytes;
   if (rows_ok) {
     const int warp = tid >> 5, lane = tid & 31, nwarp = kThreads / 32;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
       if (v != kUnk && v != kOcc) {
         const int bp = x - rn + 8, wi = bp >> 5, sh = bp & 31;
         for (int m = 0; m < A.n_pair; ++m) {
-          const int e = A.pair_yz[m].x;
+          const int e = pr_yz[m];
           if (((e >> 16) & 0xff) <= v) break;
           const int yy = y + (int)(signed char)(e & 0xff), zz = z + (int)(signed char)((e >> 8) & 0xff);
           if ((unsigned)yy >= (unsigned)dy || (unsigned)zz >= (unsigned)dz) continue;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
           int d = 99;
           if (right) d = __ffs(right) - 1;
           if (left) d = min(d, rn - (31 - __clz(left)));
-          const int val = (int)(signed char)((A.pair_vals[m] >> (8 * d)) & 0xff);
+          const int val = (int)(signed char)((pr_val[m] >> (8 * d)) & 0xff);
           v = max(v, val);
         }
       }
@@ -306,6 +309,7 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
       pair_vals.push_back(r.vals);
     }
     h->n_pair = (int)rows.size();
+    smem += 4 + 4 * (size_t)((h->n_pair + 1) & ~1) + 8 * (size_t)h->n_pair;  // the row table (and its alignment slack)
     const size_t room = 227 * 1024 - smem;  // whatever shared memory is left holds the bit rows
     h->bits_bytes = room & ~size_t(15);
     smem += h->bits_bytes;
