@@ -40,6 +40,8 @@ struct Args {
   const int8_t* pot_off;  // [n_pot][4] (dx, dy, dz, value), value descending
   // row form of the potential stencil: for every (dy, dz) the values at |dx| = 0..7, pairs sorted by their best value
   int n_pair, rn;
+  int n_irow, rn_inf;                   // row form of the inflation stencil: (dy | dz << 8 | reach << 16) per row
+  const int* irow;
   size_t bits_bytes;                    // shared memory set aside for the occupancy bit rows
   const int2* pair_yz;                  // (dy, dz) and best value packed: x = dy | dz << 8 | best << 16, y unused
   const unsigned long long* pair_vals;  // eight int8 values, |dx| = 0..7
@@ -70,9 +72,53 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
     for (int i = tid; i < nvox; i += kThreads) P[i] = src[i];
   }
   __syncthreads();
+  // Occupancy / unknown flags are packed one bit per voxel along x (bit x + 8 of a row, so that a window never
+  // starts below bit 0): "is there a set bit within +-r of x in row (y', z')" is then one 64-bit funnel shift and a
+  // mask instead of 2r + 1 byte loads.  All three passes use it when the radii are at most 7 voxels and the rows fit.
+  const int nw = (dx + 16 + 31) / 32 + 1;  // words per row, one spare
+  int* pr_yz = st_inf + ((A.n_inf + A.n_pot + 1) & ~1);  // row tables in shared memory (8-byte aligned)
+  unsigned long long* pr_val = reinterpret_cast<unsigned long long*>(pr_yz + ((A.n_pair + 1) & ~1));
+  int* ir = reinterpret_cast<int*>(pr_val + A.n_pair);
+  unsigned* bits = reinterpret_cast<unsigned*>(ir + ((A.n_irow + 3) & ~3));
+  for (int m = tid; m < A.n_pair; m += kThreads) pr_yz[m] = A.pair_yz[m].x, pr_val[m] = A.pair_vals[m];
+  for (int m = tid; m < A.n_irow; m += kThreads) ir[m] = A.irow[m];
+  const bool fits = (size_t)nw * dy * dz * 4 <= A.bits_bytes;
+  const int warp = tid >> 5, lane = tid & 31, nwarp = kThreads / 32;
+  const auto window = [&](int yy, int zz, int x, int r) -> unsigned {  // the bits of row (yy, zz) at x - r .. x + r
+    const int bp = x - r + 8;
+    const unsigned* row = bits + (yy + zz * dy) * nw + (bp >> 5);
+    return (unsigned)((((unsigned long long)row[1] << 32) | row[0]) >> (bp & 31)) & ((1u << (2 * r + 1)) - 1u);
+  };
   // ---- SetUncertainToUnknown: P -> Q.  A voxel that is not occupied turns unknown when an unknown voxel of the
   // interior [c, dim - c) lies within the cube of half-width c around it.
   const int c = A.cube;
+  if (fits && c >= 1 && c <= 7) {
+    for (int r = warp; r < dy * dz; r += nwarp) {
+      const int y = r % dy, z = r / dy;
+      const bool row_in = y >= c && y < dy - c && z >= c && z < dz - c;
+      for (int w = 0; w < nw; ++w) {
+        const int x = w * 32 + lane - 8;
+        const unsigned m = __ballot_sync(0xffffffffu, row_in && x >= c && x < dx - c && P[x + r * dx] == kUnk);
+        if (lane == 0) bits[r * nw + w] = m;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < nvox; i += kThreads) {
+      const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
+      int8_t v = P[i];
+      if (v != kOcc && v != kUnk) {
+        bool hit = false;
+        for (int zz = max(z - c, 0); zz <= min(z + c, dz - 1) && !hit; ++zz)
+          for (int yy = max(y - c, 0); yy <= min(y + c, dy - 1); ++yy)
+            if (window(yy, zz, x, c)) {
+              hit = true;
+              break;
+            }
+        if (hit) v = kUnk;
+      }
+      Q[i] = v;
+    }
+  } else
   for (int i = tid; i < nvox; i += kThreads) {
     const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
     int8_t v = P[i];
@@ -91,7 +137,32 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   }
   __syncthreads();
   // ---- InflateObstacles: Q -> P.  A voxel becomes occupied when an occupied voxel (before the pass) has it in
-  // its stencil: gather over the mirrored stencil.
+  // its stencil: gather over the mirrored stencil - row form (per stencil row the largest |dx| it reaches), or
+  // entry by entry.
+  if (fits && A.n_irow > 0 && A.rn_inf <= 7) {
+    for (int r = warp; r < dy * dz; r += nwarp)
+      for (int w = 0; w < nw; ++w) {
+        const int x = w * 32 + lane - 8;
+        const unsigned m = __ballot_sync(0xffffffffu, x >= 0 && x < dx && Q[x + r * dx] == kOcc);
+        if (lane == 0) bits[r * nw + w] = m;
+      }
+    __syncthreads();
+    for (int i = tid; i < nvox; i += kThreads) {
+      const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
+      int8_t v = Q[i];
+      if (v != kOcc) {
+        for (int m = 0; m < A.n_irow; ++m) {
+          const int e = ir[m];
+          const int yy = y + (int)(signed char)(e & 0xff), zz = z + (int)(signed char)((e >> 8) & 0xff);
+          if ((unsigned)yy < (unsigned)dy && (unsigned)zz < (unsigned)dz && window(yy, zz, x, e >> 16)) {
+            v = kOcc;
+            break;
+          }
+        }
+      }
+      P[i] = v;
+    }
+  } else
   for (int i = tid; i < nvox; i += kThreads) {
     const int z = i / (dx * dy), r = i - z * dx * dy, y = r / dx, x = r - y * dx;
     int8_t v = Q[i];
@@ -113,14 +184,8 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   // below bit 0); for a stencil row (dy, dz) the nearest occupied voxel along x is a count-leading / find-first on
   // an 11-bit window, and because the value only falls with |dx| that one voxel decides the row.  Rows are
   // visited in order of their best value and the walk stops once no row can beat what the voxel already has.
-  const int nw = (dx + 16 + 31) / 32 + 1;  // words per row, one spare
-  int* pr_yz = st_inf + ((A.n_inf + A.n_pot + 1) & ~1);  // the row table in shared memory (8-byte aligned): (dy | dz << 8 | best << 16), then the value words
-  unsigned long long* pr_val = reinterpret_cast<unsigned long long*>(pr_yz + ((A.n_pair + 1) & ~1));
-  unsigned* bits = reinterpret_cast<unsigned*>(pr_val + A.n_pair);
-  for (int m = tid; m < A.n_pair; m += kThreads) pr_yz[m] = A.pair_yz[m].x, pr_val[m] = A.pair_vals[m];
-  const bool rows_ok = A.n_pair > 0 && A.rn <= 7 && (size_t)nw * dy * dz * 4 <= A.bits_bytes;
+  const bool rows_ok = A.n_pair > 0 && A.rn <= 7 && fits;
   if (rows_ok) {
-    const int warp = tid >> 5, lane = tid & 31, nwarp = kThreads / 32;
     for (int r = warp; r < dy * dz; r += nwarp)
       for (int w = 0; w < nw; ++w) {
         const int x = w * 32 + lane - 8;
@@ -214,6 +279,8 @@ struct hdsm_map {
   cudaStream_t stream = nullptr;
   int8_t *d_inf = nullptr, *d_pot = nullptr;
   int2* d_pair = nullptr;
+  int* d_irow = nullptr;
+  int n_irow = 0, rn_inf = 0;
   unsigned long long* d_pvals = nullptr;
   int n_pair = 0, rn = 0;
   size_t bits_bytes = 0;
@@ -244,6 +311,7 @@ void hdsm_map_destroy(hdsm_map* h) {
   cudaFree(h->d_inf);
   cudaFree(h->d_pot);
   cudaFree(h->d_pair);
+  cudaFree(h->d_irow);
   cudaFree(h->d_pvals);
   cudaFree(h->d_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -283,6 +351,32 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
     delete h;
     return HDSM_ERR_INVALID;
   }
+  // row form of the inflation stencil: per (dy, dz) the largest |dx| the stencil reaches
+  std::vector<int> irow;
+  h->rn_inf = p->inflation_dist > 0 ? (int)std::ceil(p->inflation_dist / p->voxel_size) : 0;
+  if (h->rn_inf >= 1 && h->rn_inf <= 7) {
+    for (int dy = -h->rn_inf; dy <= h->rn_inf; ++dy)
+      for (int dz = -h->rn_inf; dz <= h->rn_inf; ++dz) {
+        int reach = -1;
+        for (const auto& e : inf)
+          if (e.y == dy && e.z == dz) reach = std::max(reach, std::abs(e.x));
+        bool solid = reach >= 0;  // the row form needs every |dx| <= reach to be in the stencil (bar the centre)
+        for (int x = 0; x <= reach && solid; ++x) {
+          if (x == 0 && dy == 0 && dz == 0) continue;
+          bool in = false;
+          for (const auto& e : inf) in |= e.y == dy && e.z == dz && e.x == x;
+          solid = in;
+        }
+        if (reach >= 0 && !solid) {
+          irow.clear();
+          dy = dz = 99;  // an irregular stencil: keep the entry-by-entry form
+          break;
+        }
+        if (reach >= 0) irow.push_back((dy & 0xff) | ((dz & 0xff) << 8) | (reach << 16));
+      }
+    h->n_irow = (int)irow.size();
+  }
+  smem += 4 * (size_t)((h->n_irow + 3) & ~3);
   // row form of the potential stencil (used when the radius is at most 7 voxels and the bit rows fit)
   std::vector<int2> pair_yz;
   std::vector<unsigned long long> pair_vals;
@@ -309,9 +403,10 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
       pair_vals.push_back(r.vals);
     }
     h->n_pair = (int)rows.size();
-    smem += 4 + 4 * (size_t)((h->n_pair + 1) & ~1) + 8 * (size_t)h->n_pair;  // the row table (and its alignment slack)
-    const size_t room = 227 * 1024 - smem;  // whatever shared memory is left holds the bit rows
-    h->bits_bytes = room & ~size_t(15);
+  }
+  smem += 4 + 4 * (size_t)((h->n_pair + 1) & ~1) + 8 * (size_t)h->n_pair;  // the row table (and its alignment slack)
+  if (smem + 1024 < 227 * 1024) {  // whatever shared memory is left holds the bit rows
+    h->bits_bytes = (227 * 1024 - smem) & ~size_t(15);
     smem += h->bits_bytes;
   }
   h->smem = smem;
@@ -321,6 +416,8 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
   if (e == cudaSuccess) e = cudaMalloc(&h->d_pot, hp.size());
   if (e == cudaSuccess) e = cudaMemcpy(h->d_inf, hi.data(), hi.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_pot, hp.data(), hp.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h->n_irow) e = cudaMalloc(&h->d_irow, irow.size() * sizeof(int));
+  if (e == cudaSuccess && h->n_irow) e = cudaMemcpy(h->d_irow, irow.data(), irow.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && h->n_pair) e = cudaMalloc(&h->d_pair, pair_yz.size() * sizeof(int2));
   if (e == cudaSuccess && h->n_pair) e = cudaMalloc(&h->d_pvals, pair_vals.size() * 8);
   if (e == cudaSuccess && h->n_pair) e = cudaMemcpy(h->d_pair, pair_yz.data(), pair_yz.size() * sizeof(int2), cudaMemcpyHostToDevice);
@@ -347,6 +444,7 @@ int hdsm_map_batch_device(hdsm_map* h, int n_grids, const int8_t* grids_in, cons
   a.n_grids = n_grids, a.cube = h->cube, a.n_inf = h->n_inf, a.n_pot = h->n_pot, a.stride = h->grid_stride;
   a.in = grids_in, a.out = grids_out, a.dims = dims, a.inf_off = h->d_inf, a.pot_off = h->d_pot;
   a.n_pair = h->n_pair, a.rn = h->rn, a.pair_yz = h->d_pair, a.pair_vals = h->d_pvals, a.bits_bytes = h->bits_bytes;
+  a.n_irow = h->n_irow, a.rn_inf = h->rn_inf, a.irow = h->d_irow;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   hdsm_mp::map_kernel<<<n_grids, hdsm_mp::kThreads, h->smem, s>>>(a);
   h->launches += 1;

@@ -1,6 +1,6 @@
 """Summarise an .ncu-rep (raw page + SASS source page joined with nvdisasm line info) - runs on CPU.
 
-    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-instantiation, default 10 | corridor] [lib.so]
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-instantiation, default 10 | corridor | map | reftraj] [lib.so]
 """
 import collections
 import csv
@@ -40,8 +40,9 @@ agg = {s: sum(int(r[ix[s]]) for r in data) for s in stalls}
 print("stalls:", ", ".join(f"{s[6:]} {100 * v / tot:.1f}%" for s, v in sorted(agg.items(), key=lambda x: -x[1])[:8]))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
-sym = ".text._ZN8hdsm_cor15corridor_kernel" if ninst == "corridor" else f".text._ZN4hdsm17hdsm_solve_kernelILi{ninst}E"
-srcname = "hdsm_corridor.cu" if ninst == "corridor" else "hdsm_kernel.cuh"
+sym = {"corridor": ".text._ZN8hdsm_cor15corridor_kernel", "map": ".text._ZN7hdsm_mp10map_kernel",
+       "reftraj": ".text._ZN7hdsm_rt14reftraj_kernel"}.get(ninst, f".text._ZN4hdsm17hdsm_solve_kernelILi{ninst}E")
+srcname = {"corridor": "hdsm_corridor.cu", "map": "hdsm_map.cu", "reftraj": "hdsm_reftraj.cu"}.get(ninst, "hdsm_kernel.cuh")
 for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):  # one cubin per .cu file
     dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
     if any(l.startswith(sym) for l in dis):
