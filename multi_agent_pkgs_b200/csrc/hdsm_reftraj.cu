@@ -384,7 +384,7 @@ int hdsm_reftraj_batch_device(hdsm_reftraj* h, int n, const int8_t* grids, const
   a.origins = origins, a.path = path, a.prev_ref = prev_ref, a.traj = traj, a.all_pos = all_pos;
   a.have_prev = have_prev, a.increment = increment, a.all_valid = all_valid;
   a.ref = ref, a.ref_solver = ref_solver, a.path_vel = path_vel;
-  if (h->prm.n_traj == 0 || n_rob == 0) a.prm.n_traj = n_rob == 0 ? 0 : a.prm.n_traj;
+  if (n_rob == 0) a.prm.n_traj = 0;  // nobody to sweep against
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   hdsm_rt::reftraj_kernel<<<n, 32, 0, s>>>(a);
   h->launches += 1;
