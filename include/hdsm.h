@@ -276,7 +276,7 @@ int hdsm_reftraj_batch_device(hdsm_reftraj* h, int n, const int8_t* grids, const
  * planner (mapping_util/src/map_builder.cpp:207-216): MapBuilder::SetUncertainToUnknown (:331-365),
  * VoxelGrid::InflateObstacles and VoxelGrid::CreatePotentialField (voxel_grid_util/src/voxel_grid.cpp:251-298,
  * stencils from CreateMask :192-226).  One thread block per grid, the grid held twice in shared memory; see
- * csrc/hdsm_map.cu.  The crop / merge / ray-cast clearing of map_builder.cpp:80-205 is not part of it. */
+ * csrc/hdsm_map.cu.  The crop / merge / ray-cast clearing of map_builder.cpp:80-205 is hdsm_sense_batch below. */
 typedef struct hdsm_map_params {
   double voxel_size;      /* VoxelGrid::GetVoxSize() */
   double inflation_dist;  /* inflation_dist (mapping_util/config: 0.3) */
@@ -298,6 +298,45 @@ int64_t hdsm_map_launch_count(const hdsm_map* h);
 int hdsm_map_batch(hdsm_map* h, int n_grids, const int8_t* grids_in, const int32_t* dims, int8_t* grids_out);
 int hdsm_map_batch_device(hdsm_map* h, int n_grids, const int8_t* grids_in, const int32_t* dims, int8_t* grids_out,
                           void* stream);
+
+/* ---- local-map acquisition (the part in front of hdsm_map_batch) ---------
+ * hdsm_sense_batch replaces what a map update does before the post-processing (mapping_util/src/map_builder.cpp):
+ * the frame and crop of the environment grid around the agent (:89-153), MapBuilder::RaycastAndClear (:280-329,
+ * ClearLine :367-432 on voxel_grid_util::Raycast) with the 360 degree or the limited field of view, the first
+ * update's ClearVoxelsCenter (:160-167, :434-447) and MapBuilder::MergeVoxelGrids (:242-278).  Its output is
+ * voxel_grid_curr_: the caller keeps it for the next update and passes it to hdsm_map_batch.  One thread block
+ * per agent; see csrc/hdsm_sense.cu. */
+typedef struct hdsm_sense_params {
+  double voxel_size;   /* voxel_size of the environment grid (:88) */
+  double range[3];     /* voxel_grid_range (metres); the local grid has floor(range / voxel_size) voxels per axis */
+  int32_t free_grid;   /* free_grid: 1 = known map (crop only, unknown -> free), 0 = ray-cast clearing and merge */
+  int32_t limited_fov; /* limited_fov */
+  double fov_x, fov_y; /* radians (fov_x_, fov_y_, map_builder.cpp:73-74); used with limited_fov */
+} hdsm_sense_params;
+
+typedef struct hdsm_sense hdsm_sense;
+
+/* dim = floor(range / voxel_size) per axis (:103-107): the shape of every grid this handle reads and writes */
+int hdsm_sense_grid_dims(const hdsm_sense_params* params, int32_t dim[3]);
+/* grid_stride: voxels per grid slot (>= dim[0] dim[1] dim[2]; the same value hdsm_map_create takes) */
+int hdsm_sense_create(const hdsm_sense_params* params, int max_agents, size_t grid_stride, int device, hdsm_sense** out);
+void hdsm_sense_destroy(hdsm_sense* h);
+const char* hdsm_sense_last_error(const hdsm_sense* h);
+int64_t hdsm_sense_launch_count(const hdsm_sense* h);
+
+/* env [dim_env z][y][x] int8: the environment grid all n agents share (0 free, 100 occupied); origin_env its origin.
+ * pos [n][3] agent positions (pos_curr_); rot [n][9] row-major rot_mat_cam_ (only read with limited_fov, else NULL).
+ * old_grids [n][grid_stride] / old_origin [n][3] / have_old [n]: voxel_grid_curr_ of the previous update and its
+ * origin; have_old[a] = 0 (or old_grids = NULL) is an agent's first update.  grids_out [n][grid_stride],
+ * origin_out [n][3]: the new voxel_grid_curr_.  HOST pointers, synchronous.  The _device twin takes device pointers
+ * and a stream for everything except dim_env and origin_env, which stay host pointers.  grids_out may not alias
+ * old_grids. */
+int hdsm_sense_batch(hdsm_sense* h, int n, const int8_t* env, const int32_t dim_env[3], const double origin_env[3], const double* pos,
+                     const double* rot, const int8_t* old_grids, const double* old_origin, const uint8_t* have_old, int8_t* grids_out,
+                     double* origin_out);
+int hdsm_sense_batch_device(hdsm_sense* h, int n, const int8_t* env, const int32_t dim_env[3], const double origin_env[3], const double* pos,
+                            const double* rot, const int8_t* old_grids, const double* old_origin, const uint8_t* have_old, int8_t* grids_out,
+                            double* origin_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -92,3 +92,29 @@ def test_corridor_structs_and_argument_checks():
         from multi_agent_pkgs_b200.corridor import SafeCorridorGenerator
         with pytest.raises(RuntimeError):
             SafeCorridorGenerator(4, 42, 0.3, 4, 4, 1000, 11, 16)
+
+
+def test_sense_structs_and_argument_checks():
+    """hdsm_sense_params layout, hdsm_sense_grid_dims, and hdsm_sense_create rejecting what the kernel cannot do (a ray
+    may not cross more than the reference's 1500 voxels; the grid slot must hold the grid)."""
+    from multi_agent_pkgs_b200.sensing import HdsmSenseParams, grid_dims
+    assert C.sizeof(HdsmSenseParams) == 8 + 24 + 8 + 16
+    assert grid_dims(0.3, (20.0, 20.0, 6.0)) == (66, 66, 20)          # floor(range / voxel), map_builder.cpp:103-107
+    assert grid_dims(0.2, (6.0, 5.0, 3.0)) == (30, 25, 15)
+    L = _lib.load()
+    L.hdsm_sense_create.restype = C.c_int
+    h = C.c_void_p()
+
+    def create(voxel=0.3, rng=(20.0, 20.0, 6.0), free=0, lim=0, fov=(1.57, 1.57), agents=4, stride=66 * 66 * 20):
+        p = HdsmSenseParams(voxel, (C.c_double * 3)(*rng), free, lim, fov[0], fov[1])
+        return L.hdsm_sense_create(C.byref(p), C.c_int(agents), C.c_size_t(stride), C.c_int(0), C.byref(h))
+
+    for bad in (dict(voxel=0.0), dict(rng=(20.0, 0.0, 6.0)), dict(rng=(0.1, 20.0, 6.0)), dict(agents=0), dict(stride=1000),
+                dict(voxel=0.01, rng=(10.0, 10.0, 10.0), stride=10 ** 9), dict(lim=1, fov=(0.0, 1.0))):
+        assert create(**bad) == -1, bad  # HDSM_ERR_INVALID
+    assert L.hdsm_sense_create(None, 1, C.c_size_t(8), 0, C.byref(h)) == -1
+    if not has_gpu():
+        assert create() == -2  # HDSM_ERR_CUDA: no CPU fallback
+        from multi_agent_pkgs_b200.sensing import LocalMapBuilder
+        with pytest.raises(RuntimeError):
+            LocalMapBuilder(0.3, 4)
