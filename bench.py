@@ -447,6 +447,71 @@ def map_measure(n_grids=4096, steps=10, local_rank=0):
                              "sample": f"the first {m} grids once, C restatement on all host threads"}}
 
 
+def sense_measure(n_agents=4096, steps=10, local_rank=0, cpu_agents=512):
+    """Secondary measurement of the local-map acquisition (first half): hdsm_sense_batch_device, one
+    steady-state update (kept grids merged in) of n_agents agents spread over one 120 x 120 m forest environment grid
+    (400 x 400 x 20 voxels of 0.3 m, shared by all agents), 66 x 66 x 20 local grids, 360 degree ray casting (13 992 rays
+    per agent).  Algorithmic bytes = the kept grid read once and the new grid written once per agent."""
+    import torch
+    from multi_agent_pkgs_b200 import sensing as sn
+    rng = np.random.default_rng(4)
+    vox, rng3 = 0.3, (20.0, 20.0, 6.0)
+    world = sc.Forest.density(rng, (0.0, 0.0), (114.0, 114.0), 0.2)
+    env, org = sn.environment_grid(world, vox)
+    pos0 = np.stack([rng.uniform(5, 109, n_agents), rng.uniform(5, 109, n_agents), rng.uniform(1.0, 3.0, n_agents)], 1)
+    pos1 = pos0 + rng.uniform(-0.6, 0.6, pos0.shape) * [1, 1, 0.1]
+    dev = torch.device(f"cuda:{local_rank}")
+    mb = sn.LocalMapBuilder(vox, n_agents, rng3, device=local_rank)
+    cells = mb.grid_stride
+    dim_env = (env.shape[2], env.shape[1], env.shape[0])
+    t_env = torch.from_numpy(env.reshape(-1)).to(dev)
+    t_p0, t_p1 = torch.from_numpy(pos0).to(dev), torch.from_numpy(pos1).to(dev)
+    t_g0 = torch.empty((n_agents, cells), dtype=torch.int8, device=dev)
+    t_g1 = torch.empty_like(t_g0)
+    t_o0 = torch.empty((n_agents, 3), dtype=torch.float64, device=dev)
+    t_o1 = torch.empty_like(t_o0)
+    t_have = torch.ones(n_agents, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    ev0 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev0[0].record(stream)
+    mb.update_device(t_env, dim_env, org, t_p0, None, None, None, None, t_g0, t_o0, stream.cuda_stream)  # first update
+    ev0[1].record(stream)
+    for _ in range(3):
+        mb.update_device(t_env, dim_env, org, t_p1, None, t_g0, t_o0, t_have, t_g1, t_o1, stream.cuda_stream)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        mb.update_device(t_env, dim_env, org, t_p1, None, t_g0, t_o0, t_have, t_g1, t_o1, stream.cuda_stream)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    first_ms = float(ev0[0].elapsed_time(ev0[1]))
+    m = min(n_agents, cpu_agents)  # bounded CPU sample
+    got0 = t_g0[:m].cpu().numpy()
+    got1, goto1 = t_g1[:m].cpu().numpy(), t_o1[:m].cpu().numpy()
+    launches = mb.launch_count
+    mb.close()
+    from oracle import sensing as osn
+    want0, wo0 = osn.c_update(env, org, pos0[:m], vox, rng3)
+    t0 = time.perf_counter()
+    want1, wo1 = osn.c_update(env, org, pos1[:m], vox, rng3, old_grids=want0, old_origin=wo0)
+    t_cpu = time.perf_counter() - t0
+    exact = bool(np.array_equal(got0.reshape(want0.shape), want0) and np.array_equal(got1.reshape(want1.shape), want1)
+                 and np.array_equal(goto1, wo1))
+    balg = 2.0 * cells
+    return {"workload": f"{n_agents} agents in one {dim_env[0]}x{dim_env[1]}x{dim_env[2]} forest environment grid (0.3 m voxels), "
+                        f"66x66x20 local grids, 360 degree ray casting (13 992 rays per agent), merge with the kept grids",
+            "metric": "map updates/sec (agents/s)", "value": n_agents / (ms * 1e-3), "kernel_ms": ms, "first_update_ms": first_ms,
+            "dtype": "int8 grids, f64 ray traversal", "byte_exact_vs_cpu_port": exact, "algorithmic_bytes_per_agent": balg,
+            "gpu_launches": int(launches),
+            "cpu_baseline": {"value": m / t_cpu, "unit": "agents/s", "cores": osn.max_threads(), "kind": "port",
+                             "sample": f"the first {m} agents once (steady-state update), C restatement on all host threads"}}
+
+
 def config_dict(args, world):
     return {"workload": f"config2: 10-agent circular exchange, forest map, N=10, {args.swarms} independent swarm "
                         f"instances per GPU ({args.swarms * 10} agent QPs per GPU per step)",
@@ -590,6 +655,15 @@ def run_ours(args, rank, world, local_rank):
             mp_gbs = mapping["algorithmic_bytes_per_grid"] * mapping["value"] / 1e9
             mapping["roofline"] = {"bound": "hbm", "achieved": mp_gbs, "peak": peak, "unit": "GB/s", "frac": mp_gbs / peak, "traffic": None,
                                    "note": "one read and one write per voxel reach HBM; the time goes into the stencil walks in shared memory"}
+        sensing = None
+        if args.corridor_agents > 0:
+            try:
+                sensing = sense_measure(min(args.corridor_agents, 4096), 10, local_rank)
+                sn_gbs = sensing["algorithmic_bytes_per_agent"] * sensing["value"] / 1e9
+                sensing["roofline"] = {"bound": "hbm", "achieved": sn_gbs, "peak": peak, "unit": "GB/s", "frac": sn_gbs / peak, "traffic": None,
+                                       "note": "kept grid in, new grid out; the time goes into 14 k serial FP64 voxel traversals per agent"}
+            except Exception as e:  # a secondary object never costs the headline line
+                sensing = {"error": f"{type(e).__name__}: {e}"}
         reftraj = None
         if args.corridor_agents > 0:
             reftraj = reftraj_measure(args.corridor_agents, 10, local_rank)
@@ -616,7 +690,8 @@ def run_ours(args, rank, world, local_rank):
                     ("optimal", "infeasible", "max_iter", "numerical", "node_limit", "row_overflow"), stat)},
                     "max_kkt_residual": kkt, "ipm_iters_per_solve": iters / max(1, stat.sum()),
                     "qp_relaxations_per_solve": nodes / max(1, stat.sum())},
-                "smem_bytes_per_block": pl.smem_bytes, "corridor": corridor, "reference_trajectory": reftraj, "local_map": mapping}
+                "smem_bytes_per_block": pl.smem_bytes, "corridor": corridor, "reference_trajectory": reftraj, "local_map": mapping,
+                "local_map_acquisition": sensing}
         emit(line)
     pl.close()
     if dist:

@@ -105,6 +105,10 @@ SN_HD uint32_t key_free(int seq) { return 2u * (uint32_t)(seq + 1) + 1u; }
 SN_HD uint32_t key_occ(int seq) { return 2u * (uint32_t)(seq + 1); }
 SN_HD int8_t key_value(uint32_t key) { return key == 0 ? (int8_t)-1 : ((key & 1u) ? (int8_t)0 : (int8_t)100); }
 
+// fmod(x, 1.0): x minus its integer part, exact in binary floating point (the library fmod is a long loop on the device;
+// a -0.0 result comes out as +0.0, which the + 1 that follows in intbound makes indistinguishable)
+SN_HD double frac1(double x) { return SN_SUB(x, trunc(x)); }
+
 // ClearLine (:395-431) for one ray.  occ(x, y, z): is the (inside) voxel occupied in the cropped grid;
 // put(cell, key): offer `key` to voxel `cell` (x + y dx + z dx dy).
 template <class Occ, class Put>
@@ -121,7 +125,7 @@ SN_HD void clear_line(const int dim[3], const double s[3], const double e[3], in
   for (int a = 0; a < 3; ++a) {  // intbound (raycast.cpp:10-19)
     double ss = s[a], ds = d[a];
     if (ds < 0) ss = -ss, ds = -ds;
-    ss = fmod(SN_ADD(fmod(ss, 1.0), 1.0), 1.0);
+    ss = frac1(SN_ADD(frac1(ss), 1.0));  // mod(s, 1) = fmod(fmod(s, 1) + 1, 1)
     tm[a] = SN_DIV(SN_SUB(1.0, ss), ds);
     td[a] = SN_DIV((double)st[a], d[a]);
   }
@@ -130,7 +134,8 @@ SN_HD void clear_line(const int dim[3], const double s[3], const double e[3], in
   // the reference collects the visited points and then frees the voxel under the middle of every consecutive pair
   const auto emit = [&](double x, double y, double z) {
     if (n > 0) {
-      const int vx = (int)SN_DIV(SN_ADD(px, x), 2.0), vy = (int)SN_DIV(SN_ADD(py, y), 2.0), vz = (int)SN_DIV(SN_ADD(pz, z), 2.0);
+      // (a + b) / 2.0 as a multiplication by 0.5: the same correctly rounded value, without the device's division routine
+      const int vx = (int)SN_MUL(SN_ADD(px, x), 0.5), vy = (int)SN_MUL(SN_ADD(py, y), 0.5), vz = (int)SN_MUL(SN_ADD(pz, z), 0.5);
       if (inside(dim, vx, vy, vz)) put(vx + dim[0] * (vy + dim[1] * vz), kf);
     }
     px = x, py = y, pz = z, ++n;

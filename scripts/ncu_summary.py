@@ -1,6 +1,6 @@
 """Summarise an .ncu-rep (raw page + SASS source page joined with nvdisasm line info) - runs on CPU.
 
-    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-instantiation, default 10 | corridor | map | reftraj] [lib.so]
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-instantiation, default 10 | corridor | map | reftraj | sense] [lib.so]
 """
 import collections
 import csv
@@ -41,8 +41,8 @@ print("stalls:", ", ".join(f"{s[6:]} {100 * v / tot:.1f}%" for s, v in sorted(ag
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 sym = {"corridor": ".text._ZN8hdsm_cor15corridor_kernel", "map": ".text._ZN7hdsm_mp10map_kernel",
-       "reftraj": ".text._ZN7hdsm_rt14reftraj_kernel"}.get(ninst, f".text._ZN4hdsm17hdsm_solve_kernelILi{ninst}E")
-srcname = {"corridor": "hdsm_corridor.cu", "map": "hdsm_map.cu", "reftraj": "hdsm_reftraj.cu"}.get(ninst, "hdsm_kernel.cuh")
+       "reftraj": ".text._ZN7hdsm_rt14reftraj_kernel", "sense": ".text._ZN7hdsm_sn12sense_kernel"}.get(ninst, f".text._ZN4hdsm17hdsm_solve_kernelILi{ninst}E")
+srcname = {"corridor": "hdsm_corridor.cu", "map": "hdsm_map.cu", "reftraj": "hdsm_reftraj.cu", "sense": "hdsm_sense.cu"}.get(ninst, "hdsm_kernel.cuh")
 for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):  # one cubin per .cu file
     dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
     if any(l.startswith(sym) for l in dis):
@@ -68,4 +68,6 @@ src = open(os.path.join(os.path.dirname(lib), "csrc", srcname)).read().split("\n
 print("--- top source lines by stall samples")
 for k, v in samp.most_common(int(os.environ.get("TOP", "30"))):
     s = src[k[1] - 1].strip()[:100] if k and k[0] == srcname else ""
+    if k and not s and os.path.exists(os.path.join(os.path.dirname(lib), "csrc", k[0])):
+        s = open(os.path.join(os.path.dirname(lib), "csrc", k[0])).read().split("\n")[k[1] - 1].strip()[:100]
     print(f"{str(k):30s} static {static[k]:5d} samples {100 * v / tot:5.1f}% exec {execd[k] / 1e6:8.1f}M | {s}")
