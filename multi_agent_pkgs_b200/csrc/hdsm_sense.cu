@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -137,6 +138,136 @@ __global__ void __launch_bounds__(kThreads) sense_kernel(const Args A) {
   }
 }
 
+// ---- second form of the kernel (selected with HDSM_SENSE_BITS=1 when the handle is created; not the default until it
+// has been measured against the first on the device).  The profile of the first form (profiles/r1u_ncu_sense_summary.txt)
+// has 27 % of its stall samples on the L2 round trip of the key load in front of the atomicMax.  Keys only matter for
+// voxels that receive BOTH kinds of write (occupied from one ray, free from another) - a numerical corner case of the
+// reference's nudged collision point.  So the ray loop here only sets one bit per voxel in shared memory (free-written /
+// occupied-written); if the two bitmaps intersect anywhere, the agent's rays are traversed a second time and offer their
+// keys to the intersecting voxels only.  Same result as the first form by construction: a voxel written by one kind of
+// write has that kind's value whatever the order, and the others are decided by the same largest-key rule.
+constexpr int kThreadsBits = 256;
+
+__global__ void __launch_bounds__(kThreadsBits, 3) sense_kernel_bits(const Args A) {
+  extern __shared__ uint32_t s_words[];  // [3][words]: occupancy of the crop, free-written, occupied-written
+  __shared__ Frame F;
+  __shared__ int s_off[3], s_mid[3];
+  uint32_t* keys = A.keys + (size_t)blockIdx.x * A.stride;
+  const int tid = threadIdx.x;
+
+  for (int a = blockIdx.x; a < A.n; a += gridDim.x) {
+    if (tid == 0) {
+      const double p[3] = {A.pos[3 * a], A.pos[3 * a + 1], A.pos[3 * a + 2]};
+      make_frame(A.voxel, A.range, A.origin_env, p, F);
+      const bool ho = A.have_old && A.have_old[a];
+      int off[3] = {0, 0, 0};
+      if (ho) {
+        const double oo[3] = {A.old_origin[3 * a], A.old_origin[3 * a + 1], A.old_origin[3 * a + 2]};
+        merge_offset(F.origin, oo, A.voxel, off);
+      }
+      for (int c = 0; c < 3; ++c) {
+        s_off[c] = off[c], s_mid[c] = (int)floor(F.pos_local[c]);
+        A.origin_out[3 * a + c] = F.origin[c];
+      }
+    }
+    __syncthreads();
+    const int dim[3] = {F.dim[0], F.dim[1], F.dim[2]};
+    const int start[3] = {F.start[0], F.start[1], F.start[2]};
+    const int cells = dim[0] * dim[1] * dim[2], plane = dim[0] * dim[1];
+    int8_t* out = A.out + (size_t)a * A.stride;
+
+    if (A.free_grid) {
+      for (int cell = tid; cell < cells; cell += kThreadsBits) {
+        const int z = cell / plane, r = cell - z * plane, y = r / dim[0], x = r - y * dim[0];
+        out[cell] = crop_value(A.env, A.dim_env, start, true, x, y, z);
+      }
+      __syncthreads();
+      continue;
+    }
+
+    const int words = (cells + 31) >> 5;
+    uint32_t *s_bits = s_words, *s_free = s_words + words, *s_occw = s_words + 2 * words;
+    for (int base = (tid >> 5) << 5; base < words * 32; base += kThreadsBits) {
+      const int cell = base + (tid & 31);
+      bool o = false;
+      if (cell < cells) {
+        const int z = cell / plane, r = cell - z * plane, y = r / dim[0], x = r - y * dim[0];
+        const int ie = x + start[0], je = y + start[1], ke = z + start[2];
+        o = inside(A.dim_env, ie, je, ke) && __ldg(A.env + (size_t)ie + (size_t)A.dim_env[0] * ((size_t)je + (size_t)A.dim_env[1] * ke)) == 100;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, o);
+      if ((tid & 31) == 0) s_bits[base >> 5] = m, s_free[base >> 5] = 0u, s_occw[base >> 5] = 0u;
+    }
+    __syncthreads();
+
+    const double sp[3] = {F.pos_local[0], F.pos_local[1], F.pos_local[2]};
+    const int nr = ray_count(dim);
+    const double* rot = A.limited_fov ? A.rot + 9 * a : nullptr;
+    const auto occ = [&](int x, int y, int z) {
+      const int c = x + dim[0] * (y + dim[1] * z);
+      return (s_bits[c >> 5] >> (c & 31)) & 1u;
+    };
+    // pass 1: which voxels are written free, which occupied
+    for (int seq = nr - 1 - tid; seq >= 0; seq -= kThreadsBits) {
+      double end[3];
+      ray_end(dim, seq, end);
+      if (rot && !in_fov(rot, sp, end, A.cos_half_x, A.cos_half_y)) continue;
+      clear_line(dim, sp, end, seq, occ, [&](int cell, uint32_t key) {
+        uint32_t* w = ((key & 1u) ? s_free : s_occw) + (cell >> 5);
+        const uint32_t m = 1u << (cell & 31);
+        if (!(*(volatile uint32_t*)w & m)) atomicOr(w, m);
+      });
+    }
+    __syncthreads();
+    int both = 0;
+    for (int w = tid; w < words; w += kThreadsBits) both |= (s_free[w] & s_occw[w]) != 0u;
+    // pass 2 (rare): the voxels with both kinds of write are decided by the largest key
+    if (__syncthreads_or(both)) {
+      for (int seq = nr - 1 - tid; seq >= 0; seq -= kThreadsBits) {
+        double end[3];
+        ray_end(dim, seq, end);
+        if (rot && !in_fov(rot, sp, end, A.cos_half_x, A.cos_half_y)) continue;
+        clear_line(dim, sp, end, seq, occ, [&](int cell, uint32_t key) {
+          if (((s_free[cell >> 5] & s_occw[cell >> 5]) >> (cell & 31)) & 1u) atomicMax(keys + cell, key);
+        });
+      }
+      __syncthreads();
+    }
+
+    // merge: four voxels per thread where the layout allows 32-bit stores
+    const int8_t* old_grid = A.old_grids ? A.old_grids + (size_t)a * A.stride : nullptr;
+    const bool ho = A.have_old && A.have_old[a] && old_grid;
+    const int off[3] = {s_off[0], s_off[1], s_off[2]}, mid[3] = {s_mid[0], s_mid[1], s_mid[2]};
+    const auto value_of = [&](int cell) -> int8_t {
+      const uint32_t f = (s_free[cell >> 5] >> (cell & 31)) & 1u, o = (s_occw[cell >> 5] >> (cell & 31)) & 1u;
+      int8_t v;
+      if (f & o) {
+        v = key_value(__ldcg(keys + cell));
+        __stcg(keys + cell, 0u);
+      } else {
+        v = o ? (int8_t)100 : (f ? (int8_t)0 : (int8_t)-1);
+      }
+      if (v == -1) {
+        const int z = cell / plane, r = cell - z * plane, y = r / dim[0], x = r - y * dim[0];
+        v = old_value(old_grid, ho, dim, off, mid, x, y, z);
+      }
+      return v;
+    };
+    if ((cells & 3) == 0 && (A.stride & 3) == 0 && ((size_t)A.out & 3) == 0) {
+      uint32_t* out4 = reinterpret_cast<uint32_t*>(out);
+      for (int q = tid; q < (cells >> 2); q += kThreadsBits) {
+        uint32_t pack = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pack |= (uint32_t)(uint8_t)value_of(4 * q + j) << (8 * j);
+        out4[q] = pack;
+      }
+    } else {
+      for (int cell = tid; cell < cells; cell += kThreadsBits) out[cell] = value_of(cell);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void zero_keys(uint32_t* k, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) k[i] = 0u;
 }
@@ -145,7 +276,7 @@ __global__ void zero_keys(uint32_t* k, size_t n) {
 
 struct hdsm_sense {
   hdsm_sense_params prm{};
-  int device = 0, max_agents = 0, blocks = 0, dim[3] = {0, 0, 0};
+  int device = 0, max_agents = 0, blocks = 0, dim[3] = {0, 0, 0}, bits = 0;
   size_t grid_stride = 0, env_cap = 0, smem = 0;
   double cos_half_x = 0, cos_half_y = 0;
   cudaStream_t stream = nullptr;
@@ -199,21 +330,26 @@ int hdsm_sense_create(const hdsm_sense_params* p, int max_agents, size_t grid_st
   // a ray visits at most dx + dy + dz + 1 voxels; the reference throws beyond 1500 (raycast.cpp:146-149)
   if (grid_stride < cells || dim[0] + dim[1] + dim[2] > 1400 || cells > (size_t)1 << 30) return HDSM_ERR_INVALID;
   if (p->limited_fov && !(p->fov_x > 0 && p->fov_y > 0)) return HDSM_ERR_INVALID;
-  const size_t smem = ((cells + 31) / 32) * 4;
-  if (smem > 200 * 1024) return HDSM_ERR_INVALID;  // the crop's occupancy bits must fit into one SM's shared memory
+  const char* form = std::getenv("HDSM_SENSE_BITS");
+  const int bits = form && form[0] == '1';
+  const size_t smem = ((cells + 31) / 32) * 4 * (bits ? 3 : 1);
+  if (smem > 200 * 1024) return HDSM_ERR_INVALID;  // the crop's bitmaps must fit into one SM's shared memory
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return HDSM_ERR_CUDA;  // no CPU fallback
   hdsm_sense* h = new (std::nothrow) hdsm_sense();
   if (!h) return HDSM_ERR_INVALID;
-  h->prm = *p, h->device = device, h->max_agents = max_agents, h->grid_stride = grid_stride, h->smem = smem;
+  h->prm = *p, h->device = device, h->max_agents = max_agents, h->grid_stride = grid_stride, h->smem = smem, h->bits = bits;
   h->dim[0] = dim[0], h->dim[1] = dim[1], h->dim[2] = dim[2];
   h->cos_half_x = std::cos(p->fov_x / 2), h->cos_half_y = std::cos(p->fov_y / 2);  // :390-391
   cudaError_t e = cudaSetDevice(device);
   int sms = 0, per_sm = 0;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(hdsm_sn::sense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hdsm_sn::sense_kernel, hdsm_sn::kThreads, smem);
+  if (e == cudaSuccess && !bits) e = cudaFuncSetAttribute(hdsm_sn::sense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && !bits) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hdsm_sn::sense_kernel, hdsm_sn::kThreads, smem);
+  if (e == cudaSuccess && bits) e = cudaFuncSetAttribute(hdsm_sn::sense_kernel_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && bits)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hdsm_sn::sense_kernel_bits, hdsm_sn::kThreadsBits, smem);
   if (e == cudaSuccess) {
     if (per_sm < 1) per_sm = 1;
     h->blocks = sms * per_sm;  // persistent: every resident block owns one key scratch
@@ -257,7 +393,10 @@ int hdsm_sense_batch_device(hdsm_sense* h, int n, const int8_t* env, const int32
   a.out = grids_out, a.origin_out = origin_out, a.keys = h->d_keys;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   const int blocks = n < h->blocks ? n : h->blocks;
-  hdsm_sn::sense_kernel<<<blocks, hdsm_sn::kThreads, h->smem, s>>>(a);
+  if (h->bits)
+    hdsm_sn::sense_kernel_bits<<<blocks, hdsm_sn::kThreadsBits, h->smem, s>>>(a);
+  else
+    hdsm_sn::sense_kernel<<<blocks, hdsm_sn::kThreads, h->smem, s>>>(a);
   h->launches += 1;
   SCU(cudaGetLastError());
   return HDSM_OK;

@@ -1,7 +1,8 @@
 // sense_emu.cpp - TEST INFRASTRUCTURE ONLY.  Runs the per-ray / per-voxel code of the acquisition kernel
 // (multi_agent_pkgs_b200/csrc/hdsm_sense_core.h, the header csrc/hdsm_sense.cu is built from) on the CPU,
 // following the kernel's structure: occupancy bits of the cropped grid, rays in an arbitrary (here: seeded,
-// scrambled) order offering keys to voxels, largest key wins, then the merge pass.  tests/ compare it with the
+// scrambled) order offering keys to voxels, largest key wins, then the merge pass (bits_form = 1: the kernel's second
+// form - bitmaps of free / occupied writes first, keys only for voxels that received both).  tests/ compare it with the
 // sequential restatement of the reference (sense_oracle.c): this is what shows, without a GPU, that the key scheme
 // reproduces the reference's last-write-wins order and that the shared arithmetic matches.  Never shipped, never
 // called by the product.  Compile with -ffp-contract=off.
@@ -16,7 +17,7 @@
 extern "C" int sense_emu_batch(double voxel, const double* range, int free_grid, int limited_fov, double cos_half_x, double cos_half_y, int n,
                                const int8_t* env, const int32_t* dim_env_in, const double* origin_env, const double* pos, const double* rot,
                                const int8_t* old_grids, const double* old_origin, const uint8_t* have_old, size_t stride, int8_t* out,
-                               double* origin_out, unsigned seed) {
+                               double* origin_out, unsigned seed, int bits_form, long long* conflicts) {
   using namespace hdsm_sn;
   const int dim_env[3] = {dim_env_in[0], dim_env_in[1], dim_env_in[2]};
   for (int a = 0; a < n; ++a) {
@@ -47,15 +48,35 @@ extern "C" int sense_emu_batch(double voxel, const double* range, int free_grid,
       std::swap(order[r], order[(st >> 8) % (unsigned)(r + 1)]);
     }
     const int* dim = F.dim;
-    for (int q = 0; q < nr; ++q) {
-      const int seq = order[q];
-      double end[3];
-      ray_end(dim, seq, end);
-      if (limited_fov && !in_fov(rot + 9 * a, F.pos_local, end, cos_half_x, cos_half_y)) continue;
-      clear_line(
-          dim, F.pos_local, end, seq, [&](int x, int y, int z) { const int c = x + dim[0] * (y + dim[1] * z); return (bits[c >> 5] >> (c & 31)) & 1u; },
-          [&](int cell, uint32_t key) { if (keys[cell] < key) keys[cell] = key; });
+    const auto occ = [&](int x, int y, int z) { const int c = x + dim[0] * (y + dim[1] * z); return (bits[c >> 5] >> (c & 31)) & 1u; };
+    std::vector<uint32_t> wfree(bits_form ? bits.size() : 0, 0u), wocc(bits_form ? bits.size() : 0, 0u);
+    for (int pass = 0; pass < (bits_form ? 2 : 1); ++pass) {
+      if (pass == 1) {  // the second form: keys only for voxels that received both kinds of write
+        long long both = 0;
+        for (size_t w = 0; w < bits.size(); ++w) both += __builtin_popcount(wfree[w] & wocc[w]);
+        if (conflicts) conflicts[a] = both;
+        if (!both) break;
+      }
+      for (int q = 0; q < nr; ++q) {
+        const int seq = order[q];
+        double end[3];
+        ray_end(dim, seq, end);
+        if (limited_fov && !in_fov(rot + 9 * a, F.pos_local, end, cos_half_x, cos_half_y)) continue;
+        if (!bits_form)
+          clear_line(dim, F.pos_local, end, seq, occ, [&](int cell, uint32_t key) { if (keys[cell] < key) keys[cell] = key; });
+        else if (pass == 0)
+          clear_line(dim, F.pos_local, end, seq, occ, [&](int cell, uint32_t key) { ((key & 1u) ? wfree : wocc)[cell >> 5] |= 1u << (cell & 31); });
+        else
+          clear_line(dim, F.pos_local, end, seq, occ, [&](int cell, uint32_t key) {
+            if ((((wfree[cell >> 5] & wocc[cell >> 5]) >> (cell & 31)) & 1u) && keys[cell] < key) keys[cell] = key;
+          });
+      }
     }
+    if (bits_form)  // single-kind voxels: the kind decides (expressed as a key so that the merge below is shared)
+      for (int cell = 0; cell < cells; ++cell) {
+        const uint32_t f = (wfree[cell >> 5] >> (cell & 31)) & 1u, o = (wocc[cell >> 5] >> (cell & 31)) & 1u;
+        if (f != o) keys[cell] = f ? key_free(0) : key_occ(0);
+      }
     const bool ho = have_old && have_old[a];
     int off[3] = {0, 0, 0}, mid[3];
     if (ho) merge_offset(F.origin, old_origin + 3 * a, voxel, off);

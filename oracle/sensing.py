@@ -89,7 +89,9 @@ def c_update(env, origin_env, pos, voxel, rng, free_grid=False, rot=None, fov=No
     return out, origin_out
 
 
-def emu_update(env, origin_env, pos, voxel, rng, free_grid=False, rot=None, fov=None, old_grids=None, old_origin=None, have_old=None, seed=1):
+def emu_update(env, origin_env, pos, voxel, rng, free_grid=False, rot=None, fov=None, old_grids=None, old_origin=None, have_old=None, seed=1,
+               bits_form=False, conflicts=None):
+    """conflicts: optional int64 array [n] receiving, with bits_form, the number of voxels written both free and occupied."""
     env, dim_env, origin_env, pos, n, rot, old_grids, old_origin, have_old, out, origin_out = _prep(
         env, origin_env, pos, rot, old_grids, old_origin, have_old, voxel, rng)
     L = _lib("emu")
@@ -97,7 +99,7 @@ def emu_update(env, origin_env, pos, voxel, rng, free_grid=False, rot=None, fov=
     rc = L.sense_emu_batch(C.c_double(voxel), (C.c_double * 3)(*rng), C.c_int(int(free_grid)), C.c_int(int(fov is not None)),
                            C.c_double(math.cos(fov[0] / 2) if fov else 0.0), C.c_double(math.cos(fov[1] / 2) if fov else 0.0), C.c_int(n),
                            _p(env), _p(dim_env), _p(origin_env), _p(pos), _p(rot), _p(old_grids), _p(old_origin), _p(have_old),
-                           C.c_size_t(out[0].size), _p(out), _p(origin_out), C.c_uint(seed))
+                           C.c_size_t(out[0].size), _p(out), _p(origin_out), C.c_uint(seed), C.c_int(int(bits_form)), _p(conflicts))
     if rc:
         raise RuntimeError("sense_emu_batch failed")
     return out, origin_out

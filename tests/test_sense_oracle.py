@@ -68,6 +68,22 @@ def test_kernel_code_in_scrambled_order_equals_sequential_reference_order(seed):
         g1, o1 = g3, o3
 
 
+def test_bits_form_of_the_kernel_logic_and_how_often_write_order_matters():
+    """The kernel's second form (free / occupied bitmaps first, keys only for voxels written both ways) gives the same grids;
+    and such voxels do occur in forest worlds - the reason the writes carry their position in the reference's ray order."""
+    env, org = forest_env(3)
+    pos = positions(4, 48)
+    want, wo = S.c_update(env, org, pos, VOX, RANGE)
+    conflicts = np.zeros(48, np.int64)
+    got, go = S.emu_update(env, org, pos, VOX, RANGE, seed=11, bits_form=True, conflicts=conflicts)
+    assert np.array_equal(got, want) and np.array_equal(go, wo)
+    assert (conflicts > 0).any() and (conflicts == 0).any()
+    pos2 = pos + 0.37
+    want2, _ = S.c_update(env, org, pos2, VOX, RANGE, old_grids=want, old_origin=wo)
+    got2, _ = S.emu_update(env, org, pos2, VOX, RANGE, old_grids=want, old_origin=wo, seed=12, bits_form=True)
+    assert np.array_equal(got2, want2)
+
+
 def test_limited_field_of_view_and_other_shapes():
     env, org = forest_env(5)
     pos = positions(6, 4)
