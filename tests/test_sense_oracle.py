@@ -82,6 +82,10 @@ def test_bits_form_of_the_kernel_logic_and_how_often_write_order_matters():
     want2, _ = S.c_update(env, org, pos2, VOX, RANGE, old_grids=want, old_origin=wo)
     got2, _ = S.emu_update(env, org, pos2, VOX, RANGE, old_grids=want, old_origin=wo, seed=12, bits_form=True)
     assert np.array_equal(got2, want2)
+    for vox, rng3 in ((0.2, (6.0, 5.0, 3.0)), (0.5, (10.0, 10.0, 0.5)), (0.3, (3.0, 20.0, 6.0))):
+        a, ao = S.c_update(env, org, pos[:8], vox, rng3)
+        b, bo = S.emu_update(env, org, pos[:8], vox, rng3, seed=2, bits_form=True)
+        assert np.array_equal(a, b) and np.array_equal(ao, bo)
 
 
 def test_limited_field_of_view_and_other_shapes():
