@@ -12,8 +12,9 @@
  *
  * Parity: map_create_mask, map_inflate and map_potential are PINNED - tests/test_map_oracle.py compares them
  * byte for byte with the reference's own VoxelGrid (voxel_grid.cpp compiled unmodified into
- * oracle/_ref/libref_voxel.so).  map_uncertain lives in map_builder.cpp (ROS2 node: not compilable) and is
- * restated by reading.  Grids are [dz][dy][dx] int8, x fastest: 0 free, 100 occupied, -1 unknown, 1..99 potential.
+ * oracle/_ref/libref_voxel.so).  map_uncertain lives in the ROS2 node map_builder.cpp; it is pinned through the grid that
+ * node PUBLISHES (map_builder.cpp compiled unmodified on stand-in ROS headers into oracle/_ref/libref_map.so): map_process
+ * reproduces it byte for byte (tests/test_sense_oracle.py, fixture tests/golden/mapbuilder_ref.npz).  Grids are [dz][dy][dx] int8, x fastest: 0 free, 100 occupied, -1 unknown, 1..99 potential.
  */
 #include <math.h>
 #include <pthread.h>

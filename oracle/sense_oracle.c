@@ -13,12 +13,15 @@
  *   sense_center     MapBuilder::ClearVoxelsCenter         map_builder.cpp:434-447
  *   sense_update     the sequence of map_builder.cpp:80-205 for one agent
  *
- * Parity: the ray traversal (rt_raycast, shared with reftraj_oracle.c) is PINNED bit for bit against the
- * reference's own raycast.cpp + voxel_grid.cpp (tests/test_reftraj_oracle.py).  The functions above live in
- * map_builder.cpp, a ROS2 node that cannot be compiled here (rclcpp, tf2); they are loops around that ray
- * caster and VoxelGrid::Set/GetVoxelInt (voxel_grid.cpp:84-117: writes outside the grid are dropped, reads
- * outside return -1) and are restated by reading: "parity unpinned" for those loops.  The field-of-view test
- * uses Eigen dot products whose evaluation order ((a0 b0 + a1 b1) + a2 b2) is assumed.
+ * Parity: PINNED.  The reference's map-builder node itself - mapping_util/src/map_builder.cpp with
+ * path_finding_util/src/path_tools.cpp, voxel_grid_util/src/raycast.cpp and voxel_grid.cpp, compiled UNMODIFIED from
+ * /root/reference against stand-in headers for rclcpp / tf2 / the message classes / Eigen (oracle/ref_shim/, none of it
+ * reference code) into oracle/_ref/libref_map.so - is driven through MapBuilder::EnvironmentVoxelGridCallback by
+ * oracle/ref_wrap_map.cpp.  sense_update reproduces its voxel_grid_curr_ and origin byte for byte, first and follow-up
+ * updates, 360 degree / limited field of view / known map: live where the reference is present and through the committed
+ * fixture tests/golden/mapbuilder_ref.npz (tests/golden/make_mapbuilder_golden.py) elsewhere (tests/test_sense_oracle.py).
+ * One caveat: the field-of-view test's dot products run through the Eigen stand-in, whose evaluation order
+ * ((a0 b0 + a1 b1) + a2 b2) is assumed to be real Eigen's; everything else is integer / IEEE-exact logic.
  * Grids are [dz][dy][dx] int8, x fastest: 0 free, 100 occupied, -1 unknown.
  */
 #include "reftraj_oracle.c" /* rt_raycast, vg_inside, vg_get */

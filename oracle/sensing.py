@@ -17,6 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _C_SO = os.path.join(_HERE, "libsense_oracle.so")
 _EMU_SO = os.path.join(_HERE, "libsense_emu.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libref_map.so")
 _libs = {}
 
 
@@ -31,9 +32,43 @@ def build(force=False):
 
 def _lib(which):
     if which not in _libs:
-        c_so, emu_so = build()
-        _libs[which] = C.CDLL(c_so if which == "c" else emu_so)
+        if which == "ref":
+            _libs[which] = C.CDLL(_REF_SO)
+        else:
+            c_so, emu_so = build()
+            _libs[which] = C.CDLL(c_so if which == "c" else emu_so)
     return _libs[which]
+
+
+def have_ref():
+    """oracle/_ref/libref_map.so: the reference's OWN map_builder.cpp (+ path_tools.cpp, raycast.cpp, voxel_grid.cpp) compiled
+    unmodified on stand-in ROS / Eigen headers (make -C oracle ref; needs /root/reference)."""
+    return os.path.exists(_REF_SO)
+
+
+def ref_update(env, origin_env, pos, voxel, rng, free_grid=False, rot=None, fov=None, old_grid=None, old_origin=None,
+               inflation=0.3, potential=1.5, power=4.0):
+    """One MapBuilder::EnvironmentVoxelGridCallback of ONE agent in the reference itself.  Returns (voxel_grid_curr_ after
+    the call [dz][dy][dx], its origin (3,), the published grid [dz][dy][dx])."""
+    env = np.ascontiguousarray(env, np.int8)
+    dim_env = np.array([env.shape[2], env.shape[1], env.shape[0]], np.int32)
+    origin_env = np.ascontiguousarray(origin_env, np.float64)
+    pos = np.ascontiguousarray(pos, np.float64).reshape(3)
+    dx, dy, dz = local_dims(voxel, rng)
+    cur, pub, org = np.empty((dz, dy, dx), np.int8), np.empty((dz, dy, dx), np.int8), np.empty(3)
+    rot = None if rot is None else np.ascontiguousarray(rot, np.float64).reshape(9)
+    if old_grid is not None:
+        old_grid = np.ascontiguousarray(old_grid, np.int8).reshape(dz, dy, dx)
+        old_origin = np.ascontiguousarray(old_origin, np.float64).reshape(3)
+    L = _lib("ref")
+    L.ref_map_update.restype = C.c_int
+    n = L.ref_map_update((C.c_double * 3)(*rng), C.c_int(int(free_grid)), C.c_double(inflation), C.c_double(potential), C.c_double(power),
+                         C.c_int(int(fov is not None)), C.c_double(fov[0] if fov else 1.57), C.c_double(fov[1] if fov else 1.57),
+                         _p(env), _p(dim_env), _p(origin_env), C.c_double(voxel), _p(pos), _p(rot), _p(old_grid), _p(old_origin),
+                         _p(cur), _p(org), _p(pub))
+    if n != cur.size:
+        raise RuntimeError(f"ref_map_update returned {n}")
+    return cur, org, pub
 
 
 class SenseParams(C.Structure):

@@ -95,6 +95,23 @@ def test_acquired_grids_feed_the_post_processing():
     assert (out == -1).any() and (out == 100).any() and ((out > 0) & (out < 100)).any()
 
 
+def test_golden_fixture_from_the_reference_node():
+    """The CUDA path against tests/golden/mapbuilder_ref.npz, i.e. against the reference's own map-builder node: 18 agents x 3
+    consecutive updates, 360 degree / limited field of view / known map, four grid shapes; byte-exact grids, bit-exact origins."""
+    from test_sense_oracle import golden_cases
+    n = 0
+    for c in golden_cases():
+        mb = sn.LocalMapBuilder(c["vox"], 1, c["rng3"], free_grid=c["free"], limited_fov=c["fov"] is not None,
+                                fov_x=c["fov"][0] if c["fov"] else 1.57, fov_y=c["fov"][1] if c["fov"] else 1.57)
+        for step in range(3):
+            g, o = mb.update(c["env"], c["org"], c["pos"][step][None], c["rot"][None] if c["fov"] else None)
+            assert np.array_equal(o[0], c["origin"][step]), (n, step)
+            assert np.array_equal(g[0], c["cur"][step]), (n, step, int((g[0] != c["cur"][step]).sum()))
+        mb.close()
+        n += 1
+    assert n == 18
+
+
 def test_key_form_matches_the_checker(monkeypatch):
     """HDSM_SENSE_BITS=0: the kernel's first form (keys for every write), kept for A/B measurements."""
     monkeypatch.setenv("HDSM_SENSE_BITS", "0")

@@ -2,8 +2,9 @@
 mapping_util/src/map_builder.cpp:80-205, restated in the reference's sequential order) and the kernel's own per-ray code
 (csrc/hdsm_sense_core.h) compiled for the CPU and run in a scrambled ray order (oracle/sense_emu.cpp).
 
-What is pinned: the ray traversal, against the reference's own raycast.cpp (test_reftraj_oracle.py; repeated here on the
-rays this stage casts when oracle/_ref is present).  The loops around it are restated by reading - parity unpinned."""
+PINNED: the whole stage against the reference's own MapBuilder::EnvironmentVoxelGridCallback - map_builder.cpp, path_tools.cpp,
+raycast.cpp and voxel_grid.cpp compiled unmodified on stand-in ROS / Eigen headers (oracle/_ref/libref_map.so) - through the
+committed fixture tests/golden/mapbuilder_ref.npz and, where the reference is present, live."""
 import os
 
 import numpy as np
@@ -148,3 +149,58 @@ def test_rays_of_this_stage_against_the_reference_ray_caster():
                 assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
                 n += 1
     assert n > 100
+
+
+# ---- pinned against the reference's own map-builder node ------------------------------------------------------------
+def golden_cases():
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "mapbuilder_ref.npz"))
+    for k in range(int(z["n_cases"])):
+        p = z[f"c{k}_prm"]
+        yield dict(vox=float(p[0]), rng3=tuple(float(v) for v in p[1:4]), free=bool(p[4]), fov=(float(p[6]), float(p[7])) if p[5] else None,
+                   infl=float(p[8]), pot=float(p[9]), pw=float(p[10]), env=z[f"c{k}_env"], org=z[f"c{k}_org"], rot=z[f"c{k}_rot"],
+                   pos=z[f"c{k}_pos"], cur=z[f"c{k}_cur"], origin=z[f"c{k}_origin"], pub=z[f"c{k}_pub"])
+
+
+def test_golden_fixture_from_the_reference_node():
+    """tests/golden/mapbuilder_ref.npz was produced by the reference's OWN MapBuilder::EnvironmentVoxelGridCallback
+    (map_builder.cpp compiled unmodified, tests/golden/make_mapbuilder_golden.py): 18 agents x 3 consecutive updates, 360 degree /
+    limited field of view / known map, four grid shapes.  The sequential restatement, the kernel's code in scrambled order (both
+    forms) and the post-processing restatement must reproduce voxel_grid_curr_, its origin and the published grid byte for byte."""
+    from oracle import mapping as om
+    n = 0
+    for c in golden_cases():
+        old_g = old_o = None
+        for step in range(3):
+            kw = dict(free_grid=c["free"], rot=c["rot"][None] if c["fov"] else None, fov=c["fov"],
+                      old_grids=None if old_g is None else old_g[None], old_origin=None if old_o is None else old_o[None])
+            g, o = S.c_update(c["env"], c["org"], c["pos"][step][None], c["vox"], c["rng3"], **kw)
+            assert np.array_equal(o[0], c["origin"][step]) and np.array_equal(g[0], c["cur"][step]), (n, step)
+            for bits in (False, True):
+                e, eo = S.emu_update(c["env"], c["org"], c["pos"][step][None], c["vox"], c["rng3"], seed=n + step, bits_form=bits, **kw)
+                assert np.array_equal(e, g) and np.array_equal(eo, o), (n, step, bits)
+            pub = om.c_process(g, c["vox"], c["infl"], c["pot"], int(c["pw"]))
+            assert np.array_equal(pub[0], c["pub"][step]), (n, step)
+            old_g, old_o = g[0], o[0]
+        n += 1
+    assert n == 18
+
+
+def test_live_against_the_compiled_reference_node():
+    """Same comparison on fresh random inputs at the planner's grid size, where oracle/_ref/libref_map.so exists."""
+    if not S.have_ref():
+        pytest.skip("oracle/_ref/libref_map.so not built (needs /root/reference)")
+    from oracle import mapping as om
+    env, org = forest_env(21)
+    pos = positions(22, 4)
+    rot = np.array([[0.6, -0.8, 0], [0.8, 0.6, 0], [0, 0, 1.0]])
+    for fov in (None, (1.0, 0.6)):
+        w, wo = S.c_update(env, org, pos, VOX, RANGE, rot=None if fov is None else np.stack([rot] * 4), fov=fov)
+        pos2 = pos + [0.5, -0.7, 0.04]
+        w2, wo2 = S.c_update(env, org, pos2, VOX, RANGE, rot=None if fov is None else np.stack([rot] * 4), fov=fov, old_grids=w, old_origin=wo)
+        pub2 = om.c_process(w2, VOX, 0.3, 1.5, 4)
+        for a in range(4):
+            cur, o, _ = S.ref_update(env, org, pos[a], VOX, RANGE, rot=rot if fov else None, fov=fov)
+            assert np.array_equal(cur, w[a]) and np.array_equal(o, wo[a]), (fov, a)
+            cur, o, pub = S.ref_update(env, org, pos2[a], VOX, RANGE, rot=rot if fov else None, fov=fov, old_grid=w[a], old_origin=wo[a])
+            assert np.array_equal(cur, w2[a]) and np.array_equal(o, wo2[a]) and np.array_equal(pub, pub2[a]), (fov, a)
