@@ -502,8 +502,20 @@ def sense_measure(n_agents=4096, steps=10, local_rank=0, cpu_agents=512):
     t_cpu = time.perf_counter() - t0
     exact = bool(np.array_equal(got0.reshape(want0.shape), want0) and np.array_equal(got1.reshape(want1.shape), want1)
                  and np.array_equal(goto1, wo1))
+    ref_node = None
+    if osn.have_ref():  # the reference's OWN node (map_builder.cpp compiled unmodified), one core, its own timers
+        tms, acc = np.zeros(3), np.zeros(3)
+        k = min(m, 6)
+        for a in range(k):
+            osn.ref_update(env, org, pos1[a], vox, rng3, old_grid=want0[a], old_origin=wo0[a], times_ms=tms)
+            acc += tms
+        ref_node = {"kind": "reference", "cores": 1, "raycast_ms": acc[0] / k, "merge_ms": acc[1] / k, "callback_total_ms": acc[2] / k,
+                    "value": 1e3 * k / (acc[0] + acc[1]), "unit": "agents/s",
+                    "sample": f"{k} agents, MapBuilder::EnvironmentVoxelGridCallback of the compiled reference node; value = 1 / (its ray-cast + "
+                              f"merge timers); callback_total_ms also holds its grid post-processing"}
     balg = 2.0 * cells
-    return {"workload": f"{n_agents} agents in one {dim_env[0]}x{dim_env[1]}x{dim_env[2]} forest environment grid (0.3 m voxels), "
+    return {"reference_node": ref_node,
+            "workload": f"{n_agents} agents in one {dim_env[0]}x{dim_env[1]}x{dim_env[2]} forest environment grid (0.3 m voxels), "
                         f"66x66x20 local grids, 360 degree ray casting (13 992 rays per agent), merge with the kept grids",
             "metric": "map updates/sec (agents/s)", "value": n_agents / (ms * 1e-3), "kernel_ms": ms, "first_update_ms": first_ms,
             "dtype": "int8 grids, f64 ray traversal", "byte_exact_vs_cpu_port": exact, "algorithmic_bytes_per_agent": balg,

@@ -35,11 +35,12 @@ extern "C" {
 //   env / dim_env / origin_env / voxel : the environment message;  pos : pos_curr_;  rot : rot_mat_cam_ (row-major)
 //   old_grid / old_origin (NULL = first update) : voxel_grid_curr_ before the call (dimension = floor(range / voxel))
 //   curr_out / curr_origin : voxel_grid_curr_ after the call;  pub_out : data of the published message
+//   times_ms (may be NULL) [3] : the node's own wall-clock timers raycast_comp_time_, merge_comp_time_, tot_comp_time_ (:170-236)
 // Returns the number of voxels of the local grid, or -1 when the node did not publish.
 int ref_map_update(const double* range, int free_grid, double inflation_dist, double potential_dist, double potential_pow, int limited_fov,
                    double fov_x, double fov_y, const int8_t* env, const int32_t* dim_env, const double* origin_env, double voxel,
                    const double* pos, const double* rot, const int8_t* old_grid, const double* old_origin, int8_t* curr_out,
-                   double* curr_origin, int8_t* pub_out) {
+                   double* curr_origin, int8_t* pub_out, double* times_ms) {
   auto& ov = rclcpp::parameter_overrides();
   ov.clear();
   ov["voxel_grid_range"] = rclcpp::Parameter(std::vector<double>(range, range + 3));
@@ -82,6 +83,11 @@ int ref_map_update(const double* range, int free_grid, double inflation_dist, do
         const Eigen::Vector3d o = mb.voxel_grid_curr_.GetOrigin();
         for (int a = 0; a < 3; ++a) curr_origin[a] = o(a);
         n_out = (int)n;
+        if (times_ms) {
+          times_ms[0] = mb.raycast_comp_time_.empty() ? 0.0 : mb.raycast_comp_time_.back();
+          times_ms[1] = mb.merge_comp_time_.empty() ? 0.0 : mb.merge_comp_time_.back();
+          times_ms[2] = mb.tot_comp_time_.empty() ? 0.0 : mb.tot_comp_time_.back();
+        }
       }
     }
   }

@@ -47,9 +47,10 @@ def have_ref():
 
 
 def ref_update(env, origin_env, pos, voxel, rng, free_grid=False, rot=None, fov=None, old_grid=None, old_origin=None,
-               inflation=0.3, potential=1.5, power=4.0):
+               inflation=0.3, potential=1.5, power=4.0, times_ms=None):
     """One MapBuilder::EnvironmentVoxelGridCallback of ONE agent in the reference itself.  Returns (voxel_grid_curr_ after
-    the call [dz][dy][dx], its origin (3,), the published grid [dz][dy][dx])."""
+    the call [dz][dy][dx], its origin (3,), the published grid [dz][dy][dx]).  times_ms: optional float64 array [3] receiving the node's
+    own timers of that call (ray casting, merge, whole callback) in milliseconds."""
     env = np.ascontiguousarray(env, np.int8)
     dim_env = np.array([env.shape[2], env.shape[1], env.shape[0]], np.int32)
     origin_env = np.ascontiguousarray(origin_env, np.float64)
@@ -65,7 +66,7 @@ def ref_update(env, origin_env, pos, voxel, rng, free_grid=False, rot=None, fov=
     n = L.ref_map_update((C.c_double * 3)(*rng), C.c_int(int(free_grid)), C.c_double(inflation), C.c_double(potential), C.c_double(power),
                          C.c_int(int(fov is not None)), C.c_double(fov[0] if fov else 1.57), C.c_double(fov[1] if fov else 1.57),
                          _p(env), _p(dim_env), _p(origin_env), C.c_double(voxel), _p(pos), _p(rot), _p(old_grid), _p(old_origin),
-                         _p(cur), _p(org), _p(pub))
+                         _p(cur), _p(org), _p(pub), _p(times_ms))
     if n != cur.size:
         raise RuntimeError(f"ref_map_update returned {n}")
     return cur, org, pub
