@@ -509,8 +509,8 @@ def sense_measure(n_agents=4096, steps=10, local_rank=0, cpu_agents=512):
         for a in range(k):
             osn.ref_update(env, org, pos1[a], vox, rng3, old_grid=want0[a], old_origin=wo0[a], times_ms=tms)
             acc += tms
-        ref_node = {"kind": "reference", "cores": 1, "raycast_ms": acc[0] / k, "merge_ms": acc[1] / k, "callback_total_ms": acc[2] / k,
-                    "value": 1e3 * k / (acc[0] + acc[1]), "unit": "agents/s",
+        ref_node = {"kind": "reference", "cores": 1, "raycast_ms": float(acc[0] / k), "merge_ms": float(acc[1] / k), "callback_total_ms": float(acc[2] / k),
+                    "value": float(1e3 * k / (acc[0] + acc[1])), "unit": "agents/s",
                     "sample": f"{k} agents, MapBuilder::EnvironmentVoxelGridCallback of the compiled reference node; value = 1 / (its ray-cast + "
                               f"merge timers); callback_total_ms also holds its grid post-processing"}
     balg = 2.0 * cells
