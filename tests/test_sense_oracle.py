@@ -204,3 +204,20 @@ def test_live_against_the_compiled_reference_node():
             assert np.array_equal(cur, w[a]) and np.array_equal(o, wo[a]), (fov, a)
             cur, o, pub = S.ref_update(env, org, pos2[a], VOX, RANGE, rot=rot if fov else None, fov=fov, old_grid=w[a], old_origin=wo[a])
             assert np.array_equal(cur, w2[a]) and np.array_equal(o, wo2[a]) and np.array_equal(pub, pub2[a]), (fov, a)
+
+
+def test_mixed_first_and_follow_up_agents_in_one_call():
+    """have_old is per agent: agents on their first update (all-unknown grid with the freed 5x5x5 cube) and agents with a kept grid
+    in the same batch."""
+    env, org = forest_env(7)
+    pos = positions(8, 6)
+    g0, o0 = S.c_update(env, org, pos, VOX, RANGE)
+    have = np.array([1, 0, 1, 0, 0, 1], np.uint8)
+    pos2 = pos + 0.45
+    a, ao = S.c_update(env, org, pos2, VOX, RANGE, old_grids=g0, old_origin=o0, have_old=have)
+    b, bo = S.emu_update(env, org, pos2, VOX, RANGE, old_grids=g0, old_origin=o0, have_old=have, seed=3, bits_form=True)
+    assert np.array_equal(a, b) and np.array_equal(ao, bo)
+    first, _ = S.c_update(env, org, pos2, VOX, RANGE)
+    kept, _ = S.c_update(env, org, pos2, VOX, RANGE, old_grids=g0, old_origin=o0)
+    for i in range(6):
+        assert np.array_equal(a[i], kept[i] if have[i] else first[i]), i
