@@ -18,6 +18,8 @@
 #include <utility>
 #include <vector>
 
+#include <Eigen/Dense>  // the stand-in next to this directory: in the reference Vec3f / Vec3i ARE Eigen::Vector3d / Vector3i
+
 typedef double decimal_t;
 
 template <class S, int N>
@@ -37,8 +39,12 @@ struct ShimVec {
   S dot(const ShimVec& o) const { S s = v[0] * o.v[0]; for (int i = 1; i < N; ++i) s += v[i] * o.v[i]; return s; }
 };
 
-template <int N> using Veci = ShimVec<int, N>;
-template <int N> using Vecf = ShimVec<decimal_t, N>;
+// size 3 is the Eigen stand-in's vector, so that code mixing Vec3f and Eigen::Vector3d (multi_agent_planner) sees one type
+template <class S, int N> struct ShimVecSel { typedef ShimVec<S, N> type; };
+template <> struct ShimVecSel<int, 3> { typedef Eigen::Vector3i type; };
+template <> struct ShimVecSel<decimal_t, 3> { typedef Eigen::Vector3d type; };
+template <int N> using Veci = typename ShimVecSel<int, N>::type;
+template <int N> using Vecf = typename ShimVecSel<decimal_t, N>::type;
 typedef Veci<2> Vec2i;
 typedef Veci<3> Vec3i;
 typedef Vecf<2> Vec2f;
