@@ -38,13 +38,15 @@ def build(force=False):
 
 def build_ref(force=False):
     """Compile the parts of the reference that build here (convex_decomp.cpp; voxel_grid.cpp + raycast.cpp; map_builder.cpp +
-    path_tools.cpp on stand-in ROS headers) into oracle/_ref/ when the checkout is present."""
+    path_tools.cpp and agent_class.cpp on stand-in ROS / Gurobi headers) into oracle/_ref/ when the checkout is present."""
     src = os.path.join(REFERENCE, "convex_decomp_util", "src", "convex_decomp.cpp")
     if not os.path.exists(src):
         return _REF_SO if os.path.exists(_REF_SO) else None
     voxel_so = os.path.join(_HERE, "_ref", "libref_voxel.so")
     map_so = os.path.join(_HERE, "_ref", "libref_map.so")
-    if force or not os.path.exists(_REF_SO) or not os.path.exists(voxel_so) or not os.path.exists(map_so) or \
+    agent_so = os.path.join(_HERE, "_ref", "libref_agent.so")
+    if force or not os.path.exists(_REF_SO) or not os.path.exists(voxel_so) or not os.path.exists(map_so) or not os.path.exists(agent_so) or \
+            os.path.getmtime(agent_so) < os.path.getmtime(os.path.join(_HERE, "ref_wrap_agent.cpp")) or \
             os.path.getmtime(map_so) < os.path.getmtime(os.path.join(_HERE, "ref_wrap_map.cpp")) or \
             os.path.getmtime(_REF_SO) < os.path.getmtime(os.path.join(_HERE, "ref_wrap.cpp")):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "ref", f"REFERENCE={REFERENCE}"])

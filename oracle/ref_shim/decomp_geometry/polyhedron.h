@@ -73,4 +73,54 @@ struct Polyhedron {
 };
 typedef Polyhedron<3> Polyhedron3D;
 
+// dynamic-row matrix / vector and the linear-constraint container (decomp_basis/data_type.h, polyhedron.h:98-147), as far as
+// multi_agent_planner/src/agent_class.cpp uses them: element access, rows / cols / size, row assignment, conservativeResize
+template <int N>
+struct MatDNf {
+  int r;
+  std::vector<decimal_t> d;  // row-major r x N
+  struct Row {
+    MatDNf* M; int i;
+    Row& operator=(const Vecf<N>& v) { for (int c = 0; c < N; ++c) M->d[(size_t)i * N + c] = v(c); return *this; }
+  };
+  MatDNf() : r(0) {}
+  MatDNf(int rows, int cols) : r(rows), d((size_t)rows * N, 0.0) { (void)cols; }
+  int rows() const { return r; }
+  int cols() const { return N; }
+  decimal_t& operator()(int i, int j) { return d[(size_t)i * N + j]; }
+  decimal_t operator()(int i, int j) const { return d[(size_t)i * N + j]; }
+  Row row(int i) { Row k = {this, i}; return k; }
+  void conservativeResize(int rows, int cols) { (void)cols; r = rows; d.resize((size_t)rows * N, 0.0); }
+};
+struct VecDf {
+  std::vector<decimal_t> d;
+  VecDf() {}
+  explicit VecDf(int n) : d(n, 0.0) {}
+  int size() const { return (int)d.size(); }
+  int rows() const { return (int)d.size(); }
+  decimal_t& operator()(int i) { return d[i]; }
+  decimal_t operator()(int i) const { return d[i]; }
+  decimal_t& operator[](int i) { return d[i]; }
+  decimal_t operator[](int i) const { return d[i]; }
+  void conservativeResize(int n) { d.resize(n, 0.0); }
+};
+template <int Dim>
+struct LinearConstraint {
+  LinearConstraint() {}
+  LinearConstraint(const MatDNf<Dim>& A, const VecDf& b) : A_(A), b_(b) {}
+  bool inside(const Vecf<Dim>& pt) const {
+    for (int i = 0; i < A_.rows(); ++i) {
+      decimal_t s = -b_(i);
+      for (int c = 0; c < Dim; ++c) s += A_(i, c) * pt(c);
+      if (s > 0) return false;
+    }
+    return true;
+  }
+  MatDNf<Dim> A() const { return A_; }
+  VecDf b() const { return b_; }
+  MatDNf<Dim> A_;
+  VecDf b_;
+};
+typedef LinearConstraint<3> LinearConstraint3D;
+
 #endif

@@ -4,8 +4,12 @@
 // message, subscriptions that do nothing.  No ROS2 code; nothing of the product includes this.
 #ifndef HDSM_REF_SHIM_RCLCPP_HPP_
 #define HDSM_REF_SHIM_RCLCPP_HPP_
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <functional>
+#include <future>
+#include <thread>
 #include <map>
 #include <memory>
 #include <string>
@@ -45,6 +49,20 @@ template <class T> struct Publisher {
   void publish(const T& m) { last = m; ++count; }
 };
 template <class T> struct Subscription { typedef std::shared_ptr<Subscription<T>> SharedPtr; };
+struct TimerBase { typedef std::shared_ptr<TimerBase> SharedPtr; };
+struct Logger {};
+inline bool& ok_flag() { static bool f = false; return f; }  // the node's worker loops (while (rclcpp::ok())) end at once
+inline bool ok() { return ok_flag(); }
+template <class S> struct Client {
+  typedef std::shared_ptr<Client<S>> SharedPtr;
+  typedef std::shared_future<std::shared_ptr<typename S::Response>> SharedFuture;
+  template <class D> bool wait_for_service(D) { return true; }
+  template <class F> SharedFuture async_send_request(std::shared_ptr<typename S::Request>, F&&) {
+    std::promise<std::shared_ptr<typename S::Response>> p;
+    p.set_value(std::make_shared<typename S::Response>());
+    return p.get_future().share();
+  }
+};
 class Node {
  public:
   explicit Node(const std::string&) {}
@@ -57,10 +75,16 @@ class Node {
   template <class F> void on_shutdown(F&&) {}
   template <class T, class F> typename Subscription<T>::SharedPtr create_subscription(const std::string&, int, F&&) { return std::make_shared<Subscription<T>>(); }
   template <class T> typename Publisher<T>::SharedPtr create_publisher(const std::string&, int) { return std::make_shared<Publisher<T>>(); }
+  template <class S> typename Client<S>::SharedPtr create_client(const std::string&) { return std::make_shared<Client<S>>(); }
+  template <class D, class F> TimerBase::SharedPtr create_wall_timer(D, F&&) { return std::make_shared<TimerBase>(); }
+  Logger get_logger() const { return Logger(); }
   Time now() const { return Time(); }
   Clock::SharedPtr get_clock() { return std::make_shared<Clock>(); }
  private:
   std::map<std::string, Parameter> params_;
 };
 }  // namespace rclcpp
+#define RCLCPP_INFO(logger, ...) do { (void)(logger); } while (0)
+#define RCLCPP_ERROR(logger, ...) do { (void)(logger); } while (0)
+#define RCLCPP_WARN(logger, ...) do { (void)(logger); } while (0)
 #endif

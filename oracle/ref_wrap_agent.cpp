@@ -1,0 +1,180 @@
+// TEST INFRASTRUCTURE - C entry points around the reference's own planner node.
+//
+// Linked with /root/reference/multi_agent_planner/src/agent_class.cpp (and mapping_util/src/map_builder.cpp,
+// path_finding_util/src/path_tools.cpp, voxel_grid_util/src/{voxel_grid,raycast}.cpp, convex_decomp_util/src/
+// convex_decomp.cpp), all compiled UNMODIFIED from where they lie, against the stand-ins in oracle/ref_shim/: Eigen
+// vectors, rclcpp / tf2 / message classes, jps3d planner classes that find no path (the path thread is out of scope), and
+// the RECORDING stand-in for the Gurobi C++ API (oracle/ref_shim/gurobi/gurobi_c++.h).  Result: oracle/_ref/libref_agent.so.
+//
+// ref_agent_step runs the reference's own Agent::GenerateTimeAwareSafeCorridor (agent_class.cpp:1086-1215) and
+// Agent::SolveOptimizationProblem (:858-1023) on given inputs and returns (a) the inter-agent planes it appended to every
+// polytope and (b) the optimisation MODEL it handed to Gurobi: objective, variable bounds, dynamics rows, indicator rows,
+// one-hot rows.  That pins the optimisation's DATA of oracle/hdsm_oracle.py against the reference; what Gurobi then does
+// with the model is closed source and stays unpinned.
+//
+// The node's members are private; this file - not the reference - opens them with the macro below after every standard
+// header it needs has been included.  agent_class.cpp itself is a separate, untouched translation unit.
+#include <stdint.h>
+#include <string.h>
+
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <deque>
+#include <fstream>
+#include <functional>
+#include <future>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#define private public
+#include "agent_class.hpp"
+#undef private
+
+using multi_agent_planner::Agent;
+
+extern "C" {
+
+// Parameters as the node's ROS parameters (agent_class.cpp:2190-2248).  The node object is never destroyed (its two worker
+// threads are plain std::thread members that the reference never joins); they are let through their start-up waits and,
+// with rclcpp::ok() false in the stand-in, return at once.
+void* ref_agent_create(int n_rob, int id, int n_hor, int poly_hor, double dt, int rk4, double r_u, const double* r_x, const double* r_n,
+                       double max_vel, double min_acc_xy, double max_acc_xy, double min_acc_z, double max_acc_z, double max_jerk,
+                       double drone_radius, double drone_z_offset, const double* drag, const double* state_ini) {
+  auto& ov = rclcpp::parameter_overrides();
+  ov.clear();
+  ov["n_rob"] = rclcpp::Parameter(n_rob), ov["id"] = rclcpp::Parameter(id), ov["n_hor"] = rclcpp::Parameter(n_hor);
+  ov["poly_hor"] = rclcpp::Parameter(poly_hor), ov["dt"] = rclcpp::Parameter(dt), ov["rk4"] = rclcpp::Parameter(rk4 != 0);
+  ov["r_u"] = rclcpp::Parameter(r_u);
+  ov["r_x"] = rclcpp::Parameter(std::vector<double>(r_x, r_x + 9)), ov["r_n"] = rclcpp::Parameter(std::vector<double>(r_n, r_n + 9));
+  ov["max_vel"] = rclcpp::Parameter(max_vel), ov["min_acc_xy"] = rclcpp::Parameter(min_acc_xy), ov["max_acc_xy"] = rclcpp::Parameter(max_acc_xy);
+  ov["min_acc_z"] = rclcpp::Parameter(min_acc_z), ov["max_acc_z"] = rclcpp::Parameter(max_acc_z), ov["max_jerk"] = rclcpp::Parameter(max_jerk);
+  ov["drone_radius"] = rclcpp::Parameter(drone_radius), ov["drone_z_offset"] = rclcpp::Parameter(drone_z_offset);
+  ov["drag_coeff"] = rclcpp::Parameter(std::vector<double>(drag, drag + 3));
+  ov["state_ini"] = rclcpp::Parameter(std::vector<double>(state_ini, state_ini + 9));
+  ov["path_planning_period"] = rclcpp::Parameter(0.001);
+  ov["save_stats"] = rclcpp::Parameter(false), ov["planner_verbose"] = rclcpp::Parameter(false), ov["gurobi_verbose"] = rclcpp::Parameter(false);
+  std::streambuf *keep_out = std::cout.rdbuf(), *keep_err = std::cerr.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf()), std::cerr.rdbuf(sink.rdbuf());
+  Agent* a = new Agent();
+  a->voxel_grid_ready_ = true;
+  a->path_ready_ = true;
+  if (a->path_planning_thread_.joinable()) a->path_planning_thread_.join();
+  if (a->traj_planning_thread_.joinable()) a->traj_planning_thread_.join();
+  std::cout.rdbuf(keep_out), std::cerr.rdbuf(keep_err);
+  return a;
+}
+
+int ref_agent_num_vars(void* h) { return (int)static_cast<Agent*>(h)->model_.vars.size(); }
+
+// One GenerateTimeAwareSafeCorridor + SolveOptimizationProblem of the reference.
+//   x0 [9] state_curr_;  ref [N+1][6] traj_ref_curr_;  polytopes: n_poly, rows[n_poly], A [n_poly][rmax][3], b [n_poly][rmax]
+//   have_prev / prev_traj [N+1][9]: traj_curr_ (empty before the first solve);  all_pos [n_rob][N+1][3], all_valid [n_rob]
+// Outputs (dense, nz = number of model variables: x (N+1) x 9, u N x 3, binaries N x P):
+//   final_rows [N][n_poly]: rows of poly_const_final_vec_[k][p];  final_A [N][n_poly][fmax][3], final_b [N][n_poly][fmax]
+//   obj_diag [nz], obj_lin [nz], obj_const, obj_offdiag (sum of |off-diagonal quadratic coefficients|)
+//   var_lb / var_ub [nz], var_type [nz]
+//   lin_*: the ACTIVE linear constraints (expr sense 0): n_lin, dense [cap_lin][nz], constant [cap_lin], sense [cap_lin]
+//   ind_*: the ACTIVE indicator constraints: n_ind, dense [cap_ind][nz], constant [cap_ind], bin variable [cap_ind]
+// Returns 0, or -1 when a capacity is too small.
+int ref_agent_step(void* h, const double* x0, const double* ref, int n_poly, const int32_t* rows, int rmax, const double* A, const double* b,
+                   int have_prev, const double* prev_traj, const double* all_pos, const uint8_t* all_valid, int fmax, int32_t* final_rows,
+                   double* final_A, double* final_b, double* obj_diag, double* obj_lin, double* obj_const, double* obj_offdiag, double* var_lb,
+                   double* var_ub, int8_t* var_type, int cap_lin, int32_t* n_lin, double* lin_dense, double* lin_const, int8_t* lin_sense,
+                   int cap_ind, int32_t* n_ind, double* ind_dense, double* ind_const, int32_t* ind_bin, int32_t* failed) {
+  Agent* a = static_cast<Agent*>(h);
+  const int N = a->n_hor_, n_rob = a->n_rob_;
+  std::streambuf *keep_out = std::cout.rdbuf(), *keep_err = std::cerr.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf()), std::cerr.rdbuf(sink.rdbuf());
+  a->state_curr_.assign(x0, x0 + 9);
+  a->traj_ref_curr_.assign(N + 1, std::vector<double>(6));
+  for (int i = 0; i <= N; ++i)
+    for (int j = 0; j < 6; ++j) a->traj_ref_curr_[i][j] = ref[6 * i + j];
+  a->poly_const_vec_.clear();
+  for (int p = 0; p < n_poly; ++p) {
+    MatDNf<3> Am(rows[p], 3);
+    VecDf bv(rows[p]);
+    for (int r = 0; r < rows[p]; ++r) {
+      for (int c = 0; c < 3; ++c) Am(r, c) = A[((size_t)p * rmax + r) * 3 + c];
+      bv(r) = b[(size_t)p * rmax + r];
+    }
+    a->poly_const_vec_.push_back(LinearConstraint3D(Am, bv));
+  }
+  a->traj_curr_.clear();
+  a->control_curr_.clear();
+  if (have_prev) {
+    a->traj_curr_.assign(N + 1, std::vector<double>(9));
+    for (int i = 0; i <= N; ++i)
+      for (int j = 0; j < 9; ++j) a->traj_curr_[i][j] = prev_traj[9 * i + j];
+    a->control_curr_.assign(N, std::vector<double>(3, 0.0));
+  }
+  for (int j = 0; j < n_rob; ++j) {
+    multi_agent_planner_msgs::msg::Trajectory t;
+    if (all_valid[j] && j != a->id_) {
+      t.states.resize(N + 1);
+      for (int k = 0; k <= N; ++k) {
+        const double* q = all_pos + ((size_t)j * (N + 1) + k) * 3;
+        t.states[k].position = {q[0], q[1], q[2]};
+        t.states[k].velocity = {0.0, 0.0, 0.0};
+        t.states[k].acceleration = {0.0, 0.0, 0.0};
+      }
+    }
+    a->traj_other_agents_[j] = t;
+  }
+  a->GenerateTimeAwareSafeCorridor();
+  a->SolveOptimizationProblem();
+  std::cout.rdbuf(keep_out), std::cerr.rdbuf(keep_err);
+  *failed = a->optimization_failed_ ? 1 : 0;
+
+  int rc = 0;
+  for (int k = 0; k < N; ++k)
+    for (int p = 0; p < n_poly; ++p) {
+      const LinearConstraint3D& lc = a->poly_const_final_vec_[k][p];
+      const int r_kp = lc.A_.rows();
+      final_rows[k * n_poly + p] = r_kp;
+      if (r_kp > fmax) { rc = -1; continue; }
+      for (int r = 0; r < r_kp; ++r) {
+        for (int c = 0; c < 3; ++c) final_A[(((size_t)k * n_poly + p) * fmax + r) * 3 + c] = lc.A_(r, c);
+        final_b[((size_t)k * n_poly + p) * fmax + r] = lc.b_(r);
+      }
+    }
+  const GRBModel& m = a->model_;
+  const int nz = (int)m.vars.size();
+  for (int i = 0; i < nz; ++i) obj_diag[i] = 0, obj_lin[i] = m.objective.lin.coeff_of(i), var_lb[i] = m.vars[i].lb, var_ub[i] = m.vars[i].ub, var_type[i] = m.vars[i].type;
+  *obj_const = m.objective.lin.constant;
+  *obj_offdiag = 0;
+  for (const auto& kv : m.objective.quad) {
+    if (kv.first.first == kv.first.second) obj_diag[kv.first.first] = kv.second;
+    else *obj_offdiag += std::fabs(kv.second);
+  }
+  int nl = 0;
+  for (const auto& c : m.lin) {
+    if (c.removed) continue;
+    if (nl < cap_lin) {
+      for (int i = 0; i < nz; ++i) lin_dense[(size_t)nl * nz + i] = c.expr.coeff_of(i);
+      lin_const[nl] = c.expr.constant, lin_sense[nl] = c.sense;
+    } else rc = -1;
+    ++nl;
+  }
+  *n_lin = nl;
+  int ni = 0;
+  for (const auto& c : m.ind) {
+    if (c.removed) continue;
+    if (ni < cap_ind) {
+      for (int i = 0; i < nz; ++i) ind_dense[(size_t)ni * nz + i] = c.expr.coeff_of(i);
+      ind_const[ni] = c.expr.constant - c.rhs, ind_bin[ni] = c.bin_var;
+    } else rc = -1;
+    ++ni;
+  }
+  *n_ind = ni;
+  return rc;
+}
+}

@@ -1,0 +1,119 @@
+"""The optimisation's DATA pinned against the reference's own planner node.
+
+tests/golden/agent_model_ref.npz holds what the reference's OWN Agent::GenerateTimeAwareSafeCorridor (agent_class.cpp:1086-1215)
+and Agent::SolveOptimizationProblem (:858-1023, on the model of CreateGurobiModel :2071-2153) produce on random inputs -
+agent_class.cpp compiled unmodified on stand-in ROS / Eigen headers, with a recording stand-in for the Gurobi C++ API in place of
+the closed-source solver (tests/golden/make_agent_model_golden.py).  oracle/hdsm_oracle.py - the specification the C port and the
+CUDA kernels are tested against - must reproduce: the inter-agent planes, the objective, the variable bounds, the dynamics rows,
+the one-hot rows and every indicator row.  What Gurobi then does with that model stays unpinned (KKT certificate)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import hdsm_oracle as ho
+
+GRB_INF = 1e100
+
+
+def cases():
+    z = np.load(os.path.join(GOLDEN, "agent_model_ref.npz"))
+    for c in range(int(z["n_cases"])):
+        over = eval(str(z[f"c{c}_over"]), {"__builtins__": {}})
+        n_rob, aid, n_poly, have_prev = (int(v) for v in z[f"c{c}_meta"])
+        p = ho.Params(**over)
+        g = lambda k: z[f"c{c}_{k}"]  # noqa: E731
+        yield dict(p=p, n_rob=n_rob, id=aid, x0=g("x0"), ref=g("ref"), state_ini=g("state_ini"), prev=g("prev") if have_prev else None,
+                   all_pos=g("all_pos"), all_valid=g("all_valid"), polys=[(g(f"polyA{q}"), g(f"polyb{q}")) for q in range(n_poly)],
+                   final=[[(g(f"finA{k}_{q}"), g(f"finb{k}_{q}")) for q in range(n_poly)] for k in range(p.n_hor)],
+                   obj_diag=g("obj_diag"), obj_lin=g("obj_lin"), obj_const=float(g("obj_const")), obj_offdiag=float(g("obj_offdiag")),
+                   lb=g("lb"), ub=g("ub"), vtype=g("vtype"), lin=(g("lin"), g("lin_c"), g("lin_s")), ind=(g("ind"), g("ind_c"), g("ind_b")),
+                   failed=bool(g("failed")))
+
+
+def check_against_oracle(c, r):
+    """r: what the reference produced (fixture or live); c: the inputs."""
+    p, N, P = c["p"], c["p"].n_hor, len(c["polys"])
+    nx, nzc = 9 * (N + 1), 9 * (N + 1) + 3 * N
+    P_eff = min(P, p.poly_hor)
+    # --- inter-agent planes (GenerateTimeAwareSafeCorridor + AddHyperplane): appended to EVERY polytope, neighbour-id order
+    prev_pos = c["prev"][:, :3] if c["prev"] is not None else np.tile(c["state_ini"][:3], (N + 1, 1))
+    planes = ho.time_aware_planes(p, prev_pos, c["all_pos"], c["all_valid"], c["id"])
+    for k in range(N):
+        for q in range(P):
+            A, b = r["final"][k][q]
+            R = len(c["polys"][q][1])
+            assert np.array_equal(A[:R], c["polys"][q][0]) and np.array_equal(b[:R], c["polys"][q][1])
+            assert A.shape[0] == R + len(planes[k][1])
+            assert np.allclose(A[R:], planes[k][0], rtol=0, atol=1e-14) and np.allclose(b[R:], planes[k][1], rtol=1e-14, atol=1e-14), (k, q)
+    # --- objective (:870-883 on obj_grb_ of :2098): diagonal, no cross terms, linear part, constant
+    qp = ho.build_qp_full(p, c["x0"], c["ref"][:N], c["polys"], planes, [0] * N, drop_constant_rows=False)
+    assert r["obj_offdiag"] == 0.0
+    assert np.array_equal(r["obj_diag"][:nzc], qp.Pdiag) and not r["obj_diag"][nzc:].any()
+    assert np.allclose(r["obj_lin"][:nzc], qp.q, rtol=1e-15, atol=0) and not r["obj_lin"][nzc:].any()
+    assert abs(r["obj_const"] - qp.c0) <= 1e-12 * max(1.0, abs(qp.c0))
+    # --- variables: x0 fixed through its bounds (:886-889), terminal velocity / acceleration fixed at 0 (:2078-2081), boxes, binaries
+    lb, ub = r["lb"], r["ub"]
+    assert len(lb) == nzc + N * p.poly_hor
+    assert np.array_equal(lb[:9], c["x0"]) and np.array_equal(ub[:9], c["x0"])
+    xl, xu = np.where(np.isinf(p.x_lb()), -GRB_INF, p.x_lb()), np.where(np.isinf(p.x_ub()), GRB_INF, p.x_ub())
+    for k in range(1, N):
+        assert np.array_equal(lb[9 * k:9 * k + 9], xl) and np.array_equal(ub[9 * k:9 * k + 9], xu)
+    assert np.array_equal(lb[9 * N:9 * N + 3], xl[:3]) and np.array_equal(ub[9 * N:9 * N + 3], xu[:3])
+    assert not lb[9 * N + 3:nx].any() and not ub[9 * N + 3:nx].any()
+    assert np.array_equal(lb[nx:nzc], np.tile(p.u_lb(), N)) and np.array_equal(ub[nx:nzc], np.tile(p.u_ub(), N))
+    assert (r["vtype"][:nzc] == ord("C")).all() and (r["vtype"][nzc:] == ord("B")).all()
+    # --- linear rows: 9 N dynamics equalities (:2146-2151) then N one-hot rows (:939-940)
+    L, Lc, Ls = r["lin"]
+    assert L.shape[0] == 9 * N + N and (Ls == ord("=")).all()
+    dyn = qp.Aeq[9:9 + 9 * N]                      # the oracle's rows, between its x0 rows and its terminal rows
+    assert np.allclose(L[:9 * N, :nzc], dyn, rtol=1e-14, atol=1e-16) and not L[:9 * N, nzc:].any() and not Lc[:9 * N].any()
+    for k in range(N):
+        row = L[9 * N + k]
+        want = np.zeros_like(row)
+        want[nzc + k * p.poly_hor:nzc + k * p.poly_hor + P_eff] = 1.0
+        assert np.array_equal(row, want) and Lc[9 * N + k] == -1.0
+    # --- indicator rows (:909-937 with GetGurobiPolyhedronConstraints :1071-1084): for step k, polytope q, every final row on x_k and on
+    #     x_{k+1}, position components only, switched by binary b[k][q]
+    I, Ic, Ib = r["ind"]
+    n = 0
+    for k in range(N):
+        for q in range(P_eff):
+            A, b = r["final"][k][q]
+            for i in range(len(b)):
+                for kk in (k, k + 1):
+                    want = np.zeros(I.shape[1])
+                    want[9 * kk:9 * kk + 3] = A[i]
+                    assert np.array_equal(I[n], want) and Ic[n] == -b[i] and Ib[n] == nzc + k * p.poly_hor + q, (k, q, i, kk)
+                    n += 1
+    assert n == I.shape[0]
+    # --- and the same rows are what the oracle's QP imposes for the assignment "polytope 0 everywhere"
+    rows0 = sum(2 * len(r["final"][k][0][1]) for k in range(N))
+    assert qp.C.shape[0] == 12 * (N - 1) + 6 * N + rows0
+    # without a solver the reference reports a failed optimisation (GRBException -> :988-995)
+    assert r["failed"]
+
+
+def test_oracle_reproduces_the_reference_models_of_the_fixture():
+    n = 0
+    for c in cases():
+        check_against_oracle(c, c)
+        n += 1
+    assert n == 5
+
+
+def test_live_against_the_compiled_reference_node():
+    from oracle import ref_agent as ra
+    if not ra.have_ref():
+        pytest.skip("oracle/_ref/libref_agent.so not built (needs /root/reference)")
+    for c in cases():
+        ag = ra.RefAgent(c["p"], c["n_rob"], c["id"], c["state_ini"])
+        r = ag.step(c["x0"], c["ref"], c["polys"], c["prev"], c["all_pos"], c["all_valid"])
+        check_against_oracle(c, r)
+        for key in ("obj_diag", "obj_lin", "lb", "ub"):          # and the fixture is what the reference produces today
+            assert np.array_equal(r[key], c[key]), key
+        # a second step on the same node: the reference removes and re-adds its per-step rows (:892-902)
+        r2 = ag.step(c["x0"] + 0.01, c["ref"], c["polys"], c["prev"], c["all_pos"], c["all_valid"])
+        assert r2["lin"][0].shape == r["lin"][0].shape and r2["ind"][0].shape == r["ind"][0].shape
+        assert np.array_equal(r2["lb"][:9], c["x0"] + 0.01)
