@@ -17,8 +17,14 @@ Reference functions restated here (paths relative to the reference checkout):
 PARITY PIN STATUS.  The arithmetic of the reference lives in Gurobi 10.0.x
 (closed source, licence-gated; linked at multi_agent_planner/CMakeLists.txt:46) which
 is not available, and the reference ships no tests or golden vectors for this
-path, so **parity against Gurobi itself is unpinned**.
-What pins this oracle instead:
+path, so **parity against Gurobi's SOLVE is unpinned**.
+The problem DATA is pinned: the reference's own agent_class.cpp, compiled
+unmodified on stand-in ROS / Eigen headers and a recording stand-in for the
+Gurobi C++ API (oracle/_ref/libref_agent.so, oracle/ref_wrap_agent.cpp), builds
+its model on the same inputs, and ``time_aware_planes`` / ``build_qp_full`` /
+``Params`` bounds reproduce its planes, objective, bounds, dynamics rows, one-hot
+rows and indicator rows (tests/test_ref_agent.py, fixture
+tests/golden/agent_model_ref.npz).  What pins the solutions:
 
 1. every fixed-assignment QP is strictly convex, so a KKT certificate is
    self-validating; ``kkt_residual`` checks it in the *full* (x, u) variable
