@@ -26,6 +26,7 @@ def lib():
         _lib.ref_agent_num_vars.restype = C.c_int
         _lib.ref_agent_num_vars.argtypes = [C.c_void_p]
         _lib.ref_agent_step.restype = C.c_int
+        _lib.ref_agent_reftraj.restype = C.c_int
     return _lib
 
 
@@ -83,3 +84,23 @@ class RefAgent:
         nl, ni = n_lin.value, n_ind.value
         return dict(final=final, obj_diag=obj_diag, obj_lin=obj_lin, obj_const=obj_const.value, obj_offdiag=obj_off.value, lb=lb, ub=ub,
                     vtype=vtype, lin=(lin[:nl], lin_c[:nl], lin_s[:nl]), ind=(ind[:ni], ind_c[:ni], ind_b[:ni]), failed=bool(failed.value))
+
+    def reference_trajectory(self, grid, origin, voxel, path, prev_ref, increment, traj, all_pos, all_valid, path_vel_min, path_vel_max,
+                             path_vel_dec, sens_dist, sens_pot, sens_other_agents):
+        """The reference's own GenerateReferenceTrajectory.  grid [dz][dy][dx] int8, path (n_path, 3), prev_ref (N+1, 3) or None,
+        traj (N+1, 3) or None.  Returns (traj_ref_curr_ (N+1, 6), path_vel_)."""
+        N = self.p.n_hor
+        grid = np.ascontiguousarray(grid, np.int8)
+        dim = np.array([grid.shape[2], grid.shape[1], grid.shape[0]], np.int32)
+        path = np.ascontiguousarray(path, np.float64).reshape(-1, 3)
+        prev = None if prev_ref is None else np.ascontiguousarray(prev_ref, np.float64).reshape(N + 1, 3)
+        tr = None if traj is None else np.ascontiguousarray(traj, np.float64).reshape(N + 1, 3)
+        all_pos, all_valid = np.ascontiguousarray(all_pos, np.float64), np.ascontiguousarray(all_valid, np.uint8)
+        out, vel = np.zeros((N + 1, 6)), C.c_double()
+        rows = lib().ref_agent_reftraj(self.h, _p(grid), _p(dim), _d(origin), C.c_double(voxel), _p(path), C.c_int(path.shape[0]),
+                                       C.c_int(int(prev is not None)), _p(prev), C.c_int(int(increment)), C.c_int(int(tr is not None)), _p(tr),
+                                       _p(all_pos), _p(all_valid), _d([path_vel_min, path_vel_max, path_vel_dec, sens_dist, sens_pot, sens_other_agents]),
+                                       _p(out), C.byref(vel))
+        if rows != N + 1:
+            raise RuntimeError(f"GenerateReferenceTrajectory gave {rows} rows")
+        return out, vel.value

@@ -177,4 +177,67 @@ int ref_agent_step(void* h, const double* x0, const double* ref, int n_poly, con
   *n_ind = ni;
   return rc;
 }
+// The reference's own Agent::GenerateReferenceTrajectory (agent_class.cpp:1449-1553, with SamplePath, KeepOnlyFreeReference,
+// ComputePathVelocity, GetVelocityLimit) on one agent.
+//   grid / dim / origin / voxel : voxel_grid_;  path [n_path][3] : path_curr_;  prev_ref [N+1][3] (have_prev) : positions of
+//   traj_ref_curr_;  increment : increment_traj_ref_;  traj [N+1][3] (have_traj) : positions of traj_curr_;  all_pos / all_valid
+//   sens / vel : path_vel_min, path_vel_max, path_vel_dec, sens_dist, sens_pot, sens_other_agents (the ROS parameters)
+// Outputs: ref_out [N+1][6] = traj_ref_curr_, *path_vel = path_vel_.  Returns the number of rows of traj_ref_curr_.
+int ref_agent_reftraj(void* h, const int8_t* grid, const int32_t* dim, const double* origin, double voxel, const double* path, int n_path,
+                      int have_prev, const double* prev_ref, int increment, int have_traj, const double* traj, const double* all_pos,
+                      const uint8_t* all_valid, const double* sens_vel, double* ref_out, double* path_vel) {
+  Agent* a = static_cast<Agent*>(h);
+  const int N = a->n_hor_, n_rob = a->n_rob_;
+  std::streambuf *keep_out = std::cout.rdbuf(), *keep_err = std::cerr.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf()), std::cerr.rdbuf(sink.rdbuf());
+  a->path_vel_min_ = sens_vel[0], a->path_vel_max_ = sens_vel[1], a->path_vel_dec_ = sens_vel[2];
+  a->sens_dist_ = sens_vel[3], a->sens_pot_ = sens_vel[4], a->sens_other_agents_ = sens_vel[5];
+  Eigen::Vector3d org(origin[0], origin[1], origin[2]);
+  Eigen::Vector3i d(dim[0], dim[1], dim[2]);
+  std::vector<voxel_grid_util::voxel_data_type> data(grid, grid + (size_t)dim[0] * dim[1] * dim[2]);
+  a->voxel_grid_ = voxel_grid_util::VoxelGrid(org, d, voxel, data);
+  a->path_curr_.assign(n_path, std::vector<double>(3));
+  for (int i = 0; i < n_path; ++i)
+    for (int c = 0; c < 3; ++c) a->path_curr_[i][c] = path[3 * i + c];
+  a->traj_ref_curr_.clear();
+  if (have_prev) {
+    a->traj_ref_curr_.assign(N + 1, std::vector<double>(6, 0.0));
+    for (int i = 0; i <= N; ++i)
+      for (int c = 0; c < 3; ++c) a->traj_ref_curr_[i][c] = prev_ref[3 * i + c];
+  }
+  a->reset_path_ = false;
+  a->increment_traj_ref_ = increment != 0;
+  a->traj_curr_.clear();
+  if (have_traj) {
+    a->traj_curr_.assign(N + 1, std::vector<double>(9, 0.0));
+    for (int i = 0; i <= N; ++i)
+      for (int c = 0; c < 3; ++c) a->traj_curr_[i][c] = traj[3 * i + c];
+  }
+  for (int j = 0; j < n_rob; ++j) {
+    multi_agent_planner_msgs::msg::Trajectory t;
+    if (all_valid[j] && j != a->id_) {
+      t.states.resize(N + 1);
+      for (int k = 0; k <= N; ++k) {
+        const double* q = all_pos + ((size_t)j * (N + 1) + k) * 3;
+        t.states[k].position = {q[0], q[1], q[2]};
+        t.states[k].velocity = {0.0, 0.0, 0.0};
+        t.states[k].acceleration = {0.0, 0.0, 0.0};
+      }
+    }
+    a->traj_other_agents_[j] = t;
+  }
+  int rows = -1;
+  try {
+    a->GenerateReferenceTrajectory();
+    rows = (int)a->traj_ref_curr_.size();
+    for (int i = 0; i < rows && i <= N; ++i)
+      for (int c = 0; c < 6; ++c) ref_out[6 * i + c] = c < (int)a->traj_ref_curr_[i].size() ? a->traj_ref_curr_[i][c] : 0.0;
+    *path_vel = a->path_vel_;
+  } catch (...) {
+    rows = -2;
+  }
+  std::cout.rdbuf(keep_out), std::cerr.rdbuf(keep_err);
+  return rows;
+}
 }

@@ -117,3 +117,45 @@ def test_live_against_the_compiled_reference_node():
         r2 = ag.step(c["x0"] + 0.01, c["ref"], c["polys"], c["prev"], c["all_pos"], c["all_valid"])
         assert r2["lin"][0].shape == r["lin"][0].shape and r2["ind"][0].shape == r["ind"][0].shape
         assert np.array_equal(r2["lb"][:9], c["x0"] + 0.01)
+
+
+# ---- the reference-trajectory generator against the reference's own node ---------------------------------------------
+def _reftraj_checker(rb, i, prev_ref, increment):
+    """oracle/reftraj_oracle.c on agent i of the batch with the given previous reference."""
+    import copy
+    from oracle import reftraj as ort
+    r = copy.copy(rb)
+    r.prev_ref, r.have_prev, r.increment = rb.prev_ref.copy(), rb.have_prev.copy(), rb.increment.copy()
+    if prev_ref is not None:
+        r.prev_ref[i], r.have_prev[i] = prev_ref, 1
+    else:
+        r.have_prev[i] = 0
+    r.increment[i] = increment
+    out = ort.c_generate(r)
+    return out["ref"][i], out["path_vel"][i]
+
+
+def test_reference_trajectory_checker_equals_the_reference_node():
+    """GenerateReferenceTrajectory (agent_class.cpp:1449-1553 + SamplePath, KeepOnlyFreeReference, ComputePathVelocity) of the reference's
+    own node (fixture tests/golden/reftraj_node_ref.npz, and live where the reference is present) against oracle/reftraj_oracle.c:
+    first call, follow-up call and follow-up call with increment_traj_ref_ - equal to the last bit (both run on the host's libm)."""
+    import sys
+    sys.path.insert(0, os.path.join(GOLDEN))
+    import make_reftraj_node_golden as mk
+    from oracle import ref_agent as ra
+    z = np.load(os.path.join(GOLDEN, "reftraj_node_ref.npz"))
+    rb = mk.scenario_batch()
+    for i in (int(v) for v in z["agents"]):
+        first, v0 = _reftraj_checker(rb, i, None, 0)
+        assert np.array_equal(first, z[f"a{i}_first"]) and v0 == float(z[f"a{i}_first_vel"]), i
+        for inc in (0, 1):
+            nxt, v = _reftraj_checker(rb, i, first[:, :3], inc)
+            assert np.array_equal(nxt, z[f"a{i}_next{inc}"]) and v == float(z[f"a{i}_next{inc}_vel"]), (i, inc)
+    if ra.have_ref():                       # live: every agent of the scenario
+        for i in range(rb.n):
+            got, vel = mk.run_reference(rb, i, None, 0)
+            want, wv = _reftraj_checker(rb, i, None, 0)
+            assert np.array_equal(got, want) and vel == wv, i
+            got2, vel2 = mk.run_reference(rb, i, got[:, :3], 1)
+            want2, wv2 = _reftraj_checker(rb, i, got[:, :3], 1)
+            assert np.array_equal(got2, want2) and vel2 == wv2, i
