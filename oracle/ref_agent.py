@@ -27,6 +27,7 @@ def lib():
         _lib.ref_agent_num_vars.argtypes = [C.c_void_p]
         _lib.ref_agent_step.restype = C.c_int
         _lib.ref_agent_reftraj.restype = C.c_int
+        _lib.ref_agent_corridor.restype = C.c_int
     return _lib
 
 
@@ -104,3 +105,25 @@ class RefAgent:
         if rows != N + 1:
             raise RuntimeError(f"GenerateReferenceTrajectory gave {rows} rows")
         return out, vel.value
+
+    def safe_corridor(self, grid, origin, voxel, pos, path, n_it, use_cvx_new, prev, prev_traj, rmax=18):
+        """The reference's own GenerateSafeCorridor.  prev: None or dict(rows (n,), A (n, rmax, 3), b (n, rmax), seeds (n, 3), used (n,));
+        prev_traj (n_traj, 3).  Returns (rows (P,), A (P, rmax, 3), b (P, rmax), seeds (P, 3)) padded with zeros to poly_hor entries."""
+        P = self.p.poly_hor
+        grid = np.ascontiguousarray(grid, np.int8)
+        dim = np.array([grid.shape[2], grid.shape[1], grid.shape[0]], np.int32)
+        path = np.ascontiguousarray(path, np.float64).reshape(-1, 3)
+        ptraj = np.ascontiguousarray(prev_traj, np.float64).reshape(-1, 3)
+        n_prev = 0 if prev is None else len(prev["rows"])
+        pr = pa = pb = ps = pu = None
+        if n_prev:
+            pr, pa, pb = np.ascontiguousarray(prev["rows"], np.int32), np.ascontiguousarray(prev["A"], np.float64), np.ascontiguousarray(prev["b"], np.float64)
+            ps, pu = np.ascontiguousarray(prev["seeds"], np.float64), np.ascontiguousarray(prev["used"], np.uint8)
+        cap = P + 4
+        rows, A, b, seeds = np.zeros(cap, np.int32), np.zeros((cap, rmax, 3)), np.zeros((cap, rmax)), np.zeros((cap, 3))
+        n = lib().ref_agent_corridor(self.h, _p(grid), _p(dim), _d(origin), C.c_double(voxel), _d(pos), _p(path), C.c_int(path.shape[0]), C.c_int(n_it),
+                                     C.c_int(int(use_cvx_new)), C.c_int(n_prev), _p(pr), C.c_int(rmax), _p(pa), _p(pb), _p(ps), _p(pu),
+                                     C.c_int(ptraj.shape[0]), _p(ptraj), C.c_int(cap), _p(rows), _p(A), _p(b), _p(seeds))
+        if n < 0:
+            raise RuntimeError(f"GenerateSafeCorridor failed ({n})")
+        return n, rows[:P], A[:P], b[:P], seeds[:P]

@@ -240,4 +240,67 @@ int ref_agent_reftraj(void* h, const int8_t* grid, const int32_t* dim, const dou
   std::cout.rdbuf(keep_out), std::cerr.rdbuf(keep_err);
   return rows;
 }
+// The reference's own Agent::GenerateSafeCorridor (agent_class.cpp:1236-1447: kept polytopes, walk along the path, GetPolyOcta3D /
+// GetPolyOcta3DNew, A / b conversion) on one agent.
+//   grid / dim / origin / voxel : voxel_grid_;  pos [3] : state_curr_;  path [n_path][3] : path_curr_;  n_it : n_it_decomp_
+//   previous update (prev_n > 0): prev_rows [prev_n], prev_A [prev_n][rmax][3], prev_b [prev_n][rmax], prev_seeds [prev_n][3],
+//   prev_used [prev_n] = poly_const_vec_, poly_seeds_, poly_used_idx_;  prev_traj [n_traj][3] : positions of traj_curr_
+// Outputs: rows_out [cap], A_out [cap][rmax][3], b_out [cap][rmax], seeds_out [cap][3].  Returns the number of polytopes, -1 when one
+// exceeds rmax rows or cap, -2 when the reference threw.
+int ref_agent_corridor(void* h, const int8_t* grid, const int32_t* dim, const double* origin, double voxel, const double* pos, const double* path,
+                       int n_path, int n_it, int use_cvx_new, int prev_n, const int32_t* prev_rows, int rmax, const double* prev_A,
+                       const double* prev_b, const double* prev_seeds, const uint8_t* prev_used, int n_traj, const double* prev_traj, int cap,
+                       int32_t* rows_out, double* A_out, double* b_out, double* seeds_out) {
+  Agent* a = static_cast<Agent*>(h);
+  std::streambuf *keep_out = std::cout.rdbuf(), *keep_err = std::cerr.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf()), std::cerr.rdbuf(sink.rdbuf());
+  a->n_it_decomp_ = n_it, a->use_cvx_ = true, a->use_cvx_new_ = use_cvx_new != 0;
+  Eigen::Vector3d org(origin[0], origin[1], origin[2]);
+  Eigen::Vector3i d(dim[0], dim[1], dim[2]);
+  std::vector<voxel_grid_util::voxel_data_type> data(grid, grid + (size_t)dim[0] * dim[1] * dim[2]);
+  a->voxel_grid_ = voxel_grid_util::VoxelGrid(org, d, voxel, data);
+  a->state_curr_.assign(9, 0.0);
+  for (int c = 0; c < 3; ++c) a->state_curr_[c] = pos[c];
+  a->path_curr_.assign(n_path, std::vector<double>(3));
+  for (int i = 0; i < n_path; ++i)
+    for (int c = 0; c < 3; ++c) a->path_curr_[i][c] = path[3 * i + c];
+  a->traj_curr_.assign(n_traj, std::vector<double>(9, 0.0));
+  for (int i = 0; i < n_traj; ++i)
+    for (int c = 0; c < 3; ++c) a->traj_curr_[i][c] = prev_traj[3 * i + c];
+  a->poly_const_vec_.clear(), a->poly_seeds_.clear(), a->poly_vec_.clear(), a->poly_used_idx_.clear();
+  for (int p = 0; p < prev_n; ++p) {
+    MatDNf<3> Am(prev_rows[p], 3);
+    VecDf bv(prev_rows[p]);
+    for (int r = 0; r < prev_rows[p]; ++r) {
+      for (int c = 0; c < 3; ++c) Am(r, c) = prev_A[((size_t)p * rmax + r) * 3 + c];
+      bv(r) = prev_b[(size_t)p * rmax + r];
+    }
+    a->poly_const_vec_.push_back(LinearConstraint3D(Am, bv));
+    a->poly_seeds_.push_back({prev_seeds[3 * p], prev_seeds[3 * p + 1], prev_seeds[3 * p + 2]});
+    a->poly_vec_.push_back(Polyhedron3D());
+  }
+  a->poly_used_idx_.assign(a->poly_hor_, false);
+  for (int p = 0; p < prev_n && p < a->poly_hor_; ++p) a->poly_used_idx_[p] = prev_used[p] != 0;
+  int n_out = -2;
+  try {
+    a->GenerateSafeCorridor();
+    n_out = (int)a->poly_const_vec_.size();
+    if (n_out > cap) n_out = -1;
+    for (int p = 0; p < n_out; ++p) {
+      const LinearConstraint3D& lc = a->poly_const_vec_[p];
+      rows_out[p] = lc.A_.rows();
+      if (lc.A_.rows() > rmax) { n_out = -1; break; }
+      for (int r = 0; r < lc.A_.rows(); ++r) {
+        for (int c = 0; c < 3; ++c) A_out[((size_t)p * rmax + r) * 3 + c] = lc.A_(r, c);
+        b_out[(size_t)p * rmax + r] = lc.b_(r);
+      }
+      for (int c = 0; c < 3; ++c) seeds_out[3 * p + c] = a->poly_seeds_[p][c];
+    }
+  } catch (...) {
+    n_out = -2;
+  }
+  std::cout.rdbuf(keep_out), std::cerr.rdbuf(keep_err);
+  return n_out;
+}
 }

@@ -159,3 +159,30 @@ def test_reference_trajectory_checker_equals_the_reference_node():
             got2, vel2 = mk.run_reference(rb, i, got[:, :3], 1)
             want2, wv2 = _reftraj_checker(rb, i, got[:, :3], 1)
             assert np.array_equal(got2, want2) and vel2 == wv2, i
+
+
+# ---- the safe-corridor walk against the reference's own node ---------------------------------------------------------
+def test_corridor_walk_checker_equals_the_reference_node():
+    """GenerateSafeCorridor (agent_class.cpp:1236-1447: kept polytopes, walk along the path, GetPolyOcta3D, A / b conversion) of the
+    reference's own node (fixture tests/golden/corridor_node_ref.npz, and live where the reference is present) against
+    oracle/corridor_oracle.c: a first update and a follow-up update with kept polytopes - every array bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.join(GOLDEN))
+    import make_corridor_node_golden as mk
+    from oracle import corridor as oc, ref_agent as ra
+    z = np.load(os.path.join(GOLDEN, "corridor_node_ref.npz"))
+    cb = mk.first_batch()
+    first = oc.c_safe_corridor(cb)
+    for k in ("poly_rows", "poly_A", "poly_b", "seeds"):
+        assert np.array_equal(first[k], z[f"first_{k}"]), k
+    assert not first["flags"].any()
+    cb2 = mk.follow_up_batch(cb, first)
+    nxt = oc.c_safe_corridor(cb2)
+    for k in ("poly_rows", "poly_A", "poly_b", "seeds"):
+        assert np.array_equal(nxt[k], z[f"next_{k}"]), k
+    kept = [(nxt["seeds"][i, 0] == first["seeds"][i]).all(1).any() for i in range(cb.n)]
+    assert any(kept) and (nxt["poly_rows"][:, 0] >= 6).all()           # kept polytopes lead the new list (:1245-1270)
+    if ra.have_ref():
+        live = mk.collect(cb2, True)
+        for k in ("poly_rows", "poly_A", "poly_b", "seeds"):
+            assert np.array_equal(live[k], nxt[k]), k
