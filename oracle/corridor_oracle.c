@@ -14,9 +14,11 @@
  * bit for bit with the reference's own GetPolyOcta3D (compiled unmodified into oracle/_ref/, see
  * oracle/Makefile target `ref`) live when oracle/_ref exists, and against tests/golden/corridor_*.npz
  * (generated from oracle/_ref by tests/golden/make_corridor_golden.py) everywhere.  cor_safe_corridor
- * (the path walk that picks the seeds) follows agent_class.cpp by reading: that file needs ROS2 and
- * Gurobi headers and cannot be compiled here, so the walk is unpinned; its floating-point expressions
- * are written in the reference's evaluation order (Eigen sums 3-vectors left to right).
+ * (the path walk that picks the seeds) is PINNED as well: agent_class.cpp compiles unmodified on the stand-in
+ * ROS / Gurobi headers of oracle/ref_shim/ (oracle/_ref/libref_agent.so) and its own GenerateSafeCorridor gives
+ * bit-identical polytopes and seeds, first and follow-up updates (tests/test_ref_agent.py, fixture
+ * tests/golden/corridor_node_ref.npz).  Floating-point expressions are written in the reference's evaluation
+ * order (Eigen sums 3-vectors left to right).
  *
  * The shape-aware variant GetPolyOcta3DNew (convex_decomp.cpp:590-1162 with FindCorners :378-561 and
  * SideIsEmpty :197-209; used by the reference when the seed voxel is squeezed between two occupied voxels,

@@ -12,8 +12,10 @@
  *
  * Parity: rt_raycast is PINNED - tests/test_reftraj_oracle.py compares its visited points and collision
  * point bit for bit with the reference's own Raycast (raycast.cpp and voxel_grid.cpp compiled unmodified
- * into oracle/_ref/libref_voxel.so).  The rest lives in agent_class.cpp (ROS2 + Gurobi headers: not
- * compilable) and follows it by reading, including its frame mix-up in ComputePathVelocity (the distance of a
+ * into oracle/_ref/libref_voxel.so).  The rest lives in agent_class.cpp and is PINNED too: that file compiles
+ * unmodified on the stand-in ROS / Gurobi headers of oracle/ref_shim/ (oracle/_ref/libref_agent.so) and its own
+ * GenerateReferenceTrajectory gives bit-identical references and path velocities (tests/test_ref_agent.py, fixture
+ * tests/golden/reftraj_node_ref.npz).  The restatement keeps the reference's frame mix-up in ComputePathVelocity (the distance of a
  * visited voxel is taken between the path start in WORLD metres and the voxel in LOCAL voxel units, :1735)
  * and the collision distance left in voxel units (:1755).  pow / exp come from libm here and from CUDA's
  * math library in the kernel: parity of the velocity is to 1e-12 relative, not bit for bit.
