@@ -186,3 +186,28 @@ def test_corridor_walk_checker_equals_the_reference_node():
         live = mk.collect(cb2, True)
         for k in ("poly_rows", "poly_A", "poly_b", "seeds"):
             assert np.array_equal(live[k], nxt[k]), k
+
+
+def test_c_port_planes_equal_the_reference_planes():
+    """oracle/hdsm_oracle.c builds the inter-agent planes itself (orc_plane, the same arithmetic as kernel K1): compare it directly with
+    the planes the reference's own GenerateTimeAwareSafeCorridor appended (fixture), not only through the NumPy oracle."""
+    import dataclasses
+    from oracle import c_oracle as co
+    n = 0
+    for c in cases():
+        p, N = c["p"], c["p"].n_hor
+        prm = dataclasses.asdict(p)
+        prev_pos = c["prev"][:, :3] if c["prev"] is not None else np.tile(c["state_ini"][:3], (N + 1, 1))
+        for k in range(N):
+            A, b = c["final"][k][0]
+            R = len(c["polys"][0][1])
+            row = R
+            for j in range(c["n_rob"]):
+                if j == c["id"] or not c["all_valid"][j]:
+                    continue
+                nrm, off = co.plane(prm, prev_pos[k + 1], c["all_pos"][j, k + 1])
+                assert np.allclose(nrm, A[row], rtol=0, atol=1e-14) and abs(off - b[row]) <= 1e-14 * max(1.0, abs(b[row])), (k, j)
+                row += 1
+                n += 1
+            assert row == len(b)
+    assert n > 100
