@@ -211,3 +211,76 @@ def test_c_port_planes_equal_the_reference_planes():
                 n += 1
             assert row == len(b)
     assert n > 100
+
+
+# ---- solutions checked inside the reference's own model ---------------------------------------------------------------
+def _batch_of(c):
+    """The fixture case as a scenarios.Batch (the arrays hdsm_solve_batch takes)."""
+    import dataclasses
+    from multi_agent_pkgs_b200 import scenarios as sc
+    p, N = c["p"], c["p"].n_hor
+    P, R = p.poly_hor, 18
+    pA, pb, pr = np.zeros((1, P, R, 3)), np.zeros((1, P, R)), np.zeros((1, P), np.int32)
+    for q, (A, b) in enumerate(c["polys"][:P]):
+        pA[0, q, :len(b)], pb[0, q, :len(b)], pr[0, q] = A, b, len(b)
+    prev = c["prev"][:, :3] if c["prev"] is not None else np.tile(c["state_ini"][:3], (N + 1, 1))
+    return sc.Batch(dataclasses.asdict(p), np.array([c["id"]], np.int32), np.array([0], np.int32), np.array([c["n_rob"]], np.int32),
+                    c["x0"][None].copy(), c["ref"][None, :N].copy(), pA, pb, pr, prev[None].copy(), c["all_pos"].copy(), c["all_valid"].copy(), R)
+
+
+def solution_in_reference_model(c, traj, ctrl, assign, obj, tol=1e-6):
+    """Put a solution (traj (N+1, 9), ctrl (N, 3), assign (N,)) into the model the REFERENCE built for the same inputs (fixture) and return
+    (largest violation over bounds, dynamics rows, one-hot rows and the indicator rows of the chosen binaries; objective of the reference's
+    model at that point minus the reported objective)."""
+    p, N = c["p"], c["p"].n_hor
+    nzc = 9 * (N + 1) + 3 * N
+    z = np.zeros(len(c["lb"]))
+    z[:9 * (N + 1)], z[9 * (N + 1):nzc] = traj.reshape(-1), ctrl.reshape(-1)
+    for k in range(N):
+        z[nzc + k * p.poly_hor + int(assign[k])] = 1.0
+    viol = max(np.max(c["lb"] - z), np.max(z - c["ub"]), 0.0)
+    L, Lc, _ = c["lin"]
+    viol = max(viol, np.abs(L @ z + Lc).max())
+    I, Ic, Ib = c["ind"]
+    active = z[Ib] > 0.5
+    viol = max(viol, np.max((I @ z + Ic)[active], initial=0.0))
+    val = float(z @ (c["obj_diag"] * z) + c["obj_lin"] @ z + c["obj_const"])
+    return viol, val - obj
+
+
+def test_c_port_solutions_are_feasible_and_equally_valued_in_the_reference_model():
+    """The checker's solutions, evaluated in the model the reference's own code built for the same inputs: every bound, dynamics row,
+    one-hot row and active indicator row holds to 1e-6, and the reference's objective at that point is the objective the solver reports."""
+    from oracle import c_oracle as co
+    n_opt = 0
+    for c in cases():
+        out = co.solve_batch(_batch_of(c))
+        if out["res"]["status"][0] != 0:
+            continue
+        viol, dobj = solution_in_reference_model(c, out["traj"][0], out["ctrl"][0], out["assign"][0], float(out["res"]["obj"][0]))
+        assert viol <= 1e-6, viol
+        assert abs(dobj) <= 1e-7 * max(1.0, abs(out["res"]["obj"][0])), dobj
+        n_opt += 1
+    assert n_opt >= 2
+
+
+@pytest.mark.gpu
+def test_cuda_solutions_are_feasible_and_equally_valued_in_the_reference_model():
+    """Same check for the CUDA path through the C ABI: its solutions satisfy the model the reference itself built, at the reported objective."""
+    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
+    from oracle import c_oracle as co
+    n_opt = 0
+    for c in cases():
+        b = _batch_of(c)
+        pl = TrajectoryPlanner(b.params, max_agents=1, max_neighbours=c["n_rob"], device=0)
+        out = pl.solve_batch(b)
+        pl.close()
+        want = co.solve_batch(b)
+        assert out["res"]["status"][0] == want["res"]["status"][0]
+        if out["res"]["status"][0] != 0:
+            continue
+        viol, dobj = solution_in_reference_model(c, out["traj"][0], out["ctrl"][0], out["assign"][0], float(out["res"]["obj"][0]))
+        assert viol <= 1e-6, viol
+        assert abs(dobj) <= 1e-7 * max(1.0, abs(out["res"]["obj"][0])), dobj
+        n_opt += 1
+    assert n_opt >= 2
