@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the replaced hot path: agent-QP solves per second at horizon N = 10.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--swarms S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): 10-agent circular exchange over the forest map, horizon 10,
-replicated as S (default 4096) independent swarm instances per GPU (frozen closed-loop snapshots at steps
-{1, 6, 12, 18}, rotated between timed iterations; L2 flushed between iterations).  One "step" is one
-replanning step of every agent of every instance: inter-agent plane assembly, exact assignment
-search, interior-point solves, position pack - one kernel launch - plus, for N > 1, one NCCL
-all-gather of the new plans' positions (the trajectory exchange of the reference).
+Headline workload (BASELINE.json configs[4], the north star's split): 4096 agents in a 200 x 200 m random forest,
+closed loop, the swarm block-partitioned over the N GPUs (strong scaling: 4096 / N agents per GPU).  One "step" is
+one replanning step of the whole swarm: per rank one solver launch on its shard (inter-agent planes from the
+all-gathered neighbour table, exact assignment search, interior-point solves, position pack), the on-device
+read-back / fallback / state advance, and ONE NCCL group that all-gathers the new plans' positions and validity
+flags into the table every rank's NEXT step reads.  Reference trajectories and corridor cells of every step come from
+the host producers of an untimed pre-roll of the same closed loop and are resident in HBM; everything else is live.
 
-`value`   agent-QP solves/s with inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     the same through hdsm_solve_batch with HOST buffers (pinned staging, H2D, D2H inside).
-`--impl reference`  the CPU arm: the reference's own solver is Gurobi 10 (closed source, absent), so
-          this times the C port of the oracle (oracle/hdsm_oracle.c, kind "port") on all host cores.
+`value`   agent-QP solves/s, CUDA-event timed on the launching stream, max over ranks, L2 flushed between steps.
+`e2e`     the same closed loop with every step's exogenous inputs uploaded from page-locked host memory and the
+          step's results (trajectories, controls, statuses, assignments) downloaded, wall clock per step.
+`weak`    (N > 1) 4096 agents PER GPU in a forest of N times the area, same measurement.
+`config4` BASELINE.json configs[3]: the 256-agent circle, closed loop on one GPU, C port beside it.
+`latency` what the unchanged ROS node sees: hdsm_solve_batch(n_local = 1), wall clock, p50 / p99.
+`config2_replicas`  round 1's headline (configs[1] as 4096 independent 10-agent swarms), device-resident and through
+          hdsm_solve_batch with page-locked host buffers.
+`--impl reference`  the CPU arm: the reference's own solver is Gurobi 10 (closed source, absent), so this times the
+          C port of the oracle (oracle/hdsm_oracle.c, kind "port") on all host cores on the same closed loop.
 """
 from __future__ import annotations
 
@@ -45,6 +52,7 @@ SNAP_STEPS = (1, 6, 12, 18)
 DISTINCT_SWARMS = 24
 MAX_NODES = 64
 METRIC = "agent-QP solves/sec (horizon N=10)"
+N_AGENTS = 4096
 
 
 def log(*a):
@@ -525,22 +533,294 @@ def sense_measure(n_agents=4096, steps=10, local_rank=0, cpu_agents=512):
 
 
 def config_dict(args, world):
-    return {"workload": f"config2: 10-agent circular exchange, forest map, N=10, {args.swarms} independent swarm "
-                        f"instances per GPU ({args.swarms * 10} agent QPs per GPU per step)",
-            "n_hor": 10, "poly_hor": 4, "agents_per_swarm": 10, "swarms_per_gpu": args.swarms,
-            "max_nodes": MAX_NODES, "snapshots": list(SNAP_STEPS), "l2": "flushed between timed iterations (512 MiB write)",
-            "parallelism": f"agents sharded over {world} GPU(s), one NCCL all-gather of plan positions per step; every "
-                           f"shard drawn from the same pool of {DISTINCT_SWARMS} distinct swarm instances"}
+    return {"workload": f"config5: {args.agents} agents, random forest {SIDE:.0f} x {SIDE:.0f} m (0.2 columns/m^2), N=10, "
+                        f"closed loop, sharded {args.agents // world} agents per GPU over {world} GPU(s), NCCL all-gather of plan "
+                        f"positions consumed as the next step's neighbour table",
+            "n_hor": 10, "poly_hor": 4, "n_agents": args.agents, "agents_per_gpu": args.agents // world,
+            "neighbour_candidates_per_agent": args.agents, "max_nodes": MAX_NODES, "seed": args.seed,
+            "l2": "flushed between timed steps (512 MiB write)",
+            "inputs": "ref / corridor cells of every step from the host producers of an untimed pre-roll of the same closed "
+                      "loop, resident in HBM; x0, previous plans and the neighbour table advance on the device",
+            "parallelism": f"agents block-partitioned by id over {world} GPU(s) (strong scaling), one NCCL group per step"}
+
+
+SIDE = 200.0
+
+
+def okmask(res):
+    return (res["status"] == 0) | ((res["status"] == 4) & np.isfinite(res["obj"]))
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the same closed loop with the C port of the oracle on all host threads
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import c_oracle as co
+    co.build()
+    sw = sc.config5_random(seed=args.seed, n_rob=args.agents, side=SIDE)
+    pool = sc.InputPool(sw)
+    cores = co.max_threads()
+    times = []
+    for s in range(args.warmup + args.steps):
+        b = sw.make_batch_pooled(pool)
+        t0 = time.perf_counter()
+        out = co.solve_batch(b, max_nodes=MAX_NODES)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+        sw.advance(out["traj"], out["ctrl"], okmask(out["res"]))
+    pool.close()
+    total = float(np.sum(times))
+    value = args.agents * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, world),
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": f"all {args.agents} agents of every closed-loop step ({args.steps} timed steps after "
+                                       f"{args.warmup}), C port of the oracle on all host threads; Gurobi not available"},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
-    import torch
-    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
-    from multi_agent_pkgs_b200.swarm import DeviceBatch, Exchange, algorithmic_bytes
+def timed_replay(loop, W, T, flush, dist, torch):
+    """Device-timed closed loop: steps [0, W) untimed, steps [W, T) each between two events on the launching stream,
+    L2 flushed before each.  Returns per-step ms (this rank)."""
+    loop.reset()
+    with torch.cuda.stream(loop.stream):
+        for s in range(W):
+            loop.device_step(s)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(T - W)]
+    with torch.cuda.stream(loop.stream):
+        for s in range(W, T):
+            flush.fill_(s & 0xFF)
+            ev[s - W][0].record(loop.stream)
+            loop.device_step(s)
+            ev[s - W][1].record(loop.stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    return np.array([a.elapsed_time(b) for a, b in ev])
 
+
+def e2e_replay(loop, W, T, dist, torch):
+    """Wall-clock closed loop with host buffers: every step uploads its exogenous inputs from page-locked memory and
+    downloads its results.  Returns (seconds for steps [W, T), h2d bytes, d2h bytes per step)."""
+    dev = loop.device
+    stage = {k: torch.empty_like(v) for k, v in loop.rec[0].items()}
+    outs = ("traj", "ctrl", "res", "assign_out", "poly_used")
+    host = {k: torch.empty(loop.t[k].shape, dtype=loop.t[k].dtype).pin_memory() for k in outs}
+    host_table = torch.empty(loop.current_table().shape, dtype=torch.float64).pin_memory()
+
+    def step(s):
+        with torch.cuda.stream(loop.stream):
+            for k, v in loop.rec_host[s].items():
+                stage[k].copy_(v, non_blocking=True)
+            loop.device_step(s, inputs=stage)
+            for k in outs:
+                host[k].copy_(loop.t[k], non_blocking=True)
+            host_table.copy_(loop.current_table(), non_blocking=True)
+        loop.stream.synchronize()
+
+    loop.reset()
+    for s in range(W):
+        step(s)
+    if dist:
+        dist.barrier()
+    t = 0.0
+    for s in range(W, T):
+        t0 = time.perf_counter()
+        step(s)
+        t += time.perf_counter() - t0
+    h2d = loop.input_bytes_per_step()
+    d2h = int(sum(v.numel() * v.element_size() for v in host.values()) + host_table.numel() * 8)
+    return t, h2d, d2h
+
+
+def max_over_ranks(x, dist, torch, dev):
+    if not dist:
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def quality_of(stats, W):
+    st = np.zeros(6, int)
+    kkt, iters, nodes, mx = 0.0, 0, 0, 0
+    per_agent = []
+    for r in stats[W:]:
+        st += np.bincount(r["status"], minlength=6)[:6]
+        good = r["status"] == 0
+        kkt = max(kkt, float(r["kkt_res"][good].max()) if good.any() else 0.0)
+        iters += int(r["iters"].sum())
+        nodes += int(r["nodes"].sum())
+        per_agent.append(r["iters"])
+    it = np.concatenate(per_agent) if per_agent else np.zeros(1)
+    tot = max(1, int(st.sum()))
+    return {"status_counts": {k: int(v) for k, v in zip(("optimal", "infeasible", "max_iter", "numerical", "node_limit", "row_overflow"), st)},
+            "max_kkt_residual": kkt, "ipm_iters_per_solve": iters / tot, "qp_relaxations_per_solve": nodes / tot,
+            "ipm_iters_p50_p99_max": [float(np.percentile(it, 50)), float(np.percentile(it, 99)), int(it.max())]}
+
+
+def config4_measure(args, local_rank, flush, torch):
+    """BASELINE.json configs[3]: 256 agents on a 60 m circle, forest, closed loop on one GPU; the C port on all host
+    threads beside it on the same per-step inputs; every agent of every step compared with the port."""
+    from multi_agent_pkgs_b200.swarm import ClosedLoop
+    from oracle import c_oracle as co
+    sw = sc.config4_circle256()
+    W, T = 3, 3 + args.steps
+    loop = ClosedLoop(sw, 1, 0, f"cuda:{local_rank}", MAX_NODES, None)
+    loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES)
+    loop.keep_steps, loop.keep_agents = set(range(W, T)), sw.n
+    par = loop.preroll(T, parity_sample=sw.n)
+    ms = timed_replay(loop, W, T, flush, None, torch)
+    same = loop.sums[T - 1] == __import__("multi_agent_pkgs_b200.swarm", fromlist=["table_checksum"]).table_checksum(loop.current_table())
+    t_cpu = 0.0
+    for s in range(W, T):
+        t0 = time.perf_counter()
+        co.solve_batch(loop.host_batches[s], max_nodes=MAX_NODES)
+        t_cpu += time.perf_counter() - t0
+    q = quality_of(loop.stats, W)
+    loop.close()
+    return {"workload": "config4: 256 agents, circle radius 60 m, forest 0.2 columns/m^2, N=10, closed loop, 256 neighbour candidates per agent, 1 GPU",
+            "ms_per_step": float(ms.mean()), "ms_per_step_max": float(ms.max()), "value": sw.n / (ms.mean() * 1e-3), "unit": "solves/s",
+            "steps": int(T - W), "replay_equals_preroll": bool(same), "parity_vs_c_port": par, "quality": q,
+            "cpu_baseline": {"ms_per_step": 1e3 * t_cpu / (T - W), "value": sw.n * (T - W) / t_cpu, "unit": "solves/s",
+                             "cores": co.max_threads(), "kind": "port", "sample": "the same 256 agents of the same timed steps"}}
+
+
+def latency_measure(local_rank):
+    """Single-call latency of the drop-in as the unchanged ROS node would see it (agent_class.cpp:137: 10 Hz, :952: 80 ms
+    cap): hdsm_solve_batch with n_local = 1 and ordinary (pageable) host buffers, wall clock around the call."""
+    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
+    from oracle import c_oracle as co
+    out = {}
+    for name, sw, steps in (("config1_single_agent", sc.config1_single_agent(), 60), ("config2_one_of_10_agents", sc.config2_circle(n_swarms=1), 12)):
+        pl = TrajectoryPlanner(sw.params, 1, sw.n, local_rank, max_nodes=MAX_NODES)
+        full = TrajectoryPlanner(sw.params, sw.n, sw.n, local_rank, max_nodes=MAX_NODES)
+        t_gpu, t_cpu, its = [], [], []
+        for s in range(steps):
+            b = sw.make_batch()
+            for i in range(sw.n):
+                bi = b.take([i])
+                if s == 0 and i == 0:
+                    pl.solve_batch(bi)  # first call: lazy allocations
+                t0 = time.perf_counter()
+                r = pl.solve_batch(bi)
+                t_gpu.append(time.perf_counter() - t0)
+                its.append(int(r["res"]["iters"][0]))
+                t0 = time.perf_counter()
+                co.solve_batch(bi, max_nodes=MAX_NODES, n_threads=1)
+                t_cpu.append(time.perf_counter() - t0)
+            o = full.solve_batch(b)
+            sw.advance(o["traj"], o["ctrl"], okmask(o["res"]))
+        pl.close()
+        full.close()
+        g, c = 1e3 * np.array(t_gpu), 1e3 * np.array(t_cpu)
+        out[name] = {"calls": len(g), "gpu_ms_p50": float(np.percentile(g, 50)), "gpu_ms_p99": float(np.percentile(g, 99)),
+                     "gpu_ms_max": float(g.max()), "cpu_port_1thread_ms_p50": float(np.percentile(c, 50)),
+                     "cpu_port_1thread_ms_p99": float(np.percentile(c, 99)), "ipm_iters_p50_max": [float(np.median(its)), int(max(its))]}
+    out["note"] = ("wall clock of hdsm_solve_batch(n_local=1) incl. staging, H2D, kernels, D2H; the reference allows 80 ms per solve "
+                   "(TimeLimit) in a 100 ms period; CPU column = the C port on one thread (Gurobi runs single-threaded too, :948)")
+    return out
+
+
+def config2_measure(args, local_rank, flush, torch, swarms, steps):
+    """Round 1's headline: BASELINE.json configs[1] as `swarms` independent 10-agent swarm instances, frozen snapshots,
+    device-resident and end to end through hdsm_solve_batch with page-locked host buffers."""
+    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
+    from multi_agent_pkgs_b200.swarm import DeviceBatch, algorithmic_bytes
+    from multi_agent_pkgs_b200._lib import RESULT_DTYPE
+    dev = torch.device(f"cuda:{local_rank}")
+    params = sc.agile_params(10)
+    gen = TrajectoryPlanner(params, max_agents=DISTINCT_SWARMS * 10, max_neighbours=10, device=local_rank, max_nodes=MAX_NODES)
+    snaps = make_snapshots(gen.solve_batch, 2, swarms)
+    gen.close()
+    n_local = swarms * 10
+    pl = TrajectoryPlanner(params, max_agents=n_local, max_neighbours=10, device=local_rank, max_nodes=MAX_NODES)
+    dbs = [DeviceBatch(s_, dev) for s_ in snaps]
+    balg = float(np.mean([algorithmic_bytes(s_).mean() for s_ in snaps]))
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    for k in range(4):
+        pl.solve_batch_device(dbs[k % len(dbs)].t, dbs[k % len(dbs)].n_rob, sp)
+    torch.cuda.synchronize()
+    stat, iters, nodes = np.zeros(6, int), 0, 0
+    for db in dbs:
+        r = db.results()
+        stat += np.bincount(r["status"], minlength=6)[:6]
+        iters += int(r["iters"].sum())
+        nodes += int(r["nodes"].sum())
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        pl.solve_batch_device(dbs[k % len(dbs)].t, dbs[k % len(dbs)].n_rob, sp)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    # end to end: every input array and every result array page-locked (no staging copy inside the library)
+    IN = ("global_id", "nbr_begin", "nbr_end", "x0", "ref", "poly_A", "poly_b", "poly_rows", "prev_self_pos", "all_pos", "all_valid")
+    keep = []
+    for s_ in snaps:
+        for k in IN:
+            tt = torch.from_numpy(np.ascontiguousarray(getattr(s_, k))).pin_memory()
+            keep.append(tt)
+            setattr(s_, k, tt.numpy())
+    N, P = 10, 4
+    outs = {"traj": torch.empty((n_local, N + 1, 9), dtype=torch.float64).pin_memory(), "ctrl": torch.empty((n_local, N, 3), dtype=torch.float64).pin_memory(),
+            "poly_used": torch.empty((n_local, P), dtype=torch.uint8).pin_memory(), "assign": torch.empty((n_local, N), dtype=torch.int32).pin_memory(),
+            "res": torch.empty((n_local, RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()}
+    out_np = {k: v.numpy() for k, v in outs.items()}
+    out_np["res"] = out_np["res"].view(RESULT_DTYPE).reshape(n_local)
+    for k in range(2):
+        pl.solve_batch(snaps[k % len(snaps)], out=out_np)
+    t_e2e = 0.0
+    for k in range(steps):
+        t1 = time.perf_counter()
+        pl.solve_batch(snaps[k % len(snaps)], out=out_np)
+        t_e2e += time.perf_counter() - t1
+    h2d = dbs[0].input_bytes()
+    d2h = int(sum(v.numel() * v.element_size() for v in outs.values()))
+    pl.close()
+    tot = max(1, int(stat.sum()))
+    return {"workload": f"config2: 10-agent circular exchange, forest map, N=10, {swarms} independent swarm instances ({n_local} agent QPs per step), "
+                        f"frozen closed-loop snapshots at steps {list(SNAP_STEPS)} rotated, L2 flushed",
+            "value": n_local / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms, "steps": steps,
+            "e2e": {"value": n_local * steps / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "hdsm_solve_batch with page-locked caller buffers: copied by the copy engine directly, no staging memcpy"},
+            "algorithmic_bytes_per_solve": balg, "ipm_iters_per_solve": iters / tot, "qp_relaxations_per_solve": nodes / tot,
+            "status_counts": [int(v) for v in stat]}
+
+
+def run_ours(args, rank, world, local_rank):
+    # host-side producers first: the fork pools must exist before this process touches CUDA
+    if args.agents % world:
+        raise SystemExit(f"bench.py: {args.agents} agents do not split evenly over {world} GPUs")
+    procs = max(1, (os.cpu_count() or 1) // world)
+    W, T = max(args.warmup, 3), max(args.warmup, 3) + args.steps
+    t0 = time.time()
+    sw = sc.config5_random(seed=args.seed, n_rob=args.agents, side=SIDE)
+    pool = sc.InputPool(sw, procs)
+    sw_weak = pool_weak = None
+    if world > 1 and args.weak_steps > 0:
+        sw_weak = sc.config5_random(seed=args.seed, n_rob=args.agents * world, side=SIDE * float(np.sqrt(world)))
+        pool_weak = sc.InputPool(sw_weak, procs)
+    log(f"[rank {rank}] scenarios built in {time.time() - t0:.1f}s, {procs} producer processes")
+
+    import torch
+    from multi_agent_pkgs_b200.swarm import ClosedLoop, table_checksum
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
     dev = torch.device(f"cuda:{local_rank}")
@@ -549,95 +829,51 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    n_swarms = args.swarms
-    n_local = n_swarms * 10
-    params = sc.agile_params(10)
-    gen = TrajectoryPlanner(params, max_agents=DISTINCT_SWARMS * 10, max_neighbours=10, device=local_rank,
-                            max_nodes=MAX_NODES)
-    t0 = time.time()
-    # Every rank's shard is drawn from the same pool of DISTINCT_SWARMS swarm instances (same seed): the work is
-    # heavy-tailed (a handful of agents dominate), so shards drawn from different small pools differ by +-20 % in
-    # cost and max-over-ranks would measure that sampling noise instead of the system.  Weak scaling = exactly
-    # the same work per GPU as N grows; the all-gather still moves every rank's plans.
-    snaps = make_snapshots(gen.solve_batch, args.seed, n_swarms)
-    gen.close()
-    log(f"[rank {rank}] {len(snaps)} snapshots x {snaps[0].n} agent QPs generated in {time.time() - t0:.1f}s")
-
-    pl = TrajectoryPlanner(params, max_agents=n_local, max_neighbours=10, device=local_rank, max_nodes=MAX_NODES)
-    n_rob_global = n_local * world
-    ex = Exchange(n_rob_global, 10, world, rank, dev, pl)
-    dbs = [DeviceBatch(s, dev) for s in snaps]
-    balg = float(np.mean([algorithmic_bytes(s).mean() for s in snaps]))
+    from oracle import c_oracle as co  # checker of the parity column and CPU baseline legs only
+    if rank == 0:
+        co.build()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: NULL means "the handle's own stream" in the ABI
-    torch.cuda.set_stream(stream)
-    sp = stream.cuda_stream
 
-    def step(db):
-        pl.solve_batch_device(db.t, db.n_rob, sp)
-        if world > 1:
-            ex.allgather(db.t["pos_out"], sp)
-
-    for k in range(max(args.warmup, 3)):
-        step(dbs[k % len(dbs)])
-    torch.cuda.synchronize()
-    # quality of what is being timed: statuses and KKT residuals of one pass over the snapshots
-    stat = np.zeros(6, int)
-    kkt = 0.0
-    iters = nodes = 0
-    for db in dbs:
-        step(db)
-        torch.cuda.synchronize()
-        r = db.results()
-        stat += np.bincount(r["status"], minlength=6)
-        good = r["status"] == 0
-        kkt = max(kkt, float(r["kkt_res"][good].max()) if good.any() else 0.0)
-        iters += int(r["iters"].sum())
-        nodes += int(r["nodes"].sum())
-
-    # ---- device-resident timing: K steps, CUDA events on the launching stream, L2 flushed between
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
+    # ---- headline: config 5, strong scaling, closed loop
+    loop = ClosedLoop(sw, world, rank, dev, MAX_NODES, pool, record_host=True)
+    if rank == 0:
+        loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES)
+        loop.keep_steps, loop.keep_agents = {W, W + (T - W) // 2, T - 1}, min(loop.n, 2048)
+    par = loop.preroll(T, parity_sample=512 if rank == 0 else 0, log=log)
+    pool.close()
     clocks = ClockSampler(local_rank)
-    launches0 = pl.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
-        ev[k][0].record(stream)
-        step(dbs[k % len(dbs)])
-        ev[k][1].record(stream)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
+    launches0 = loop.planner.launch_count
+    ms = timed_replay(loop, W, T, flush, dist, torch)
+    launches = loop.planner.launch_count - launches0
     clk = clocks.stop()
-    launches = pl.launch_count - launches0
-    ms = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = float(ms.sum())
-    if dist:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    value = n_local * world * args.steps / (total_ms * 1e-3)
+    replay_sum = table_checksum(loop.current_table())
+    same = replay_sum == loop.sums[T - 1]
+    total_ms = max_over_ranks(ms.sum(), dist, torch, dev)
+    value = args.agents * (T - W) / (total_ms * 1e-3)
+    t_e2e, h2d, d2h = e2e_replay(loop, W, T, dist, torch)
+    same = same and table_checksum(loop.current_table()) == loop.sums[T - 1]
+    t_e2e = max_over_ranks(t_e2e, dist, torch, dev)
+    same_all = max_over_ranks(0.0 if same else 1.0, dist, torch, dev) == 0.0
+    quality = quality_of(loop.stats, W)
+    from multi_agent_pkgs_b200.swarm import algorithmic_bytes
+    balg = float(np.mean([algorithmic_bytes(b).mean() for b in loop.host_batches.values()])) if rank == 0 else 0.0
+    smem = loop.planner.smem_bytes
 
-    # ---- end to end through the host-pointer C ABI call (pinned staging, H2D + D2H inside)
-    for k in range(2):
-        pl.solve_batch(snaps[k % len(snaps)])
-    if dist:
-        dist.barrier()
-    t_e2e = 0.0
-    for k in range(args.steps):
-        b = snaps[k % len(snaps)]
-        t1 = time.perf_counter()
-        out = pl.solve_batch(b)
-        t_e2e += time.perf_counter() - t1
-    if dist:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_value = n_local * world * args.steps / t_e2e
-    h2d = dbs[0].input_bytes()
-    d2h = int(sum(out[k].nbytes for k in ("traj", "ctrl", "poly_used", "assign", "res")))
+    # ---- weak scaling beside it (N > 1): 4096 agents per GPU
+    weak = None
+    if sw_weak is not None:
+        Ww, Tw = 3, 3 + args.weak_steps
+        lw = ClosedLoop(sw_weak, world, rank, dev, MAX_NODES, pool_weak)
+        lw.preroll(Tw, log=log)
+        pool_weak.close()
+        msw = timed_replay(lw, Ww, Tw, flush, dist, torch)
+        okw = max_over_ranks(0.0 if table_checksum(lw.current_table()) == lw.sums[Tw - 1] else 1.0, dist, torch, dev) == 0.0
+        tw = max_over_ranks(msw.sum(), dist, torch, dev)
+        weak = {"workload": f"config5 at {args.agents} agents PER GPU: {sw_weak.n} agents in a {SIDE * np.sqrt(world):.0f} m forest, "
+                            f"{sw_weak.n} neighbour candidates per agent, closed loop",
+                "value": sw_weak.n * (Tw - Ww) / (tw * 1e-3), "unit": "solves/s", "ms_per_step": tw / (Tw - Ww), "steps": Tw - Ww,
+                "scaling": "weak", "replay_equals_preroll": okw, "quality": quality_of(lw.stats, Ww)}
+        lw.close()
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -645,67 +881,83 @@ def run_ours(args, rank, world, local_rank):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
-        kernel_ms = total_ms / args.steps
-        achieved = balg * n_local / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per agent QP from the ncu --set full capture
-        pipes = None
+        kernel_ms = total_ms / (T - W)
+        achieved = balg * loop.n / (kernel_ms * 1e-3) / 1e9
+        traffic, pipes, tnote = None, None, "no ncu capture of this launch size committed"
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            traffic = float(tj["dram_bytes_per_agent_qp"]) * n_local
-            pipes = {k: tj[k] for k in ("fp64_pipe_pct", "issue_active_pct", "warps_active_pct", "stall_barrier_pct",
-                                        "stall_wait_pct") if k in tj}
-        cpu_rate, cores, cpu_n, cpu_t = cpu_solve_rate(snaps, min_seconds=args.cpu_seconds, max_agents=20000)
-        corridor = None
-        if args.corridor_agents > 0:
-            corridor, cor_gbs = corridor_measure(args.corridor_agents, 10, local_rank)
-            corridor["roofline"] = {"bound": "hbm", "achieved": cor_gbs, "peak": peak, "unit": "GB/s", "frac": cor_gbs / peak,
-                                    "traffic": None, "note": "serial list logic in shared memory: latency bound, not HBM bound"}
-        mapping = None
-        if args.corridor_agents > 0:
-            mapping = map_measure(min(args.corridor_agents, 4096), 10, local_rank)
-            mp_gbs = mapping["algorithmic_bytes_per_grid"] * mapping["value"] / 1e9
-            mapping["roofline"] = {"bound": "hbm", "achieved": mp_gbs, "peak": peak, "unit": "GB/s", "frac": mp_gbs / peak, "traffic": None,
-                                   "note": "one read and one write per voxel reach HBM; the time goes into the stencil walks in shared memory"}
-        reftraj = None
-        if args.corridor_agents > 0:
-            reftraj = reftraj_measure(args.corridor_agents, 10, local_rank)
-            rt_gbs = reftraj["algorithmic_bytes_per_agent"] * reftraj["value"] / 1e9
-            reftraj["roofline"] = {"bound": "hbm", "achieved": rt_gbs, "peak": peak, "unit": "GB/s", "frac": rt_gbs / peak,
-                                   "traffic": None, "note": "serial voxel traversal and pow/exp per visited voxel: latency bound"}
-        sensing = None
-        if args.corridor_agents > 0:
+            key = f"config5_{loop.n}_agents"
+            if key in tj:
+                traffic = float(tj[key]["dram_bytes_per_launch"])
+                pipes = {k: v for k, v in tj[key].items() if k != "dram_bytes_per_launch"}
+                tnote = f"dram bytes and pipe / stall figures of one {loop.n}-agent launch of this workload: ncu --set full capture in profiles/ ({tj[key].get('source', '?')})"
+        # CPU baseline: the C port on all host threads on the kept steps of the same closed loop (bounded sample)
+        cpu_n = cpu_t = 0.0
+        reps = 0
+        while cpu_t < args.cpu_seconds and reps < 50:
+            for hb in loop.host_batches.values():
+                t1 = time.perf_counter()
+                co.solve_batch(hb, max_nodes=MAX_NODES)
+                cpu_t += time.perf_counter() - t1
+                cpu_n += hb.n
+            reps += 1
+    loop.close()
+
+    secondary = {}
+    if rank == 0:
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+        for name, fn in (("config4", lambda: config4_measure(args, local_rank, flush, torch)),
+                         ("latency", lambda: latency_measure(local_rank)),
+                         ("config2_replicas", lambda: config2_measure(args, local_rank, flush, torch, args.swarms, min(args.steps, 12)) if (world == 1 and args.swarms > 0) else None)):
             try:
-                sensing = sense_measure(min(args.corridor_agents, 4096), 10, local_rank)
-                sn_gbs = sensing["algorithmic_bytes_per_agent"] * sensing["value"] / 1e9
-                sensing["roofline"] = {"bound": "hbm", "achieved": sn_gbs, "peak": peak, "unit": "GB/s", "frac": sn_gbs / peak, "traffic": None,
-                                       "note": "kept grid in, new grid out; the time goes into 14 k serial FP64 voxel traversals per agent (bitmap form of the kernel)"}
+                secondary[name] = fn()
             except Exception as e:  # a secondary object never costs the headline line
-                sensing = {"error": f"{type(e).__name__}: {e}"}
-        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                secondary[name] = {"error": f"{type(e).__name__}: {e}"}
+        producers = {}
+        if world == 1 and args.corridor_agents > 0:
+            def roof(gbs, note):
+                return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None, "note": note}
+            try:
+                corridor, cor_gbs = corridor_measure(args.corridor_agents, 10, local_rank)
+                corridor["roofline"] = roof(cor_gbs, "serial list logic in shared memory: latency bound, not HBM bound")
+                producers["corridor"] = corridor
+                mapping = map_measure(min(args.corridor_agents, 4096), 10, local_rank)
+                mapping["roofline"] = roof(mapping["algorithmic_bytes_per_grid"] * mapping["value"] / 1e9,
+                                           "one read and one write per voxel reach HBM; the time goes into the stencil walks in shared memory")
+                producers["local_map"] = mapping
+                reftraj = reftraj_measure(args.corridor_agents, 10, local_rank)
+                reftraj["roofline"] = roof(reftraj["algorithmic_bytes_per_agent"] * reftraj["value"] / 1e9,
+                                           "serial voxel traversal and pow/exp per visited voxel: latency bound")
+                producers["reference_trajectory"] = reftraj
+                sensing = sense_measure(min(args.corridor_agents, 4096), 10, local_rank)
+                sensing["roofline"] = roof(sensing["algorithmic_bytes_per_agent"] * sensing["value"] / 1e9,
+                                           "kept grid in, new grid out; the time goes into 14 k serial FP64 voxel traversals per agent")
+                producers["local_map_acquisition"] = sensing
+            except Exception as e:
+                producers["error"] = f"{type(e).__name__}: {e}"
+        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": T - W,
+                "warmup": W, "ms_per_step": total_ms / (T - W), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(args, world),
-                "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": args.agents * (T - W) / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
+                "closed_loop": {"replay_equals_preroll_on_every_rank": bool(same_all), "table_checksum": replay_sum,
+                                "note": "checksum of the all-gathered plan table after the last timed step; identical on any number of GPUs"},
+                "parity_vs_c_port": par,
+                "quality": quality,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_solve": balg, "ncu": pipes,
-                             "note": "the solve is FP64-latency bound, not HBM bound (DESIGN.md section 5); traffic and "
-                                     "the pipe / stall figures under `ncu` come from the --set full capture in profiles/ "
-                                     "(profiles/traffic.json), not from this run"},
-                "cpu_baseline": {"value": cpu_rate, "unit": "solves/s", "cores": cores, "kind": "port",
-                                 "sample": f"{cpu_n} agent QPs of the same snapshots in {cpu_t:.1f}s, C port of the "
-                                           f"oracle on all host threads (Gurobi not available)"},
-                "clocks": clk,
-                "quality": {"status_counts": {k: int(v) for k, v in zip(
-                    ("optimal", "infeasible", "max_iter", "numerical", "node_limit", "row_overflow"), stat)},
-                    "max_kkt_residual": kkt, "ipm_iters_per_solve": iters / max(1, stat.sum()),
-                    "qp_relaxations_per_solve": nodes / max(1, stat.sum())},
-                "smem_bytes_per_block": pl.smem_bytes, "corridor": corridor, "reference_trajectory": reftraj, "local_map": mapping,
-                "local_map_acquisition": sensing}
+                             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_solve": balg, "ncu": pipes,
+                             "note": "algorithmic bytes per solve x agents per launch / launch time (SURVEY 8(d)); at 4096 neighbour candidates "
+                                     "the 1.08 MB plan table is L2 resident and the solve itself is FP64-latency bound (DESIGN.md section 5). " + tnote},
+                "cpu_baseline": {"value": cpu_n / cpu_t, "unit": "solves/s", "cores": co.max_threads(), "kind": "port",
+                                 "sample": f"{int(cpu_n)} agent QPs ({len(loop.host_batches)} kept steps of the same closed loop, first "
+                                           f"{loop.keep_agents} agents of rank 0's shard) in {cpu_t:.1f}s, C port of the oracle on all host "
+                                           f"threads (Gurobi not available)"},
+                "clocks": clk, "weak": weak, "smem_bytes_per_block": smem}
+        line.update(secondary)
+        line.update(producers)
         emit(line)
-    pl.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -717,11 +969,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--swarms", type=int, default=4096, help="independent 10-agent swarm instances per GPU")
-    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--agents", type=int, default=N_AGENTS, help="agents of the config-5 swarm (whole job)")
+    ap.add_argument("--weak-steps", type=int, default=8, help="timed steps of the weak-scaling object at N > 1 (0 = skip)")
+    ap.add_argument("--swarms", type=int, default=4096, help="independent 10-agent swarm instances of the config-2 object (0 = skip)")
+    ap.add_argument("--seed", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--corridor-agents", type=int, default=16384,
-                    help="agents of the secondary corridor-generation measurement (0 = skip)")
+    ap.add_argument("--corridor-agents", type=int, default=8192,
+                    help="agents of the secondary producer measurements at N = 1 (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

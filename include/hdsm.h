@@ -54,15 +54,16 @@ extern "C" {
                                 (the reference accepts a TimeLimit incumbent the same way, :952-987) */
 #define HDSM_ROW_OVERFLOW 5  /* more active constraint rows than the handle's shared-memory budget */
 
+#define HDSM_MIN_HOR 5   /* kernels are instantiated for horizons 5..12 */
 #define HDSM_MAX_HOR 12
 #define HDSM_MAX_POLY 8
 
 /* POD mirror of the ROS parameters that enter the optimisation (agent_class.cpp:2190-2248;
  * values e.g. multi_agent_planner/config/agent_agile_config.yaml). */
 typedef struct hdsm_params {
-  int32_t n_hor;             /* n_hor: horizon N, 3..HDSM_MAX_HOR (n_x = 9, n_u = 3 fixed: ModelODE :2155) */
+  int32_t n_hor;             /* n_hor: horizon N, HDSM_MIN_HOR..HDSM_MAX_HOR (n_x = 9, n_u = 3 fixed: ModelODE :2155) */
   int32_t poly_hor;          /* poly_hor: polytopes per step P, 1..HDSM_MAX_POLY */
-  int32_t max_rows_per_poly; /* row stride Rmax of poly_A / poly_b, <= 32 */
+  int32_t max_rows_per_poly; /* row stride Rmax of poly_A / poly_b, <= 32 and poly_hor * Rmax <= 255 */
   int32_t rk4;               /* rk4: 0 = Euler (:2140-2151), 1 = RK4 (:2123-2139) */
   int32_t max_iter;          /* interior-point iterations per QP (0 -> 60) */
   int32_t max_nodes;         /* branch-and-bound nodes per agent (0 -> 64); plays the role of TimeLimit */
@@ -141,6 +142,12 @@ int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_i
                             const int32_t* assign_in, double* traj, double* ctrl, uint8_t* poly_used,
                             int32_t* assign_out, hdsm_result* res, double* pos_out, void* stream);
 
+/* K1 alone, HOST pointers, synchronous: the inter-agent plane of n point pairs exactly as the solver builds it
+ * (agent_class.cpp:1152-1205 with pert = 0): own_pos / other_pos [n][3] -> planes [n][4] = (n_f, n_f . pt); NaN for
+ * coincident points.  Lets a caller (and the parity tests) look at the rows GenerateTimeAwareSafeCorridor appends
+ * to every polytope without solving anything. */
+int hdsm_planes(hdsm_handle* h, int n, const double* own_pos, const double* other_pos, double* planes);
+
 /* Number of kernels the library launched on this handle so far (bench.py's gpu_launches). */
 int64_t hdsm_launch_count(const hdsm_handle* h);
 /* Dynamic shared memory per thread block of the solver kernel, bytes. */
@@ -154,6 +161,27 @@ int hdsm_comm_unique_id(uint8_t id_out[128]);
 int hdsm_comm_init(hdsm_handle* h, int n_ranks, int rank, const uint8_t id[128]);
 int hdsm_allgather_positions(hdsm_handle* h, const double* send, double* recv, int n_local, void* stream);
 void hdsm_comm_destroy(hdsm_handle* h);
+/* The complete per-step exchange of the harness: plan positions as above plus the "plan received" flags
+ * (traj.states.size() != 0 of traj_other_agents_, agent_class.cpp:1134) - send_valid [n_local] -> recv_valid
+ * [n_ranks * n_local] - as one NCCL group (one launch). */
+int hdsm_exchange_plans(hdsm_handle* h, const double* send_pos, double* recv_pos, const uint8_t* send_valid,
+                        uint8_t* recv_valid, int n_local, void* stream);
+
+/* Read-back and failure fallback of one replanning step for callers that keep the swarm state in HBM (DEVICE
+ * pointers, enqueued on `stream`): what the reference does after optimize() with the solver's outputs
+ * (agent_class.cpp:962-987 read-back; :997-1019 on failure the previous plan is shifted by one step and its last
+ * element duplicated; :180-190 without a previous plan nothing is published) followed by the state advance
+ * state_curr_ := traj_curr_[step_plan_] with step_plan_ = 1 (:233-238).
+ *
+ *  traj / ctrl / res   this step's outputs of hdsm_solve_batch_device
+ *  traj_curr [n][N+1][9], ctrl_curr [n][N][3]   traj_curr_ / control_curr_, updated in place
+ *  have_plan [n]       in: a plan exists (traj_curr_.size() > 0); out: same after this step
+ *  x0 [n][9]           state_curr_, advanced in place for agents with a plan
+ *  prev_self_pos [n][N+1][3] (may be NULL)  positions of traj_curr_ - the next call's prev_self_pos and this
+ *                      step's all-gather payload; state_curr_ repeated while there is no plan (:1103-1110) */
+int hdsm_advance_device(hdsm_handle* h, int n_local, const double* traj, const double* ctrl, const hdsm_result* res,
+                        double* traj_curr, double* ctrl_curr, uint8_t* have_plan, double* x0, double* prev_self_pos,
+                        void* stream);
 
 /* ---- safe-corridor generation ----------------------------------
  * hdsm_corridor_batch replaces Agent::GenerateSafeCorridor (agent_class.cpp:1236-1447) together with

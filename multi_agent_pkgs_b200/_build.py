@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdsm.so")
 SOURCES = ["hdsm_capi.cu", "hdsm_corridor.cu", "hdsm_reftraj.cu", "hdsm_map.cu", "hdsm_sense.cu"]
-DEPS = ["hdsm_capi.cu", "hdsm_corridor.cu", "hdsm_reftraj.cu", "hdsm_map.cu", "hdsm_sense.cu", "hdsm_sense_core.h", "hdsm_kernel.cuh", "hdsm_tables.h", os.path.join("..", "..", "include", "hdsm.h")]
+DEPS = ["hdsm_capi.cu", "hdsm_corridor.cu", "hdsm_reftraj.cu", "hdsm_map.cu", "hdsm_sense.cu", "hdsm_sense_core.h", "hdsm_common.h", "hdsm_kernel.cuh", "hdsm_tables.h", os.path.join("..", "..", "include", "hdsm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-diag-suppress", "68", "-shared", "-Xcompiler", "-fPIC,-pthread"]
 

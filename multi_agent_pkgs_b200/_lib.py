@@ -13,7 +13,7 @@ OPTIMAL, INFEASIBLE, MAX_ITER, NUMERICAL, NODE_LIMIT, ROW_OVERFLOW = range(6)
 
 EXPORTS = ["hdsm_version", "hdsm_create", "hdsm_destroy", "hdsm_last_error", "hdsm_solve_batch",
            "hdsm_solve_batch_device", "hdsm_launch_count", "hdsm_smem_bytes", "hdsm_comm_unique_id",
-           "hdsm_comm_init", "hdsm_allgather_positions", "hdsm_comm_destroy",
+           "hdsm_comm_init", "hdsm_allgather_positions", "hdsm_comm_destroy", "hdsm_exchange_plans", "hdsm_advance_device", "hdsm_planes",
            "hdsm_corridor_create", "hdsm_corridor_destroy", "hdsm_corridor_last_error", "hdsm_corridor_launch_count",
            "hdsm_corridor_smem_bytes", "hdsm_corridor_batch", "hdsm_corridor_batch_device",
            "hdsm_reftraj_create", "hdsm_reftraj_destroy", "hdsm_reftraj_last_error", "hdsm_reftraj_launch_count",
@@ -84,6 +84,12 @@ def load(build: bool = True) -> C.CDLL:
     L.hdsm_comm_init.argtypes = [vp, C.c_int, C.c_int, u8p]
     L.hdsm_allgather_positions.restype = C.c_int
     L.hdsm_allgather_positions.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.hdsm_exchange_plans.restype = C.c_int
+    L.hdsm_exchange_plans.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.hdsm_advance_device.restype = C.c_int
+    L.hdsm_advance_device.argtypes = [vp, C.c_int] + [vp] * 9
+    L.hdsm_planes.restype = C.c_int
+    L.hdsm_planes.argtypes = [vp, C.c_int, dp, dp, dp]
     L.hdsm_comm_destroy.restype = None
     L.hdsm_comm_destroy.argtypes = [vp]
     _lib = L

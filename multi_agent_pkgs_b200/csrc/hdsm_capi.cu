@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/hdsm.h"
+#include "hdsm_common.h"
 #include "hdsm_kernel.cuh"
 
 using namespace hdsm;
@@ -29,6 +30,8 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, Id128, int) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -48,6 +51,8 @@ NcclApi* nccl_api() {
   api.CommInitRank = reinterpret_cast<int (*)(void**, int, Id128, int)>(dlsym(api.lib, "ncclCommInitRank"));
   api.AllGather =
       reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(api.lib, "ncclAllGather"));
+  api.GroupStart = reinterpret_cast<int (*)()>(dlsym(api.lib, "ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<int (*)()>(dlsym(api.lib, "ncclGroupEnd"));
   api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
   api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
   if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) {
@@ -77,9 +82,10 @@ struct hdsm_handle {
   int64_t launches = 0;
   // longest-first dispatch: order[slot] of the previous call per pipeline chunk (valid while n matches)
   int32_t* d_order = nullptr;
-  int order_n[kMaxChunks] = {};
+  int order_n[kMaxChunks] = {};         // n_local the cached order of a slot was computed for (0: none)
+  size_t order_off[kMaxChunks] = {};    // ... and its offset into d_order: both must match for the order to be reused
   bool use_order = true;
-  int smem_configured = -1;
+  bool smem_configured = false;
   long long* d_prof = nullptr;  // HDSM_PROFILE=1: per-agent phase cycle counters (host path prints a summary)
   int warps = 4;  // warps per agent (HDSM_WARPS=1 selects the single-warp kernel)
   std::string err;
@@ -104,13 +110,10 @@ int cuda_fail(hdsm_handle* h, cudaError_t e, const char* what) {
 
 template <int N, int W>
 cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
-  // the dynamic shared-memory limit is an attribute of the kernel on the current device: set once per handle
-  // (a handle has one horizon and one device), not once per process
-  const int need = h->smem_bytes[h->n_tiers - 1];
-  if (h->smem_configured < need) {
-    cudaError_t e = cudaFuncSetAttribute(hdsm_solve_kernel<N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+  if (!h->smem_configured) {  // raised to the device maximum, never to this handle's own need (see hdsm_common.h)
+    cudaError_t e = raise_smem_limit(hdsm_solve_kernel<N, W>, h->device);
     if (e != cudaSuccess) return e;
-    h->smem_configured = need;
+    h->smem_configured = true;
   }
   for (int t = 0; t < h->n_tiers; ++t) {  // t > 0: only agents whose rows did not fit the previous pool
     a.row_cap = h->row_cap[t], a.only_status = t == 0 ? -1 : HDSM_ROW_OVERFLOW;
@@ -140,6 +143,18 @@ cudaError_t dispatch(hdsm_handle* h, const KernelArgs& a, cudaStream_t s) {
 }
 
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// true when the copy engine can read / write `p` directly (cudaMallocHost / cudaHostRegister memory): the staging
+// memcpy into the handle's own pinned arena is then skipped
+bool is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
 
 // memcpy between caller memory and the pinned arenas; large blocks are split over a few threads (one
 // core moves ~10 GB/s, the 140 MB of a 40 960-agent batch would otherwise cost more than its H2D copy)
@@ -175,7 +190,13 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   if (h->prm.max_iter <= 0) h->prm.max_iter = 60;
   if (h->prm.max_nodes <= 0) h->prm.max_nodes = 64;
   if (!(h->prm.tol > 0)) h->prm.tol = 1e-8;
-  if (h->prm.n_hor < 5 || h->prm.n_hor > HDSM_MAX_HOR || build_tables(h->prm, h->host_tables) != 0) {
+  if (h->prm.n_hor < HDSM_MIN_HOR || h->prm.n_hor > HDSM_MAX_HOR) {
+    std::fprintf(stderr, "hdsm_create: n_hor = %d is outside the supported range %d..%d\n", h->prm.n_hor, HDSM_MIN_HOR, HDSM_MAX_HOR);
+    delete h;
+    return HDSM_ERR_INVALID;
+  }
+  if (int rc = build_tables(h->prm, h->host_tables)) {
+    std::fprintf(stderr, "hdsm_create: unsupported parameter set (build_tables code %d)\n", rc);
     delete h;
     return HDSM_ERR_INVALID;
   }
@@ -204,6 +225,12 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   if ((e = cudaMemcpy(h->dev_tables, &h->host_tables, sizeof(Tables), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail(e, "copy tables");
   if ((e = cudaMalloc(&h->d_order, sizeof(int32_t) * (size_t)max_agents)) != cudaSuccess) return bail(e, "cudaMalloc order");
+  {
+    std::vector<int32_t> ident((size_t)max_agents);
+    for (int i = 0; i < max_agents; ++i) ident[i] = i;
+    if ((e = cudaMemcpy(h->d_order, ident.data(), ident.size() * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail(e, "init order");
+  }
   // Shared-memory budget.  Worst case per agent: 2 planes per neighbour and variable position step
   // plus two polytopes' rows per step.  Exact pruning usually leaves a few dozen rows, so the first
   // pass runs with a small row pool (more resident blocks per SM); agents that overflow it are
@@ -279,13 +306,19 @@ static int solve_device(hdsm_handle* h, int slot, size_t order_offset, int n_loc
   a.assign_out = assign_out, a.res = res, a.prof = h->d_prof;
   a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
   const bool ordered = h->use_order && n_local >= 1024;  // below ~2 waves of blocks the order cannot matter
-  a.order = ordered && h->order_n[slot] == n_local ? h->d_order + order_offset : nullptr;
+  a.order = ordered && h->order_n[slot] == n_local && h->order_off[slot] == order_offset ? h->d_order + order_offset : nullptr;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   CU(dispatch(h, a, s));
   if (ordered) {
     hdsm_order_kernel<<<1, 1024, 0, s>>>(res, n_local, h->d_order + order_offset);
     h->launches += 1;
-    h->order_n[slot] = n_local;
+    // this call's region of d_order now holds a permutation of [0, n_local): cached orders of other slots that
+    // overlap it are stale
+    for (int c = 0; c < kMaxChunks; ++c)
+      if (c != slot && h->order_n[c] > 0 && h->order_off[c] < order_offset + (size_t)n_local &&
+          order_offset < h->order_off[c] + (size_t)h->order_n[c])
+        h->order_n[c] = 0;
+    h->order_n[slot] = n_local, h->order_off[slot] = order_offset;
     CU(cudaGetLastError());
   }
   return HDSM_OK;
@@ -316,6 +349,17 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
   CU(cudaSetDevice(h->device));
   const int N = h->prm.n_hor, P = h->prm.poly_hor, R = h->prm.max_rows_per_poly;
   const size_t n = n_local;
+  // per-agent indices the kernel uses as array offsets (the device entry point clamps them instead)
+  for (size_t i = 0; i < n; ++i) {
+    if (n_rob > 0 && (global_id[i] < 0 || global_id[i] >= n_rob)) return fail(h, HDSM_ERR_INVALID, "global_id outside [0, n_rob)");
+    if (nbr_begin && (nbr_begin[i] < 0 || nbr_begin[i] > nbr_end[i] || nbr_end[i] > n_rob))
+      return fail(h, HDSM_ERR_INVALID, "neighbour range outside 0 <= nbr_begin <= nbr_end <= n_rob");
+    for (int p = 0; p < P; ++p)
+      if (poly_rows[i * P + p] < 0 || poly_rows[i * P + p] > R) return fail(h, HDSM_ERR_INVALID, "poly_rows outside [0, max_rows_per_poly]");
+    if (assign_in)
+      for (int k = 0; k < N; ++k)
+        if (assign_in[i * N + k] < -1 || assign_in[i * N + k] >= P) return fail(h, HDSM_ERR_INVALID, "assign_in outside [-1, poly_hor)");
+  }
   // ---- input arena: one pinned block, one H2D copy
   struct Seg {
     const void* src;
@@ -378,10 +422,17 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
   if (const char* e = std::getenv("HDSM_CHUNKS")) n_chunks = std::max(1, std::min(std::atoi(e), kMaxChunks));
   if (h->d_prof) n_chunks = 1;
   const int per = (n_local + n_chunks - 1) / n_chunks;
+  bool in_pinned[12], out_pinned[5];
+  for (int i = 0; i < 12; ++i) in_pinned[i] = in[i].bytes && is_pinned(in[i].src);
+  for (int i = 0; i < 5; ++i) out_pinned[i] = is_pinned(outs[i].dst);
   for (int i = 10; i < 12; ++i)
     if (in[i].bytes) {
-      std::memcpy(h->h_in + in[i].off, in[i].src, in[i].bytes);
-      CU(cudaMemcpyAsync(h->d_in + in[i].off, h->h_in + in[i].off, in[i].bytes, cudaMemcpyHostToDevice, h->stream));
+      const void* src = in[i].src;
+      if (!in_pinned[i]) {
+        std::memcpy(h->h_in + in[i].off, in[i].src, in[i].bytes);
+        src = h->h_in + in[i].off;
+      }
+      CU(cudaMemcpyAsync(h->d_in + in[i].off, src, in[i].bytes, cudaMemcpyHostToDevice, h->stream));
     }
   CU(cudaEventRecord(h->ev_shared, h->stream));
   CU(cudaStreamWaitEvent(h->stream2, h->ev_shared, 0));
@@ -396,8 +447,12 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
     for (int i = 0; i < 10; ++i) {
       if (!in[i].bytes) continue;
       const size_t o = in[i].off + first * in_stride[i], bytes = cnt * in_stride[i];
-      staged_copy(h->h_in + o, (const char*)in[i].src + first * in_stride[i], bytes);
-      CU(cudaMemcpyAsync(h->d_in + o, h->h_in + o, bytes, cudaMemcpyHostToDevice, s));
+      const char* src = (const char*)in[i].src + first * in_stride[i];
+      if (!in_pinned[i]) {
+        staged_copy(h->h_in + o, src, bytes);
+        src = (const char*)h->h_in + o;
+      }
+      CU(cudaMemcpyAsync(h->d_in + o, src, bytes, cudaMemcpyHostToDevice, s));
     }
     if (trace) CU(cudaEventRecord(h->ev_begin[c], s));
     int rc = solve_device(
@@ -409,9 +464,11 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
         (int32_t*)(h->d_out + o_asg + first * outs[3].stride), (hdsm_result*)(h->d_out + o_res + first * outs[2].stride),
         nullptr, s);
     if (rc != HDSM_OK) return rc;
-    for (const Out& o : outs)
-      CU(cudaMemcpyAsync(h->h_out + o.off + first * o.stride, h->d_out + o.off + first * o.stride, cnt * o.stride,
-                         cudaMemcpyDeviceToHost, s));
+    for (int i = 0; i < 5; ++i) {
+      const Out& o = outs[i];
+      void* dst = out_pinned[i] ? (void*)((char*)o.dst + first * o.stride) : (void*)(h->h_out + o.off + first * o.stride);
+      CU(cudaMemcpyAsync(dst, h->d_out + o.off + first * o.stride, cnt * o.stride, cudaMemcpyDeviceToHost, s));
+    }
     CU(cudaEventRecord(h->ev_chunk[c], s));
     t_enq[c] = ms_since();
   }
@@ -419,7 +476,11 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
     const size_t first = (size_t)c * per, cnt = std::min<size_t>(per, n - first);
     CU(cudaEventSynchronize(h->ev_chunk[c]));
     t_done[c] = ms_since();
-    for (const Out& o : outs) staged_copy((char*)o.dst + first * o.stride, h->h_out + o.off + first * o.stride, cnt * o.stride);
+    for (int i = 0; i < 5; ++i)
+      if (!out_pinned[i]) {
+        const Out& o = outs[i];
+        staged_copy((char*)o.dst + first * o.stride, h->h_out + o.off + first * o.stride, cnt * o.stride);
+      }
   }
   if (trace) {
     std::fprintf(stderr, "[hdsm trace] %d chunks, total %.2f ms\n", n_chunks, ms_since());
@@ -476,6 +537,60 @@ int hdsm_allgather_positions(hdsm_handle* h, const double* send, double* recv, i
   int rc = n->AllGather(send, recv, count, /*ncclFloat64*/ 8, h->comm, s);
   if (rc != 0) return fail(h, HDSM_ERR_NCCL, std::string("ncclAllGather: ") + (n->GetErrorString ? n->GetErrorString(rc) : "?"));
   h->launches += 1;
+  return HDSM_OK;
+}
+
+int hdsm_exchange_plans(hdsm_handle* h, const double* send_pos, double* recv_pos, const uint8_t* send_valid, uint8_t* recv_valid,
+                        int n_local, void* stream) {
+  if (!h || !send_pos || !recv_pos || !send_valid || !recv_valid || n_local < 0) return HDSM_ERR_INVALID;
+  NcclApi* n = nccl_api();
+  if (!n || !h->comm) return fail(h, HDSM_ERR_NCCL, "communicator not initialised");
+  const size_t count = (size_t)n_local * (h->prm.n_hor + 1) * 3;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  // both gathers in one NCCL group: one launch, one synchronisation of the ranks per replanning step
+  if (n->GroupStart && n->GroupEnd) n->GroupStart();
+  int rc = n->AllGather(send_pos, recv_pos, count, /*ncclFloat64*/ 8, h->comm, s);
+  int rc2 = rc == 0 ? n->AllGather(send_valid, recv_valid, (size_t)n_local, /*ncclUint8*/ 1, h->comm, s) : 0;
+  int rc3 = (n->GroupStart && n->GroupEnd) ? n->GroupEnd() : 0;
+  rc = rc ? rc : (rc2 ? rc2 : rc3);
+  if (rc != 0) return fail(h, HDSM_ERR_NCCL, std::string("ncclAllGather: ") + (n->GetErrorString ? n->GetErrorString(rc) : "?"));
+  h->launches += 1;
+  return HDSM_OK;
+}
+
+int hdsm_advance_device(hdsm_handle* h, int n_local, const double* traj, const double* ctrl, const hdsm_result* res,
+                        double* traj_curr, double* ctrl_curr, uint8_t* have_plan, double* x0, double* prev_self_pos, void* stream) {
+  if (!h) return HDSM_ERR_INVALID;
+  if (n_local == 0) return HDSM_OK;
+  if (n_local < 0 || !traj || !ctrl || !res || !traj_curr || !ctrl_curr || !have_plan || !x0)
+    return fail(h, HDSM_ERR_INVALID, "hdsm_advance_device: null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  hdsm_advance_kernel<<<(n_local + 7) / 8, 256, 0, s>>>(n_local, h->prm.n_hor, traj, ctrl, res, traj_curr, ctrl_curr, have_plan, x0,
+                                                        prev_self_pos);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return HDSM_OK;
+}
+
+int hdsm_planes(hdsm_handle* h, int n, const double* own_pos, const double* other_pos, double* planes) {
+  if (!h || n < 0 || (n > 0 && (!own_pos || !other_pos || !planes))) return HDSM_ERR_INVALID;
+  if (n == 0) return HDSM_OK;
+  CU(cudaSetDevice(h->device));
+  double *d_in = nullptr, *d_out = nullptr;
+  CU(cudaMalloc(&d_in, (size_t)n * 6 * 8));
+  cudaError_t e = cudaMalloc(&d_out, (size_t)n * 4 * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, own_pos, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + (size_t)n * 3, other_pos, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    hdsm_planes_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->prm, n, d_in, d_in + (size_t)n * 3, d_out);
+    h->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(planes, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_in), cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(h, e, "hdsm_planes");
   return HDSM_OK;
 }
 

@@ -31,6 +31,7 @@
 #include <thread>
 
 #include "../../include/hdsm.h"
+#include "hdsm_common.h"
 
 namespace hdsm_cor {
 
@@ -881,7 +882,7 @@ int hdsm_corridor_create(const hdsm_corridor_params* p, int max_agents, int max_
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_shared, cudaEventDisableTiming);
   for (int c = 0; c < 8 && e == cudaSuccess; ++c) e = cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(hdsm_cor::corridor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  if (e == cudaSuccess) e = hdsm::raise_smem_limit(hdsm_cor::corridor_kernel, device);
   if (e != cudaSuccess) {
     hdsm_corridor_destroy(h);
     return HDSM_ERR_CUDA;

@@ -54,7 +54,7 @@ struct KernelArgs {
 // time, follow.
 struct FixedLayout {
   int Ks, invd, diag0, bs, bl, DQ, TQ, FQ, qv, dq, dqc, qbar, Mk, Tk, Fk, p, dp, dpc, pbar, plo, phi, w, dw, dwc, g, bestw, s0,
-      viol, red, ints, var;
+      viol, red, sbnd, cbox, ints, var;
 };
 HDSM_HD constexpr FixedLayout make_layout(int N) {
   const int NW = 3 * (N - 2), NQ3 = 3 * (3 * N - 2), K3 = 3 * (N + 1);
@@ -89,6 +89,8 @@ HDSM_HD constexpr FixedLayout make_layout(int N) {
   s.s0 = o, o += 12;   // x0 (9), c0, spare
   s.red = o, o += 2 * 4 * 4;  // block reductions: 2 buffers x 4 warps x 4 values
   s.viol = o, o += N * kMaxP;
+  s.sbnd = o, o += kStackCap;   // parent bound of every open node
+  s.cbox = o, o += kMaxP * 6;   // axis-aligned bounding box of every cell: lo[3], hi[3]
   s.ints = o;
   // int32 region: segment tables 4(N+2), bestsig N, fullsig N, prow_n 8, cur 16 B, stack, pair table u16
   const int int_words = 4 * (N + 2) + 2 * N + kMaxP + 4 + kStackCap * 4 + (NW * (NW + 1) / 2 + 1) / 2 + 2 + 8;
@@ -171,7 +173,7 @@ struct Solver {
                 *const dp = sm + L.dp, *const dpc = sm + L.dpc, *const pbar = sm + L.pbar, *const plo = sm + L.plo,
                 *const phi = sm + L.phi, *const w = sm + L.w, *const dw = sm + L.dw, *const dwc = sm + L.dwc,
                 *const g = sm + L.g, *const bestw = sm + L.bestw, *const s0 = sm + L.s0, *const viol = sm + L.viol,
-                *const red = sm + L.red;
+                *const red = sm + L.red, *const sbnd = sm + L.sbnd, *const cbox = sm + L.cbox;
   int* const ip = reinterpret_cast<int*>(sm + L.ints);
   int *const segb = ip, *const sege = ip + 2 * (N + 2), *const bestsig = ip + 4 * (N + 2), *const fullsig = bestsig + N,
              *const prow_n = fullsig + N;  // segb/sege[2*slot + {0: inter-agent, 1: corridor}]
@@ -315,7 +317,8 @@ struct Solver {
       poly[4 * i + 2] = A.poly_A[base * 3 + 2];
       poly[4 * i + 3] = A.poly_b[base];
     }
-    if (tid < kMaxP) prow_n[tid] = tid < A.P ? A.poly_rows[(size_t)agent * A.P + tid] : 0;
+    // clamped: the host entry point validates its arrays, the device entry point cannot
+    if (tid < kMaxP) prow_n[tid] = tid < A.P ? min(max(A.poly_rows[(size_t)agent * A.P + tid], 0), A.rmax) : 0;
     // lower-triangle pairs ordered by column descending: the trailing update of Cholesky step j
     // touches exactly the first (NW-1-j)(NW-j)/2 entries
     for (int t = tid; t < NW * NW; t += NT) {
@@ -351,6 +354,22 @@ struct Solver {
         for (int r2 = 0; r2 < prow_n[j]; ++r2)
           if (nid[j * A.rmax + r2] == i) bm = fmin(bm, poly[4 * (j * A.rmax + r2) + 3]);
       bmin[t] = bm;
+    }
+    // axis-aligned bounding box of every cell from its rows with a single non-zero component (the six faces
+    // GetPolyOcta3D always emits, convex_decomp.cpp:359-373): cbox[6 j + a] = lo_a, cbox[6 j + 3 + a] = hi_a
+    if (tid < 6 * kMaxP) {
+      const int j = tid / 6, c = tid - 6 * j, a = c % 3;
+      const bool upper = c >= 3;
+      double v = upper ? INFINITY : -INFINITY;
+      if (j < Peff)
+        for (int r = 0; r < prow_n[j]; ++r) {
+          const double* q = poly + 4 * (j * A.rmax + r);
+          if ((q[0] != 0.0) + (q[1] != 0.0) + (q[2] != 0.0) != 1 || q[a] == 0.0) continue;
+          const double x = q[3] / q[a];
+          if (upper && q[a] > 0) v = fmin(v, x);
+          if (!upper && q[a] < 0) v = fmax(v, x);
+        }
+      cbox[tid] = v;
     }
     bsync();
   }
@@ -455,7 +474,7 @@ struct Solver {
   // not-yet-used slack array); ctl[2 + w] = entries of warp w, or -1 if its sub-list overflowed.
   __device__ void scan_neighbours(int agent) {
     const int gid = A.global_id[agent];
-    const int nb0 = A.nbr_begin ? A.nbr_begin[agent] : 0, nb1 = A.nbr_end ? A.nbr_end[agent] : A.n_rob;
+    const int nb0 = A.nbr_begin ? max(A.nbr_begin[agent], 0) : 0, nb1 = A.nbr_end ? min(A.nbr_end[agent], A.n_rob) : A.n_rob;
     const double* prev = A.prev + (size_t)agent * K3;
     double* thr2k = viol;  // scratch: viol is first written after the first QP
     if (tid < N) {
@@ -500,7 +519,7 @@ struct Solver {
   __device__ int build_neighbour_rows(int agent) {
     const hdsm_params& P = T.prm;
     const int gid = A.global_id[agent];
-    const int nb0 = A.nbr_begin ? A.nbr_begin[agent] : 0, nb1 = A.nbr_end ? A.nbr_end[agent] : A.n_rob;
+    const int nb0 = A.nbr_begin ? max(A.nbr_begin[agent], 0) : 0, nb1 = A.nbr_end ? min(A.nbr_end[agent], A.n_rob) : A.n_rob;
     const double* prev = A.prev + (size_t)agent * K3;
     bool use_list = true;
     for (int w2 = 0; w2 < W; ++w2) use_list &= ctl[2 + w2] >= 0;
@@ -603,6 +622,53 @@ struct Solver {
     }
     __syncwarp();
     return !any_empty;
+  }
+
+  // Per-step dominance between cells.  Cell A dominates cell B at step k when every point the segment
+  // (p_k, p_k+1) can reach inside B also lies in A: a trajectory that uses B at step k may use A instead at the
+  // same cost, so B leaves the candidate set (the optimum value is unchanged; near-duplicate overlapping cells
+  // otherwise make the search enumerate assignments that tie).  Sufficient test per row (n, b) of A and per
+  // variable point kp in {k, k+1}: B holds the same normal at least as tight, or the row cannot be violated
+  // inside reach_box(kp) /\ bbox(B).  One row of A per lane.
+  __device__ __forceinline__ bool dominates(int k, int ca, int cb) const {
+    bool fail = false;
+    if (lane < prow_n[ca]) {
+      const int i = ca * A.rmax + lane;
+      const double* r = poly + 4 * i;
+      const double same = bmin[nid[i] * A.P + cb];
+      if (!(same <= r[3])) {
+        const double *lo = cbox + 6 * cb, *hi = lo + 3;
+        for (int kp = k; kp <= k + 1; ++kp) {
+          if (T.slot_of_kp[kp] < 0) continue;  // a constant point was checked against both cells already
+          double mx = 0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            mx += r[a] >= 0 ? r[a] * fmin(phi[3 * kp + a], hi[a]) : r[a] * fmax(plo[3 * kp + a], lo[a]);
+          if (!(mx <= r[3])) fail = true;
+        }
+      }
+    }
+    return !__any_sync(kFull, fail);
+  }
+  // all warps, one step per warp and round: drop dominated cells from the root sets (equal cells: the lower index stays)
+  __device__ void dominance_filter() {
+    for (int k = wid; k < N; k += W) {
+      unsigned mask = cur[k];
+      if (__popc(mask) > 1) {
+        for (int cb = Peff - 1; cb >= 0; --cb) {
+          if (!(mask >> cb & 1)) continue;
+          for (int ca = 0; ca < Peff; ++ca) {
+            if (ca == cb || !(mask >> ca & 1)) continue;
+            if (!dominates(k, ca, cb)) continue;
+            if (ca > cb && dominates(k, cb, ca)) continue;
+            mask &= ~(1u << cb);
+            break;
+          }
+        }
+        if (lane == 0) cur[k] = (unsigned char)mask;
+      }
+    }
+    bsync();
   }
 
   // Row of a candidate set for the distinct normal whose first occurrence is flat row i: offset = max
@@ -1192,8 +1258,14 @@ struct Solver {
     if (wid == 0) {
       if (st < 0) st = build_neighbour_rows(agent);
       if (st < 0 && !root_sets(agent)) st = HDSM_INFEASIBLE;
+      if (lane == 0) ctl[1] = st;
+    }
+    bsync();
+    if (ctl[1] < 0) dominance_filter();  // uniform over the block
+    if (wid == 0) {
       if (st < 0) {
         if (lane < 16) stack[lane] = lane < N ? cur[lane] : 0;
+        if (lane == 0) sbnd[0] = -INFINITY;
         top = 1;
         __syncwarp();
       }
@@ -1205,7 +1277,10 @@ struct Solver {
         if (st < 0 && !overflow) {
           if (top > 0 && nodes >= A.max_nodes) {
             exhausted = false;
-          } else if (top > 0) {
+          }
+          // a node whose parent's optimum already reaches the incumbent cannot improve it: dropped unsolved
+          while (exhausted && top > 0 && sbnd[top - 1] >= best - kPruneRel * fmax(1.0, fabs(best))) --top;
+          if (exhausted && top > 0) {
             --top;
             if (lane < 16) cur[lane] = stack[top * 16 + lane];
             __syncwarp();
@@ -1326,6 +1401,7 @@ struct Solver {
           break;
         }
         if (lane < 16) stack[top * 16 + lane] = lane == bk ? (unsigned char)m : cur[lane];
+        if (lane == 0) sbnd[top] = q.obj;
         ++top;
         __syncwarp();
       }
@@ -1444,6 +1520,72 @@ __global__ void __launch_bounds__(1024) hdsm_order_kernel(const hdsm_result* __r
   hist[tid] = incl - v + (tid >= 32 ? wsum[(tid >> 5) - 1] : 0);
   __syncthreads();
   for (int i = tid; i < n; i += 1024) order[atomicAdd(&hist[1023 - min(max(res[i].iters, 0), 1023)], 1)] = i;
+}
+
+// K1 alone: the separating plane of every (own point, neighbour point) pair, out[i] = (n_f, b); NaN rows for
+// coincident points.  The solver kernel inlines the same function; this entry exists so that the plane
+// coefficients themselves can be compared with the reference's (agent_class.cpp:1152-1205).
+__global__ void hdsm_planes_kernel(const hdsm_params prm, int n, const double* __restrict__ pc, const double* __restrict__ po,
+                                   double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a[3] = {pc[3 * i], pc[3 * i + 1], pc[3 * i + 2]}, b[3] = {po[3 * i], po[3 * i + 1], po[3 * i + 2]};
+  double nf[3], off;
+  if (!interagent_plane(prm, a, b, nf, off)) nf[0] = nf[1] = nf[2] = off = NAN;
+  out[4 * i] = nf[0], out[4 * i + 1] = nf[1], out[4 * i + 2] = nf[2], out[4 * i + 3] = off;
+}
+
+// Read-back and failure fallback of one replanning step on the device, for callers that keep the swarm state in
+// HBM (agent_class.cpp:962-987 read-back, :997-1019 fallback, :233-238 state advance with step_plan = 1):
+//   usable result (OPTIMAL, or NODE_LIMIT with an incumbent)  traj_curr_ := traj, control_curr_ := ctrl, plan valid
+//   otherwise, with a previous plan                            both shifted by one step, last element duplicated
+//   otherwise                                                  nothing changes (no plan is published, :180-190)
+// then state_curr_ := traj_curr_[1] for agents with a plan, and prev_pos := positions of traj_curr_ (the next
+// call's prev_self_pos; state_ini_ repeated while there is no plan, :1103-1110).  One thread per (agent, entry).
+__global__ void __launch_bounds__(256) hdsm_advance_kernel(int n, int N, const double* __restrict__ traj,
+                                                             const double* __restrict__ ctrl, const hdsm_result* __restrict__ res,
+                                                             double* __restrict__ traj_curr, double* __restrict__ ctrl_curr,
+                                                             uint8_t* __restrict__ have_plan, double* __restrict__ x0,
+                                                             double* __restrict__ prev_pos) {
+  const int agent = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (agent >= n) return;
+  const hdsm_result r = res[agent];
+  const bool ok = r.status == HDSM_OPTIMAL || (r.status == HDSM_NODE_LIMIT && isfinite(r.obj));
+  const bool had = have_plan[agent] != 0;
+  double* tc = traj_curr + (size_t)agent * (N + 1) * 9;
+  double* cc = ctrl_curr + (size_t)agent * N * 3;
+  const int nt = (N + 1) * 9, nc = N * 3;
+  if (ok) {
+    for (int i = lane; i < nt; i += 32) tc[i] = traj[(size_t)agent * nt + i];
+    for (int i = lane; i < nc; i += 32) cc[i] = ctrl[(size_t)agent * nc + i];
+  } else if (had) {  // every lane reads its elements before any lane writes (the shift moves data across lanes)
+    double tv[4], cv[1];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int i = lane + 32 * m;
+      tv[m] = i < nt ? tc[i + 9 < nt ? i + 9 : i] : 0.0;
+    }
+    cv[0] = lane < nc ? cc[lane + 3 < nc ? lane + 3 : lane] : 0.0;
+    double cv2 = lane + 32 < nc ? cc[lane + 35 < nc ? lane + 35 : lane + 32] : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int i = lane + 32 * m;
+      if (i < nt) tc[i] = tv[m];
+    }
+    if (lane < nc) cc[lane] = cv[0];
+    if (lane + 32 < nc) cc[lane + 32] = cv2;
+  }
+  __syncwarp();
+  const bool have = ok || had;
+  if (lane == 0) have_plan[agent] = have ? 1 : 0;
+  if (have && lane < 9) x0[(size_t)agent * 9 + lane] = tc[9 + lane];
+  __syncwarp();
+  if (prev_pos)
+    for (int i = lane; i < 3 * (N + 1); i += 32) {
+      const int k = i / 3, a = i - 3 * k;
+      prev_pos[(size_t)agent * 3 * (N + 1) + i] = have ? tc[k * 9 + a] : x0[(size_t)agent * 9 + a];
+    }
 }
 
 }  // namespace hdsm

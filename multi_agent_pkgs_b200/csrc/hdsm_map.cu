@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/hdsm.h"
+#include "hdsm_common.h"
 
 namespace hdsm_mp {
 
@@ -422,7 +423,7 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
   if (e == cudaSuccess && h->n_pair) e = cudaMalloc(&h->d_pvals, pair_vals.size() * 8);
   if (e == cudaSuccess && h->n_pair) e = cudaMemcpy(h->d_pair, pair_yz.data(), pair_yz.size() * sizeof(int2), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && h->n_pair) e = cudaMemcpy(h->d_pvals, pair_vals.data(), pair_vals.size() * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(hdsm_mp::map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = hdsm::raise_smem_limit(hdsm_mp::map_kernel, device);
   if (e != cudaSuccess) {
     hdsm_map_destroy(h);
     return HDSM_ERR_CUDA;

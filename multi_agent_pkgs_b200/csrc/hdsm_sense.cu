@@ -28,6 +28,7 @@
 #include <string>
 
 #include "../../include/hdsm.h"
+#include "hdsm_common.h"
 #include "hdsm_sense_core.h"
 
 namespace hdsm_sn {
@@ -345,9 +346,9 @@ int hdsm_sense_create(const hdsm_sense_params* p, int max_agents, size_t grid_st
   int sms = 0, per_sm = 0;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (e == cudaSuccess && !bits) e = cudaFuncSetAttribute(hdsm_sn::sense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && !bits) e = hdsm::raise_smem_limit(hdsm_sn::sense_kernel, device);
   if (e == cudaSuccess && !bits) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hdsm_sn::sense_kernel, hdsm_sn::kThreads, smem);
-  if (e == cudaSuccess && bits) e = cudaFuncSetAttribute(hdsm_sn::sense_kernel_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && bits) e = hdsm::raise_smem_limit(hdsm_sn::sense_kernel_bits, device);
   if (e == cudaSuccess && bits)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hdsm_sn::sense_kernel_bits, hdsm_sn::kThreadsBits, smem);
   if (e == cudaSuccess) {

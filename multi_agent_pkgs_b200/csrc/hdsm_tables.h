@@ -142,8 +142,10 @@ inline bool cholesky_inverse(const double H[kMaxNZ][kMaxNZ], int n, double Hinv[
 // Returns 0 on success.
 inline int build_tables(const hdsm_params& P, Tables& T) {
   const int N = P.n_hor;
-  if (N < 3 || N > kMaxN || P.poly_hor < 1 || P.poly_hor > kMaxP || P.max_rows_per_poly < 1 ||
-      P.max_rows_per_poly > 32 || !(P.dt > 0) || !(P.drone_z_offset > 0) || !(P.max_jerk > 0))
+  // flat polytope-row indices are stored in a byte with 255 as the padding marker: poly_hor * Rmax <= 255
+  if (N < HDSM_MIN_HOR || N > kMaxN || P.poly_hor < 1 || P.poly_hor > kMaxP || P.max_rows_per_poly < 1 ||
+      P.max_rows_per_poly > 32 || P.poly_hor * P.max_rows_per_poly > 255 || !(P.dt > 0) || !(P.drone_z_offset > 0) ||
+      !(P.max_jerk > 0))
     return 1;
   std::memset(&T, 0, sizeof(T));
   T.prm = P;

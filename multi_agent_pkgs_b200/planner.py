@@ -77,8 +77,10 @@ class TrajectoryPlanner:
         return int(self.lib.hdsm_smem_bytes(self._h))
 
     # -- host-pointer path (what the ROS node calls with n_local = 1) -----------------------------
-    def solve_batch(self, batch, assign_in: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
-        """``batch`` has the attributes of :class:`multi_agent_pkgs_b200.scenarios.Batch`."""
+    def solve_batch(self, batch, assign_in: Optional[np.ndarray] = None, out: Optional[Dict] = None) -> Dict[str, np.ndarray]:
+        """``batch`` has the attributes of :class:`multi_agent_pkgs_b200.scenarios.Batch`.  ``out``: optional dict of
+        preallocated result arrays (traj, ctrl, poly_used, assign, res) - page-locked ones are written by the copy
+        engine directly, like page-locked inputs are read directly (no staging copy inside the library)."""
         n, N, P, R = int(batch.x0.shape[0]), self.N, self.P, self.rmax
         gid = _c(batch.global_id, np.int32)
         nb0 = _c(batch.nbr_begin, np.int32) if batch.nbr_begin is not None else None
@@ -92,11 +94,17 @@ class TrajectoryPlanner:
                 or allv.shape != (allp.shape[0],):
             raise ValueError("array shapes do not match the handle's n_hor / poly_hor / max_rows_per_poly")
         ain = _c(assign_in, np.int32) if assign_in is not None else None
-        traj = np.zeros((n, N + 1, 9))
-        ctrl = np.zeros((n, N, 3))
-        used = np.zeros((n, P), np.uint8)
-        aout = np.zeros((n, N), np.int32)
-        res = np.zeros(n, RESULT_DTYPE)
+        if out is not None:
+            traj, ctrl, used, aout, res = out["traj"], out["ctrl"], out["poly_used"], out["assign"], out["res"]
+            if traj.shape != (n, N + 1, 9) or ctrl.shape != (n, N, 3) or used.shape != (n, P) or aout.shape != (n, N) \
+                    or res.shape != (n,) or res.dtype != RESULT_DTYPE:
+                raise ValueError("preallocated outputs do not match the batch")
+        else:
+            traj = np.zeros((n, N + 1, 9))
+            ctrl = np.zeros((n, N, 3))
+            used = np.zeros((n, P), np.uint8)
+            aout = np.zeros((n, N), np.int32)
+            res = np.zeros(n, RESULT_DTYPE)
         i32, f64, u8 = C.c_int32, C.c_double, C.c_uint8
         self._check(self.lib.hdsm_solve_batch(
             self._h, n, _p(gid, i32), _p(nb0, i32), _p(nb1, i32), _p(x0, f64), _p(ref, f64), _p(pA, f64), _p(pb, f64),
@@ -118,6 +126,14 @@ class TrajectoryPlanner:
             dp("assign_in"), dp("traj"), dp("ctrl"), dp("poly_used"), dp("assign_out"), dp("res"), dp("pos_out"),
             C.c_void_p(stream_ptr) if stream_ptr else None))
 
+    # -- K1 alone -----------------------------------------------------------------------------------
+    def planes(self, own_pos: np.ndarray, other_pos: np.ndarray) -> np.ndarray:
+        """Inter-agent planes (n_f, b) of n point pairs as the solver builds them (agent_class.cpp:1152-1205)."""
+        a, b = _c(own_pos, np.float64).reshape(-1, 3), _c(other_pos, np.float64).reshape(-1, 3)
+        out = np.zeros((a.shape[0], 4))
+        self._check(self.lib.hdsm_planes(self._h, a.shape[0], _p(a, C.c_double), _p(b, C.c_double), _p(out, C.c_double)))
+        return out
+
     # -- NCCL exchange ----------------------------------------------------------------------------
     def comm_unique_id(self) -> bytes:
         buf = (C.c_uint8 * 128)()
@@ -133,6 +149,25 @@ class TrajectoryPlanner:
     def allgather_positions(self, send, recv, n_local: int, stream_ptr: int = 0):
         self._check(self.lib.hdsm_allgather_positions(self._h, C.c_void_p(send.data_ptr()), C.c_void_p(recv.data_ptr()),
                                                       int(n_local), C.c_void_p(stream_ptr) if stream_ptr else None))
+
+
+    def exchange_plans(self, send_pos, recv_pos, send_valid, recv_valid, n_local: int, stream_ptr: int = 0):
+        """Plan positions and "plan received" flags of all ranks in one NCCL group (hdsm_exchange_plans)."""
+        self._check(self.lib.hdsm_exchange_plans(self._h, C.c_void_p(send_pos.data_ptr()), C.c_void_p(recv_pos.data_ptr()),
+                                                 C.c_void_p(send_valid.data_ptr()), C.c_void_p(recv_valid.data_ptr()),
+                                                 int(n_local), C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    # -- read-back / fallback / state advance on the device (agent_class.cpp:962-1019, :233-238) ---------
+    def advance_device(self, t: Dict, stream_ptr: int = 0):
+        """``t`` holds this step's ``traj``/``ctrl``/``res`` and the persistent ``traj_curr``, ``ctrl_curr``,
+        ``have_plan``, ``x0`` and (optionally) ``prev_self_pos`` tensors; all but the first three are updated in place."""
+        def dp(name):
+            x = t.get(name)
+            return C.c_void_p(x.data_ptr()) if x is not None else None
+        n = int(t["x0"].shape[0])
+        self._check(self.lib.hdsm_advance_device(self._h, n, dp("traj"), dp("ctrl"), dp("res"), dp("traj_curr"), dp("ctrl_curr"),
+                                                 dp("have_plan"), dp("x0"), dp("prev_self_pos"),
+                                                 C.c_void_p(stream_ptr) if stream_ptr else None))
 
 
 class _OneAgentBatch:

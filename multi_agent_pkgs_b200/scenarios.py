@@ -75,16 +75,45 @@ class Forest:
         n = int(per_m2 * float(np.prod(hi - lo)))
         return Forest(lo + rng.random((n, 2)) * (hi - lo))
 
+    _CELL = 4.0  # bucket size of the lazily built index (metres)
+
+    def _index(self):
+        """Uniform-grid buckets over the columns (built on first use; large forests only): `near` then looks at a
+        few buckets instead of every column.  Candidates are visited in ascending column order, so results are
+        identical to the plain scan."""
+        ix = self.__dict__.get("_ix")
+        if ix is None:
+            key = np.floor(self.cols / self._CELL).astype(np.int64)
+            ix = {}
+            for i, (a, b) in enumerate(key):
+                ix.setdefault((int(a), int(b)), []).append(i)
+            ix = {k: np.asarray(v) for k, v in ix.items()}
+            self.__dict__["_ix"] = ix
+        return ix
+
+    def _candidates(self, xy, rad):
+        if len(self.cols) < 512:
+            return self.cols
+        ix = self._index()
+        x0, x1 = int(math.floor((xy[0] - rad) / self._CELL)), int(math.floor((xy[0] + rad) / self._CELL))
+        y0, y1 = int(math.floor((xy[1] - rad) / self._CELL)), int(math.floor((xy[1] + rad) / self._CELL))
+        got = [ix[(a, b)] for a in range(x0, x1 + 1) for b in range(y0, y1 + 1) if (a, b) in ix]
+        if not got:
+            return self.cols[:0]
+        return self.cols[np.sort(np.concatenate(got))]
+
     def near(self, xy, rad):
         if len(self.cols) == 0:
             return self.cols
-        d = np.abs(self.cols - np.asarray(xy)[None, :2])
-        return self.cols[(d[:, 0] < rad) & (d[:, 1] < rad)]
+        c = self._candidates(xy, rad)
+        d = np.abs(c - np.asarray(xy)[None, :2])
+        return c[(d[:, 0] < rad) & (d[:, 1] < rad)]
 
     def is_free(self, xy, margin=0.0):
         if len(self.cols) == 0:
             return True
-        d = np.abs(self.cols - np.asarray(xy)[None, :2])
+        c = self._candidates(xy, KEEP_OUT + margin)
+        d = np.abs(c - np.asarray(xy)[None, :2])
         return not np.any((d[:, 0] < KEEP_OUT + margin) & (d[:, 1] < KEEP_OUT + margin))
 
     def push_free(self, xy, margin=0.1):
@@ -370,24 +399,56 @@ class Swarm:
         if self.traj is not None:
             all_pos[:] = self.traj[:, :, :3]
         x0 = self.state[ids].copy()
-        refs = np.zeros((len(ids), N, 6))
-        polys_all = []
         prev = np.zeros((len(ids), N + 1, 3))
         for r, i in enumerate(ids):
-            pos = self.state[i, :3]
-            path = plan_path(pos, self.goal[i], self.world)
-            refs[r] = sample_path(path, self.path_vel[i], N, self.params["dt"])[:N]
-            # per-agent, per-step stream: a shard of the swarm generates the same inputs as the whole
-            rng_i = np.random.default_rng([self.seed, self.step_count, int(i)])
-            polys_all.append(corridor(pos, path, self.world, rng_i, P, self.rmax, self.extra_chamfers))
             if self.have_plan[i]:
                 prev[r] = self.traj[i, :, :3]
             else:
-                prev[r] = pos[None, :]  # state_ini_ before the first solve (agent_class.cpp:1108-1110)
-        A, b, rows = pack_polys(polys_all, P, self.rmax)
+                prev[r] = self.state[i, None, :3]  # state_ini_ before the first solve (agent_class.cpp:1108-1110)
+        refs, A, b, rows = self.make_inputs(ids)
         return Batch(self.params, ids.astype(np.int32), self.group_begin[ids].astype(np.int32),
                      self.group_end[ids].astype(np.int32), x0, refs, A, b, rows, prev, all_pos,
                      self.have_plan.copy(), self.rmax)
+
+    def make_batch_pooled(self, pool) -> "Batch":
+        """make_batch() of the whole swarm with the input producers spread over an InputPool."""
+        b = self.make_batch(np.zeros(0, np.int64))
+        ids = np.arange(self.n)
+        ref, A, bb, rows = self.make_inputs(ids, pool=pool)
+        N = self.params["n_hor"]
+        prev = np.repeat(self.state[:, None, :3], N + 1, axis=1)  # state_ini_ before the first solve (:1108-1110)
+        if self.traj is not None:
+            have = self.have_plan != 0
+            prev[have] = self.traj[have][:, :, :3]
+        return Batch(self.params, ids.astype(np.int32), self.group_begin.astype(np.int32), self.group_end.astype(np.int32),
+                     self.state.copy(), ref, A, bb, rows, np.ascontiguousarray(prev), b.all_pos, b.all_valid, self.rmax)
+
+    def agent_inputs(self, i, pos, step):
+        """Reference trajectory and corridor cells of agent i standing at `pos` in replanning step `step` - the
+        stand-ins for GenerateReferenceTrajectory / GenerateSafeCorridor.  Random choices come from a per-agent,
+        per-step stream, so a shard of the swarm generates the same inputs as the whole."""
+        P, N = self.params["poly_hor"], self.params["n_hor"]
+        path = plan_path(pos, self.goal[i], self.world)
+        ref = sample_path(path, self.path_vel[i], N, self.params["dt"])[:N]
+        rng_i = np.random.default_rng([self.seed, int(step), int(i)])
+        return ref, corridor(pos, path, self.world, rng_i, P, self.rmax, self.extra_chamfers)
+
+    def make_inputs(self, ids=None, pos=None, step=None, pool=None):
+        """(ref [n][N][6], poly_A, poly_b, poly_rows) for agents `ids` standing at `pos` (default: their current
+        states) in step `step` (default: the current one).  `pool`: an InputPool over this swarm."""
+        P, N = self.params["poly_hor"], self.params["n_hor"]
+        ids = np.arange(self.n) if ids is None else np.asarray(ids)
+        pos = self.state[ids, :3] if pos is None else np.asarray(pos, float)
+        step = self.step_count if step is None else int(step)
+        if pool is not None:
+            res = pool.map(step, ids, pos)
+        else:
+            res = [self.agent_inputs(int(i), pos[r], step) for r, i in enumerate(ids)]
+        refs = np.zeros((len(ids), N, 6))
+        for r, (ref, _) in enumerate(res):
+            refs[r] = ref
+        A, b, rows = pack_polys([p for _, p in res], P, self.rmax)
+        return refs, A, b, rows
 
     def advance(self, traj, ctrl, ok, ids=None):
         """Apply one step's results: failed agents shift their previous plan (agent_class.cpp:1000-1019)."""
@@ -515,3 +576,42 @@ def config5_random(seed=5, n_rob=4096, n_hor=10, side=200.0):
                 goals[i] = g
                 break
     return _mk_swarm(params, world, starts, goals, [(0, n_rob)], rng, seed=seed)
+
+
+# --------------------------------------------------------------------------------------
+# process pool for the host-side input producers (pure Python: ~5 ms per agent and step)
+# --------------------------------------------------------------------------------------
+_POOL_SWARM = None
+
+
+def _pool_chunk(args):
+    step, ids, pos = args
+    return [_POOL_SWARM.agent_inputs(int(i), pos[r], step) for r, i in enumerate(ids)]
+
+
+class InputPool:
+    """Fork pool over one Swarm's static data (world, goals, speeds, seed).  Create it BEFORE the process
+    initialises CUDA: the workers are forked copies and must never touch the GPU."""
+
+    def __init__(self, swarm: Swarm, procs: Optional[int] = None):
+        import multiprocessing as mp
+        import os
+        global _POOL_SWARM
+        self.procs = max(1, int(procs or (os.cpu_count() or 1)))
+        _POOL_SWARM = swarm
+        self.pool = mp.get_context("fork").Pool(self.procs) if self.procs > 1 else None
+        self.swarm = swarm
+
+    def map(self, step, ids, pos):
+        ids, pos = np.asarray(ids), np.asarray(pos, float)
+        if self.pool is None or len(ids) < 4 * self.procs:
+            return [self.swarm.agent_inputs(int(i), pos[r], step) for r, i in enumerate(ids)]
+        cuts = np.linspace(0, len(ids), 4 * self.procs + 1).astype(int)
+        parts = self.pool.map(_pool_chunk, [(step, ids[a:b], pos[a:b]) for a, b in zip(cuts[:-1], cuts[1:]) if b > a])
+        return [x for part in parts for x in part]
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.terminate()
+            self.pool.join()
+            self.pool = None

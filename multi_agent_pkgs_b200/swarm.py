@@ -175,3 +175,189 @@ class ShardedSwarm:
         else:
             self.have = have_local
         return res
+
+
+def table_checksum(t) -> str:
+    """Order-sensitive 64-bit checksum of a float64 tensor's bit patterns (xor of bits rotated by position parity,
+    plus the wrapped integer sum): equal tables give equal checksums on any number of GPUs."""
+    import torch
+    bits = t.contiguous().view(torch.int64).flatten()
+    odd = bits[1::2]
+    x = int(torch.bitwise_xor(bits[0::2].sum(), (odd * 3).sum()).item()) & 0xFFFFFFFFFFFFFFFF
+    return f"{x:016x}"
+
+
+class ClosedLoop:
+    """Closed-loop replanning of a sharded swarm with the swarm state resident in HBM.
+
+    Per replanning step and rank, all on one stream and without host synchronisation:
+      1. hdsm_solve_batch_device on the rank's shard - inter-agent planes from the neighbour table the previous
+         exchange produced, assignment search, interior-point solves, position pack (agent_class.cpp:168, :174);
+      2. hdsm_advance_device - read-back, failure fallback, state advance (:962-1019, :233-238);
+      3. hdsm_exchange_plans - ONE NCCL group: all-gather of the packed plan positions into the table every rank
+         reads in the next step, and of the "plan received" flags (the ROS2 broadcast, :645-677 / :629-643).
+    The path's exogenous inputs - reference trajectory and corridor cells, whose producers stay on the host in this
+    harness - are computed once per step by `preroll` (host producers, untimed) and kept in HBM; `replay` then runs the
+    same closed loop from the same initial state with only device work.  The solver is deterministic, so the replay
+    reproduces the pre-roll bit for bit (`checks` compares the tables), on any number of ranks.
+    """
+
+    def __init__(self, swarm, world: int = 1, rank: int = 0, device="cuda:0", max_nodes: int = 64, pool=None,
+                 record_host: bool = False, **planner_kw):
+        import torch
+        from .planner import TrajectoryPlanner
+        self.torch = torch
+        self.swarm, self.world, self.rank, self.device, self.pool = swarm, world, rank, torch.device(device), pool
+        self.lo, self.hi = shard_range(swarm.n, world, rank)
+        self.n, self.n_rob = self.hi - self.lo, swarm.n
+        if world > 1 and swarm.n % world:
+            raise ValueError("ClosedLoop needs equal shards (ncclAllGather): n_rob must be a multiple of the world size")
+        p = swarm.params
+        self.N, self.P, self.R = int(p["n_hor"]), int(p["poly_hor"]), int(swarm.rmax)
+        nn = int((swarm.group_end - swarm.group_begin).max())
+        self.planner = TrajectoryPlanner(p, self.n, nn, self.device.index or 0, rmax=self.R, max_nodes=max_nodes, **planner_kw)
+        if world > 1:
+            import torch.distributed as dist
+            uid = [self.planner.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            self.planner.comm_init(world, rank, uid[0])
+        dev, f64, n, N, P, R = self.device, torch.float64, self.n, self.N, self.P, self.R
+        ids = np.arange(self.lo, self.hi)
+        self.ids = ids
+        z = lambda *s, dt=f64: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
+        self.t = {
+            "global_id": torch.from_numpy(ids.astype(np.int32)).to(dev),
+            "nbr_begin": torch.from_numpy(swarm.group_begin[ids].astype(np.int32)).to(dev),
+            "nbr_end": torch.from_numpy(swarm.group_end[ids].astype(np.int32)).to(dev),
+            "x0": z(n, 9), "traj_curr": z(n, N + 1, 9), "ctrl_curr": z(n, N, 3), "have_plan": z(n, dt=torch.uint8),
+            "traj": z(n, N + 1, 9), "ctrl": z(n, N, 3), "poly_used": z(n, P, dt=torch.uint8),
+            "assign_out": z(n, N, dt=torch.int32), "res": z(n, 32, dt=torch.uint8),
+        }
+        self.pos = [z(n, N + 1, 3), z(n, N + 1, 3)]           # ping-pong: prev_self_pos (read) / pos_out (written)
+        self.table = z(self.n_rob, N + 1, 3) if world > 1 else None
+        self.valid = z(self.n_rob, dt=torch.uint8) if world > 1 else None
+        self.x0_init = torch.from_numpy(np.ascontiguousarray(swarm.state[ids])).to(dev)
+        self.rec: list = []        # per step: dict(ref, poly_A, poly_b, poly_rows) on the device
+        self.rec_host: list = []   # the same in pinned host memory (end-to-end timing)
+        self.record_host = record_host
+        self.sums: list = []       # per step: checksum of the table after the exchange
+        self.stats: list = []      # per step: hdsm_result array of the shard
+        self.step_index = 0
+        self.stream = torch.cuda.Stream(device=dev)
+        self.reset()
+
+    # ------------------------------------------------------------------------------------------------
+    def reset(self):
+        """Back to the swarm's initial state: no plans, no neighbour planes (agent_class.cpp:1134)."""
+        t = self.t
+        with self.torch.cuda.stream(self.stream):
+            t["x0"].copy_(self.x0_init)
+            t["have_plan"].zero_()
+            t["traj_curr"].copy_(self.x0_init[:, None, :].expand(-1, self.N + 1, -1))
+            t["ctrl_curr"].zero_()
+            self.pos[0].copy_(self.x0_init[:, None, :3].expand(-1, self.N + 1, -1))
+            self.pos[1].zero_()
+            if self.world > 1:
+                self.table.zero_()
+                self.valid.zero_()
+        self.stream.synchronize()
+        self.step_index = 0
+
+    def _bind(self, s):
+        """Argument dictionary of step s: recorded exogenous inputs + live state."""
+        t, r = self.t, self.rec[s]
+        t["ref"], t["poly_A"], t["poly_b"], t["poly_rows"] = r["ref"], r["poly_A"], r["poly_b"], r["poly_rows"]
+        t["prev_self_pos"], t["pos_out"] = self.pos[s & 1], self.pos[(s & 1) ^ 1]
+        if self.world > 1:
+            t["all_pos"], t["all_valid"] = self.table, self.valid
+        else:  # one rank: the previous step's packed plans ARE the table
+            t["all_pos"], t["all_valid"] = self.pos[s & 1], t["have_plan"]
+        return t
+
+    def device_step(self, s, inputs=None):
+        """Enqueue step s on self.stream (no synchronisation).  `inputs`: dict(ref, poly_A, poly_b, poly_rows) of
+        device tensors to use instead of the recorded ones (end-to-end timing uploads them every step)."""
+        sp = self.stream.cuda_stream
+        t = self._bind(s)
+        if inputs is not None:
+            t.update(inputs)
+        self.planner.solve_batch_device(t, self.n_rob, sp)
+        prev = t.pop("prev_self_pos")  # the advance call must not overwrite the buffer the table aliases
+        self.planner.advance_device(t, sp)
+        t["prev_self_pos"] = prev
+        if self.world > 1:
+            self.planner.exchange_plans(t["pos_out"], self.table, t["have_plan"], self.valid, self.n, sp)
+        self.step_index = s + 1
+
+    def current_table(self):
+        return self.table if self.world > 1 else self.pos[self.step_index & 1]
+
+    # ------------------------------------------------------------------------------------------------
+    def preroll(self, steps: int, parity_sample: int = 0, log=None):
+        """Run `steps` closed-loop steps with the host producers in the loop, recording their outputs.  With
+        parity_sample > 0 the first that many agents of the shard are also solved by the caller-supplied checker
+        (`self.checker(batch) -> dict(res=...)`, set by tests / bench) on the same inputs; returns the parity record."""
+        import time
+        torch, sw = self.torch, self.swarm
+        par = {"agents": 0, "status_mismatches": 0, "max_rel_obj_gap": 0.0}
+        t_host = t_dev = 0.0
+        keep = getattr(self, "keep_steps", ())  # steps whose complete host-side inputs are kept (CPU baseline legs)
+        if not hasattr(self, "host_batches"):
+            self.host_batches = {}
+        for s in range(len(self.rec), steps):
+            t0 = time.perf_counter()
+            x0 = self.t["x0"].cpu().numpy()
+            ref, pA, pb, pr = sw.make_inputs(self.ids, pos=x0[:, :3], step=s, pool=self.pool)
+            rec = {"ref": torch.from_numpy(ref), "poly_A": torch.from_numpy(pA), "poly_b": torch.from_numpy(pb),
+                   "poly_rows": torch.from_numpy(pr)}
+            if self.record_host:
+                self.rec_host.append({k: v.pin_memory() for k, v in rec.items()})
+            self.rec.append({k: v.to(self.device) for k, v in rec.items()})
+            t1 = time.perf_counter()
+            check = parity_sample > 0 and getattr(self, "checker", None) is not None
+            if check or s in keep:
+                m = min(max(parity_sample, getattr(self, "keep_agents", 0) if s in keep else 0), self.n)
+                tab = self.current_table().cpu().numpy()
+                val = (self.valid if self.world > 1 else self.t["have_plan"]).cpu().numpy()
+                if self.world == 1 and s == 0:
+                    tab, val = np.zeros((self.n_rob, self.N + 1, 3)), np.zeros(self.n_rob, np.uint8)
+                from .scenarios import Batch
+                hb = Batch(sw.params, self.ids[:m].astype(np.int32), sw.group_begin[self.ids[:m]].astype(np.int32),
+                           sw.group_end[self.ids[:m]].astype(np.int32), x0[:m], ref[:m], pA[:m], pb[:m], pr[:m],
+                           self.pos[s & 1][:m].cpu().numpy(), tab, val, self.R)
+                if s in keep:
+                    self.host_batches[s] = hb
+                if check:
+                    m = min(parity_sample, self.n)
+                    want = self.checker(hb.take(np.arange(m)) if hb.n > m else hb)["res"]
+            with torch.cuda.stream(self.stream):
+                self.device_step(s)
+            self.stream.synchronize()
+            res = np.frombuffer(self.t["res"].cpu().numpy().tobytes(), dtype=_result_dtype()).copy()
+            self.stats.append(res)
+            self.sums.append(table_checksum(self.current_table()))
+            if check:
+                got = res[:m]
+                par["agents"] += m
+                par["status_mismatches"] += int((got["status"] != want["status"]).sum())
+                both = (got["status"] == 0) & (want["status"] == 0)
+                if both.any():
+                    gap = np.abs(got["obj"][both] - want["obj"][both]) / np.maximum(1.0, np.abs(want["obj"][both]))
+                    par["max_rel_obj_gap"] = max(par["max_rel_obj_gap"], float(gap.max()))
+            t_host += t1 - t0
+            t_dev += time.perf_counter() - t1
+        if log:
+            log(f"[rank {self.rank}] pre-roll: {steps} steps x {self.n} agents, host producers {t_host:.1f}s, rest {t_dev:.1f}s")
+        return par
+
+    def input_bytes_per_step(self) -> int:
+        r = self.rec[0]
+        return int(sum(v.numel() * v.element_size() for v in r.values()))
+
+    def close(self):
+        self.planner.close()
+
+
+def _result_dtype():
+    from ._lib import RESULT_DTYPE
+    return RESULT_DTYPE

@@ -34,6 +34,7 @@
 #define MAXQ (3 * MAXN - 2)
 #define FEAS_TOL 1e-6
 #define PRUNE_MARGIN 1e-6
+#define PRUNE_REL 1e-7 /* bound pruning, relative (the kernels' kPruneRel) */
 #define STEP_FRAC 0.97
 #define LOOSE_TOL 1e-6 /* accepted when the iteration limit is reached: still inside the 1e-6 KKT target */
 
@@ -762,6 +763,46 @@ static double seg_violation(const double *A, const double *b, int n, const doubl
   return v;
 }
 
+
+/* ------------------------------------------------------------------ per-step dominance between cells
+ * Cell A dominates cell B at step k when every point the segment (p_k, p_k+1) can reach inside B also lies in
+ * A: then any trajectory that uses B at step k may use A instead at the same cost, and B is dropped from the
+ * candidate set (the optimum value is unchanged; near-duplicate overlapping cells otherwise make the search
+ * enumerate assignments that tie).  Sufficient test per row (n, b) of A and per variable point kp in {k, k+1}:
+ * the row cannot be violated inside reach_box(kp) /\ bbox(B), or B holds the same normal at least as tight. */
+static void cell_bbox(const double *A, const double *b, int n, double lo[3], double hi[3]) {
+  for (int a = 0; a < 3; a++) lo[a] = -INFINITY, hi[a] = INFINITY;
+  for (int r = 0; r < n; r++) {
+    const double *v = A + 3 * r;
+    int nzc = (v[0] != 0.0) + (v[1] != 0.0) + (v[2] != 0.0);
+    if (nzc != 1) continue;
+    int a = v[0] != 0.0 ? 0 : (v[1] != 0.0 ? 1 : 2);
+    double x = b[r] / v[a];
+    if (v[a] > 0) hi[a] = fmin(hi[a], x);
+    else lo[a] = fmax(lo[a], x);
+  }
+}
+static int cell_dominates(const prob_t *pb, const tables_t *T, int k, const double *AA, const double *bA, int nA,
+                          const double *AB, const double *bB, int nB) {
+  double lo[3], hi[3];
+  cell_bbox(AB, bB, nB, lo, hi);
+  for (int r = 0; r < nA; r++) {
+    const double *n = AA + 3 * r;
+    double same = INFINITY;
+    for (int q = 0; q < nB; q++)
+      if (AB[3 * q] == n[0] && AB[3 * q + 1] == n[1] && AB[3 * q + 2] == n[2]) same = fmin(same, bB[q]);
+    if (same <= bA[r]) continue;
+    for (int kp = k; kp <= k + 1; kp++) {
+      if (T->kp_const[kp]) continue; /* a constant point was checked against both cells already */
+      double mx = 0;
+      for (int a = 0; a < 3; a++)
+        mx += n[a] >= 0 ? n[a] * fmin(pb->phi[kp][a], hi[a]) : n[a] * fmax(pb->plo[kp][a], lo[a]);
+      if (!(mx <= bA[r])) return 0;
+    }
+  }
+  return 1;
+}
+
 /* ------------------------------------------------------------------ one agent */
 static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0, int nb1, const double *x0, const double *ref,
                         const double *pA, const double *pb_, const int32_t *prow_n, int rmax, const double *prev,
@@ -818,9 +859,26 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
     free(planes);
     return;
   }
+  /* per-step dominance: drop a cell another candidate of the same step covers wherever the segment can be
+   * (equal cells: the lower index stays) */
+  for (int k = 0; k < N; k++)
+    for (int B = Peff - 1; B >= 0; B--) {
+      if (!(root[k] >> B & 1)) continue;
+      for (int A = 0; A < Peff; A++) {
+        if (A == B || !(root[k] >> A & 1)) continue;
+        const double *AA = pA + (size_t)A * rmax * 3, *bA = pb_ + (size_t)A * rmax;
+        const double *AB = pA + (size_t)B * rmax * 3, *bB = pb_ + (size_t)B * rmax;
+        if (!cell_dominates(&pb, T, k, AA, bA, prow_n[A], AB, bB, prow_n[B])) continue;
+        if (A > B && cell_dominates(&pb, T, k, AB, bB, prow_n[B], AA, bA, prow_n[A])) continue; /* equal cells */
+        root[k] &= ~(1u << B);
+        break;
+      }
+    }
   /* depth-first branch and bound over candidate sets */
   int cap = 4 * N * MAXP + 8, top = 0;
   unsigned(*stack)[MAXN] = malloc(sizeof(unsigned[MAXN]) * cap);
+  double *sbound = malloc(sizeof(double) * cap);
+  sbound[top] = -INFINITY;
   memcpy(stack[top++], root, sizeof(root));
   double best = INFINITY, bestw[MAXNW];
   int bestsig[MAXN], nodes = 0, iters = 0, exhausted = 1, maxrows = 0, anyfail = 0;
@@ -832,6 +890,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
     }
     unsigned sets[MAXN];
     memcpy(sets, stack[--top], sizeof(sets));
+    if (sbound[top] >= best - PRUNE_REL * fmax(1.0, fabs(best))) continue; /* the parent's optimum bounds this node: not solved, not counted */
     pb.m = 0;
     for (int i = 0; i < nplanes; i++) push_row(&pb, planes[i].n, planes[i].b, planes[i].kp);
     for (int k = 0; k < N; k++) {
@@ -845,7 +904,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
     }
     if (pb.m > maxrows) maxrows = pb.m;
     qp_out q;
-    pb.cutoff = best < INFINITY ? best - 1e-7 * fmax(1.0, fabs(best)) : INFINITY;
+    pb.cutoff = best < INFINITY ? best - PRUNE_REL * fmax(1.0, fabs(best)) : INFINITY;
     solve_qp(&pb, &q);
     nodes++;
     iters += q.iters;
@@ -858,7 +917,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
       if (q.status != ORC_INFEASIBLE && q.status != ORC_CUTOFF) anyfail = q.status;
       continue;
     }
-    if (q.obj >= best - 1e-7 * fmax(1.0, fabs(best))) continue;
+    if (q.obj >= best - PRUNE_REL * fmax(1.0, fabs(best))) continue;
     double p[MAXN + 1][3];
     positions(&pb, q.w, p, 1);
     int full[MAXN], bk = -1, order[MAXP], no = 0;
@@ -929,6 +988,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
         break;
       }
       memcpy(stack[top], sets, sizeof(sets));
+      sbound[top] = q.obj;
       stack[top++][bk] = m;
     }
     if (overflow) {
@@ -966,6 +1026,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
     res->status = !exhausted ? ORC_NODE_LIMIT : (anyfail ? anyfail : ORC_INFEASIBLE);
   }
   free(stack);
+  free(sbound);
   free(planes);
   free(pb.rows), free(pb.s), free(pb.lam);
 }
