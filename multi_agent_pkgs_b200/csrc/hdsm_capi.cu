@@ -305,6 +305,7 @@ static int solve_device(hdsm_handle* h, int slot, size_t order_offset, int n_loc
   a.all_valid = all_valid, a.traj = traj, a.ctrl = ctrl, a.pos_out = pos_out, a.poly_used = poly_used;
   a.assign_out = assign_out, a.res = res, a.prof = h->d_prof;
   a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
+  if (const char* e = std::getenv("HDSM_DEBUG")) a.dbg = std::atoi(e);
   const bool ordered = h->use_order && n_local >= 1024;  // below ~2 waves of blocks the order cannot matter
   a.order = ordered && h->order_n[slot] == n_local && h->order_off[slot] == order_offset ? h->d_order + order_offset : nullptr;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;

@@ -13,7 +13,10 @@ inline cudaError_t raise_smem_limit(Kernel kernel, int device) {
   int optin = 0;
   cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncAttributes fa{};
+  if ((e = cudaFuncGetAttributes(&fa, kernel)) != cudaSuccess) return e;
+  // the opt-in maximum covers static + dynamic shared memory of a block
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
 }
 
 }  // namespace hdsm

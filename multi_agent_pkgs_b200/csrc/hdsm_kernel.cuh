@@ -46,6 +46,7 @@ struct KernelArgs {
   int only_status; // >= 0: solve only agents whose res[].status equals this (second, large-memory pass)
   long long* prof; // optional [n_local][16] cycle counters per phase (HDSM_PROFILE=1), else null
   int max_iter, max_nodes, prune;
+  int dbg;  // debugging switches (HDSM_DEBUG): 1 = no dominance filter, 2 = no parent-bound pruning
   double tol;
 };
 
@@ -1261,7 +1262,7 @@ struct Solver {
       if (lane == 0) ctl[1] = st;
     }
     bsync();
-    if (ctl[1] < 0) dominance_filter();  // uniform over the block
+    if (ctl[1] < 0 && !(A.dbg & 1)) dominance_filter();  // uniform over the block
     if (wid == 0) {
       if (st < 0) {
         if (lane < 16) stack[lane] = lane < N ? cur[lane] : 0;
@@ -1279,7 +1280,7 @@ struct Solver {
             exhausted = false;
           }
           // a node whose parent's optimum already reaches the incumbent cannot improve it: dropped unsolved
-          while (exhausted && top > 0 && sbnd[top - 1] >= best - kPruneRel * fmax(1.0, fabs(best))) --top;
+          while (!(A.dbg & 2) && exhausted && top > 0 && sbnd[top - 1] >= best - kPruneRel * fmax(1.0, fabs(best))) --top;
           if (exhausted && top > 0) {
             --top;
             if (lane < 16) cur[lane] = stack[top * 16 + lane];

@@ -244,6 +244,7 @@ class ClosedLoop:
         self.stats: list = []      # per step: hdsm_result array of the shard
         self.step_index = 0
         self.stream = torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize(dev)  # the uploads above ran on another stream than the one every step is enqueued on
         self.reset()
 
     # ------------------------------------------------------------------------------------------------
@@ -312,7 +313,8 @@ class ClosedLoop:
                    "poly_rows": torch.from_numpy(pr)}
             if self.record_host:
                 self.rec_host.append({k: v.pin_memory() for k, v in rec.items()})
-            self.rec.append({k: v.to(self.device) for k, v in rec.items()})
+            with torch.cuda.stream(self.stream):  # stream-ordered with the kernels that read them
+                self.rec.append({k: v.to(self.device, non_blocking=False) for k, v in rec.items()})
             t1 = time.perf_counter()
             check = parity_sample > 0 and getattr(self, "checker", None) is not None
             if check or s in keep:

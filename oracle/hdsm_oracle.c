@@ -32,6 +32,7 @@
 #define MAXNW (3 * MAXNZ)
 #define MAXP 8
 #define MAXQ (3 * MAXN - 2)
+#define MAXW 8 /* widest search round */
 #define FEAS_TOL 1e-6
 #define PRUNE_MARGIN 1e-6
 #define PRUNE_REL 1e-7 /* bound pruning, relative (the kernels' kPruneRel) */
@@ -42,7 +43,7 @@ enum { ORC_OPTIMAL = 0, ORC_INFEASIBLE = 1, ORC_MAX_ITER = 2, ORC_NUMERICAL = 3,
        ORC_CUTOFF = 6 /* internal: the dual bound of a relaxation reached the incumbent, solve abandoned */ };
 
 typedef struct {
-  int32_t n_hor, poly_hor, rk4, max_iter, max_nodes, prune;
+  int32_t n_hor, poly_hor, rk4, max_iter, max_nodes, prune, width, pad_;
   double dt, drag[3], r_u, r_x[6], r_n[6];
   double max_vel, min_acc_xy, max_acc_xy, min_acc_z, max_acc_z, max_jerk;
   double drone_radius, drone_z_offset, tilt, tol;
@@ -881,121 +882,149 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
   sbound[top] = -INFINITY;
   memcpy(stack[top++], root, sizeof(root));
   double best = INFINITY, bestw[MAXNW];
-  int bestsig[MAXN], nodes = 0, iters = 0, exhausted = 1, maxrows = 0, anyfail = 0;
+  int bestsig[MAXN], nodes = 0, iters = 0, exhausted = 1, maxrows = 0, anyfail = 0, lat_iters = 0;
   rowset_t rs;
-  while (top > 0) {
-    if (nodes >= P->max_nodes) {
-      exhausted = 0;
-      break;
-    }
+  /* The search runs in rounds of up to `width` open nodes (width = 1: plain depth-first search).  The nodes of a
+   * round are solved independently, all against the incumbent the round started with - on the GPU by the thread
+   * blocks of one cluster at the same time - and then merged in a fixed order, so the result does not depend on
+   * which of them finishes first: incumbents in pop order, then children pushed so that the first node's
+   * children are on top of the stack. */
+  const int width = P->width > 1 ? (P->width < MAXW ? P->width : MAXW) : 1;
+  typedef struct {
     unsigned sets[MAXN];
-    memcpy(sets, stack[--top], sizeof(sets));
-    if (sbound[top] >= best - PRUNE_REL * fmax(1.0, fabs(best))) continue; /* the parent's optimum bounds this node: not solved, not counted */
-    pb.m = 0;
-    for (int i = 0; i < nplanes; i++) push_row(&pb, planes[i].n, planes[i].b, planes[i].kp);
-    for (int k = 0; k < N; k++) {
-      set_rows(pA, pb_, prow_n, rmax, sets[k], &rs);
-      for (int kp = k; kp <= k + 1; kp++) {
-        if (T->kp_const[kp]) continue;
-        if (kp == k && k > 0 && sets[k - 1] == sets[k]) continue; /* same rows already on p_k from step k-1 */
-        for (int r = 0; r < rs.n; r++)
-          if (!P->prune || row_reachable(&pb, rs.A[r], rs.b[r], kp)) push_row(&pb, rs.A[r], rs.b[r], kp);
-      }
-    }
-    if (pb.m > maxrows) maxrows = pb.m;
     qp_out q;
-    pb.cutoff = best < INFINITY ? best - PRUNE_REL * fmax(1.0, fabs(best)) : INFINITY;
-    solve_qp(&pb, &q);
-    nodes++;
-    iters += q.iters;
-    if (getenv("ORC_TRACE")) {
-      fprintf(stderr, "node %d sets", nodes);
-      for (int k = 0; k < N; k++) fprintf(stderr, " %x", sets[k]);
-      fprintf(stderr, " rows %d status %d it %d obj %.6f best %.6f\n", pb.m, q.status, q.iters, q.obj, best);
-    }
-    if (q.status != ORC_OPTIMAL) {
-      if (q.status != ORC_INFEASIBLE && q.status != ORC_CUTOFF) anyfail = q.status;
-      continue;
-    }
-    if (q.obj >= best - PRUNE_REL * fmax(1.0, fabs(best))) continue;
+    int full[MAXN], bk, no, order[MAXP];
     double p[MAXN + 1][3];
-    positions(&pb, q.w, p, 1);
-    int full[MAXN], bk = -1, order[MAXP], no = 0;
-    double viol[MAXP], bkv = 0;
-    for (int k = 0; k < N; k++) {
-      full[k] = -1;
-      double v[MAXP];
-      for (int j = 0; j < Peff; j++) {
-        v[j] = INFINITY;
-        if (sets[k] >> j & 1) {
-          v[j] = seg_violation(pA + (size_t)j * rmax * 3, pb_ + (size_t)j * rmax, prow_n[j], p[k], p[k + 1]);
-          if (full[k] < 0 && v[j] <= 1e-7) full[k] = j;
-        }
-      }
-      double vmin = INFINITY;
-      for (int j = 0; j < Peff; j++) vmin = fmin(vmin, v[j]);
-      /* branch on the uncovered step that is farthest from all of its candidates: ~4x fewer nodes
-       * than "first uncovered" on the config-2 closed loop */
-      int take = full[k] < 0 && (bk < 0 || vmin > bkv);
-      if (take) {
-        bkv = vmin;
-        bk = k;
-        no = 0;
-        for (int j = 0; j < Peff; j++)
-          if (sets[k] >> j & 1) order[no] = j, viol[no++] = v[j];
-        for (int x = 1; x < no; x++) /* insertion sort by (violation, index) */
-          for (int y = x; y > 0 && viol[y] < viol[y - 1]; y--) {
-            double tv = viol[y];
-            viol[y] = viol[y - 1], viol[y - 1] = tv;
-            int to = order[y];
-            order[y] = order[y - 1], order[y - 1] = to;
-          }
-      }
-    }
-    if (bk < 0) {
-      best = q.obj;
-      memcpy(bestw, q.w, sizeof(bestw));
-      memcpy(bestsig, full, sizeof(full));
-      res->kkt = q.kkt;
-      continue;
-    }
-    if (no <= 1) continue;
-    /* Split the candidates of step bk, ordered by violation, in two halves (least violated explored first).
-     * A half whose hull still contains the segment of the node optimum would be solved to the very same point
-     * and then split again on the same step: that solve is skipped and the half is split right away. */
-    struct { int x0, x1; } work[2 * MAXP];
-    int nw = 0, overflow = 0;
-    const int h = (no + 1) / 2;
-    work[nw].x0 = 0, work[nw++].x1 = h;   /* processed last-in first-out: the upper half is pushed first */
-    work[nw].x0 = h, work[nw++].x1 = no;
-    while (nw > 0 && !overflow) {
-      const int x0 = work[--nw].x0, x1 = work[nw].x1;
-      unsigned m = 0;
-      for (int x = x0; x < x1; x++) m |= 1u << order[x];
-      int contains = 0;
-      if (x1 - x0 > 1) {
-        set_rows(pA, pb_, prow_n, rmax, m, &rs);
-        contains = seg_violation(&rs.A[0][0], rs.b, rs.n, p[bk], p[bk + 1]) <= 1e-7; /* the coverage tolerance */
-      }
-      if (contains) {
-        const int hh = (x1 - x0 + 1) / 2;
-        work[nw].x0 = x0, work[nw++].x1 = x0 + hh;
-        work[nw].x0 = x0 + hh, work[nw++].x1 = x1;
-        continue;
-      }
-      if (top + 1 > cap) {
-        overflow = 1;
+  } node_t;
+  node_t *nd = (node_t *)malloc(sizeof(node_t) * width);
+  while (top > 0 && exhausted) {
+    /* ---- pop */
+    int cnt = 0;
+    while (cnt < width && top > 0) {
+      if (nodes + cnt >= P->max_nodes) {
+        if (cnt == 0) exhausted = 0;
         break;
       }
-      memcpy(stack[top], sets, sizeof(sets));
-      sbound[top] = q.obj;
-      stack[top++][bk] = m;
+      --top;
+      if (sbound[top] >= best - PRUNE_REL * fmax(1.0, fabs(best))) continue; /* the parent's optimum bounds this node: not solved, not counted */
+      memcpy(nd[cnt++].sets, stack[top], sizeof(nd[0].sets));
     }
-    if (overflow) {
-      exhausted = 0;
-      break;
+    if (cnt == 0) continue;
+    /* ---- solve (independent; cutoff from the incumbent at the start of the round) */
+    const double cutoff = best < INFINITY ? best - PRUNE_REL * fmax(1.0, fabs(best)) : INFINITY;
+    int round_iters = 0;
+    for (int c = 0; c < cnt; c++) {
+      node_t *n = &nd[c];
+      pb.m = 0;
+      for (int i = 0; i < nplanes; i++) push_row(&pb, planes[i].n, planes[i].b, planes[i].kp);
+      for (int k = 0; k < N; k++) {
+        set_rows(pA, pb_, prow_n, rmax, n->sets[k], &rs);
+        for (int kp = k; kp <= k + 1; kp++) {
+          if (T->kp_const[kp]) continue;
+          if (kp == k && k > 0 && n->sets[k - 1] == n->sets[k]) continue; /* same rows already on p_k from step k-1 */
+          for (int r = 0; r < rs.n; r++)
+            if (!P->prune || row_reachable(&pb, rs.A[r], rs.b[r], kp)) push_row(&pb, rs.A[r], rs.b[r], kp);
+        }
+      }
+      if (pb.m > maxrows) maxrows = pb.m;
+      pb.cutoff = cutoff;
+      solve_qp(&pb, &n->q);
+      nodes++;
+      iters += n->q.iters;
+      if (n->q.iters > round_iters) round_iters = n->q.iters;
+      if (getenv("ORC_TRACE")) {
+        fprintf(stderr, "node %d sets", nodes);
+        for (int k = 0; k < N; k++) fprintf(stderr, " %x", n->sets[k]);
+        fprintf(stderr, " rows %d status %d it %d obj %.6f best %.6f\n", pb.m, n->q.status, n->q.iters, n->q.obj, best);
+      }
+      n->bk = -1, n->no = 0;
+      if (n->q.status != ORC_OPTIMAL) continue;
+      /* coverage of every segment by one member of its candidate set; the uncovered step that is farthest from all
+       * of its candidates is the one to branch on (~4x fewer nodes than "first uncovered" on the config-2 loop) */
+      positions(&pb, n->q.w, n->p, 1);
+      double viol[MAXP], bkv = 0;
+      for (int k = 0; k < N; k++) {
+        n->full[k] = -1;
+        double v[MAXP];
+        for (int j = 0; j < Peff; j++) {
+          v[j] = INFINITY;
+          if (n->sets[k] >> j & 1) {
+            v[j] = seg_violation(pA + (size_t)j * rmax * 3, pb_ + (size_t)j * rmax, prow_n[j], n->p[k], n->p[k + 1]);
+            if (n->full[k] < 0 && v[j] <= 1e-7) n->full[k] = j;
+          }
+        }
+        double vmin = INFINITY;
+        for (int j = 0; j < Peff; j++) vmin = fmin(vmin, v[j]);
+        if (n->full[k] < 0 && (n->bk < 0 || vmin > bkv)) {
+          bkv = vmin;
+          n->bk = k;
+          n->no = 0;
+          for (int j = 0; j < Peff; j++)
+            if (n->sets[k] >> j & 1) n->order[n->no] = j, viol[n->no++] = v[j];
+          for (int x = 1; x < n->no; x++) /* insertion sort by (violation, index) */
+            for (int y = x; y > 0 && viol[y] < viol[y - 1]; y--) {
+              double tv = viol[y];
+              viol[y] = viol[y - 1], viol[y - 1] = tv;
+              int to = n->order[y];
+              n->order[y] = n->order[y - 1], n->order[y - 1] = to;
+            }
+        }
+      }
+    }
+    lat_iters += round_iters;
+    /* ---- merge 1: incumbents, in pop order */
+    for (int c = 0; c < cnt; c++) {
+      node_t *n = &nd[c];
+      if (n->q.status != ORC_OPTIMAL) {
+        if (n->q.status != ORC_INFEASIBLE && n->q.status != ORC_CUTOFF) anyfail = n->q.status;
+        continue;
+      }
+      if (n->bk >= 0 || n->q.obj >= best - PRUNE_REL * fmax(1.0, fabs(best))) continue;
+      best = n->q.obj;
+      memcpy(bestw, n->q.w, sizeof(bestw));
+      memcpy(bestsig, n->full, sizeof(n->full));
+      res->kkt = n->q.kkt;
+    }
+    /* ---- merge 2: children, last node first so that the first node's children end up on top */
+    for (int c = cnt - 1; c >= 0 && exhausted; c--) {
+      node_t *n = &nd[c];
+      if (n->q.status != ORC_OPTIMAL || n->bk < 0 || n->no <= 1) continue;
+      if (n->q.obj >= best - PRUNE_REL * fmax(1.0, fabs(best))) continue;
+      /* Split the candidates of step bk, ordered by violation, in two halves (least violated explored first).
+       * A half whose hull still contains the segment of the node optimum would be solved to the very same point
+       * and then split again on the same step: that solve is skipped and the half is split right away. */
+      struct { int x0, x1; } work[2 * MAXP];
+      int nw = 0;
+      const int bk = n->bk, h = (n->no + 1) / 2;
+      work[nw].x0 = 0, work[nw++].x1 = h;   /* processed last-in first-out: the upper half is pushed first */
+      work[nw].x0 = h, work[nw++].x1 = n->no;
+      while (nw > 0) {
+        const int x0 = work[--nw].x0, x1 = work[nw].x1;
+        unsigned m = 0;
+        for (int x = x0; x < x1; x++) m |= 1u << n->order[x];
+        int contains = 0;
+        if (x1 - x0 > 1) {
+          set_rows(pA, pb_, prow_n, rmax, m, &rs);
+          contains = seg_violation(&rs.A[0][0], rs.b, rs.n, n->p[bk], n->p[bk + 1]) <= 1e-7; /* the coverage tolerance */
+        }
+        if (contains) {
+          const int hh = (x1 - x0 + 1) / 2;
+          work[nw].x0 = x0, work[nw++].x1 = x0 + hh;
+          work[nw].x0 = x0 + hh, work[nw++].x1 = x1;
+          continue;
+        }
+        if (top + 1 > cap) {
+          exhausted = 0; /* stack full: the optimum stays unproven */
+          break;
+        }
+        memcpy(stack[top], n->sets, sizeof(n->sets));
+        sbound[top] = n->q.obj;
+        stack[top++][bk] = m;
+      }
     }
   }
+  free(nd);
+  if (getenv("ORC_LAT")) maxrows = lat_iters; /* experiment: report the critical-path iterations in `rows` */
   res->nodes = nodes, res->iters = iters, res->rows = maxrows;
   if (best < INFINITY) {
     res->status = (exhausted && !anyfail) ? ORC_OPTIMAL : ORC_NODE_LIMIT; /* a lost node leaves the optimum unproven */

@@ -28,6 +28,7 @@ def lib():
         _lib.ref_agent_step.restype = C.c_int
         _lib.ref_agent_reftraj.restype = C.c_int
         _lib.ref_agent_corridor.restype = C.c_int
+        _lib.ref_agent_loop_step.restype = C.c_int
     return _lib
 
 
@@ -85,6 +86,33 @@ class RefAgent:
         nl, ni = n_lin.value, n_ind.value
         return dict(final=final, obj_diag=obj_diag, obj_lin=obj_lin, obj_const=obj_const.value, obj_offdiag=obj_off.value, lb=lb, ub=ub,
                     vtype=vtype, lin=(lin[:nl], lin_c[:nl], lin_s[:nl]), ind=(ind[:ni], ind_c[:ni], ind_b[:ni]), failed=bool(failed.value))
+
+    def loop_step(self, ref, polys, all_pos, all_valid, solver, rmax=18):
+        """One closed-loop replanning iteration of the node on an external solver (see ref_agent_loop_step in ref_wrap_agent.cpp).
+        ref (N+1, 6); polys [(A, b)]; all_pos (n_rob, N+1, 3) / all_valid (n_rob,): the other agents' last published plans.
+        solver: ("hdsm", TrajectoryPlanner)  - hdsm_solve_batch of the CUDA library through its C ABI, or
+                ("port", OrcParams)          - orc_solve_batch of the C port of the oracle (CPU-only runs).
+        Returns dict(x0, traj, ctrl, poly_used, have_traj, failed, status) read from the node's members afterwards."""
+        N, P = self.p.n_hor, self.p.poly_hor
+        rows = np.array([len(b) for _, b in polys], np.int32)
+        A, b = np.zeros((len(polys), rmax, 3)), np.zeros((len(polys), rmax))
+        for i, (Ai, bi) in enumerate(polys):
+            A[i, :len(bi)], b[i, :len(bi)] = Ai, bi
+        ref = np.ascontiguousarray(ref, np.float64).reshape(N + 1, 6)
+        all_pos, all_valid = np.ascontiguousarray(all_pos, np.float64), np.ascontiguousarray(all_valid, np.uint8)
+        kind, obj = solver
+        if kind == "hdsm":
+            fn, ctx, k = C.cast(obj.lib.hdsm_solve_batch, C.c_void_p), obj._h, 0
+        else:
+            from . import c_oracle
+            fn, ctx, k = C.cast(c_oracle.lib().orc_solve_batch, C.c_void_p), C.cast(C.pointer(obj), C.c_void_p), 1
+        x0, traj, ctrl, used = np.zeros(9), np.zeros((N + 1, 9)), np.zeros((N, 3)), np.zeros(P, np.uint8)
+        have, failed, status = C.c_int32(), C.c_int32(), C.c_int32()
+        rc = lib().ref_agent_loop_step(self.h, _p(ref), C.c_int(len(polys)), _p(rows), C.c_int(rmax), _p(A), _p(b), _p(all_pos), _p(all_valid),
+                                       C.c_int(k), fn, ctx, _p(x0), _p(traj), _p(ctrl), _p(used), C.byref(have), C.byref(failed), C.byref(status))
+        if rc != 0:
+            raise RuntimeError(f"ref_agent_loop_step failed ({rc})")
+        return dict(x0=x0, traj=traj, ctrl=ctrl, poly_used=used, have_traj=bool(have.value), failed=bool(failed.value), status=status.value)
 
     def reference_trajectory(self, grid, origin, voxel, path, prev_ref, increment, traj, all_pos, all_valid, path_vel_min, path_vel_max,
                              path_vel_dec, sens_dist, sens_pot, sens_other_agents):

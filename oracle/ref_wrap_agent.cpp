@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <array>
 #include <chrono>
 #include <cmath>
@@ -177,6 +178,129 @@ int ref_agent_step(void* h, const double* x0, const double* ref, int n_poly, con
   *n_ind = ni;
   return rc;
 }
+// ---- the reference's node running CLOSED LOOP on an external solver ----------------------------------------------------
+// ref_agent_loop_step is one replanning iteration of the node as TrajPlanningIteration runs it (agent_class.cpp:157-258),
+// minus the producers that are given as inputs: state advance state_curr_ := traj_curr_[step_plan_] (:233-238, step_plan_ = 1),
+// GenerateTimeAwareSafeCorridor() (:168) and SolveOptimizationProblem() (:174) - the reference's own, unmodified code.
+// Inside the latter, model_.optimize() (:959) reaches GRBModel::solver_hook of the stand-in; the hook packs the NODE'S OWN
+// MEMBERS (state_curr_, traj_ref_curr_, poly_const_vec_, traj_curr_, traj_other_agents_ - exactly what the patch in
+// INTEGRATION.md reads) into the C-ABI arrays, calls the solver through a function pointer with the signature of
+// hdsm_solve_batch (kind 0: libhdsm, the CUDA library) or orc_solve_batch (kind 1: the C port of the oracle, for the
+// CPU-only run of this test) and writes the solution into the model's variables; the reference's own read-back (:962-987)
+// and, when the solver reports no usable solution (the hook throws like Gurobi does), its own fallback (:997-1019)
+// consume it.  Outputs are the node's members after the iteration.
+typedef int (*hdsm_solve_fn)(void*, int, const int32_t*, const int32_t*, const int32_t*, const double*, const double*, const double*,
+                             const double*, const int32_t*, const double*, const double*, const uint8_t*, int, const int32_t*, double*,
+                             double*, uint8_t*, int32_t*, void*);
+typedef int (*orc_solve_fn)(const void*, int, const int32_t*, const int32_t*, const int32_t*, const double*, const double*, const double*,
+                            const double*, const int32_t*, int, const double*, const double*, const uint8_t*, int, const int32_t*, double*,
+                            double*, uint8_t*, int32_t*, void*, int);
+struct LoopResult { int32_t status, iters, nodes, rows; double obj, kkt; };  // layout of hdsm_result / orc_result
+
+int ref_agent_loop_step(void* h, const double* ref, int n_poly, const int32_t* rows, int rmax, const double* A, const double* b,
+                        const double* all_pos, const uint8_t* all_valid, int kind, void* fn, void* ctx, double* x0_out, double* traj_out,
+                        double* ctrl_out, uint8_t* used_out, int32_t* have_traj, int32_t* failed, int32_t* solver_status) {
+  Agent* a = static_cast<Agent*>(h);
+  const int N = a->n_hor_, n_rob = a->n_rob_, P = a->poly_hor_;
+  std::streambuf *keep_out = std::cout.rdbuf(), *keep_err = std::cerr.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf()), std::cerr.rdbuf(sink.rdbuf());
+  if (!a->traj_curr_.empty()) a->state_curr_ = a->traj_curr_[1];  // :233-238 with step_plan_ = 1
+  for (int j = 0; j < 9; ++j) x0_out[j] = a->state_curr_[j];
+  a->traj_ref_curr_.assign(N + 1, std::vector<double>(6));
+  for (int i = 0; i <= N; ++i)
+    for (int j = 0; j < 6; ++j) a->traj_ref_curr_[i][j] = ref[6 * i + j];
+  a->poly_const_vec_.clear();
+  for (int p = 0; p < n_poly; ++p) {
+    MatDNf<3> Am(rows[p], 3);
+    VecDf bv(rows[p]);
+    for (int r = 0; r < rows[p]; ++r) {
+      for (int c = 0; c < 3; ++c) Am(r, c) = A[((size_t)p * rmax + r) * 3 + c];
+      bv(r) = b[(size_t)p * rmax + r];
+    }
+    a->poly_const_vec_.push_back(LinearConstraint3D(Am, bv));
+  }
+  for (int j = 0; j < n_rob; ++j) {  // what TrajectoryOtherAgentsCallback stored (:629-643); the own slot stays empty
+    multi_agent_planner_msgs::msg::Trajectory t;
+    if (all_valid[j] && j != a->id_) {
+      t.states.resize(N + 1);
+      for (int k = 0; k <= N; ++k) {
+        const double* q = all_pos + ((size_t)j * (N + 1) + k) * 3;
+        t.states[k].position = {q[0], q[1], q[2]};
+        t.states[k].velocity = {0.0, 0.0, 0.0};
+        t.states[k].acceleration = {0.0, 0.0, 0.0};
+      }
+    }
+    a->traj_other_agents_[j] = t;
+  }
+  *solver_status = -1;
+  GRBModel::solver_hook() = [&](GRBModel& m) {
+    // pack the node's members into the C-ABI arrays (include/hdsm.h)
+    std::vector<double> x0(a->state_curr_.begin(), a->state_curr_.begin() + 9), rf((size_t)N * 6), pA((size_t)P * rmax * 3, 0.0),
+        pb((size_t)P * rmax, 0.0), prev((size_t)(N + 1) * 3), ap((size_t)n_rob * (N + 1) * 3, 0.0), traj((size_t)(N + 1) * 9), ctrl((size_t)N * 3);
+    std::vector<int32_t> prow(P, 0), sig(N, -1);
+    std::vector<uint8_t> av(n_rob, 0), used(P, 0);
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < 6; ++j) rf[(size_t)i * 6 + j] = a->traj_ref_curr_[i][j];
+    const int np = std::min<int>(P, (int)a->poly_const_vec_.size());
+    for (int p = 0; p < np; ++p) {
+      const LinearConstraint3D& lc = a->poly_const_vec_[p];
+      prow[p] = (int32_t)lc.A_.rows();
+      for (int r = 0; r < lc.A_.rows(); ++r) {
+        for (int c = 0; c < 3; ++c) pA[((size_t)p * rmax + r) * 3 + c] = lc.A_(r, c);
+        pb[(size_t)p * rmax + r] = lc.b_(r);
+      }
+    }
+    for (int k = 0; k <= N; ++k)
+      for (int c = 0; c < 3; ++c) prev[(size_t)k * 3 + c] = a->traj_curr_.empty() ? a->state_ini_[c] : a->traj_curr_[k][c];  // :1103-1110
+    for (int j = 0; j < n_rob; ++j) {
+      const auto& st = a->traj_other_agents_[j].states;
+      av[j] = !st.empty();
+      for (int k = 0; k <= N && k < (int)st.size(); ++k)
+        for (int c = 0; c < 3; ++c) ap[((size_t)j * (N + 1) + k) * 3 + c] = st[k].position[c];
+    }
+    const int32_t gid = a->id_;
+    LoopResult res{};
+    int rc;
+    if (kind == 0)
+      rc = reinterpret_cast<hdsm_solve_fn>(fn)(ctx, 1, &gid, nullptr, nullptr, x0.data(), rf.data(), pA.data(), pb.data(), prow.data(), prev.data(),
+                                               ap.data(), av.data(), n_rob, nullptr, traj.data(), ctrl.data(), used.data(), sig.data(), &res);
+    else
+      rc = reinterpret_cast<orc_solve_fn>(fn)(ctx, 1, &gid, nullptr, nullptr, x0.data(), rf.data(), pA.data(), pb.data(), prow.data(), rmax,
+                                              prev.data(), ap.data(), av.data(), n_rob, nullptr, traj.data(), ctrl.data(), used.data(), sig.data(),
+                                              &res, 1);
+    *solver_status = rc != 0 ? -2 : res.status;
+    const bool usable = rc == 0 && (res.status == 0 || (res.status == 4 && std::isfinite(res.obj)));
+    if (!usable) throw GRBException("no solution from the external solver", 10005);  // what reading X without an incumbent raises
+    for (int i = 0; i <= N; ++i)
+      for (int j = 0; j < 9; ++j) m.vars[a->x_grb_[i][j].index].x = traj[(size_t)i * 9 + j];
+    for (int i = 0; i < N; ++i) {
+      for (int j = 0; j < 3; ++j) m.vars[a->u_grb_[i][j].index].x = ctrl[(size_t)i * 3 + j];
+      for (int j = 0; j < P; ++j) m.vars[a->b_grb_[i][j].index].x = sig[i] == j ? 1.0 : 0.0;
+    }
+  };
+  try {
+    a->GenerateTimeAwareSafeCorridor();
+    a->SolveOptimizationProblem();
+  } catch (...) {
+    GRBModel::solver_hook() = nullptr;
+    std::cout.rdbuf(keep_out), std::cerr.rdbuf(keep_err);
+    return -2;
+  }
+  GRBModel::solver_hook() = nullptr;
+  std::cout.rdbuf(keep_out), std::cerr.rdbuf(keep_err);
+  *failed = a->optimization_failed_ ? 1 : 0;
+  *have_traj = a->traj_curr_.empty() ? 0 : 1;
+  if (!a->traj_curr_.empty()) {
+    for (int i = 0; i <= N; ++i)
+      for (int j = 0; j < 9; ++j) traj_out[(size_t)i * 9 + j] = a->traj_curr_[i][j];
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < 3; ++j) ctrl_out[(size_t)i * 3 + j] = a->control_curr_[i][j];
+  }
+  for (int j = 0; j < P; ++j) used_out[j] = j < (int)a->poly_used_idx_.size() && a->poly_used_idx_[j] ? 1 : 0;
+  return 0;
+}
+
 // The reference's own Agent::GenerateReferenceTrajectory (agent_class.cpp:1449-1553, with SamplePath, KeepOnlyFreeReference,
 // ComputePathVelocity, GetVelocityLimit) on one agent.
 //   grid / dim / origin / voxel : voxel_grid_;  path [n_path][3] : path_curr_;  prev_ref [N+1][3] (have_prev) : positions of

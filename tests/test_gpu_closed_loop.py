@@ -76,10 +76,13 @@ def test_failure_fallback_on_the_device():
     t["ctrl_curr"] = torch.from_numpy(prev_ctrl).to(dev)
     t["have_plan"] = torch.from_numpy(have.copy()).to(dev)
     x0_before = b.x0.copy()
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream(device=dev)   # a real stream: 0 would select the handle's own one
+    torch.cuda.synchronize()                 # uploads above ran on the default stream
+    st = stream.cuda_stream
     pl.solve_batch_device(t, db.n_rob, st)
     prev_pos = t.pop("prev_self_pos")
-    t["prev_self_pos"] = torch.zeros_like(prev_pos)
+    with torch.cuda.stream(stream):
+        t["prev_self_pos"] = torch.zeros_like(prev_pos)
     pl.advance_device(t, st)
     torch.cuda.synchronize()
     res = db.results()
@@ -122,7 +125,7 @@ def test_plane_coefficients_match_the_reference_chain():
         d[4000:4500] = rng.permutation(np.eye(3))[0]                        # axis parallel
         po = pc + d * dist[:, None]
         got = pl.planes(pc, po)
-        want = np.array([co.plane(params, pc[i], po[i]) for i in range(len(pc))])
+        want = np.array([np.r_[co.plane(params, pc[i], po[i])] for i in range(len(pc))])
         scale = np.maximum(1.0, np.abs(want).max(axis=1, keepdims=True))
         assert np.isfinite(got).all()
         assert (np.abs(got - want) / scale).max() <= 1e-13, (np.abs(got - want) / scale).max()
