@@ -51,6 +51,7 @@ from multi_agent_pkgs_b200 import scenarios as sc  # noqa: E402
 SNAP_STEPS = (1, 6, 12, 18)
 DISTINCT_SWARMS = 24
 MAX_NODES = 64
+WIDTH = 4          # nodes per round of the assignment search in the closed-loop workloads (hdsm_params.search_width)
 METRIC = "agent-QP solves/sec (horizon N=10)"
 N_AGENTS = 4096
 
@@ -537,7 +538,7 @@ def config_dict(args, world):
                         f"closed loop, sharded {args.agents // world} agents per GPU over {world} GPU(s), NCCL all-gather of plan "
                         f"positions consumed as the next step's neighbour table",
             "n_hor": 10, "poly_hor": 4, "n_agents": args.agents, "agents_per_gpu": args.agents // world,
-            "neighbour_candidates_per_agent": args.agents, "max_nodes": MAX_NODES, "seed": args.seed,
+            "neighbour_candidates_per_agent": args.agents, "max_nodes": MAX_NODES, "search_width": WIDTH, "seed": args.seed,
             "l2": "flushed between timed steps (512 MiB write)",
             "inputs": "ref / corridor cells of every step from the host producers of an untimed pre-roll of the same closed "
                       "loop, resident in HBM; x0, previous plans and the neighbour table advance on the device",
@@ -566,7 +567,7 @@ def run_reference(args, rank, world):
     for s in range(args.warmup + args.steps):
         b = sw.make_batch_pooled(pool)
         t0 = time.perf_counter()
-        out = co.solve_batch(b, max_nodes=MAX_NODES)
+        out = co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH)
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             times.append(dt)
@@ -680,8 +681,8 @@ def config4_measure(args, local_rank, flush, torch):
     from oracle import c_oracle as co
     sw = sc.config4_circle256()
     W, T = 3, 3 + args.steps
-    loop = ClosedLoop(sw, 1, 0, f"cuda:{local_rank}", MAX_NODES, None)
-    loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES)
+    loop = ClosedLoop(sw, 1, 0, f"cuda:{local_rank}", MAX_NODES, None, width=WIDTH)
+    loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH)
     loop.keep_steps, loop.keep_agents = set(range(W, T)), sw.n
     par = loop.preroll(T, parity_sample=sw.n)
     ms = timed_replay(loop, W, T, flush, None, torch)
@@ -689,7 +690,7 @@ def config4_measure(args, local_rank, flush, torch):
     t_cpu = 0.0
     for s in range(W, T):
         t0 = time.perf_counter()
-        co.solve_batch(loop.host_batches[s], max_nodes=MAX_NODES)
+        co.solve_batch(loop.host_batches[s], max_nodes=MAX_NODES, width=WIDTH)
         t_cpu += time.perf_counter() - t0
     q = quality_of(loop.stats, W)
     loop.close()
@@ -835,9 +836,9 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     # ---- headline: config 5, strong scaling, closed loop
-    loop = ClosedLoop(sw, world, rank, dev, MAX_NODES, pool, record_host=True)
+    loop = ClosedLoop(sw, world, rank, dev, MAX_NODES, pool, record_host=True, width=WIDTH)
     if rank == 0:
-        loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES)
+        loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH)
         loop.keep_steps, loop.keep_agents = {W, W + (T - W) // 2, T - 1}, min(loop.n, 2048)
     par = loop.preroll(T, parity_sample=512 if rank == 0 else 0, log=log)
     pool.close()
@@ -863,7 +864,7 @@ def run_ours(args, rank, world, local_rank):
     weak = None
     if sw_weak is not None:
         Ww, Tw = 3, 3 + args.weak_steps
-        lw = ClosedLoop(sw_weak, world, rank, dev, MAX_NODES, pool_weak)
+        lw = ClosedLoop(sw_weak, world, rank, dev, MAX_NODES, pool_weak, width=WIDTH)
         lw.preroll(Tw, log=log)
         pool_weak.close()
         msw = timed_replay(lw, Ww, Tw, flush, dist, torch)
@@ -898,7 +899,7 @@ def run_ours(args, rank, world, local_rank):
         while cpu_t < args.cpu_seconds and reps < 50:
             for hb in loop.host_batches.values():
                 t1 = time.perf_counter()
-                co.solve_batch(hb, max_nodes=MAX_NODES)
+                co.solve_batch(hb, max_nodes=MAX_NODES, width=WIDTH)
                 cpu_t += time.perf_counter() - t1
                 cpu_n += hb.n
             reps += 1

@@ -26,7 +26,7 @@ EXPORTS = ["hdsm_version", "hdsm_create", "hdsm_destroy", "hdsm_last_error", "hd
 
 class HdsmParams(C.Structure):
     _fields_ = [("n_hor", C.c_int32), ("poly_hor", C.c_int32), ("max_rows_per_poly", C.c_int32), ("rk4", C.c_int32),
-                ("max_iter", C.c_int32), ("max_nodes", C.c_int32), ("prune", C.c_int32), ("reserved", C.c_int32),
+                ("max_iter", C.c_int32), ("max_nodes", C.c_int32), ("prune", C.c_int32), ("search_width", C.c_int32),
                 ("dt", C.c_double), ("drag", C.c_double * 3), ("r_u", C.c_double), ("r_x", C.c_double * 6),
                 ("r_n", C.c_double * 6), ("max_vel", C.c_double), ("min_acc_xy", C.c_double),
                 ("max_acc_xy", C.c_double), ("min_acc_z", C.c_double), ("max_acc_z", C.c_double),
@@ -96,10 +96,10 @@ def load(build: bool = True) -> C.CDLL:
     return L
 
 
-def make_params(d, rmax=18, max_iter=60, max_nodes=64, prune=True, tol=1e-8) -> HdsmParams:
+def make_params(d, rmax=18, max_iter=60, max_nodes=64, prune=True, tol=1e-8, width=1) -> HdsmParams:
     p = HdsmParams()
     p.n_hor, p.poly_hor, p.max_rows_per_poly, p.rk4 = int(d["n_hor"]), int(d["poly_hor"]), int(rmax), int(bool(d["rk4"]))
-    p.max_iter, p.max_nodes, p.prune = int(max_iter), int(max_nodes), int(bool(prune))
+    p.max_iter, p.max_nodes, p.prune, p.search_width = int(max_iter), int(max_nodes), int(bool(prune)), int(width)
     p.dt = float(d["dt"])
     p.drag[:] = [float(x) for x in d["drag"]]
     p.r_u = float(d["r_u"])

@@ -88,6 +88,8 @@ struct hdsm_handle {
   bool smem_configured = false;
   long long* d_prof = nullptr;  // HDSM_PROFILE=1: per-agent phase cycle counters (host path prints a summary)
   int warps = 4;  // warps per agent (HDSM_WARPS=1 selects the single-warp kernel)
+  int block_slots = 592;  // resident solver blocks of the device (SMs x HDSM_MINBLOCKS)
+  int force_csize = 0;    // HDSM_CLUSTER: blocks per agent, overriding the batch-size rule (experiments)
   std::string err;
   void* comm = nullptr;
   int n_ranks = 1;
@@ -115,9 +117,27 @@ cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     h->smem_configured = true;
   }
+  // Thread blocks per agent: the nodes of a search round are dealt to a cluster of up to `width` blocks when the
+  // batch is small enough that the extra blocks find room (a hard agent then finishes up to `width` times sooner
+  // and the launch is as long as its hardest agent); large batches keep one block per agent.  Results do not
+  // depend on this choice (see Solver::run).
+  int csize = 1;
+  if (W == 4) {
+    csize = a.width;
+    while (csize > 1 && (long)a.n_local * csize > 4L * h->block_slots) csize >>= 1;
+    if (h->force_csize > 0) csize = std::min(h->force_csize, a.width);
+  }
+  a.csize = csize;
   for (int t = 0; t < h->n_tiers; ++t) {  // t > 0: only agents whose rows did not fit the previous pool
     a.row_cap = h->row_cap[t], a.only_status = t == 0 ? -1 : HDSM_ROW_OVERFLOW;
-    hdsm_solve_kernel<N, W><<<a.n_local, 32 * W, h->smem_bytes[t], s>>>(h->dev_tables, a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)a.n_local * csize), cfg.blockDim = dim3(32 * W), cfg.dynamicSmemBytes = h->smem_bytes[t], cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = csize > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, hdsm_solve_kernel<N, W>, (const Tables*)h->dev_tables, a);
+    if (e != cudaSuccess) return e;
     h->launches += 1;
   }
   return cudaGetLastError();
@@ -203,6 +223,13 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   h->device = device, h->max_agents = max_agents, h->max_neighbours = max_neighbours;
   if (const char* e = std::getenv("HDSM_WARPS")) h->warps = std::atoi(e) == 1 ? 1 : 4;
   if (const char* e = std::getenv("HDSM_NO_ORDER")) h->use_order = std::atoi(e) == 0;
+  if (const char* e = std::getenv("HDSM_CLUSTER")) h->force_csize = std::max(0, std::min(std::atoi(e), kMaxWidth));
+  if (h->prm.search_width != 0 && h->prm.search_width != 1 && h->prm.search_width != 2 && h->prm.search_width != 4) {
+    std::fprintf(stderr, "hdsm_create: search_width must be 0, 1, 2 or 4\n");
+    delete h;
+    return HDSM_ERR_INVALID;
+  }
+  if (h->prm.search_width == 0) h->prm.search_width = 1;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || device < 0 || device >= ndev) {  // no CPU fallback: fail loudly
@@ -215,6 +242,10 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
     return HDSM_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->block_slots = sms * HDSM_MINBLOCKS;
+  }
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
   if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream2");
   if ((e = cudaEventCreateWithFlags(&h->ev_shared, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
@@ -305,6 +336,7 @@ static int solve_device(hdsm_handle* h, int slot, size_t order_offset, int n_loc
   a.all_valid = all_valid, a.traj = traj, a.ctrl = ctrl, a.pos_out = pos_out, a.poly_used = poly_used;
   a.assign_out = assign_out, a.res = res, a.prof = h->d_prof;
   a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
+  a.width = h->prm.search_width, a.csize = 1;
   if (const char* e = std::getenv("HDSM_DEBUG")) a.dbg = std::atoi(e);
   const bool ordered = h->use_order && n_local >= 1024;  // below ~2 waves of blocks the order cannot matter
   a.order = ordered && h->order_n[slot] == n_local && h->order_off[slot] == order_offset ? h->d_order + order_offset : nullptr;

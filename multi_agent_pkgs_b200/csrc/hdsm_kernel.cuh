@@ -27,6 +27,7 @@ constexpr double kStepFrac = 0.97;
 constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still inside the 1e-6 KKT target
 constexpr int kStackCap = 96;          // >= 1 + N * (P - 1) open nodes (a branching can push up to P sets)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxWidth = 4;           // widest search round
 constexpr int kCutoff = 6;             // internal QP status: the dual bound reached the incumbent, solve abandoned
 #ifndef HDSM_MINBLOCKS
 #define HDSM_MINBLOCKS 4  // resident 4-warp blocks per SM the register allocation aims for (128 registers; 5 spills badly)
@@ -46,6 +47,8 @@ struct KernelArgs {
   int only_status; // >= 0: solve only agents whose res[].status equals this (second, large-memory pass)
   long long* prof; // optional [n_local][16] cycle counters per phase (HDSM_PROFILE=1), else null
   int max_iter, max_nodes, prune;
+  int width;  // nodes per search round (1 = depth-first search); the result depends on it
+  int csize;  // thread blocks per agent = cluster size (1, 2 or 4): execution only, never changes a result
   int dbg;  // debugging switches (HDSM_DEBUG): 1 = no dominance filter, 2 = no parent-bound pruning
   double tol;
 };
@@ -101,8 +104,10 @@ HDSM_HD constexpr FixedLayout make_layout(int N) {
 }
 // run-time part after FixedLayout::var: poly [P*rmax*4], bmin [P*rmax*P], rown [rows*4], rs [rows], rl [rows],
 // nid [P*rmax bytes]
+// ... then the outcome slots of the search rounds [2][kMaxWidth][6 + (N+1)/2 + 3(N-2)] and the round's node masks
 HDSM_HD inline int smem_doubles(int N, int P, int rmax, int row_cap) {
-  return make_layout(N).var + P * rmax * 4 + P * rmax * P + row_cap * 6 + (P * rmax + 7) / 8;
+  return make_layout(N).var + P * rmax * 4 + P * rmax * P + row_cap * 6 + (P * rmax + 7) / 8 +
+         2 * kMaxWidth * (6 + (N + 1) / 2 + 3 * (N - 2)) + kMaxWidth * 2;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -1241,13 +1246,143 @@ struct Solver {
   }
 
   // ---------------------------------------------------------------- K3 + epilogue
-  // Warp 0 owns the search state (stack, incumbent, counters); the other warps only join solve_qp.
-  // ctl[0]: 1 = a node is ready to be solved, 0 = finished.
-  __device__ void run(int agent) {
+  // The search runs in ROUNDS of up to A.width open nodes (width 1: plain depth-first search).  The nodes of a
+  // round are solved independently, all against the incumbent the round started with, and merged in a fixed
+  // order - incumbents in pop order, then children pushed so that the first node's children end up on top of
+  // the stack - so the result depends on the width only, never on who solved what or when.  That leaves the
+  // execution free: a round's nodes are dealt to the `csize` thread blocks of the agent's cluster (node j to
+  // block j mod csize); every block keeps an identical copy of the stack and the incumbent, solves its nodes,
+  // publishes each outcome (status, objective, branching step and children, or the integral solution) in its
+  // own shared memory, and after one cluster barrier reads the others' through distributed shared memory.
+  // csize = 1 runs the same rounds sequentially in one block.  Warp 0 owns the search state; the other warps
+  // only join solve_qp.  ctl[0]: 0 = finished, 1 = a node is ready to be solved, 2 = nothing for this block.
+  static constexpr int kMsgDoubles = 6 + (N + 1) / 2 + NW;  // header (2), obj, kkt, children (1), pad, fullsig, w
+  struct Msg {  // view of one outcome slot
+    double* d;
+    __device__ int& status() const { return reinterpret_cast<int*>(d)[0]; }
+    __device__ int& iters() const { return reinterpret_cast<int*>(d)[1]; }
+    __device__ int& bk() const { return reinterpret_cast<int*>(d)[2]; }      // branching step, -1: integral
+    __device__ int& nchild() const { return reinterpret_cast<int*>(d)[3]; }
+    __device__ double& obj() const { return d[2]; }
+    __device__ double& kkt() const { return d[3]; }
+    __device__ unsigned char* child() const { return reinterpret_cast<unsigned char*>(d + 4); }  // masks of step bk, push order
+    __device__ int& rows() const { return reinterpret_cast<int*>(d + 5)[0]; }
+    __device__ int* sig() const { return reinterpret_cast<int*>(d + 6); }
+    __device__ double* w() const { return d + 6 + (N + 1) / 2; }
+  };
+  double* xch;  // [2 parities][kMaxWidth] slots of kMsgDoubles, behind the row pool
+
+  __device__ __forceinline__ static void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  // generic pointer to `mine` in the shared memory of block `rank` of this cluster
+  __device__ __forceinline__ static double* peer(double* mine, unsigned rank) {
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<unsigned long long>(mine)), "r"(rank));
+    return reinterpret_cast<double*>(out);
+  }
+
+  // warp 0, after a node's relaxation was solved: coverage of every segment (p_k, p_k+1) by one member of its
+  // candidate set; integral -> the solution goes into the slot, otherwise the step to branch on and the children
+  __device__ void publish(const QpOut& q, Msg m, int nrows) {
+    if (lane == 0) m.status() = q.status, m.iters() = q.iters, m.obj() = q.obj, m.kkt() = q.kkt, m.bk() = -1, m.nchild() = 0, m.rows() = nrows;
+    __syncwarp();
+    if (q.status != HDSM_OPTIMAL) return;
+    for (int idx = lane; idx < N * Peff; idx += 32) {
+      const int k = idx / Peff, j = idx - k * Peff;
+      double v = INFINITY;
+      if (cur[k] >> j & 1) {
+        v = -INFINITY;
+        const double ax_ = p[3 * k], ay = p[3 * k + 1], az = p[3 * k + 2];
+        const double bx = p[3 * k + 3], by = p[3 * k + 4], bz = p[3 * k + 5];
+        for (int r = 0; r < prow_n[j]; ++r) {
+          const double* c = poly + 4 * (j * A.rmax + r);
+          v = fmax(v, fmax(c[0] * ax_ + c[1] * ay + c[2] * az, c[0] * bx + c[1] * by + c[2] * bz) - c[3]);
+        }
+      }
+      viol[k * kMaxP + j] = v;
+    }
+    __syncwarp();
+    // branch on the uncovered step that is farthest from all of its candidates
+    int bk = -1;
+    double bkv = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+      int fk = -1;
+      double vmin = INFINITY;
+#pragma unroll 1
+      for (int j = 0; j < Peff; ++j) {
+        const double v = viol[k * kMaxP + j];
+        vmin = fmin(vmin, v);
+        if (fk < 0 && v <= kContainTol) fk = j;
+      }
+      if (lane == 0) m.sig()[k] = fk;
+      if (fk < 0 && (bk < 0 || vmin > bkv)) bk = k, bkv = vmin;
+    }
+    if (bk < 0) {  // node optimum is feasible for the mixed-integer problem
+      if (lane < NW) m.w()[lane] = w[lane];
+      __syncwarp();
+      return;
+    }
+    // split the candidate set of step bk in two halves ordered by (violation, index), least violated explored
+    // first.  A half whose hull still contains the segment of the node optimum would be solved to the very same
+    // point and then split again on the same step: that solve is skipped, the half is split right away.
+    int order[kMaxP], no = 0;
+    double vv[kMaxP];
+    for (int j = 0; j < Peff; ++j)
+      if (cur[bk] >> j & 1) order[no] = j, vv[no++] = viol[bk * kMaxP + j];
+    for (int x = 1; x < no; ++x)
+      for (int y = x; y > 0 && vv[y] < vv[y - 1]; --y) {
+        const double tv = vv[y];
+        vv[y] = vv[y - 1], vv[y - 1] = tv;
+        const int to = order[y];
+        order[y] = order[y - 1], order[y - 1] = to;
+      }
+    int nchild = 0;
+    if (no > 1) {
+      int wx0[2 * kMaxP], wx1[2 * kMaxP], nw = 0;
+      const int h = (no + 1) / 2;
+      wx0[nw] = 0, wx1[nw++] = h;  // last in, first out: the upper half is pushed on the search stack first
+      wx0[nw] = h, wx1[nw++] = no;
+      const double sax = p[3 * bk], say = p[3 * bk + 1], saz = p[3 * bk + 2];
+      const double sbx = p[3 * bk + 3], sby = p[3 * bk + 4], sbz = p[3 * bk + 5];
+#pragma unroll 1
+      while (nw > 0) {
+        const int x0 = wx0[--nw], x1 = wx1[nw];
+        unsigned mm = 0;
+        for (int x = x0; x < x1; ++x) mm |= 1u << order[x];
+        bool contains = false;
+        if (x1 - x0 > 1) {
+          bool out = false;
+          for (int i = lane; i < A.P * A.rmax; i += 32) {
+            double n[3], b;
+            if (hull_row(mm, i, n, b))
+              out |= fmax(n[0] * sax + n[1] * say + n[2] * saz, n[0] * sbx + n[1] * sby + n[2] * sbz) - b > kContainTol;
+          }
+          contains = !__any_sync(kFull, out);
+        }
+        if (contains) {
+          const int hh = (x1 - x0 + 1) / 2;
+          wx0[nw] = x0, wx1[nw++] = x0 + hh;
+          wx0[nw] = x0 + hh, wx1[nw++] = x1;
+          continue;
+        }
+        if (lane == 0) m.child()[nchild] = (unsigned char)mm;
+        ++nchild;
+      }
+    }
+    if (lane == 0) m.bk() = bk, m.nchild() = nchild;
+    __syncwarp();
+  }
+
+  __device__ void run(int agent, int crank, int csize) {
     hdsm_result R{HDSM_INFEASIBLE, 0, 0, 0, INFINITY, INFINITY};
-    int st = -1, top = 0, nodes = 0, iters = 0, maxrows = 0, fail = 0;
+    int st = -1, top = 0, nodes = 0, iters = 0, maxrows = 0, fail = 0, parity = 0;
     double best = INFINITY, bestkkt = INFINITY;
     bool exhausted = true, overflow = false;
+    const int width = min(max(A.width, 1), kMaxWidth);
+    xch = rl + A.row_cap + (A.P * A.rmax + 7) / 8;
+    unsigned char* pop = reinterpret_cast<unsigned char*>(xch + 2 * kMaxWidth * kMsgDoubles);  // [kMaxWidth][16] masks of the round
     if (wid == 0) tick_start();
     load_and_index(agent);
     if (wid == 0) {
@@ -1272,146 +1407,108 @@ struct Solver {
       }
       tick(0);
     }
+    int cnt = 0;       // nodes of the current round (warp 0)
     for (;;) {
+      // ---- pop the round (identical in every block of the cluster)
       if (wid == 0) {
-        int cmd = 0;
+        cnt = 0;
         if (st < 0 && !overflow) {
-          if (top > 0 && nodes >= A.max_nodes) {
-            exhausted = false;
-          }
-          // a node whose parent's optimum already reaches the incumbent cannot improve it: dropped unsolved
-          while (!(A.dbg & 2) && exhausted && top > 0 && sbnd[top - 1] >= best - kPruneRel * fmax(1.0, fabs(best))) --top;
-          if (exhausted && top > 0) {
-            --top;
-            if (lane < 16) cur[lane] = stack[top * 16 + lane];
-            __syncwarp();
-            tick(10);
-            const int nstat = build_static_rows();
-            tick(1);
-            if (nstat < 0) {  // the row pool is too small for this agent: the large-memory pass redoes it
-              overflow = true;
-            } else {
-              maxrows = max(maxrows, nstat + n_nbr_rows);
-              cmd = 1;
+          while (exhausted && cnt == 0 && top > 0) {
+            while (cnt < width && top > 0) {
+              if (nodes + cnt >= A.max_nodes) {
+                if (cnt == 0) exhausted = false;
+                break;
+              }
+              --top;
+              // a node whose parent's optimum already reaches the incumbent cannot improve it: dropped unsolved
+              if (!(A.dbg & 2) && sbnd[top] >= best - kPruneRel * fmax(1.0, fabs(best))) continue;
+              if (lane < 16) pop[cnt * 16 + lane] = stack[top * 16 + lane];
+              ++cnt;
             }
           }
+          __syncwarp();
         }
         if (lane == 0) {
-          ctl[0] = cmd;
+          ctl[0] = cnt > 0 ? 1 : 0;
+          ctl[2] = cnt;
           s0[10] = best < INFINITY ? best - kPruneRel * fmax(1.0, fabs(best)) : INFINITY;  // cutoff of the dual bound
         }
       }
       bsync();
       if (ctl[0] == 0) break;
-      tick_start();
-      const QpOut q = solve_qp();  // all warps; the result is uniform over the block
+      const int rcnt = ctl[2];
+      // ---- solve this block's nodes of the round, one after the other
+#pragma unroll 1
+      for (int j = crank; j < rcnt; j += csize) {
+        Msg m{xch + (parity * kMaxWidth + j) * kMsgDoubles};
+        if (wid == 0) {
+          if (lane < 16) cur[lane] = pop[j * 16 + lane];
+          __syncwarp();
+          tick(10);
+          const int nstat = build_static_rows();
+          tick(1);
+          if (lane == 0) ctl[0] = nstat < 0 ? 2 : 1;
+          if (nstat < 0 && lane == 0)  // the row pool is too small for this agent: the large-memory pass redoes it
+            m.status() = HDSM_ROW_OVERFLOW, m.iters() = 0, m.bk() = -1, m.nchild() = 0, m.rows() = 0, m.obj() = INFINITY;
+          if (nstat >= 0) maxrows = max(maxrows, nstat + n_nbr_rows);
+        }
+        bsync();
+        if (ctl[0] == 1) {  // uniform over the block
+          tick_start();
+          const QpOut q = solve_qp();  // all warps; the result is uniform over the block
+          if (wid == 0) publish(q, m, maxrows);
+        }
+        bsync();
+      }
+      if (csize > 1) cluster_sync();  // outcomes of all blocks visible (release / acquire at cluster scope)
       if (wid != 0) continue;
-      ++nodes;
-      iters += q.iters;
-      if (q.status != HDSM_OPTIMAL) {
-        if (q.status != HDSM_INFEASIBLE && q.status != kCutoff) fail = q.status;
-        continue;
-      }
-      if (q.obj >= best - kPruneRel * fmax(1.0, fabs(best))) continue;
-      // coverage of every segment (p_k, p_k+1) by one member of its candidate set
-      for (int idx = lane; idx < N * Peff; idx += 32) {
-        const int k = idx / Peff, j = idx - k * Peff;
-        double v = INFINITY;
-        if (cur[k] >> j & 1) {
-          v = -INFINITY;
-          const double ax_ = p[3 * k], ay = p[3 * k + 1], az = p[3 * k + 2];
-          const double bx = p[3 * k + 3], by = p[3 * k + 4], bz = p[3 * k + 5];
-          for (int r = 0; r < prow_n[j]; ++r) {
-            const double* c = poly + 4 * (j * A.rmax + r);
-            v = fmax(v, fmax(c[0] * ax_ + c[1] * ay + c[2] * az, c[0] * bx + c[1] * by + c[2] * bz) - c[3]);
-          }
-        }
-        viol[k * kMaxP + j] = v;
-      }
-      __syncwarp();
-      // branch on the uncovered step that is farthest from all of its candidates
-      int bk = -1;
-      double bkv = 0.0;
+      // ---- merge 1: incumbents, in pop order
 #pragma unroll 1
-      for (int k = 0; k < N; ++k) {
-        int fk = -1;
-        double vmin = INFINITY;
-#pragma unroll 1
-        for (int j = 0; j < Peff; ++j) {
-          const double v = viol[k * kMaxP + j];
-          vmin = fmin(vmin, v);
-          if (fk < 0 && v <= kContainTol) fk = j;
-        }
-        if (lane == 0) fullsig[k] = fk;
-        if (fk < 0 && (bk < 0 || vmin > bkv)) bk = k, bkv = vmin;
-      }
-      __syncwarp();
-      if (bk < 0) {  // node optimum is feasible for the mixed-integer problem: new incumbent
-        best = q.obj, bestkkt = q.kkt;
-        if (lane < NW) bestw[lane] = w[lane];
-        if (lane < N) bestsig[lane] = fullsig[lane];
-        __syncwarp();
-        continue;
-      }
-      // split the candidate set of step bk in two halves ordered by (violation, index)
-      int order[kMaxP], no = 0;
-      double vv[kMaxP];
-      for (int j = 0; j < Peff; ++j)
-        if (cur[bk] >> j & 1) order[no] = j, vv[no++] = viol[bk * kMaxP + j];
-      for (int x = 1; x < no; ++x)
-        for (int y = x; y > 0 && vv[y] < vv[y - 1]; --y) {
-          const double tv = vv[y];
-          vv[y] = vv[y - 1], vv[y - 1] = tv;
-          const int to = order[y];
-          order[y] = order[y - 1], order[y - 1] = to;
-        }
-      if (no <= 1) continue;
-      // Split the candidates of step bk, ordered by violation, in two halves (least violated explored
-      // first).  A half whose hull still contains the segment of the node optimum would be solved to the very
-      // same point and then split again on the same step: that solve is skipped, the half is split right away.
-      int wx0[2 * kMaxP], wx1[2 * kMaxP], nw = 0;
-      const int h = (no + 1) / 2;
-      wx0[nw] = 0, wx1[nw++] = h;  // last in, first out: the upper half is pushed on the search stack first
-      wx0[nw] = h, wx1[nw++] = no;
-      bool full = false;
-      const double sax = p[3 * bk], say = p[3 * bk + 1], saz = p[3 * bk + 2];
-      const double sbx = p[3 * bk + 3], sby = p[3 * bk + 4], sbz = p[3 * bk + 5];
-#pragma unroll 1
-      while (nw > 0) {
-        const int x0 = wx0[--nw], x1 = wx1[nw];
-        unsigned m = 0;
-        for (int x = x0; x < x1; ++x) m |= 1u << order[x];
-        bool contains = false;
-        if (x1 - x0 > 1) {
-          bool out = false;
-          for (int i = lane; i < A.P * A.rmax; i += 32) {
-            double n[3], b;
-            if (hull_row(m, i, n, b))
-              out |= fmax(n[0] * sax + n[1] * say + n[2] * saz, n[0] * sbx + n[1] * sby + n[2] * sbz) - b > kContainTol;
-          }
-          contains = !__any_sync(kFull, out);
-        }
-        if (contains) {
-          const int hh = (x1 - x0 + 1) / 2;
-          wx0[nw] = x0, wx1[nw++] = x0 + hh;
-          wx0[nw] = x0 + hh, wx1[nw++] = x1;
+      for (int j = 0; j < cnt; ++j) {
+        double* slot = xch + (parity * kMaxWidth + j) * kMsgDoubles;
+        Msg m{csize > 1 ? peer(slot, j % csize) : slot};
+        const int ms = m.status();
+        ++nodes;
+        iters += m.iters();
+        maxrows = max(maxrows, m.rows());
+        if (ms == HDSM_ROW_OVERFLOW) overflow = true;
+        if (ms != HDSM_OPTIMAL) {
+          if (ms != HDSM_INFEASIBLE && ms != kCutoff && ms != HDSM_ROW_OVERFLOW) fail = ms;
           continue;
         }
-        if (top + 1 > kStackCap) {
-          full = true;
-          break;
-        }
-        if (lane < 16) stack[top * 16 + lane] = lane == bk ? (unsigned char)m : cur[lane];
-        if (lane == 0) sbnd[top] = q.obj;
-        ++top;
+        const double mo = m.obj();
+        if (m.bk() >= 0 || mo >= best - kPruneRel * fmax(1.0, fabs(best))) continue;
+        best = mo, bestkkt = m.kkt();
+        if (lane < NW) bestw[lane] = m.w()[lane];
+        if (lane < N) bestsig[lane] = m.sig()[lane];
         __syncwarp();
       }
-      if (full) {
-        exhausted = false;
-        top = 0;
+      // ---- merge 2: children, last node first so that the first node's children end up on top of the stack
+#pragma unroll 1
+      for (int j = cnt - 1; j >= 0 && exhausted && !overflow; --j) {
+        double* slot = xch + (parity * kMaxWidth + j) * kMsgDoubles;
+        Msg m{csize > 1 ? peer(slot, j % csize) : slot};
+        if (m.status() != HDSM_OPTIMAL || m.bk() < 0) continue;
+        const double mo = m.obj();
+        if (mo >= best - kPruneRel * fmax(1.0, fabs(best))) continue;
+        const int bk = m.bk(), nc = m.nchild();
+#pragma unroll 1
+        for (int i = 0; i < nc; ++i) {
+          if (top + 1 > kStackCap) {  // stack full: the optimum stays unproven
+            exhausted = false;
+            break;
+          }
+          const unsigned char cm = m.child()[i];
+          if (lane < 16) stack[top * 16 + lane] = lane == bk ? cm : pop[j * 16 + lane];
+          if (lane == 0) sbnd[top] = mo;
+          ++top;
+        }
+        __syncwarp();
       }
+      parity ^= 1;
     }
-    if (wid != 0) return;
+    if (csize > 1) cluster_sync();  // no block leaves while another may still read its outcome slots
+    if (wid != 0 || crank != 0) return;
     if (st < 0) {
       R.nodes = nodes, R.iters = iters, R.rows = maxrows;
       if (overflow) {
@@ -1481,11 +1578,13 @@ struct Solver {
 template <int N, int W>
 __global__ void __launch_bounds__(32 * W, W == 4 ? HDSM_MINBLOCKS : 1) hdsm_solve_kernel(const Tables* __restrict__ tables, const KernelArgs args) {
   extern __shared__ double smem[];
-  if ((int)blockIdx.x >= args.n_local) return;
-  const int agent = args.order ? args.order[blockIdx.x] : (int)blockIdx.x;
+  // args.csize consecutive blocks (one thread-block cluster when csize > 1) work on one agent
+  const int slot = (int)blockIdx.x / args.csize, crank = (int)blockIdx.x - slot * args.csize;
+  if (slot >= args.n_local) return;
+  const int agent = args.order ? args.order[slot] : slot;
   if (args.only_status >= 0 && args.res[agent].status != args.only_status) return;
   Solver<N, W> s(*tables, args, smem);
-  s.run(agent);
+  s.run(agent, crank, args.csize);
 }
 
 // Dispatch order for the next call on the same slots: agents sorted by the interior-point iterations they

@@ -200,6 +200,42 @@ def test_two_live_handles_of_different_size_and_changing_batch_sizes():
     small.close()
 
 
+def test_search_rounds_depend_on_the_width_only():
+    """search_width 1 / 2 / 4 against the C port run with the same width (status exact, objective 1e-6), and for each width
+    the same outputs bit for bit whether a round's nodes run in one block or on a cluster of 2 or 4 blocks."""
+    from oracle import c_oracle as co
+    sw = sc.config5_random(seed=13, n_rob=400, side=60.0)
+    for _ in range(3):
+        b = sw.make_batch()
+        r = co.solve_batch(b, max_nodes=64)
+        sw.advance(r["traj"], r["ctrl"], _ok(r["res"]))
+    b = sw.make_batch()
+    assert co.solve_batch(b, max_nodes=64)["res"]["nodes"].max() >= 8      # the slice does branch
+    for width in (1, 2, 4):
+        ref = co.solve_batch(b, max_nodes=64, width=width)
+        outs = []
+        for csize in (1, 2, 4):
+            if csize > width:
+                continue
+            os.environ["HDSM_CLUSTER"] = str(csize)
+            try:
+                pl = TrajectoryPlanner(sw.params, max_agents=b.n, max_neighbours=b.n, max_nodes=64, width=width)
+                outs.append(pl.solve_batch(b))
+                pl.close()
+            finally:
+                del os.environ["HDSM_CLUSTER"]
+        out = outs[0]
+        assert np.array_equal(out["res"]["status"], ref["res"]["status"]), width
+        ok = ref["res"]["status"] == OPTIMAL
+        gap = np.abs(out["res"]["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1, np.abs(ref["res"]["obj"][ok]))
+        assert gap.max() <= 1e-6, (width, gap.max())
+        assert np.array_equal(out["res"]["nodes"], ref["res"]["nodes"]), width
+        for o in outs[1:]:
+            for k in ("traj", "ctrl", "assign", "poly_used"):
+                assert np.array_equal(o[k], out[k]), (width, k)
+            assert np.array_equal(o["res"]["obj"], out["res"]["obj"]) and np.array_equal(o["res"]["nodes"], out["res"]["nodes"])
+
+
 def test_host_entry_point_rejects_bad_indices():
     sw = sc.config2_circle(n_swarms=1)
     b = sw.make_batch()
