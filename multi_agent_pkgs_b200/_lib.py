@@ -55,11 +55,12 @@ def load(build: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if build:
+    path = os.environ.get("HDSM_LIB") or _build.LIB   # HDSM_LIB: another build of the same ABI (A/B experiments)
+    if build and path == _build.LIB:
         _build.build_lib()
-    if not os.path.exists(_build.LIB):
-        raise RuntimeError(f"{_build.LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    L = C.CDLL(_build.LIB)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(path)
     vp, ip, dp, u8p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8)
     L.hdsm_version.restype = C.c_int
     L.hdsm_create.restype = C.c_int

@@ -90,6 +90,7 @@ struct hdsm_handle {
   int warps = 4;  // warps per agent (HDSM_WARPS=1 selects the single-warp kernel)
   int block_slots = 592;  // resident solver blocks of the device (SMs x HDSM_MINBLOCKS)
   int force_csize = 0;    // HDSM_CLUSTER: blocks per agent, overriding the batch-size rule (experiments)
+  bool single_pass = false;  // HDSM_SINGLE_PASS=1: no cluster pass for the long searches of a large batch (experiments)
   std::string err;
   void* comm = nullptr;
   int n_ranks = 1;
@@ -127,18 +128,33 @@ cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
     while (csize > 1 && (long)a.n_local * csize > 4L * h->block_slots) csize >>= 1;
     if (h->force_csize > 0) csize = std::min(h->force_csize, a.width);
   }
-  a.csize = csize;
-  for (int t = 0; t < h->n_tiers; ++t) {  // t > 0: only agents whose rows did not fit the previous pool
-    a.row_cap = h->row_cap[t], a.only_status = t == 0 ? -1 : HDSM_ROW_OVERFLOW;
+  // When the batch is too large for a cluster per agent, the few agents whose search is long would still set
+  // the length of the launch.  They are picked out instead: the first pass (one block per agent) gives up on an
+  // agent after kFirstPassRounds rounds, and a cluster pass redoes those agents alone with `width` blocks each.
+  // Rounds are deterministic, so the redone search is the same search.
+  constexpr int kFirstPassRounds = 2;
+  const bool two_pass = W == 4 && csize < a.width && !h->single_pass;
+  auto go = [&](int cs, unsigned mask, int budget, int ovf, int tier) -> cudaError_t {
+    KernelArgs k = a;
+    k.csize = cs, k.only_mask = mask, k.round_budget = budget, k.overflow_status = ovf, k.row_cap = h->row_cap[tier];
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)a.n_local * csize), cfg.blockDim = dim3(32 * W), cfg.dynamicSmemBytes = h->smem_bytes[t], cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)k.n_local * cs), cfg.blockDim = dim3(32 * W), cfg.dynamicSmemBytes = h->smem_bytes[tier], cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = csize, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-    cfg.attrs = at, cfg.numAttrs = csize > 1 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, hdsm_solve_kernel<N, W>, (const Tables*)h->dev_tables, a);
-    if (e != cudaSuccess) return e;
+    at[0].val.clusterDim.x = cs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = cs > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, hdsm_solve_kernel<N, W>, (const Tables*)h->dev_tables, k);
     h->launches += 1;
+    return e;
+  };
+  for (int t = 0; t < h->n_tiers; ++t) {  // t > 0: only agents whose rows did not fit the previous pool
+    const bool last = t == h->n_tiers - 1;
+    cudaError_t e = go(csize, t == 0 ? 0u : 1u << HDSM_ROW_OVERFLOW, two_pass ? kFirstPassRounds : 0, HDSM_ROW_OVERFLOW, t);
+    if (e != cudaSuccess) return e;
+    if (two_pass) {
+      e = go(a.width, (1u << kDeferred) | (t > 0 ? 1u << kDeferredOverflow : 0u), 0, last ? HDSM_ROW_OVERFLOW : kDeferredOverflow, t);
+      if (e != cudaSuccess) return e;
+    }
   }
   return cudaGetLastError();
 }
@@ -223,6 +239,7 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   h->device = device, h->max_agents = max_agents, h->max_neighbours = max_neighbours;
   if (const char* e = std::getenv("HDSM_WARPS")) h->warps = std::atoi(e) == 1 ? 1 : 4;
   if (const char* e = std::getenv("HDSM_NO_ORDER")) h->use_order = std::atoi(e) == 0;
+  if (const char* e = std::getenv("HDSM_SINGLE_PASS")) h->single_pass = std::atoi(e) != 0;
   if (const char* e = std::getenv("HDSM_CLUSTER")) h->force_csize = std::max(0, std::min(std::atoi(e), kMaxWidth));
   if (h->prm.search_width != 0 && h->prm.search_width != 1 && h->prm.search_width != 2 && h->prm.search_width != 4) {
     std::fprintf(stderr, "hdsm_create: search_width must be 0, 1, 2 or 4\n");

@@ -11,9 +11,10 @@ for step in range(4):
     b = sw.make_batch()
     base = co.solve_batch(b, max_nodes=64)
     if step >= 2:
-        for width in (1, 2, 4):
+        for width in (1,):
             ref = co.solve_batch(b, max_nodes=64, width=width)
-            for csize in (1, 2, 4):
+            for csize, dbg in ((1, 0), (1, 4)):
+                os.environ["HDSM_DEBUG"] = str(dbg)
                 if csize > width:
                     continue
                 os.environ["HDSM_CLUSTER"] = str(csize)
@@ -24,6 +25,8 @@ for step in range(4):
                 mis = out["res"]["status"] != ref["res"]["status"]
                 ok = (out["res"]["status"] == 0) & (ref["res"]["status"] == 0)
                 gap = np.abs(out["res"]["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1, np.abs(ref["res"]["obj"][ok]))
-                print(f"step {step} width {width} csize {csize}: mismatches {int(mis.sum())} gap {gap.max():.1e} nodes equal {np.array_equal(out['res']['nodes'], ref['res']['nodes'])} "
+                for i in np.nonzero(mis)[0][:6]:
+                    print("   agent", i, "gpu", out["res"][i], "port", ref["res"][i])
+                print(f"step {step} dbg {dbg} width {width} csize {csize}: mismatches {int(mis.sum())} gap {gap.max():.1e} nodes equal {np.array_equal(out['res']['nodes'], ref['res']['nodes'])} "
                       f"iters gpu {out['res']['iters'].mean():.1f} port {ref['res']['iters'].mean():.1f} max {out['res']['iters'].max()} wall {1e3 * dt:.2f} ms", flush=True)
     sw.advance(base["traj"], base["ctrl"], (base["res"]["status"] == 0))

@@ -64,10 +64,11 @@ for i in range(n):
     static[per[i]] += 1
     samp[per[i]] += int(data[i][ix["# Samples"]])
     execd[per[i]] += int(data[i][ix["Instructions Executed"]])
-src = open(os.path.join(os.path.dirname(lib), "csrc", srcname)).read().split("\n")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multi_agent_pkgs_b200", "csrc")
+src = open(os.path.join(CSRC, srcname)).read().split("\n")
 print("--- top source lines by stall samples")
 for k, v in samp.most_common(int(os.environ.get("TOP", "30"))):
     s = src[k[1] - 1].strip()[:100] if k and k[0] == srcname else ""
-    if k and not s and os.path.exists(os.path.join(os.path.dirname(lib), "csrc", k[0])):
-        s = open(os.path.join(os.path.dirname(lib), "csrc", k[0])).read().split("\n")[k[1] - 1].strip()[:100]
+    if k and not s and os.path.exists(os.path.join(CSRC, k[0])):
+        s = open(os.path.join(CSRC, k[0])).read().split("\n")[k[1] - 1].strip()[:100]
     print(f"{str(k):30s} static {static[k]:5d} samples {100 * v / tot:5.1f}% exec {execd[k] / 1e6:8.1f}M | {s}")
