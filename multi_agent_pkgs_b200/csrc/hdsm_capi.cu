@@ -81,6 +81,8 @@ struct hdsm_handle {
   size_t in_cap = 0, out_cap = 0;
   int64_t launches = 0;
   // longest-first dispatch: order[slot] of the previous call per pipeline chunk (valid while n matches)
+  double* d_bounds = nullptr;  // [bounds_cap][4] plan spheres of the neighbour table, rebuilt every call
+  int bounds_cap = 0;
   int32_t* d_order = nullptr;
   int order_n[kMaxChunks] = {};         // n_local the cached order of a slot was computed for (0: none)
   size_t order_off[kMaxChunks] = {};    // ... and its offset into d_order: both must match for the order to be reused
@@ -315,6 +317,7 @@ void hdsm_destroy(hdsm_handle* h) {
   if (h->stream2) cudaStreamDestroy(h->stream2);
   cudaFree(h->dev_tables);
   cudaFree(h->d_order);
+  cudaFree(h->d_bounds);
   cudaFree(h->d_prof);
   cudaFree(h->d_in);
   cudaFree(h->d_out);
@@ -331,7 +334,26 @@ int hdsm_smem_bytes(const hdsm_handle* h) { return h ? h->smem_bytes[0] : 0; }
 // `slot` / `order_offset`: which pipeline chunk of the handle this call is (the public device entry point is
 // slot 0); the dispatch order computed after the previous call of the same slot and size is used, then
 // recomputed from this call's iteration counts.
-static int solve_device(hdsm_handle* h, int slot, size_t order_offset, int n_local, const int32_t* global_id,
+// Plan spheres of the neighbour table for the solver's neighbour scan (hdsm_plan_bounds_kernel), enqueued on `s`;
+// *out stays null for small tables, where the scan is cheap anyway.
+static int build_bounds(hdsm_handle* h, int n_rob, const double* all_pos, const uint8_t* all_valid, cudaStream_t s, const double** out) {
+  *out = nullptr;
+  if (n_rob < 256 || !h->prm.prune || !all_pos || !all_valid) return HDSM_OK;
+  if (n_rob > h->bounds_cap) {
+    CU(cudaDeviceSynchronize());  // rare (first call / larger table): nothing may still read the old buffer
+    cudaFree(h->d_bounds);
+    h->d_bounds = nullptr, h->bounds_cap = 0;
+    CU(cudaMalloc(&h->d_bounds, (size_t)n_rob * 32));
+    h->bounds_cap = n_rob;
+  }
+  hdsm_plan_bounds_kernel<<<(n_rob + 127) / 128, 128, 0, s>>>(n_rob, h->prm.n_hor, all_pos, all_valid, h->d_bounds);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  *out = h->d_bounds;
+  return HDSM_OK;
+}
+
+static int solve_device(hdsm_handle* h, int slot, size_t order_offset, const double* bounds, int n_local, const int32_t* global_id,
                         const int32_t* nbr_begin, const int32_t* nbr_end, const double* x0, const double* ref,
                         const double* poly_A, const double* poly_b, const int32_t* poly_rows, const double* prev_self_pos,
                         const double* all_pos, const uint8_t* all_valid, int n_rob, const int32_t* assign_in, double* traj,
@@ -355,9 +377,10 @@ static int solve_device(hdsm_handle* h, int slot, size_t order_offset, int n_loc
   a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
   a.width = h->prm.search_width, a.csize = 1;
   if (const char* e = std::getenv("HDSM_DEBUG")) a.dbg = std::atoi(e);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  a.bounds = bounds;
   const bool ordered = h->use_order && n_local >= 1024;  // below ~2 waves of blocks the order cannot matter
   a.order = ordered && h->order_n[slot] == n_local && h->order_off[slot] == order_offset ? h->d_order + order_offset : nullptr;
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   CU(dispatch(h, a, s));
   if (ordered) {
     hdsm_order_kernel<<<1, 1024, 0, s>>>(res, n_local, h->d_order + order_offset);
@@ -380,7 +403,13 @@ int hdsm_solve_batch_device(hdsm_handle* h, int n_local, const int32_t* global_i
                             const double* all_pos, const uint8_t* all_valid, int n_rob, const int32_t* assign_in,
                             double* traj, double* ctrl, uint8_t* poly_used, int32_t* assign_out, hdsm_result* res,
                             double* pos_out, void* stream) {
-  return solve_device(h, 0, 0, n_local, global_id, nbr_begin, nbr_end, x0, ref, poly_A, poly_b, poly_rows, prev_self_pos,
+  if (!h) return HDSM_ERR_INVALID;
+  const double* bounds = nullptr;
+  if (n_local > 0 && n_rob > 0) {
+    CU(cudaSetDevice(h->device));
+    if (int rc = build_bounds(h, n_rob, all_pos, all_valid, stream ? static_cast<cudaStream_t>(stream) : h->stream, &bounds)) return rc;
+  }
+  return solve_device(h, 0, 0, bounds, n_local, global_id, nbr_begin, nbr_end, x0, ref, poly_A, poly_b, poly_rows, prev_self_pos,
                       all_pos, all_valid, n_rob, assign_in, traj, ctrl, poly_used, assign_out, res, pos_out, stream);
 }
 
@@ -484,6 +513,9 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
       }
       CU(cudaMemcpyAsync(h->d_in + in[i].off, src, in[i].bytes, cudaMemcpyHostToDevice, h->stream));
     }
+  const double* bounds = nullptr;
+  if (n_rob > 0)
+    if (int rc = build_bounds(h, n_rob, (const double*)(h->d_in + in[10].off), (const uint8_t*)(h->d_in + in[11].off), h->stream, &bounds)) return rc;
   CU(cudaEventRecord(h->ev_shared, h->stream));
   CU(cudaStreamWaitEvent(h->stream2, h->ev_shared, 0));
   auto dp = [&](int i, size_t first) -> const void* { return in[i].bytes ? h->d_in + in[i].off + first * in_stride[i] : nullptr; };
@@ -506,7 +538,7 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
     }
     if (trace) CU(cudaEventRecord(h->ev_begin[c], s));
     int rc = solve_device(
-        h, c, first, (int)cnt, (const int32_t*)dp(0, first), (const int32_t*)dp(1, first), (const int32_t*)dp(2, first),
+        h, c, first, bounds, (int)cnt, (const int32_t*)dp(0, first), (const int32_t*)dp(1, first), (const int32_t*)dp(2, first),
         (const double*)dp(5, first), (const double*)dp(6, first), (const double*)dp(7, first), (const double*)dp(8, first),
         (const int32_t*)dp(3, first), (const double*)dp(9, first), (const double*)dp(10, 0), (const uint8_t*)dp(11, 0), n_rob,
         (const int32_t*)dp(4, first), (double*)(h->d_out + o_traj + first * outs[0].stride),

@@ -40,6 +40,7 @@ struct KernelArgs {
   const int32_t *global_id, *nbr_begin, *nbr_end, *poly_rows, *assign_in;
   const double *x0, *ref, *poly_A, *poly_b, *prev, *all_pos;
   const uint8_t* all_valid;
+  const double* bounds;  // optional [n_rob][4]: centre and radius of every plan's points 1..N (radius < 0: no plan), see hdsm_plan_bounds_kernel
   double *traj, *ctrl, *pos_out;
   uint8_t* poly_used;
   int32_t* assign_out;
@@ -493,6 +494,25 @@ struct Solver {
     }
     for (int i = tid; i < K3; i += NT) dp[i] = prev[i];  // own previous positions (dp is scratch here)
     bsync();
+    // bounding sphere of the own previous plan (points 1..N) and the largest per-step threshold: a candidate whose
+    // plan sphere lies farther than r_own + r_cand + thr_max from it cannot come close at any step, and is skipped
+    // on 32 bytes instead of its 24 N bytes of plan (exact: the per-step test below decides everything that remains)
+    double cs[3], lim0 = 0;
+    if (A.bounds && A.prune) {
+      double lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY}, thrmax2 = 0, rown2 = 0;
+      for (int kk = 0; kk < N; ++kk) {
+        thrmax2 = fmax(thrmax2, thr2k[kk]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) lo3[a] = fmin(lo3[a], dp[3 * kk + 3 + a]), hi3[a] = fmax(hi3[a], dp[3 * kk + 3 + a]);
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) cs[a] = 0.5 * (lo3[a] + hi3[a]);
+      for (int kk = 0; kk < N; ++kk) {
+        const double dx = dp[3 * kk + 3] - cs[0], dy = dp[3 * kk + 4] - cs[1], dz = dp[3 * kk + 5] - cs[2];
+        rown2 = fmax(rown2, dx * dx + dy * dy + dz * dz);
+      }
+      lim0 = (sqrt(rown2) + sqrt(thrmax2)) * (1.0 + 1e-9) + 1e-9;
+    }
     unsigned short* list = reinterpret_cast<unsigned short*>(rs) + wid * A.row_cap;
     const int n = nb1 - nb0, chunk = (n + W - 1) / W;
     const int j_beg = nb0 + wid * chunk, j_end = min(nb1, j_beg + chunk);
@@ -502,6 +522,11 @@ struct Solver {
       for (int j0 = j_beg; j0 < j_end; j0 += 32) {
         const int j = j0 + lane;
         bool near = j < j_end && j != gid && A.all_valid[j] != 0;
+        if (near && A.prune && A.bounds) {
+          const double4 bj = *reinterpret_cast<const double4*>(A.bounds + 4 * (size_t)j);
+          const double dx = bj.x - cs[0], dy = bj.y - cs[1], dz = bj.z - cs[2], lim = lim0 + bj.w;
+          near = bj.w >= 0.0 && dx * dx + dy * dy + dz * dz <= lim * lim;
+        }
         if (near && A.prune) {
           const double* q = A.all_pos + (size_t)j * K3;
           near = false;
@@ -1630,6 +1655,28 @@ __global__ void __launch_bounds__(1024) hdsm_order_kernel(const hdsm_result* __r
   hist[tid] = incl - v + (tid >= 32 ? wsum[(tid >> 5) - 1] : 0);
   __syncthreads();
   for (int i = tid; i < n; i += 1024) order[atomicAdd(&hist[1023 - min(max(res[i].iters, 0), 1023)], 1)] = i;
+}
+
+// Centre and radius of every agent's plan points 1..N (the points the inter-agent planes are built from): one
+// thread per agent, run once per call in front of the solver kernel, whose neighbour scan then rejects far
+// candidates on these 32 bytes.  The radius is rounded up; agents without a plan get radius -1.
+__global__ void hdsm_plan_bounds_kernel(int n_rob, int N, const double* __restrict__ all_pos, const uint8_t* __restrict__ all_valid,
+                                        double* __restrict__ bounds) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rob) return;
+  const double* q = all_pos + (size_t)j * 3 * (N + 1);
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int k = 1; k <= N; ++k)
+    for (int a = 0; a < 3; ++a) lo[a] = fmin(lo[a], q[3 * k + a]), hi[a] = fmax(hi[a], q[3 * k + a]);
+  const double c[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+  double r2 = 0;
+  for (int k = 1; k <= N; ++k) {
+    const double dx = q[3 * k] - c[0], dy = q[3 * k + 1] - c[1], dz = q[3 * k + 2] - c[2];
+    r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+  }
+  const double r = sqrt(r2) * (1.0 + 1e-9) + 1e-9;
+  double* b = bounds + 4 * (size_t)j;
+  b[0] = c[0], b[1] = c[1], b[2] = c[2], b[3] = (all_valid[j] != 0 && r == r) ? r : -1.0;  // NaN plans: never near
 }
 
 // K1 alone: the separating plane of every (own point, neighbour point) pair, out[i] = (n_f, b); NaN rows for

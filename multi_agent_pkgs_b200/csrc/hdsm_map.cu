@@ -48,8 +48,31 @@ struct Args {
   const unsigned long long* pair_vals;  // eight int8 values, |dx| = 0..7
 };
 
+// ---- bulk asynchronous copies (TMA engine, sm_90+): one thread moves a whole grid between HBM and shared memory
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* mbar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_addr(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, unsigned parity) {
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smem_addr(mbar)), "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_addr(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
-  extern __shared__ __align__(16) int8_t smem[];
+  extern __shared__ __align__(128) int8_t smem[];
+  __shared__ __align__(8) unsigned long long mbar;
   const int g = blockIdx.x;
   if (g >= A.n_grids) return;
   const int dx = A.dims[3 * g], dy = A.dims[3 * g + 1], dz = A.dims[3 * g + 2];
@@ -64,14 +87,18 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   const int tid = threadIdx.x;
   for (int m = tid; m < A.n_inf; m += kThreads) st_inf[m] = reinterpret_cast<const int*>(A.inf_off)[m];
   for (int m = tid; m < A.n_pot; m += kThreads) st_pot[m] = reinterpret_cast<const int*>(A.pot_off)[m];
-  // ---- load (16-byte accesses where the grid start allows it)
-  if ((reinterpret_cast<size_t>(src) & 15) == 0) {
-    const int n16 = nvox / 16;
-    for (int i = tid; i < n16; i += kThreads) reinterpret_cast<int4*>(P)[i] = __ldg(reinterpret_cast<const int4*>(src) + i);
-    for (int i = n16 * 16 + tid; i < nvox; i += kThreads) P[i] = src[i];
-  } else {
-    for (int i = tid; i < nvox; i += kThreads) P[i] = src[i];
+  // ---- load: one bulk asynchronous copy of the whole grid (cp.async.bulk, completion on an mbarrier) where the grid
+  // start allows it, issued by one thread while the others fetch the stencils; the last < 16 bytes by plain loads
+  const bool bulk = (reinterpret_cast<size_t>(src) & 15) == 0 && (reinterpret_cast<size_t>(dst) & 15) == 0;
+  const unsigned nbulk = bulk ? (unsigned)(nvox / 16) * 16u : 0u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  if (tid == 0 && nbulk) bulk_load(P, src, nbulk, &mbar);
+  for (int i = (int)nbulk + tid; i < nvox; i += kThreads) P[i] = src[i];
+  if (nbulk) mbar_wait(&mbar, 0);
   __syncthreads();
   // Occupancy / unknown flags are packed one bit per voxel along x (bit x + 8 of a row, so that a window never
   // starts below bit 0): "is there a set bit within +-r of x in row (y', z')" is then one 64-bit funnel shift and a
@@ -241,14 +268,12 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
     }
   }
   __syncthreads();
-  // ---- store
-  if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
-    const int n16 = nvox / 16;
-    for (int i = tid; i < n16; i += kThreads) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(Q)[i];
-    for (int i = n16 * 16 + tid; i < nvox; i += kThreads) dst[i] = Q[i];
-  } else {
-    for (int i = tid; i < nvox; i += kThreads) dst[i] = Q[i];
-  }
+  // ---- store: the finished grid leaves shared memory as one bulk asynchronous copy (the writes above were made
+  // through the generic proxy: fenced for the async proxy before the barrier)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0 && nbulk) bulk_store(dst, Q, nbulk);
+  for (int i = (int)nbulk + tid; i < nvox; i += kThreads) dst[i] = Q[i];
 }
 
 // VoxelGrid::CreateMask (voxel_grid.cpp:192-226) on the host
@@ -348,7 +373,7 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
   const std::vector<int8_t> hi = pack(inf), hp = pack(pot);
   h->n_inf = (int)inf.size(), h->n_pot = (int)pot.size();
   smem += 4 * (size_t)(h->n_inf + h->n_pot);
-  if (smem > 227 * 1024) {
+  if (smem > 227 * 1024 - 256) {
     delete h;
     return HDSM_ERR_INVALID;
   }
@@ -407,7 +432,7 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
   }
   smem += 4 + 4 * (size_t)((h->n_pair + 1) & ~1) + 8 * (size_t)h->n_pair;  // the row table (and its alignment slack)
   if (smem + 1024 < 227 * 1024) {  // whatever shared memory is left holds the bit rows
-    h->bits_bytes = (227 * 1024 - smem) & ~size_t(15);
+    h->bits_bytes = (227 * 1024 - 256 - smem) & ~size_t(15);  // 256 bytes stay free for the kernel's static shared memory (mbarrier)
     smem += h->bits_bytes;
   }
   h->smem = smem;
