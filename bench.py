@@ -533,6 +533,157 @@ def sense_measure(n_agents=4096, steps=10, local_rank=0, cpu_agents=512):
                              "sample": f"the first {m} agents once (steady-state update), C restatement on all host threads"}}
 
 
+def full_step_measure(n_agents=2048, steps=10, local_rank=0):
+    """The complete replanning step of the reference's agent and map-builder nodes on the device, one stream, every stage
+    reading its predecessor's output in place (TrajPlanningIteration agent_class.cpp:157-258 behind EnvironmentVoxelGridCallback
+    map_builder.cpp:80-240): local-map acquisition -> post-processing -> safe corridor -> reference trajectory -> optimisation ->
+    read-back / advance.  Only the agent poses are uploaded per step; paths come from the (out-of-scope) host path planner and
+    stay resident.  n_agents agents in one 120 x 120 m forest environment grid, first planning step of every agent (corridor grown
+    from scratch, no previous plan), every other agent a static neighbour (planes and velocity sweep active)."""
+    import torch
+    from multi_agent_pkgs_b200 import sensing as sn, mapping as mp, corridor as cr, reftraj as rtj
+    from multi_agent_pkgs_b200.planner import TrajectoryPlanner
+    from multi_agent_pkgs_b200._lib import RESULT_DTYPE
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(7)
+    vox, rng3, N, P, R = 0.3, (20.0, 20.0, 6.0), 10, 4, 18
+    params = sc.agile_params(N)
+    world = sc.Forest.density(rng, (0.0, 0.0), (114.0, 114.0), 0.2)
+    env, org = sn.environment_grid(world, vox)
+    n = n_agents
+    pos0 = np.stack([rng.uniform(12, 102, n), rng.uniform(12, 102, n), rng.uniform(1.2, 2.8, n)], 1)
+    for i in range(n):
+        pos0[i, :2] = world.push_free(pos0[i, :2], 0.35)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    goal = pos0 + np.stack([30 * np.cos(ang), 30 * np.sin(ang), np.zeros(n)], 1)
+    pos1 = pos0.copy()
+    path, n_path = np.zeros((n, 16, 3)), np.zeros(n, np.int32)
+    for i in range(n):
+        pts = np.vstack([pos1[i][None], cr.clipped_path(pos1[i], goal[i], world)])[:16]
+        path[i, :len(pts)], n_path[i] = pts, len(pts)
+    dev = torch.device(f"cuda:{local_rank}")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    mb = sn.LocalMapBuilder(vox, n, rng3, device=local_rank)
+    cells = mb.grid_stride
+    gd = sn.grid_dims(vox, rng3)
+    mproc = mp.MapProcessor(vox, n, cells, device=local_rank)
+    gen = cr.SafeCorridorGenerator(P, 42, vox, n, n, cells, N + 1, 16, device=local_rank)
+    rb0 = rtj.RefTrajBatch(N, 0.1, vox, np.zeros((1, gd[2], gd[1], gd[0]), np.int8), None, np.zeros((n, 3), np.int32), np.zeros((n, 3)), path, n_path,
+                           np.zeros((n, N + 1, 3)), np.zeros(n, np.uint8), np.ones(n, np.uint8), np.zeros((n, N + 1, 3)), np.arange(n, dtype=np.int32),
+                           np.zeros(n, np.int32), np.full(n, n, np.int32), np.zeros((n, N + 1, 3)), np.ones(n, np.uint8))
+    rgen = rtj.ReferenceTrajectoryGenerator(rb0, max_agents=n, max_grids=n, device=local_rank)
+    pl = TrajectoryPlanner(params, n, n, local_rank, max_nodes=MAX_NODES, width=WIDTH)
+    f64, T = torch.float64, torch.from_numpy
+    dim_env = (env.shape[2], env.shape[1], env.shape[0])
+    t_env = T(env.reshape(-1)).to(dev)
+    h_pos = T(pos1.copy()).pin_memory()
+    t_pos = torch.empty((n, 3), dtype=f64, device=dev)
+    g_old, g_new, g_map = (torch.empty((n, cells), dtype=torch.int8, device=dev) for _ in range(3))
+    o_old, o_new = torch.empty((n, 3), dtype=f64, device=dev), torch.empty((n, 3), dtype=f64, device=dev)
+    have_old = torch.ones(n, dtype=torch.uint8, device=dev)
+    dims = T(np.tile(np.array(gd, np.int32), (n, 1))).to(dev)
+    plan = torch.empty((n, N + 1, 3), dtype=f64, device=dev)            # every agent's "plan": its position repeated
+    ones = torch.ones(n, dtype=torch.uint8, device=dev)
+    cor = {"grids": g_map, "dims": dims, "origins": o_new, "pos": t_pos, "path": T(path).to(dev), "n_path": T(n_path).to(dev),
+           "poly_A": torch.zeros((n, P, R, 3), dtype=f64, device=dev), "poly_b": torch.zeros((n, P, R), dtype=f64, device=dev),
+           "poly_rows": torch.zeros((n, P), dtype=torch.int32, device=dev), "seeds": torch.zeros((n, P, 3), dtype=f64, device=dev),
+           "flags": torch.zeros(n, dtype=torch.int32, device=dev)}
+    ids = torch.arange(n, dtype=torch.int32, device=dev)
+    zeros_i, full_i = torch.zeros(n, dtype=torch.int32, device=dev), torch.full((n,), n, dtype=torch.int32, device=dev)
+    ref = {"grids": g_map, "dims": dims, "origins": o_new, "path": cor["path"], "n_path": cor["n_path"],
+           "prev_ref": torch.zeros((n, N + 1, 3), dtype=f64, device=dev), "have_prev": torch.zeros(n, dtype=torch.uint8, device=dev),
+           "increment": ones, "traj": plan, "global_id": ids, "nbr_begin": zeros_i, "nbr_end": full_i, "all_pos": plan, "all_valid": ones,
+           "ref": torch.zeros((n, N + 1, 6), dtype=f64, device=dev), "ref_solver": torch.zeros((n, N, 6), dtype=f64, device=dev),
+           "path_vel": torch.zeros(n, dtype=f64, device=dev)}
+    sol = {"global_id": ids, "nbr_begin": zeros_i, "nbr_end": full_i, "x0": torch.zeros((n, 9), dtype=f64, device=dev), "ref": ref["ref_solver"],
+           "poly_A": cor["poly_A"], "poly_b": cor["poly_b"], "poly_rows": cor["poly_rows"], "prev_self_pos": plan, "all_pos": plan, "all_valid": ones,
+           "traj": torch.zeros((n, N + 1, 9), dtype=f64, device=dev), "ctrl": torch.zeros((n, N, 3), dtype=f64, device=dev),
+           "poly_used": torch.zeros((n, P), dtype=torch.uint8, device=dev), "assign_out": torch.zeros((n, N), dtype=torch.int32, device=dev),
+           "res": torch.zeros((n, 32), dtype=torch.uint8, device=dev), "pos_out": torch.zeros((n, N + 1, 3), dtype=f64, device=dev),
+           "traj_curr": torch.zeros((n, N + 1, 9), dtype=f64, device=dev), "ctrl_curr": torch.zeros((n, N, 3), dtype=f64, device=dev),
+           "have_plan": torch.zeros(n, dtype=torch.uint8, device=dev)}
+    h_traj = torch.empty((n, N + 1, 9), dtype=f64).pin_memory()
+    h_res = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+    # the kept grids of the previous map update (taken a little earlier on the way)
+    t_prev = T(pos0 - 0.4 * (goal - pos0) / 30.0).to(dev)
+    mb.update_device(t_env, dim_env, org, t_prev, None, None, None, None, g_old, o_old, sp)
+    names = ("upload", "acquisition", "post-processing", "corridor", "reference", "optimisation", "advance")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+
+    def step(record=False):
+        if record:
+            ev[0].record(stream)
+        t_pos.copy_(h_pos, non_blocking=True)
+        plan.copy_(t_pos[:, None, :].expand(-1, N + 1, -1))
+        sol["x0"].zero_()
+        sol["x0"][:, :3].copy_(t_pos)
+        sol["have_plan"].zero_()
+        if record:
+            ev[1].record(stream)
+        mb.update_device(t_env, dim_env, org, t_pos, None, g_old, o_old, have_old, g_new, o_new, sp)
+        if record:
+            ev[2].record(stream)
+        mproc.process_device(g_new, dims, g_map, sp)
+        if record:
+            ev[3].record(stream)
+        gen.generate_device(cor, n, sp)
+        if record:
+            ev[4].record(stream)
+        rgen.generate_device(ref, n, n, sp)
+        if record:
+            ev[5].record(stream)
+        pl.solve_batch_device(sol, n, sp)
+        if record:
+            ev[6].record(stream)
+        prev = sol.pop("prev_self_pos")
+        pl.advance_device(sol, sp)
+        sol["prev_self_pos"] = prev
+        if record:
+            ev[7].record(stream)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    per = np.zeros(len(names))
+    for _ in range(steps):
+        step(record=True)
+        torch.cuda.synchronize()
+        per += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
+    per /= steps
+    t_wall = 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        h_traj.copy_(sol["traj_curr"], non_blocking=True)
+        h_res.copy_(sol["res"], non_blocking=True)
+        stream.synchronize()
+        t_wall += time.perf_counter() - t0
+    res = np.frombuffer(h_res.numpy().tobytes(), dtype=RESULT_DTYPE)
+    # the optimisation of the first 256 agents against the C port on the rows / references the device stages produced
+    m = min(n, 256)
+    hb = sc.Batch(params, np.arange(m, dtype=np.int32), np.zeros(m, np.int32), np.full(m, n, np.int32), np.c_[pos1[:m], np.zeros((m, 6))],
+                  ref["ref_solver"][:m].cpu().numpy(), cor["poly_A"][:m].cpu().numpy(), cor["poly_b"][:m].cpu().numpy(), cor["poly_rows"][:m].cpu().numpy(),
+                  np.repeat(pos1[:m, None, :], N + 1, 1), np.repeat(pos1[:, None, :], N + 1, 1), np.ones(n, np.uint8), R)
+    want = co.solve_batch(hb, max_nodes=MAX_NODES, width=WIDTH)["res"]
+    both = (res["status"][:m] == 0) & (want["status"] == 0)
+    gap = float((np.abs(res["obj"][:m][both] - want["obj"][both]) / np.maximum(1.0, np.abs(want["obj"][both]))).max()) if both.any() else 0.0
+    launches = mb.launch_count + mproc.launch_count + gen.launch_count + rgen.launch_count + pl.launch_count
+    for h in (mb, mproc, gen, rgen, pl):
+        h.close()
+    total = float(per.sum())
+    return {"workload": f"{n} agents in one {dim_env[0]}x{dim_env[1]}x{dim_env[2]} forest environment grid, 66x66x20 local grids; acquisition (13 992 rays), "
+                        f"post-processing, corridor (4 polytopes grown), reference trajectory, optimisation ({n} neighbour candidates), read-back",
+            "metric": "full replanning steps/sec (agents/s)", "value": n / (total * 1e-3), "unit": "agents/s", "ms_per_step": total,
+            "stage_ms": {k: float(v) for k, v in zip(names, per)},
+            "e2e": {"value": n * steps / t_wall, "unit": "agents/s", "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": int(n * ((N + 1) * 72 + 32)),
+                    "note": "wall clock per step: agent poses up from page-locked memory, all stages, trajectories and statuses down"},
+            "status_counts": [int(v) for v in np.bincount(res["status"], minlength=6)[:6]],
+            "optimisation_vs_c_port": {"agents": int(m), "status_mismatches": int((res["status"][:m] != want["status"]).sum()), "max_rel_obj_gap": gap},
+            "gpu_launches_total": int(launches)}
+
+
 def config_dict(args, world):
     return {"workload": f"config5: {args.agents} agents, random forest {SIDE:.0f} x {SIDE:.0f} m (0.2 columns/m^2), N=10, "
                         f"closed loop, sharded {args.agents // world} agents per GPU over {world} GPU(s), NCCL all-gather of plan "
@@ -931,6 +1082,7 @@ def run_ours(args, rank, world, local_rank):
                 reftraj["roofline"] = roof(reftraj["algorithmic_bytes_per_agent"] * reftraj["value"] / 1e9,
                                            "serial voxel traversal and pow/exp per visited voxel: latency bound")
                 producers["reference_trajectory"] = reftraj
+                producers["full_step"] = full_step_measure(min(args.corridor_agents, 2048), 10, local_rank)
                 sensing = sense_measure(min(args.corridor_agents, 4096), 10, local_rank)
                 sensing["roofline"] = roof(sensing["algorithmic_bytes_per_agent"] * sensing["value"] / 1e9,
                                            "kept grid in, new grid out; the time goes into 14 k serial FP64 voxel traversals per agent")
