@@ -68,7 +68,7 @@ typedef struct hdsm_params {
   int32_t max_iter;          /* interior-point iterations per QP (0 -> 60) */
   int32_t max_nodes;         /* branch-and-bound nodes per agent (0 -> 64); plays the role of TimeLimit */
   int32_t prune;             /* 1 = drop rows that can never be active inside the reachable box (exact) */
-  int32_t search_width;      /* open nodes the assignment search solves per round: 0 / 1 = depth-first search, 2 or 4 =
+  int32_t search_width;      /* open nodes the assignment search solves per round: 0 / 1 = depth-first search, 2, 4 or 8 =
                                 rounds whose nodes are independent and run on a thread-block cluster when the batch is
                                 small (lower latency of hard agents, some speculative work).  Results are a function of
                                 this value only - not of the batch size, the GPU or the number of GPUs. */

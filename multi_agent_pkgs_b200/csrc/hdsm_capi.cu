@@ -113,6 +113,18 @@ int cuda_fail(hdsm_handle* h, cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);    \
   } while (0)
 
+// Thread blocks per agent: the nodes of a search round are dealt to a cluster of up to `width` blocks when the batch
+// is small enough that the extra blocks find room (a hard agent then finishes up to `width` times sooner and the
+// launch is as long as its hardest agent); large batches keep one block per agent.  Results do not depend on this
+// choice (see Solver::run).
+int blocks_per_agent(const hdsm_handle* h, int n_local) {
+  if (h->warps != 4) return 1;
+  int csize = h->prm.search_width;
+  while (csize > 1 && (long)n_local * csize > 4L * h->block_slots) csize >>= 1;
+  if (h->force_csize > 0) csize = std::min(h->force_csize, h->prm.search_width);
+  return csize;
+}
+
 template <int N, int W>
 cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
   if (!h->smem_configured) {  // raised to the device maximum, never to this handle's own need (see hdsm_common.h)
@@ -120,16 +132,7 @@ cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     h->smem_configured = true;
   }
-  // Thread blocks per agent: the nodes of a search round are dealt to a cluster of up to `width` blocks when the
-  // batch is small enough that the extra blocks find room (a hard agent then finishes up to `width` times sooner
-  // and the launch is as long as its hardest agent); large batches keep one block per agent.  Results do not
-  // depend on this choice (see Solver::run).
-  int csize = 1;
-  if (W == 4) {
-    csize = a.width;
-    while (csize > 1 && (long)a.n_local * csize > 4L * h->block_slots) csize >>= 1;
-    if (h->force_csize > 0) csize = std::min(h->force_csize, a.width);
-  }
+  const int csize = W == 4 ? blocks_per_agent(h, a.n_local) : 1;
   // When the batch is too large for a cluster per agent, the few agents whose search is long would still set
   // the length of the launch.  They are picked out instead: the first pass (one block per agent) gives up on an
   // agent after kFirstPassRounds rounds, and a cluster pass redoes those agents alone with `width` blocks each.
@@ -243,8 +246,9 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   if (const char* e = std::getenv("HDSM_NO_ORDER")) h->use_order = std::atoi(e) == 0;
   if (const char* e = std::getenv("HDSM_SINGLE_PASS")) h->single_pass = std::atoi(e) != 0;
   if (const char* e = std::getenv("HDSM_CLUSTER")) h->force_csize = std::max(0, std::min(std::atoi(e), kMaxWidth));
-  if (h->prm.search_width != 0 && h->prm.search_width != 1 && h->prm.search_width != 2 && h->prm.search_width != 4) {
-    std::fprintf(stderr, "hdsm_create: search_width must be 0, 1, 2 or 4\n");
+  if (h->prm.search_width != 0 && h->prm.search_width != 1 && h->prm.search_width != 2 && h->prm.search_width != 4 &&
+      h->prm.search_width != 8) {
+    std::fprintf(stderr, "hdsm_create: search_width must be 0, 1, 2, 4 or 8\n");
     delete h;
     return HDSM_ERR_INVALID;
   }
@@ -379,7 +383,8 @@ static int solve_device(hdsm_handle* h, int slot, size_t order_offset, const dou
   if (const char* e = std::getenv("HDSM_DEBUG")) a.dbg = std::atoi(e);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   a.bounds = bounds;
-  const bool ordered = h->use_order && n_local >= 1024;  // below ~2 waves of blocks the order cannot matter
+  // longest-first dispatch once the blocks of the call do not all fit at once (below that the order cannot matter)
+  const bool ordered = h->use_order && (n_local >= 1024 || (long)n_local * blocks_per_agent(h, n_local) > h->block_slots);
   a.order = ordered && h->order_n[slot] == n_local && h->order_off[slot] == order_offset ? h->d_order + order_offset : nullptr;
   CU(dispatch(h, a, s));
   if (ordered) {

@@ -27,7 +27,7 @@ constexpr double kStepFrac = 0.97;
 constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still inside the 1e-6 KKT target
 constexpr int kStackCap = 96;          // >= 1 + N * (P - 1) open nodes (a branching can push up to P sets)
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kMaxWidth = 4;           // widest search round
+constexpr int kMaxWidth = 8;           // widest search round = largest portable thread-block cluster
 constexpr int kCutoff = 6;             // internal QP status: the dual bound reached the incumbent, solve abandoned
 constexpr int kDeferred = 7;           // internal agent status between the passes of one call: search budget of the first pass used up
 constexpr int kDeferredOverflow = 8;   // ... and its rows did not fit the row pool of the cluster pass of this tier

@@ -201,8 +201,8 @@ def test_two_live_handles_of_different_size_and_changing_batch_sizes():
 
 
 def test_search_rounds_depend_on_the_width_only():
-    """search_width 1 / 2 / 4 against the C port run with the same width (status exact, objective 1e-6), and for each width
-    the same outputs bit for bit whether a round's nodes run in one block or on a cluster of 2 or 4 blocks."""
+    """search_width 1 / 2 / 4 / 8 against the C port run with the same width (status exact, objective 1e-6), and for each width
+    the same outputs bit for bit whether a round's nodes run in one block (then in two passes) or on a cluster of 2, 4 or 8."""
     from oracle import c_oracle as co
     sw = sc.config5_random(seed=13, n_rob=400, side=60.0)
     for _ in range(3):
@@ -211,10 +211,10 @@ def test_search_rounds_depend_on_the_width_only():
         sw.advance(r["traj"], r["ctrl"], _ok(r["res"]))
     b = sw.make_batch()
     assert co.solve_batch(b, max_nodes=64)["res"]["nodes"].max() >= 8      # the slice does branch
-    for width in (1, 2, 4):
+    for width in (1, 2, 4, 8):
         ref = co.solve_batch(b, max_nodes=64, width=width)
         outs = []
-        for csize in (1, 2, 4):
+        for csize in (1, 2, 4, 8):
             if csize > width:
                 continue
             os.environ["HDSM_CLUSTER"] = str(csize)
