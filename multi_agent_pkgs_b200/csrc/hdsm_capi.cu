@@ -92,6 +92,7 @@ struct hdsm_handle {
   int warps = 4;  // warps per agent (HDSM_WARPS=1 selects the single-warp kernel)
   int block_slots = 592;  // resident solver blocks of the device (SMs x HDSM_MINBLOCKS)
   int force_csize = 0;    // HDSM_CLUSTER: blocks per agent, overriding the batch-size rule (experiments)
+  int first_rounds = 2;      // rounds an agent gets in the first pass of a large batch before it is left to the cluster pass (HDSM_FIRST_ROUNDS)
   bool single_pass = false;  // HDSM_SINGLE_PASS=1: no cluster pass for the long searches of a large batch (experiments)
   std::string err;
   void* comm = nullptr;
@@ -137,7 +138,7 @@ cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
   // the length of the launch.  They are picked out instead: the first pass (one block per agent) gives up on an
   // agent after kFirstPassRounds rounds, and a cluster pass redoes those agents alone with `width` blocks each.
   // Rounds are deterministic, so the redone search is the same search.
-  constexpr int kFirstPassRounds = 2;
+  const int kFirstPassRounds = h->first_rounds;
   const bool two_pass = W == 4 && csize < a.width && !h->single_pass;
   auto go = [&](int cs, unsigned mask, int budget, int ovf, int tier) -> cudaError_t {
     KernelArgs k = a;
@@ -244,6 +245,7 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   h->device = device, h->max_agents = max_agents, h->max_neighbours = max_neighbours;
   if (const char* e = std::getenv("HDSM_WARPS")) h->warps = std::atoi(e) == 1 ? 1 : 4;
   if (const char* e = std::getenv("HDSM_NO_ORDER")) h->use_order = std::atoi(e) == 0;
+  if (const char* e = std::getenv("HDSM_FIRST_ROUNDS")) h->first_rounds = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("HDSM_SINGLE_PASS")) h->single_pass = std::atoi(e) != 0;
   if (const char* e = std::getenv("HDSM_CLUSTER")) h->force_csize = std::max(0, std::min(std::atoi(e), kMaxWidth));
   if (h->prm.search_width != 0 && h->prm.search_width != 1 && h->prm.search_width != 2 && h->prm.search_width != 4 &&
@@ -285,16 +287,24 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
     if ((e = cudaMemcpy(h->d_order, ident.data(), ident.size() * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
       return bail(e, "init order");
   }
-  // Shared-memory budget.  Worst case per agent: 2 planes per neighbour and variable position step
-  // plus two polytopes' rows per step.  Exact pruning usually leaves a few dozen rows, so the first
-  // pass runs with a small row pool (more resident blocks per SM); agents that overflow it are
-  // re-solved by a second launch with the worst-case pool (or what one SM can hold).
+  // Shared-memory budget.  Worst case per agent: 2 planes per neighbour and variable position step plus two
+  // polytopes' rows per step.  Exact pruning usually leaves a few dozen to a few hundred rows, so the first pass
+  // runs with the largest row pool that still lets HDSM_MINBLOCKS blocks share an SM (the register allocation allows
+  // no more than that anyway: a smaller pool would buy no occupancy, only a second launch for the crowded agents,
+  // whose searches are the long ones); agents that overflow it are re-solved by a second launch with the worst-case
+  // pool (or what one SM can hold).
   const int nkp = h->host_tables.nkp, rmax = h->prm.max_rows_per_poly, N = h->prm.n_hor, P = h->prm.poly_hor;
   const long worst = 2L * max_neighbours * nkp + 2L * rmax * nkp;
-  int smem_max = 0;
+  int smem_max = 0, smem_sm = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const long fit = std::max(16L, (long)(smem_max - smem_doubles(N, P, rmax, 0) * 8 - 1024) / 48);
-  const long tiers[3] = {h->prm.prune ? 96 : worst, 384, worst};
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+  const long fixed = (long)smem_doubles(N, P, rmax, 0) * 8;
+  const long fit = std::max(16L, (long)(smem_max - fixed - 1024) / 48);
+  // pool of HDSM_MINBLOCKS co-resident blocks inside the 196 KB carve-out (the next one, 228 KB, would leave the
+  // parameter tables only 28 KB of L1: measured 3 % slower on the 10-neighbour workload)
+  const long carve = std::min<long>(smem_sm, 196 * 1024);
+  const long shared4 = std::max(96L, (carve / HDSM_MINBLOCKS - 1024 - fixed) / 48 & ~7L);
+  const long tiers[2] = {h->prm.prune ? shared4 : worst, worst};
   long prev = 0;
   for (long t : tiers) {
     const long cap = std::min(std::min(t, worst), fit);
