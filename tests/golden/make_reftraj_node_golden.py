@@ -33,10 +33,30 @@ def run_reference(rb, i, prev_ref, increment):
                                    rb.path_vel_dec, rb.sens_dist, rb.sens_pot, rb.sens_other_agents)
 
 
+RB_ARRAYS = ("grids", "dims", "origins", "path", "n_path", "prev_ref", "have_prev", "increment", "traj", "global_id", "nbr_begin",
+             "nbr_end", "all_pos", "all_valid")
+
+
+def save_batch(rb):
+    """The scenario batch itself goes into the fixture: it comes out of two closed-loop steps of the solver, whose tie-breaking
+    may change from one version to the next, and the fixture must not move with it."""
+    out = {f"rb_{k}": np.asarray(getattr(rb, k)) for k in RB_ARRAYS}
+    out["rb_scalars"] = np.array([rb.n_hor, rb.dt, rb.voxel])
+    return out
+
+
+def load_batch(z):
+    n_hor, dt, voxel = z["rb_scalars"]
+    a = {k: z[f"rb_{k}"] for k in RB_ARRAYS}
+    return rtj.RefTrajBatch(int(n_hor), float(dt), float(voxel), a["grids"], None, a["dims"], a["origins"], a["path"], a["n_path"], a["prev_ref"],
+                            a["have_prev"], a["increment"], a["traj"], a["global_id"], a["nbr_begin"], a["nbr_end"], a["all_pos"], a["all_valid"])
+
+
 def main():
     rb = scenario_batch()
     agents = [0, 3, 7]
     out = {"agents": np.array(agents)}
+    out.update(save_batch(rb))
     for i in agents:
         first, v0 = run_reference(rb, i, None, 0)
         out[f"a{i}_first"], out[f"a{i}_first_vel"] = first, np.array(v0)

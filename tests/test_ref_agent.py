@@ -144,7 +144,7 @@ def test_reference_trajectory_checker_equals_the_reference_node():
     import make_reftraj_node_golden as mk
     from oracle import ref_agent as ra
     z = np.load(os.path.join(GOLDEN, "reftraj_node_ref.npz"))
-    rb = mk.scenario_batch()
+    rb = mk.load_batch(z)   # the batch the fixture was generated on (stored with it: independent of the solver's tie-breaking)
     for i in (int(v) for v in z["agents"]):
         first, v0 = _reftraj_checker(rb, i, None, 0)
         assert np.array_equal(first, z[f"a{i}_first"]) and v0 == float(z[f"a{i}_first_vel"]), i
