@@ -52,6 +52,7 @@ SNAP_STEPS = (1, 6, 12, 18)
 DISTINCT_SWARMS = 24
 MAX_NODES = 64
 WIDTH = 4          # nodes per round of the assignment search in the closed-loop workloads (hdsm_params.search_width)
+WARM = True        # hdsm_params.warm_start in the same workloads (the previous plan's assignment is tried in the second round)
 METRIC = "agent-QP solves/sec (horizon N=10)"
 N_AGENTS = 4096
 
@@ -574,7 +575,7 @@ def full_step_measure(n_agents=2048, steps=10, local_rank=0):
                            np.zeros((n, N + 1, 3)), np.zeros(n, np.uint8), np.ones(n, np.uint8), np.zeros((n, N + 1, 3)), np.arange(n, dtype=np.int32),
                            np.zeros(n, np.int32), np.full(n, n, np.int32), np.zeros((n, N + 1, 3)), np.ones(n, np.uint8))
     rgen = rtj.ReferenceTrajectoryGenerator(rb0, max_agents=n, max_grids=n, device=local_rank)
-    pl = TrajectoryPlanner(params, n, n, local_rank, max_nodes=MAX_NODES, width=WIDTH)
+    pl = TrajectoryPlanner(params, n, n, local_rank, max_nodes=MAX_NODES, width=WIDTH, warm_start=WARM)
     f64, T = torch.float64, torch.from_numpy
     dim_env = (env.shape[2], env.shape[1], env.shape[0])
     t_env = T(env.reshape(-1)).to(dev)
@@ -666,7 +667,7 @@ def full_step_measure(n_agents=2048, steps=10, local_rank=0):
     hb = sc.Batch(params, np.arange(m, dtype=np.int32), np.zeros(m, np.int32), np.full(m, n, np.int32), np.c_[pos1[:m], np.zeros((m, 6))],
                   ref["ref_solver"][:m].cpu().numpy(), cor["poly_A"][:m].cpu().numpy(), cor["poly_b"][:m].cpu().numpy(), cor["poly_rows"][:m].cpu().numpy(),
                   np.repeat(pos1[:m, None, :], N + 1, 1), np.repeat(pos1[:, None, :], N + 1, 1), np.ones(n, np.uint8), R)
-    want = co.solve_batch(hb, max_nodes=MAX_NODES, width=WIDTH)["res"]
+    want = co.solve_batch(hb, max_nodes=MAX_NODES, width=WIDTH, warm_start=WARM)["res"]
     both = (res["status"][:m] == 0) & (want["status"] == 0)
     gap = float((np.abs(res["obj"][:m][both] - want["obj"][both]) / np.maximum(1.0, np.abs(want["obj"][both]))).max()) if both.any() else 0.0
     launches = mb.launch_count + mproc.launch_count + gen.launch_count + rgen.launch_count + pl.launch_count
@@ -689,7 +690,7 @@ def config_dict(args, world):
                         f"closed loop, sharded {args.agents // world} agents per GPU over {world} GPU(s), NCCL all-gather of plan "
                         f"positions consumed as the next step's neighbour table",
             "n_hor": 10, "poly_hor": 4, "n_agents": args.agents, "agents_per_gpu": args.agents // world,
-            "neighbour_candidates_per_agent": args.agents, "max_nodes": MAX_NODES, "search_width": WIDTH, "seed": args.seed,
+            "neighbour_candidates_per_agent": args.agents, "max_nodes": MAX_NODES, "search_width": WIDTH, "warm_start": WARM, "seed": args.seed,
             "l2": "flushed between timed steps (512 MiB write)",
             "inputs": "ref / corridor cells of every step from the host producers of an untimed pre-roll of the same closed "
                       "loop, resident in HBM; x0, previous plans and the neighbour table advance on the device",
@@ -718,7 +719,7 @@ def run_reference(args, rank, world):
     for s in range(args.warmup + args.steps):
         b = sw.make_batch_pooled(pool)
         t0 = time.perf_counter()
-        out = co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH)
+        out = co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH, warm_start=WARM)
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             times.append(dt)
@@ -832,8 +833,8 @@ def config4_measure(args, local_rank, flush, torch):
     from oracle import c_oracle as co
     sw = sc.config4_circle256()
     W, T = 3, 3 + args.steps
-    loop = ClosedLoop(sw, 1, 0, f"cuda:{local_rank}", MAX_NODES, None, width=WIDTH)
-    loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH)
+    loop = ClosedLoop(sw, 1, 0, f"cuda:{local_rank}", MAX_NODES, None, width=WIDTH, warm_start=WARM)
+    loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH, warm_start=WARM)
     loop.keep_steps, loop.keep_agents = set(range(W, T)), sw.n
     par = loop.preroll(T, parity_sample=sw.n)
     ms = timed_replay(loop, W, T, flush, None, torch)
@@ -841,7 +842,7 @@ def config4_measure(args, local_rank, flush, torch):
     t_cpu = 0.0
     for s in range(W, T):
         t0 = time.perf_counter()
-        co.solve_batch(loop.host_batches[s], max_nodes=MAX_NODES, width=WIDTH)
+        co.solve_batch(loop.host_batches[s], max_nodes=MAX_NODES, width=WIDTH, warm_start=WARM)
         t_cpu += time.perf_counter() - t0
     q = quality_of(loop.stats, W)
     loop.close()
@@ -987,9 +988,9 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     # ---- headline: config 5, strong scaling, closed loop
-    loop = ClosedLoop(sw, world, rank, dev, MAX_NODES, pool, record_host=True, width=WIDTH)
+    loop = ClosedLoop(sw, world, rank, dev, MAX_NODES, pool, record_host=True, width=WIDTH, warm_start=WARM)
     if rank == 0:
-        loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH)
+        loop.checker = lambda b: co.solve_batch(b, max_nodes=MAX_NODES, width=WIDTH, warm_start=WARM)
         loop.keep_steps, loop.keep_agents = {W, W + (T - W) // 2, T - 1}, min(loop.n, 2048)
     par = loop.preroll(T, parity_sample=512 if rank == 0 else 0, log=log)
     pool.close()
@@ -1015,7 +1016,7 @@ def run_ours(args, rank, world, local_rank):
     weak = None
     if sw_weak is not None:
         Ww, Tw = 3, 3 + args.weak_steps
-        lw = ClosedLoop(sw_weak, world, rank, dev, MAX_NODES, pool_weak, width=WIDTH)
+        lw = ClosedLoop(sw_weak, world, rank, dev, MAX_NODES, pool_weak, width=WIDTH, warm_start=WARM)
         lw.preroll(Tw, log=log)
         pool_weak.close()
         msw = timed_replay(lw, Ww, Tw, flush, dist, torch)
@@ -1050,7 +1051,7 @@ def run_ours(args, rank, world, local_rank):
         while cpu_t < args.cpu_seconds and reps < 50:
             for hb in loop.host_batches.values():
                 t1 = time.perf_counter()
-                co.solve_batch(hb, max_nodes=MAX_NODES, width=WIDTH)
+                co.solve_batch(hb, max_nodes=MAX_NODES, width=WIDTH, warm_start=WARM)
                 cpu_t += time.perf_counter() - t1
                 cpu_n += hb.n
             reps += 1
@@ -1110,6 +1111,23 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clk, "weak": weak, "smem_bytes_per_block": smem}
         line.update(secondary)
         line.update(producers)
+        # the line is long; whoever keeps only its head or only its tail still gets the essentials
+        def g(d, *ks):
+            for k in ks:
+                d = d.get(k) if isinstance(d, dict) else None
+            return d
+        line["digest"] = {
+            "config5_ms_per_step": total_ms / (T - W), "config5_solves_per_s": value, "config5_e2e_solves_per_s": args.agents * (T - W) / t_e2e,
+            "n_gpus": world, "table_checksum": replay_sum, "replay_equals_preroll": bool(same_all),
+            "parity_status_mismatches": par.get("status_mismatches"), "parity_max_rel_obj_gap": par.get("max_rel_obj_gap"),
+            "status_counts": quality["status_counts"], "weak_solves_per_s": g(weak, "value"), "weak_ms_per_step": g(weak, "ms_per_step"),
+            "config4_ms_per_step": g(secondary, "config4", "ms_per_step"), "config4_cpu_port_ms_per_step": g(secondary, "config4", "cpu_baseline", "ms_per_step"),
+            "latency_ms_p50_p99_config1": [g(secondary, "latency", "config1_single_agent", "gpu_ms_p50"), g(secondary, "latency", "config1_single_agent", "gpu_ms_p99")],
+            "latency_ms_p50_p99_config2_agent": [g(secondary, "latency", "config2_one_of_10_agents", "gpu_ms_p50"), g(secondary, "latency", "config2_one_of_10_agents", "gpu_ms_p99")],
+            "config2_replicas_solves_per_s": g(secondary, "config2_replicas", "value"), "config2_replicas_e2e": g(secondary, "config2_replicas", "e2e", "value"),
+            "chained_step_status_counts": g(producers, "corridor", "chained_step", "status_counts"), "chained_step_ms": g(producers, "corridor", "chained_step", "ms"),
+            "full_step_ms": g(producers, "full_step", "ms_per_step"), "full_step_stage_ms": g(producers, "full_step", "stage_ms"),
+            "cpu_port_solves_per_s": cpu_n / cpu_t, "cpu_cores": co.max_threads()}
         emit(line)
     if dist:
         dist.barrier()

@@ -84,6 +84,12 @@ typedef struct hdsm_params {
   double drone_z_offset;
   double tilt;               /* var_tmp = 0.1 (:1180) */
   double tol;                /* KKT tolerance of a QP solve (0 -> 1e-8) */
+  int32_t warm_start;        /* 1 = warm start of the assignment search (the reference keeps the polytopes the
+                                last plan used for the same purpose, agent_class.cpp:1269-1282): once the root relaxation has
+                                branched, the previous plan shifted by one step (prev_self_pos) names a cell per step, and that
+                                assignment is solved in the next round, so that an incumbent exists early.  Changes which nodes
+                                are explored, never the optimum */
+  int32_t reserved;
 } hdsm_params;
 
 typedef struct hdsm_result {

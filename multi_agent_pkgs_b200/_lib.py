@@ -31,7 +31,7 @@ class HdsmParams(C.Structure):
                 ("r_n", C.c_double * 6), ("max_vel", C.c_double), ("min_acc_xy", C.c_double),
                 ("max_acc_xy", C.c_double), ("min_acc_z", C.c_double), ("max_acc_z", C.c_double),
                 ("max_jerk", C.c_double), ("drone_radius", C.c_double), ("drone_z_offset", C.c_double),
-                ("tilt", C.c_double), ("tol", C.c_double)]
+                ("tilt", C.c_double), ("tol", C.c_double), ("warm_start", C.c_int32), ("reserved", C.c_int32)]
 
 
 class HdsmResult(C.Structure):
@@ -97,7 +97,7 @@ def load(build: bool = True) -> C.CDLL:
     return L
 
 
-def make_params(d, rmax=18, max_iter=60, max_nodes=64, prune=True, tol=1e-8, width=1) -> HdsmParams:
+def make_params(d, rmax=18, max_iter=60, max_nodes=64, prune=True, tol=1e-8, width=1, warm_start=False) -> HdsmParams:
     p = HdsmParams()
     p.n_hor, p.poly_hor, p.max_rows_per_poly, p.rk4 = int(d["n_hor"]), int(d["poly_hor"]), int(rmax), int(bool(d["rk4"]))
     p.max_iter, p.max_nodes, p.prune, p.search_width = int(max_iter), int(max_nodes), int(bool(prune)), int(width)
@@ -110,4 +110,5 @@ def make_params(d, rmax=18, max_iter=60, max_nodes=64, prune=True, tol=1e-8, wid
               "drone_z_offset", "tilt"):
         setattr(p, k, float(d[k]))
     p.tol = float(tol)
+    p.warm_start = int(bool(warm_start))
     return p

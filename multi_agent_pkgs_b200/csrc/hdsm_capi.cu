@@ -389,7 +389,7 @@ static int solve_device(hdsm_handle* h, int slot, size_t order_offset, const dou
   a.all_valid = all_valid, a.traj = traj, a.ctrl = ctrl, a.pos_out = pos_out, a.poly_used = poly_used;
   a.assign_out = assign_out, a.res = res, a.prof = h->d_prof;
   a.max_iter = h->prm.max_iter, a.max_nodes = h->prm.max_nodes, a.prune = h->prm.prune, a.tol = h->prm.tol;
-  a.width = h->prm.search_width, a.csize = 1;
+  a.width = h->prm.search_width, a.csize = 1, a.warm_start = h->prm.warm_start;
   if (const char* e = std::getenv("HDSM_DEBUG")) a.dbg = std::atoi(e);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   a.bounds = bounds;

@@ -53,6 +53,7 @@ struct KernelArgs {
   long long* prof; // optional [n_local][16] cycle counters per phase (HDSM_PROFILE=1), else null
   int max_iter, max_nodes, prune;
   int width;  // nodes per search round (1 = depth-first search); the result depends on it
+  int warm_start;  // 1: after the root has branched, the previous plan's assignment is solved in the next round
   int csize;  // thread blocks per agent = cluster size (1, 2 or 4): execution only, never changes a result
   int dbg;  // debugging switches (HDSM_DEBUG): 1 = no dominance filter, 2 = no parent-bound pruning
   double tol;
@@ -1438,6 +1439,7 @@ struct Solver {
       tick(0);
     }
     int cnt = 0;       // nodes of the current round (warp 0)
+    double root_obj = INFINITY;
     for (;;) {
       // ---- pop the round (identical in every block of the cluster)
       if (wid == 0) {
@@ -1508,6 +1510,7 @@ struct Solver {
           continue;
         }
         const double mo = m.obj();
+        if (rounds == 0 && j == 0) root_obj = mo;
         if (m.bk() >= 0 || mo >= best - kPruneRel * fmax(1.0, fabs(best))) continue;
         best = mo, bestkkt = m.kkt();
         if (lane < NW) bestw[lane] = m.w()[lane];
@@ -1532,6 +1535,44 @@ struct Solver {
           const unsigned char cm = m.child()[i];
           if (lane < 16) stack[top * 16 + lane] = lane == bk ? cm : pop[j * 16 + lane];
           if (lane == 0) sbnd[top] = mo;
+          ++top;
+        }
+        __syncwarp();
+      }
+      // ---- warm start (optional): the root has branched - the previous plan shifted by one step names a cell per step
+      // (the member of the root's candidate set the segment (prev[k+1], prev[k+2]) lies deepest in, if it lies in one);
+      // that assignment goes on top of the stack, the next round solves it first and an incumbent exists early
+      if (A.warm_start && rounds == 0 && top > 0 && exhausted && !overflow && top + 1 <= kStackCap) {
+        const double* prev = A.prev + (size_t)agent * K3;
+        for (int idx = lane; idx < N * Peff; idx += 32) {
+          const int k = idx / Peff, j = idx - k * Peff;
+          double v = INFINITY;
+          if (pop[k] >> j & 1) {
+            v = -INFINITY;
+            const double* a0 = prev + 3 * min(k + 1, N);
+            const double* a1 = prev + 3 * min(k + 2, N);
+            for (int r = 0; r < prow_n[j]; ++r) {
+              const double* c = poly + 4 * (j * A.rmax + r);
+              v = fmax(v, fmax(c[0] * a0[0] + c[1] * a0[1] + c[2] * a0[2], c[0] * a1[0] + c[1] * a1[1] + c[2] * a1[2]) - c[3]);
+            }
+          }
+          viol[k * kMaxP + j] = v;
+        }
+        __syncwarp();
+        unsigned hm = 0;
+        if (lane < N) {
+          int bj = -1;
+          double bv = INFINITY;
+          for (int j = 0; j < Peff; ++j) {
+            const double v = viol[lane * kMaxP + j];
+            if (v < bv) bv = v, bj = j;
+          }
+          if (bj >= 0 && bv <= kContainTol) hm = 1u << bj;
+        }
+        const bool okh = __all_sync(kFull, lane >= N || hm != 0);
+        if (okh) {
+          if (lane < 16) stack[top * 16 + lane] = (unsigned char)hm;
+          if (lane == 0) sbnd[top] = root_obj;
           ++top;
         }
         __syncwarp();

@@ -39,12 +39,13 @@ class TrajectoryPlanner:
     """One library handle = one ``GRBModel`` worth of set-up, valid for a fixed parameter set."""
 
     def __init__(self, params: Dict, max_agents: int, max_neighbours: int, device: int = 0, rmax: int = 18,
-                 max_iter: int = 60, max_nodes: int = 64, prune: bool = True, tol: float = 1e-8, width: int = 1):
+                 max_iter: int = 60, max_nodes: int = 64, prune: bool = True, tol: float = 1e-8, width: int = 1,
+                 warm_start: bool = False):
         self.lib = _lib.load()
         self.params = dict(params)
         self.N, self.P, self.rmax = int(params["n_hor"]), int(params["poly_hor"]), int(rmax)
         self.max_agents = int(max_agents)
-        self._cparams = _lib.make_params(params, rmax, max_iter, max_nodes, prune, tol, width)
+        self._cparams = _lib.make_params(params, rmax, max_iter, max_nodes, prune, tol, width, warm_start)
         h = C.c_void_p()
         rc = self.lib.hdsm_create(C.byref(self._cparams), int(max_agents), int(max_neighbours), int(device), C.byref(h))
         if rc != 0:

@@ -19,7 +19,7 @@ STATUS_NAMES = {0: "OPTIMAL", 1: "INFEASIBLE", 2: "MAX_ITER", 3: "NUMERICAL", 4:
 
 class OrcParams(C.Structure):
     _fields_ = [("n_hor", C.c_int32), ("poly_hor", C.c_int32), ("rk4", C.c_int32), ("max_iter", C.c_int32),
-                ("max_nodes", C.c_int32), ("prune", C.c_int32), ("width", C.c_int32), ("pad_", C.c_int32),
+                ("max_nodes", C.c_int32), ("prune", C.c_int32), ("width", C.c_int32), ("warm_start", C.c_int32),
                 ("dt", C.c_double), ("drag", C.c_double * 3), ("r_u", C.c_double), ("r_x", C.c_double * 6),
                 ("r_n", C.c_double * 6), ("max_vel", C.c_double), ("min_acc_xy", C.c_double),
                 ("max_acc_xy", C.c_double), ("min_acc_z", C.c_double), ("max_acc_z", C.c_double),
@@ -53,10 +53,10 @@ def lib():
     return _LIB
 
 
-def make_params(d, max_iter=60, max_nodes=100000, prune=True, tol=1e-8, width=1):
+def make_params(d, max_iter=60, max_nodes=100000, prune=True, tol=1e-8, width=1, warm_start=False):
     p = OrcParams()
     p.n_hor, p.poly_hor, p.rk4 = int(d["n_hor"]), int(d["poly_hor"]), int(bool(d["rk4"]))
-    p.max_iter, p.max_nodes, p.prune, p.width = max_iter, max_nodes, int(prune), int(width)
+    p.max_iter, p.max_nodes, p.prune, p.width, p.warm_start = max_iter, max_nodes, int(prune), int(width), int(bool(warm_start))
     p.dt = d["dt"]
     p.drag[:] = d["drag"]
     p.r_u = d["r_u"]

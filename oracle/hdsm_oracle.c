@@ -43,7 +43,7 @@ enum { ORC_OPTIMAL = 0, ORC_INFEASIBLE = 1, ORC_MAX_ITER = 2, ORC_NUMERICAL = 3,
        ORC_CUTOFF = 6 /* internal: the dual bound of a relaxation reached the incumbent, solve abandoned */ };
 
 typedef struct {
-  int32_t n_hor, poly_hor, rk4, max_iter, max_nodes, prune, width, pad_;
+  int32_t n_hor, poly_hor, rk4, max_iter, max_nodes, prune, width, warm_start;
   double dt, drag[3], r_u, r_x[6], r_n[6];
   double max_vel, min_acc_xy, max_acc_xy, min_acc_z, max_acc_z, max_jerk;
   double drone_radius, drone_z_offset, tilt, tol;
@@ -972,6 +972,7 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
       }
     }
     lat_iters += round_iters;
+    const int first_round = nodes == cnt; /* this round was the root alone */
     /* ---- merge 1: incumbents, in pop order */
     for (int c = 0; c < cnt; c++) {
       node_t *n = &nd[c];
@@ -1020,6 +1021,29 @@ static void solve_agent(const orc_params *P, const tables_t *T, int gid, int nb0
         memcpy(stack[top], n->sets, sizeof(n->sets));
         sbound[top] = n->q.obj;
         stack[top++][bk] = m;
+      }
+    }
+    /* ---- warm start (optional): when the root has branched, the previous plan shifted by one step names a
+     * cell per step - the cell of the root's candidate set the segment (prev[k+1], prev[k+2]) lies deepest in, if it lies in
+     * one; that assignment goes on top of the stack, so the next round solves it first and an incumbent exists early */
+    if (P->warm_start && first_round && top > 0 && exhausted && top + 1 <= cap) {
+      unsigned hs[MAXN];
+      int okh = 1;
+      for (int k = 0; k < N && okh; k++) {
+        const double *a0 = prev + 3 * (k + 1 <= N ? k + 1 : N), *a1 = prev + 3 * (k + 2 <= N ? k + 2 : N);
+        int bj = -1;
+        double bv = INFINITY;
+        for (int j = 0; j < Peff; j++) {
+          if (!(root[k] >> j & 1)) continue;
+          double v = seg_violation(pA + (size_t)j * rmax * 3, pb_ + (size_t)j * rmax, prow_n[j], a0, a1);
+          if (v < bv) bv = v, bj = j;
+        }
+        if (bj < 0 || bv > 1e-7) okh = 0;
+        else hs[k] = 1u << bj;
+      }
+      if (okh) {
+        memcpy(stack[top], hs, sizeof(hs));
+        sbound[top++] = nd[0].q.obj;
       }
     }
   }

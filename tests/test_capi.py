@@ -35,7 +35,7 @@ def test_header_cites_reference_lines():
 
 def test_struct_layouts():
     assert C.sizeof(_lib.HdsmResult) == 32 and _lib.RESULT_DTYPE.itemsize == 32
-    assert C.sizeof(_lib.HdsmParams) == 8 * 4 + 8 * (1 + 3 + 1 + 6 + 6 + 6 + 3 + 1)
+    assert C.sizeof(_lib.HdsmParams) == 8 * 4 + 8 * (1 + 3 + 1 + 6 + 6 + 6 + 3 + 1) + 2 * 4
     p = _lib.make_params(sc.agile_params())
     assert (p.n_hor, p.poly_hor, p.max_rows_per_poly) == (10, 4, 18) and p.max_jerk == 60.0
 

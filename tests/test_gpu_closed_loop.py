@@ -234,6 +234,18 @@ def test_search_rounds_depend_on_the_width_only():
             for k in ("traj", "ctrl", "assign", "poly_used"):
                 assert np.array_equal(o[k], out[k]), (width, k)
             assert np.array_equal(o["res"]["obj"], out["res"]["obj"]) and np.array_equal(o["res"]["nodes"], out["res"]["nodes"])
+    # the warm start of the search (previous plan's assignment solved in the second round): same optimum, same search as the port's
+    ref = co.solve_batch(b, max_nodes=64, width=4, warm_start=True)
+    cold = co.solve_batch(b, max_nodes=64, width=4)
+    pl = TrajectoryPlanner(sw.params, max_agents=b.n, max_neighbours=b.n, max_nodes=64, width=4, warm_start=True)
+    out = pl.solve_batch(b)
+    pl.close()
+    assert np.array_equal(out["res"]["status"], ref["res"]["status"]) and np.array_equal(out["res"]["nodes"], ref["res"]["nodes"])
+    ok = (ref["res"]["status"] == OPTIMAL) & (cold["res"]["status"] == OPTIMAL)
+    for other in (ref, cold):
+        gap = np.abs(out["res"]["obj"][ok] - other["res"]["obj"][ok]) / np.maximum(1, np.abs(other["res"]["obj"][ok]))
+        assert gap.max() <= 1e-6, gap.max()
+    assert not np.array_equal(ref["res"]["nodes"], cold["res"]["nodes"])   # it does change the search
 
 
 def test_host_entry_point_rejects_bad_indices():
