@@ -369,8 +369,8 @@ struct Solver {
     }
     // axis-aligned bounding box of every cell from its rows with a single non-zero component (the six faces
     // GetPolyOcta3D always emits, convex_decomp.cpp:359-373): cbox[6 j + a] = lo_a, cbox[6 j + 3 + a] = hi_a
-    if (tid < 6 * kMaxP) {
-      const int j = tid / 6, c = tid - 6 * j, a = c % 3;
+    for (int t = tid; t < 6 * kMaxP; t += NT) {
+      const int j = t / 6, c = t - 6 * j, a = c % 3;
       const bool upper = c >= 3;
       double v = upper ? INFINITY : -INFINITY;
       if (j < Peff)
@@ -381,7 +381,7 @@ struct Solver {
           if (upper && q[a] > 0) v = fmin(v, x);
           if (!upper && q[a] < 0) v = fmax(v, x);
         }
-      cbox[tid] = v;
+      cbox[t] = v;
     }
     bsync();
   }

@@ -248,6 +248,32 @@ def test_search_rounds_depend_on_the_width_only():
     assert not np.array_equal(ref["res"]["nodes"], cold["res"]["nodes"])   # it does change the search
 
 
+def test_single_warp_variant_gives_the_same_results():
+    """HDSM_WARPS=1 selects the one-warp-per-agent instantiation of the kernel (same code, W = 1): identical statuses and
+    node counts, objectives to 1e-9, for the depth-first search and for rounds of 4 with the warm start."""
+    sw = sc.config5_random(seed=17, n_rob=200, side=45.0)
+    from oracle import c_oracle as co
+    for _ in range(2):
+        b = sw.make_batch()
+        r = co.solve_batch(b, max_nodes=64)
+        sw.advance(r["traj"], r["ctrl"], _ok(r["res"]))
+    b = sw.make_batch()
+    for kw in (dict(width=1), dict(width=4, warm_start=True)):
+        outs = []
+        for warps in ("4", "1"):
+            os.environ["HDSM_WARPS"] = warps
+            try:
+                pl = TrajectoryPlanner(sw.params, max_agents=b.n, max_neighbours=b.n, max_nodes=64, **kw)
+                outs.append(pl.solve_batch(b))
+                pl.close()
+            finally:
+                del os.environ["HDSM_WARPS"]
+        a, c = outs
+        assert np.array_equal(a["res"]["status"], c["res"]["status"]) and np.array_equal(a["res"]["nodes"], c["res"]["nodes"]), kw
+        ok = a["res"]["status"] == OPTIMAL
+        assert (np.abs(a["res"]["obj"][ok] - c["res"]["obj"][ok]) / np.maximum(1, np.abs(a["res"]["obj"][ok]))).max() <= 1e-9, kw
+
+
 def test_host_entry_point_rejects_bad_indices():
     sw = sc.config2_circle(n_swarms=1)
     b = sw.make_batch()
