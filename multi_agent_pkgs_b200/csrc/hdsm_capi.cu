@@ -76,6 +76,9 @@ struct hdsm_handle {
   int n_tiers = 0, row_cap[3] = {0, 0, 0}, smem_bytes[3] = {0, 0, 0};
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second lane of the chunked host-pointer pipeline
   cudaEvent_t ev_shared = nullptr, ev_chunk[kMaxChunks] = {}, ev_begin[kMaxChunks] = {};
+  cudaStream_t stream_early = nullptr;  // head start of the agents expected to search long (see launch)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int early_div = 16;  // HDSM_EARLY_DIV: the first n_local / early_div agents of the dispatch order get the head start (0: none)
   // staging for the host-pointer entry point
   unsigned char *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
   size_t in_cap = 0, out_cap = 0;
@@ -140,11 +143,13 @@ cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
   // Rounds are deterministic, so the redone search is the same search.
   const int kFirstPassRounds = h->first_rounds;
   const bool two_pass = W == 4 && csize < a.width && !h->single_pass;
-  auto go = [&](int cs, unsigned mask, int budget, int ovf, int tier) -> cudaError_t {
+  auto go = [&](int cs, unsigned mask, int budget, int ovf, int tier, int slot0 = 0, int slot1 = -1, cudaStream_t on = nullptr) -> cudaError_t {
     KernelArgs k = a;
     k.csize = cs, k.only_mask = mask, k.round_budget = budget, k.overflow_status = ovf, k.row_cap = h->row_cap[tier];
+    k.slot0 = slot0;
+    if (slot1 >= 0) k.n_local = slot1;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)k.n_local * cs), cfg.blockDim = dim3(32 * W), cfg.dynamicSmemBytes = h->smem_bytes[tier], cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)(k.n_local - slot0) * cs), cfg.blockDim = dim3(32 * W), cfg.dynamicSmemBytes = h->smem_bytes[tier], cfg.stream = on ? on : s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
@@ -153,10 +158,28 @@ cudaError_t launch(hdsm_handle* h, KernelArgs a, cudaStream_t s) {
     h->launches += 1;
     return e;
   };
+  // Head start: hardness persists from one replanning step to the next, and the dispatch order of this call is last
+  // call's iteration count, longest first.  Its first few agents are the ones a first pass would give up on, and the
+  // cluster pass that redoes them is as long as the longest search - after a first pass that was just as long.  So
+  // they skip the first pass: a cluster launch for the head of the order starts on a second (high-priority) stream
+  // while the first pass works through the rest, and the two overlap.  Agents the prediction missed are still picked
+  // up by the cluster pass; which launch solves an agent never changes its result.
+  const int n_early = (two_pass && a.order && h->early_div > 0 && h->stream_early) ? a.n_local / h->early_div : 0;
   for (int t = 0; t < h->n_tiers; ++t) {  // t > 0: only agents whose rows did not fit the previous pool
     const bool last = t == h->n_tiers - 1;
-    cudaError_t e = go(csize, t == 0 ? 0u : 1u << HDSM_ROW_OVERFLOW, two_pass ? kFirstPassRounds : 0, HDSM_ROW_OVERFLOW, t);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+    if (t == 0 && n_early > 0) {
+      if ((e = cudaEventRecord(h->ev_fork, s)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(h->stream_early, h->ev_fork, 0)) != cudaSuccess) return e;
+      if ((e = go(a.width, 0u, 0, HDSM_ROW_OVERFLOW, t, 0, n_early, h->stream_early)) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(h->ev_join, h->stream_early)) != cudaSuccess) return e;
+      e = go(csize, 0u, kFirstPassRounds, HDSM_ROW_OVERFLOW, t, n_early);
+      if (e != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(s, h->ev_join, 0)) != cudaSuccess) return e;
+    } else {
+      e = go(csize, t == 0 ? 0u : 1u << HDSM_ROW_OVERFLOW, two_pass ? kFirstPassRounds : 0, HDSM_ROW_OVERFLOW, t);
+      if (e != cudaSuccess) return e;
+    }
     if (two_pass) {
       e = go(a.width, (1u << kDeferred) | (t > 0 ? 1u << kDeferredOverflow : 0u), 0, last ? HDSM_ROW_OVERFLOW : kDeferredOverflow, t);
       if (e != cudaSuccess) return e;
@@ -274,6 +297,14 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
   if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream2");
   if ((e = cudaEventCreateWithFlags(&h->ev_shared, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&h->stream_early, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(e, "stream_early");
+    if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    if (const char* ev = std::getenv("HDSM_EARLY_DIV")) h->early_div = std::max(0, std::atoi(ev));
+  }
   for (int c = 0; c < kMaxChunks; ++c)
     if ((e = cudaEventCreate(&h->ev_chunk[c])) != cudaSuccess || (e = cudaEventCreate(&h->ev_begin[c])) != cudaSuccess)
       return bail(e, "event");
@@ -300,9 +331,12 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
   cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
   const long fixed = (long)smem_doubles(N, P, rmax, 0) * 8;
   const long fit = std::max(16L, (long)(smem_max - fixed - 1024) / 48);
-  // pool of HDSM_MINBLOCKS co-resident blocks inside the 196 KB carve-out (the next one, 228 KB, would leave the
-  // parameter tables only 28 KB of L1: measured 3 % slower on the 10-neighbour workload)
-  const long carve = std::min<long>(smem_sm, 196 * 1024);
+  // pool of HDSM_MINBLOCKS co-resident blocks inside the 228 KB carve-out.  (Round 1 stopped at 196 KB because the
+  // parameter tables then lived in L1, and 28 KB of L1 cost 3 % on the 10-neighbour workload; the tables the
+  // iterations walk are now copies in shared memory.  HDSM_CARVE_KB=196 restores the old split for A/B runs.)
+  long carve_kb = 228;
+  if (const char* e = std::getenv("HDSM_CARVE_KB")) carve_kb = std::max(64L, std::atol(e));
+  const long carve = std::min<long>(smem_sm, carve_kb * 1024);
   const long shared4 = std::max(96L, (carve / HDSM_MINBLOCKS - 1024 - fixed) / 48 & ~7L);
   const long tiers[2] = {h->prm.prune ? shared4 : worst, worst};
   long prev = 0;
@@ -325,6 +359,9 @@ void hdsm_destroy(hdsm_handle* h) {
   hdsm_comm_destroy(h);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream2) cudaStreamSynchronize(h->stream2);
+  if (h->stream_early) cudaStreamSynchronize(h->stream_early), cudaStreamDestroy(h->stream_early);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_shared) cudaEventDestroy(h->ev_shared);
   for (int c = 0; c < kMaxChunks; ++c)
     if (h->ev_chunk[c]) cudaEventDestroy(h->ev_chunk[c]), cudaEventDestroy(h->ev_begin[c]);
@@ -590,15 +627,20 @@ int hdsm_solve_batch(hdsm_handle* h, int n_local, const int32_t* global_id, cons
   if (h->d_prof) {
     std::vector<long long> hp((size_t)n_local * 16);
     CU(cudaMemcpy(hp.data(), h->d_prof, hp.size() * 8, cudaMemcpyDeviceToHost));
-    double tot[12] = {0};
+    double tot[16] = {0};
     for (int i = 0; i < n_local; ++i)
-      for (int s = 0; s < 12; ++s) tot[s] += (double)hp[(size_t)i * 16 + s];
-    const char* names[12] = {"setup+planes", "static rows", "qp init", "pass1", "residual/rhs", "kkt assembly", "factor",
-                             "solves", "dense products", "other passes", "search", "-"};
+      for (int s = 0; s < 16; ++s) tot[s] += (double)hp[(size_t)i * 16 + s];
+    const char* names[16] = {"dominance filter", "static rows", "qp init", "pass1", "residual/rhs", "kkt assembly", "factor",
+                             "solves", "dense products", "other passes", "search", "load + index", "objective/boxes",
+                             "neighbour scan", "neighbour rows", "root sets"};
+#ifdef HDSM_PROF_PASS1
+    names[11] = "p1 rows", names[12] = "p1 butterflies", names[13] = "p1 boxes", names[14] = "step-length passes", names[15] = "corrector rhs rows";
+    names[3] = "p1 reduction", names[9] = "rhs product + update";
+#endif
     double all = 0;
     for (double t : tot) all += t;
     std::fprintf(stderr, "[hdsm profile] warp-0 cycles per agent: %.0f\n", all / n_local);
-    for (int s = 0; s < 11; ++s) std::fprintf(stderr, "  %-16s %6.1f%%  %10.0f cycles/agent\n", names[s], 100 * tot[s] / all, tot[s] / n_local);
+    for (int s = 0; s < 16; ++s) std::fprintf(stderr, "  %-16s %6.1f%%  %10.0f cycles/agent\n", names[s], 100 * tot[s] / all, tot[s] / n_local);
   }
   return HDSM_OK;
 }

@@ -24,6 +24,7 @@ constexpr double kPruneMargin = 1e-6;  // a row is dropped only if it keeps this
 constexpr double kContainTol = 1e-7;   // segment-in-polytope test on a node optimum
 constexpr double kPruneRel = 1e-7;     // bound pruning, relative
 constexpr double kStepFrac = 0.97;
+constexpr double kFastPivot = 1e-6;    // pivots that kept this share of their diagonal: solves through the explicit inverse of the factor
 constexpr double kLooseTol = 1e-6;     // accepted at the iteration limit: still inside the 1e-6 KKT target
 constexpr int kStackCap = 96;          // >= 1 + N * (P - 1) open nodes (a branching can push up to P sets)
 constexpr unsigned kFull = 0xffffffffu;
@@ -55,6 +56,7 @@ struct KernelArgs {
   int width;  // nodes per search round (1 = depth-first search); the result depends on it
   int warm_start;  // 1: after the root has branched, the previous plan's assignment is solved in the next round
   int csize;  // thread blocks per agent = cluster size (1, 2 or 4): execution only, never changes a result
+  int slot0;  // first dispatch slot of this launch (its blocks cover the slots [slot0, n_local))
   int dbg;  // debugging switches (HDSM_DEBUG): 1 = no dominance filter, 2 = no parent-bound pruning
   double tol;
 };
@@ -64,7 +66,7 @@ struct KernelArgs {
 // time, follow.
 struct FixedLayout {
   int Ks, invd, diag0, bs, bl, DQ, TQ, FQ, qv, dq, dqc, qbar, Mk, Tk, Fk, p, dp, dpc, pbar, plo, phi, w, dw, dwc, g, bestw, s0,
-      viol, red, sbnd, cbox, ints, var;
+      viol, red, sbnd, cbox, tEQ, tQP, tqlo, tqhi, prof, ints, var;
 };
 HDSM_HD constexpr FixedLayout make_layout(int N) {
   const int NW = 3 * (N - 2), NQ3 = 3 * (3 * N - 2), K3 = 3 * (N + 1);
@@ -101,14 +103,26 @@ HDSM_HD constexpr FixedLayout make_layout(int N) {
   s.viol = o, o += N * kMaxP;
   s.sbnd = o, o += kStackCap;   // parent bound of every open node
   s.cbox = o, o += kMaxP * 6;   // axis-aligned bounding box of every cell: lo[3], hi[3]
+  // copies of the parameter tables every interior-point iteration walks (Tables::EQ, QP, qlo, qhi; 8.8 KB at N = 10):
+  // read through L1 they cost an L2 round trip whenever the neighbour scans, spills and polytope loads of the four
+  // resident blocks have pushed them out, and the assembly loops are chains of such loads
+  o += o & 1;  // 16-byte aligned rows
+  s.tEQ = o, o += NQ3 * (N - 2);
+  s.tQP = o, o += K3 * (N - 2);
+  s.tqlo = o, o += NQ3;
+  s.tqhi = o, o += NQ3;
+  s.prof = o;
+#ifdef HDSM_ENABLE_PROFILE
+  o += 18;
+#endif
   s.ints = o;
-  // int32 region: segment tables 4(N+2), bestsig N, fullsig N, prow_n 8, cur 16 B, stack, pair table u16
-  const int int_words = 4 * (N + 2) + 2 * N + kMaxP + 4 + kStackCap * 4 + (NW * (NW + 1) / 2 + 1) / 2 + 2 + 8;
+  // int32 region: segment tables 4(N+2), bestsig N, fullsig N, prow_n 8, cur 16 B, stack, ctl 8, kp_of_slot N+2, qconst NQ3, pair table u16
+  const int int_words = 4 * (N + 2) + 2 * N + kMaxP + 4 + kStackCap * 4 + (NW * (NW + 1) / 2 + 1) / 2 + 2 + 8 + (N + 2) + NQ3;
   o += (int_words + 1) / 2;
   s.var = o;
   return s;
 }
-// run-time part after FixedLayout::var: poly [P*rmax*4], bmin [P*rmax*P], rown [rows*4], rs [rows], rl [rows],
+// run-time part after FixedLayout::var: poly [P*rmax*4], bmin [P*rmax*P], rown [4][rows] (component-major), rs [rows], rl [rows],
 // nid [P*rmax bytes]
 // ... then the outcome slots of the search rounds [2][kMaxWidth][6 + (N+1)/2 + 3(N-2)] and the round's node masks
 HDSM_HD inline int smem_doubles(int N, int P, int rmax, int row_cap) {
@@ -131,10 +145,16 @@ __device__ __forceinline__ double warp_min(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
   return v;
 }
-__device__ __forceinline__ double quad_sum(unsigned gmask, double v) {
-  v += __shfl_xor_sync(gmask, v, 1);
-  v += __shfl_xor_sync(gmask, v, 2);
-  return v;
+// 1 / d for a normal, positive d: hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps - four dependent
+// multiply-adds, no slow-path call, at most one unit in the last place off the rounded quotient.  The interior-point
+// iterations divide only by slacks, multipliers and accepted pivots (all positive and far from the subnormal range).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
 }
 
 // Separating plane between own point pc and neighbour point po: agent_class.cpp:1152-1205, pert = 0.
@@ -142,9 +162,12 @@ __device__ __forceinline__ double quad_sum(unsigned gmask, double v) {
 __device__ __forceinline__ bool interagent_plane(const hdsm_params& P, const double pc[3], const double po[3], double nf[3],
                                                  double& b) {
   const double nx = po[0] - pc[0], ny = po[1] - pc[1], nz = po[2] - pc[2];
-  const double nrm = sqrt(nx * nx + ny * ny + nz * nz);
-  if (!(nrm > 0.0)) return false;
-  const double ux = nx / nrm, uy = ny / nrm, uz = nz / nrm;
+  const double n2 = nx * nx + ny * ny + nz * nz;
+  if (!(n2 > 0.0)) return false;
+  // one reciprocal square root (1 ulp) instead of a square root and three divisions; the planes are compared with the
+  // reference's chain at 1e-13 of the row scale (test_plane_coefficients_match_the_reference_chain)
+  const double inrm = rsqrt(n2), nrm = n2 * inrm;
+  const double ux = nx * inrm, uy = ny * inrm, uz = nz * inrm;
   // Safety distance of the reference (:1159-1165): ang = pi/2 - |acos(uz)| = asin(uz),
   // t = atan((r/h) tan(ang)), s = hypot(r cos t, h sin t).  With c = uz, rho = r/h:
   // tan(ang) = c / sqrt(1 - c^2), tan(t) = rho c / sqrt(1 - c^2) and
@@ -185,14 +208,18 @@ struct Solver {
                 *const dp = sm + L.dp, *const dpc = sm + L.dpc, *const pbar = sm + L.pbar, *const plo = sm + L.plo,
                 *const phi = sm + L.phi, *const w = sm + L.w, *const dw = sm + L.dw, *const dwc = sm + L.dwc,
                 *const g = sm + L.g, *const bestw = sm + L.bestw, *const s0 = sm + L.s0, *const viol = sm + L.viol,
-                *const red = sm + L.red, *const sbnd = sm + L.sbnd, *const cbox = sm + L.cbox;
+                *const red = sm + L.red, *const sbnd = sm + L.sbnd, *const cbox = sm + L.cbox, *const sEQ = sm + L.tEQ,
+                *const sQP = sm + L.tQP, *const sqlo = sm + L.tqlo, *const sqhi = sm + L.tqhi;
   int* const ip = reinterpret_cast<int*>(sm + L.ints);
   int *const segb = ip, *const sege = ip + 2 * (N + 2), *const bestsig = ip + 4 * (N + 2), *const fullsig = bestsig + N,
              *const prow_n = fullsig + N;  // segb/sege[2*slot + {0: inter-agent, 1: corridor}]
   unsigned char* const cur = reinterpret_cast<unsigned char*>(prow_n + kMaxP);  // current node's masks [N]
   unsigned char* const stack = cur + 16;  // kStackCap entries of 16 bytes: per-step candidate masks
   int* const ctl = reinterpret_cast<int*>(stack + kStackCap * 16);  // block-wide control words (8)
-  unsigned short* const tab = reinterpret_cast<unsigned short*>(ctl + 8);  // pairs (i << 8 | k)
+  int *const skp = ctl + 8, *const sqc = skp + (N + 2);  // Tables::kp_of_slot, Tables::qconst (flat [3 NQ])
+  unsigned short* const tab = reinterpret_cast<unsigned short*>(sqc + NQ3);  // pairs (i << 8 | k)
+  __device__ __forceinline__ const double* eq_row(int a, int q) const { return sEQ + (a * NQ + q) * NZ; }
+  __device__ __forceinline__ const double* qp_row(int a, int k) const { return sQP + (a * (N + 1) + k) * NZ; }
   double *poly, *bmin, *rown, *rs, *rl;  // bmin[id][j]: tightest offset of normal `id` in polytope j (inf: absent)
   unsigned char* nid;  // per polytope row: id of the first row with the same normal
   double c0;
@@ -211,22 +238,24 @@ struct Solver {
   }
 
   // ---------------------------------------------------------------- small dense products
-  // out[k][a] = (bar ? bar[k][a] : 0) + QP[a][k] . x[a*NZ ...]   (static + noinline: one copy, no `this`)
-  __device__ __forceinline__ static void positions_of(const Tables& T, const double* x, const double* bar, double* out) {
-    for (int idx = threadIdx.x; idx < K3; idx += NT) {
+  // out[k][a] = (bar ? bar[k][a] : 0) + QP[a][k] . x[a*NZ ...]   (tables from shared memory)
+  __device__ __forceinline__ void positions_of(const double* x, const double* bar, double* out) const {
+    for (int idx = tid; idx < K3; idx += NT) {
       const int k = idx / 3, a = idx - 3 * k;
+      const double* t = qp_row(a, k);
       double v = bar ? bar[idx] : 0.0;
 #pragma unroll
-      for (int z = 0; z < NZ; ++z) v += T.QP[a][k][z] * x[a * NZ + z];
+      for (int z = 0; z < NZ; ++z) v += t[z] * x[a * NZ + z];
       out[idx] = v;
     }
   }
-  __device__ __forceinline__ static void quantities_of(const Tables& T, const double* x, const double* bar, double* out) {
-    for (int idx = threadIdx.x; idx < NQ3; idx += NT) {
-      const int a = idx / NQ, q = idx - a * NQ;
+  __device__ __forceinline__ void quantities_of(const double* x, const double* bar, double* out) const {
+    for (int idx = tid; idx < NQ3; idx += NT) {
+      const int a = idx / NQ;
+      const double* t = sEQ + idx * NZ;
       double v = bar ? bar[idx] : 0.0;
 #pragma unroll
-      for (int z = 0; z < NZ; ++z) v += T.EQ[a][q][z] * x[a * NZ + z];
+      for (int z = 0; z < NZ; ++z) v += t[z] * x[a * NZ + z];
       out[idx] = v;
     }
   }
@@ -243,16 +272,10 @@ struct Solver {
   // variable position step, rows strided over the group: the 3x3 barrier blocks reduce inside the
   // group with shuffles.  W = 1: 4 lanes per step at N = 10; W = 4: 16.
   int lps, slot_of_thread, sub;
-  unsigned gmask;
   __device__ __forceinline__ void init_groups() {
     lps = 32;
     while (lps * nkp > NT) lps >>= 1;
     slot_of_thread = tid / lps, sub = tid % lps;
-    gmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (lane & ~(lps - 1)));
-  }
-  __device__ __forceinline__ double group_sum(double v) const {
-    for (int o = lps >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
-    return v;
   }
   template <class F>
   __device__ __forceinline__ void for_my_rows(F&& f) {
@@ -261,30 +284,51 @@ struct Solver {
     for (int sg = 0; sg < 2; ++sg) {
       const int end = sege[2 * slot_of_thread + sg];
 #pragma unroll 1
-      for (int i = segb[2 * slot_of_thread + sg] + sub; i < end; i += lps) f(rown + 4 * i, rs[i], rl[i]);
+      for (int i = segb[2 * slot_of_thread + sg] + sub; i < end; i += lps) {
+        // rows are stored component by component (rown[c][row]): adjacent lanes read adjacent words - with the four
+        // components of a row side by side the 32-byte stride cost four shared-memory wavefronts per load
+        const double r4[4] = {rown[i], rown[A.row_cap + i], rown[2 * A.row_cap + i], rown[3 * A.row_cap + i]};
+        f(r4, rs[i], rl[i]);
+      }
     }
   }
   // phase cycle counters: compiled in only with -DHDSM_ENABLE_PROFILE (HDSM_PROFILE=1 then prints them)
 #ifdef HDSM_ENABLE_PROFILE
-  long long tprof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long tlast = 0;
+  // counters in shared memory, kept by thread 0 alone: registers would perturb exactly the phases that are short of them
+  long long* const tp = reinterpret_cast<long long*>(sm + L.prof);  // [16] phases, [16] time of the last tick
   __device__ __forceinline__ void tick(int slot) {  // attribute the cycles since the last tick to `slot`
-    if (A.prof) {
+    if (A.prof && tid == 0) {
       const long long now = clock64();
-      tprof[slot] += now - tlast;
-      tlast = now;
+      tp[slot] += now - tp[16];
+      tp[16] = now;
     }
   }
   __device__ __forceinline__ void tick_start() {
-    if (A.prof) tlast = clock64();
+    if (A.prof && tid == 0) tp[16] = clock64();
   }
+  __device__ __forceinline__ void tick_init() {
+    if (A.prof && tid == 0) {
+      for (int i = 0; i < 16; ++i) tp[i] = 0;
+      tp[16] = clock64();
+    }
+  }
+#ifdef HDSM_PROF_PASS1  // slots 11-15 split pass 1 instead of the set-up
+  __device__ __forceinline__ void tick2(int slot) { tick(slot); }
+  __device__ __forceinline__ void tick1(int) {}
+#else
+  __device__ __forceinline__ void tick2(int) {}
+  __device__ __forceinline__ void tick1(int slot) { tick(slot); }
+#endif
   __device__ __forceinline__ void tick_flush(int agent) {
-    if (A.prof && lane == 0)
-      for (int i = 0; i < 12; ++i) A.prof[(size_t)agent * 16 + i] = tprof[i];
+    if (A.prof && tid == 0)
+      for (int i = 0; i < 16; ++i) A.prof[(size_t)agent * 16 + i] = tp[i];
   }
 #else
   __device__ __forceinline__ void tick(int) {}
+  __device__ __forceinline__ void tick1(int) {}
+  __device__ __forceinline__ void tick2(int) {}
   __device__ __forceinline__ void tick_start() {}
+  __device__ __forceinline__ void tick_init() {}
   __device__ __forceinline__ void tick_flush(int) {}
 #endif
   __device__ __forceinline__ void bsync() const {
@@ -321,6 +365,19 @@ struct Solver {
   // block-wide part of the set-up: inputs into shared memory, normal ids, per-polytope offsets, pair table
   __device__ void load_and_index(int agent) {
     if (tid < 9) s0[tid] = A.x0[(size_t)agent * 9 + tid];  // x0 = (p, v, a): s0^a = (x0[a], x0[3+a], x0[6+a])
+    for (int t = tid; t < NQ3 * NZ; t += NT) {
+      const int aq = t / NZ, z = t - aq * NZ, a = aq / NQ, q = aq - a * NQ;
+      sEQ[t] = T.EQ[a][q][z];
+    }
+    for (int t = tid; t < K3 * NZ; t += NT) {
+      const int ak = t / NZ, z = t - ak * NZ, a = ak / (N + 1), k = ak - a * (N + 1);
+      sQP[t] = T.QP[a][k][z];
+    }
+    for (int t = tid; t < NQ3; t += NT) {
+      const int a = t / NQ, q = t - a * NQ;
+      sqlo[t] = T.qlo[a][q], sqhi[t] = T.qhi[a][q], sqc[t] = T.qconst[a][q];
+    }
+    if (tid < N + 2) skp[tid] = tid < T.nkp ? T.kp_of_slot[tid] : 0;
     const int PR = A.P * A.rmax;
     for (int i = tid; i < PR; i += NT) {
       const size_t base = (size_t)agent * PR + i;
@@ -331,11 +388,11 @@ struct Solver {
     }
     // clamped: the host entry point validates its arrays, the device entry point cannot
     if (tid < kMaxP) prow_n[tid] = tid < A.P ? min(max(A.poly_rows[(size_t)agent * A.P + tid], 0), A.rmax) : 0;
-    // lower-triangle pairs ordered by column descending: the trailing update of Cholesky step j
-    // touches exactly the first (NW-1-j)(NW-j)/2 entries
+    // lower-triangle pairs (i, k), k <= i, ordered by row descending: step j of the factorisation touches
+    // exactly the pairs with i > j, which are the first NW(NW+1)/2 - (j+1)(j+2)/2 entries
     for (int t = tid; t < NW * NW; t += NT) {
-      const int k = t / NW, i = t - k * NW;
-      if (i >= k) tab[(NW - 1 - k) * (NW - k) / 2 + (i - k)] = (unsigned short)((i << 8) | k);
+      const int i = t / NW, k = t - i * NW;
+      if (k <= i) tab[NW * (NW + 1) / 2 - (i + 1) * (i + 2) / 2 + k] = (unsigned short)((i << 8) | k);
     }
     bsync();
     Peff = 0;
@@ -551,32 +608,13 @@ struct Solver {
     bsync();
   }
 
-  // K1 phase B, warp 0: planes of the listed neighbours, packed by position step
-  __device__ int build_neighbour_rows(int agent) {
+  // K1 phase B, general form on warp 0 (any list length, or no list at all): one plane per (position step, step, neighbour)
+  __device__ int build_neighbour_rows_serial(int agent, bool use_list, int n_list) {
     const hdsm_params& P = T.prm;
     const int gid = A.global_id[agent];
     const int nb0 = A.nbr_begin ? max(A.nbr_begin[agent], 0) : 0, nb1 = A.nbr_end ? min(A.nbr_end[agent], A.n_rob) : A.n_rob;
     const double* prev = A.prev + (size_t)agent * K3;
-    bool use_list = true;
-    for (int w2 = 0; w2 < W; ++w2) use_list &= ctl[2 + w2] >= 0;
     unsigned short* lists = reinterpret_cast<unsigned short*>(rs);
-    // The W sub-lists are packed into one: every round below costs a full plane computation for all 32 lanes,
-    // and with a dozen neighbours four quarter-full rounds per step are four times the work of one.
-    int n_list = 0;
-    if (use_list) {
-      n_list = ctl[2];
-      for (int w2 = 1; w2 < W; ++w2) {
-        const int nl = ctl[2 + w2];
-        for (int i0 = 0; i0 < nl; i0 += 32) {  // destination never lies behind the source: read, then write
-          const int i = i0 + lane;
-          const unsigned short v = i < nl ? lists[w2 * A.row_cap + i] : (unsigned short)0;
-          __syncwarp();
-          if (i < nl) lists[n_list + i] = v;
-          __syncwarp();
-        }
-        n_list += nl;
-      }
-    }
     int cnt = 0, status = -1;
     const unsigned lt = (1u << lane) - 1;
     for (int kp = 0; kp <= N; ++kp) {
@@ -609,7 +647,7 @@ struct Solver {
           if (valid) {
             const int pos = cnt + __popc(m & lt);
             if (pos < A.row_cap) {
-              rown[4 * pos] = nf[0], rown[4 * pos + 1] = nf[1], rown[4 * pos + 2] = nf[2], rown[4 * pos + 3] = b;
+              rown[pos] = nf[0], rown[A.row_cap + pos] = nf[1], rown[2 * A.row_cap + pos] = nf[2], rown[3 * A.row_cap + pos] = b;
             }
           }
           cnt += __popc(m);
@@ -633,6 +671,181 @@ struct Solver {
     if (cnt > A.row_cap) return HDSM_ROW_OVERFLOW;
     __syncwarp();
     return status;
+  }
+
+  // The plane of (step k, neighbour j) and what becomes of it on the two points it acts on: bit 0 / bit 1 of `use` =
+  // it is a row on p_k / on p_k+1 (close enough - thr0 / thr1 are reject_thr2 of the two points - and active somewhere
+  // in the reachable box); st = -1 or the status it forces (coincident points: NUMERICAL; violated at a constant
+  // point: INFEASIBLE).  Static and not inlined: three call sites, and a member function would pin the whole solver
+  // object in local memory.
+  struct PlaneEval {
+    double n0, n1, n2, b;
+    int use, st;
+  };
+  __device__ __noinline__ static void eval_plane(const Tables& T, const KernelArgs& A, const double* sm, double ps0, double ps1,
+                                                 double ps2, double thr0, double thr1, int j, int k, PlaneEval& e) {
+    e.n0 = e.n1 = e.n2 = e.b = 0.0, e.use = 0, e.st = -1;
+    if (j < 0) return;
+    const double *plo = sm + L.plo, *phi = sm + L.phi, *pbar = sm + L.pbar;
+    const double ps[3] = {ps0, ps1, ps2};
+    const double* q = A.all_pos + ((size_t)j * (N + 1) + k + 1) * 3;
+    const double po[3] = {q[0], q[1], q[2]};
+    const double dx = po[0] - ps[0], dy = po[1] - ps[1], dz = po[2] - ps[2], d2 = dx * dx + dy * dy + dz * dz;
+    const bool v[2] = {!A.prune || !(d2 > thr0), !A.prune || !(d2 > thr1)};
+    if (!v[0] && !v[1]) return;
+    double nf[3], b;
+    if (!interagent_plane(T.prm, ps, po, nf, b)) {
+      e.st = HDSM_NUMERICAL;
+      return;
+    }
+    e.n0 = nf[0], e.n1 = nf[1], e.n2 = nf[2], e.b = b;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!v[h]) continue;
+      const int kp = k + h;
+      if (T.slot_of_kp[kp] < 0) {  // constant point: the row is a number (agent_class.cpp rows on p_0..)
+        if (nf[0] * pbar[3 * kp] + nf[1] * pbar[3 * kp + 1] + nf[2] * pbar[3 * kp + 2] - b > kFeasTol) e.st = max(e.st, (int)HDSM_INFEASIBLE);
+      } else {
+        bool act = true;
+        if (A.prune) {  // reachable(): can the row be active inside the reachable box of p_kp?
+          double mx = 0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) mx += nf[a] >= 0 ? nf[a] * phi[3 * kp + a] : nf[a] * plo[3 * kp + a];
+          act = !(mx <= b - kPruneMargin);
+        }
+        if (act) e.use |= 1 << h;
+      }
+    }
+  }
+
+  // K1 phase B, all warps: planes of the listed neighbours, packed by position step.  The plane of (step k, neighbour)
+  // acts on p_k and on p_k+1 and is computed once for both (round 2 computed it for either point), by the warp that
+  // owns step k (k = w, w + W, ...).  Two sweeps around one block barrier: the first counts the rows of every
+  // (step, point) pair, the second writes them where the segment order (kp ascending; inside kp the rows of step
+  // kp - 1, then those of step kp; neighbours in list order - the order the serial form produces) puts them.  Lists of
+  // up to 64 neighbours keep their planes in registers between the sweeps, longer ones are evaluated again.  Without
+  // a list (a sub-list overflowed) the serial form runs on warp 0.  Returns -1 or an HDSM_* status, uniform over the block.
+  __device__ int build_neighbour_rows(int agent) {
+    const int nb0 = A.nbr_begin ? max(A.nbr_begin[agent], 0) : 0;
+    const double* prev = A.prev + (size_t)agent * K3;
+    unsigned short* lists = reinterpret_cast<unsigned short*>(rs);
+    int* cnts = reinterpret_cast<int*>(stack);  // [2N] scratch: the search stack is not in use yet
+    if (wid == 0) {
+      bool use_list = true;
+      for (int w2 = 0; w2 < W; ++w2) use_list &= ctl[2 + w2] >= 0;
+      // The W sub-lists are packed into one: every round below costs a full plane computation for all 32 lanes,
+      // and with a dozen neighbours four quarter-full rounds per step are four times the work of one.
+      int n_list = 0;
+      if (use_list) {
+        n_list = ctl[2];
+        for (int w2 = 1; w2 < W; ++w2) {
+          const int nl = ctl[2 + w2];
+          for (int i0 = 0; i0 < nl; i0 += 32) {  // destination never lies behind the source: read, then write
+            const int i = i0 + lane;
+            const unsigned short v = i < nl ? lists[w2 * A.row_cap + i] : (unsigned short)0;
+            __syncwarp();
+            if (i < nl) lists[n_list + i] = v;
+            __syncwarp();
+          }
+          n_list += nl;
+        }
+      }
+      int serial = -2;
+      if (W == 1 || !use_list) serial = build_neighbour_rows_serial(agent, use_list, n_list);
+      if (lane == 0) ctl[6] = n_list, ctl[7] = serial;
+    }
+    bsync();
+    if (W == 1 || ctl[7] != -2) return ctl[7];
+    const int n_list = ctl[6];
+    const bool cached = n_list <= 64;
+    constexpr int KPW = W == 1 ? 1 : (N + W - 1) / W;  // steps per warp
+    double cn[KPW][2][4];
+    unsigned mk[KPW][2];  // per cached round: ballots of bit 0 (low half) and bit 1 (high half) of `use`
+    int status = -1;
+#pragma unroll
+    for (int t = 0; t < KPW; ++t) {
+      const int k = wid + t * W, kc = min(k, N - 1);
+      const double ps[3] = {prev[3 * (kc + 1)], prev[3 * (kc + 1) + 1], prev[3 * (kc + 1) + 2]};
+      const double thr0 = reject_thr2(ps, kc), thr1 = reject_thr2(ps, kc + 1);
+      int c0 = 0, c1 = 0;
+      PlaneEval e;
+      if (cached) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int i = r * 32 + lane;
+          eval_plane(T, A, sm, ps[0], ps[1], ps[2], thr0, thr1, (k < N && i < n_list) ? nb0 + lists[i] : -1, kc, e);
+          status = max(status, e.st);
+          cn[t][r][0] = e.n0, cn[t][r][1] = e.n1, cn[t][r][2] = e.n2, cn[t][r][3] = e.b;
+          const unsigned m0 = __ballot_sync(kFull, e.use & 1), m1 = __ballot_sync(kFull, e.use & 2);
+          mk[t][r] = (m0 >> lane & 1) | ((m1 >> lane & 1) << 1);  // own bits are enough: the sweeps recount by ballot
+          c0 += __popc(m0), c1 += __popc(m1);
+        }
+      } else if (k < N) {
+        for (int i0 = 0; i0 < n_list; i0 += 32) {
+          const int i = i0 + lane;
+          eval_plane(T, A, sm, ps[0], ps[1], ps[2], thr0, thr1, i < n_list ? nb0 + lists[i] : -1, k, e);
+          status = max(status, e.st);
+          c0 += __popc(__ballot_sync(kFull, e.use & 1)), c1 += __popc(__ballot_sync(kFull, e.use & 2));
+        }
+      }
+      if (k < N && lane == 0) cnts[2 * k] = c0, cnts[2 * k + 1] = c1;
+    }
+    status = __reduce_max_sync(kFull, status);
+    if (lane == 0) ctl[2 + wid] = status;
+    bsync();
+    // segment f = 2 k + h starts at the sum of the counts before it; position step kp owns f = 2 kp - 1 and 2 kp
+    if (wid == 0) {
+      int run = 0;
+      for (int f = 0; f < 2 * N; ++f) {
+        const int c = cnts[f];
+        const int kp_b = (f + 1) / 2;  // f opens the segment of kp_b when f = 2 kp_b - 1 (or f = 0)
+        if ((f == 0 || (f & 1)) && lane == 0 && T.slot_of_kp[kp_b] >= 0) segb[2 * T.slot_of_kp[kp_b]] = run;
+        run += c;
+        const int kp_e = f / 2;        // f closes the segment of kp_e when f = 2 kp_e (or f = 2 N - 1: kp = N)
+        if (!(f & 1) && lane == 0 && T.slot_of_kp[kp_e] >= 0) sege[2 * T.slot_of_kp[kp_e]] = run;
+        if (f == 2 * N - 1 && lane == 0 && T.slot_of_kp[N] >= 0) sege[2 * T.slot_of_kp[N]] = run;
+      }
+      if (lane == 0) ctl[6] = run;
+    }
+    const unsigned lt = (1u << lane) - 1;
+    const auto put = [&](int pos, double n0, double n1, double n2, double b) {
+      if (pos < A.row_cap) rown[pos] = n0, rown[A.row_cap + pos] = n1, rown[2 * A.row_cap + pos] = n2, rown[3 * A.row_cap + pos] = b;
+    };
+#pragma unroll
+    for (int t = 0; t < KPW; ++t) {
+      const int k = wid + t * W;
+      if (k >= N) continue;
+      int base0 = 0;
+      for (int f = 0; f < 2 * k; ++f) base0 += cnts[f];
+      int base1 = base0 + cnts[2 * k];
+      if (cached) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const unsigned m0 = __ballot_sync(kFull, mk[t][r] & 1), m1 = __ballot_sync(kFull, mk[t][r] & 2);
+          if (mk[t][r] & 1) put(base0 + __popc(m0 & lt), cn[t][r][0], cn[t][r][1], cn[t][r][2], cn[t][r][3]);
+          if (mk[t][r] & 2) put(base1 + __popc(m1 & lt), cn[t][r][0], cn[t][r][1], cn[t][r][2], cn[t][r][3]);
+          base0 += __popc(m0), base1 += __popc(m1);
+        }
+      } else {
+        const double ps[3] = {prev[3 * (k + 1)], prev[3 * (k + 1) + 1], prev[3 * (k + 1) + 2]};
+        const double thr0 = reject_thr2(ps, k), thr1 = reject_thr2(ps, k + 1);
+        PlaneEval e;
+        for (int i0 = 0; i0 < n_list; i0 += 32) {
+          const int i = i0 + lane;
+          eval_plane(T, A, sm, ps[0], ps[1], ps[2], thr0, thr1, i < n_list ? nb0 + lists[i] : -1, k, e);
+          const unsigned m0 = __ballot_sync(kFull, e.use & 1), m1 = __ballot_sync(kFull, e.use & 2);
+          if (e.use & 1) put(base0 + __popc(m0 & lt), e.n0, e.n1, e.n2, e.b);
+          if (e.use & 2) put(base1 + __popc(m1 & lt), e.n0, e.n1, e.n2, e.b);
+          base0 += __popc(m0), base1 += __popc(m1);
+        }
+      }
+    }
+    int st = -1;
+    for (int w2 = 0; w2 < W; ++w2) st = max(st, ctl[2 + w2]);
+    bsync();
+    n_nbr_rows = ctl[6];
+    if (n_nbr_rows > A.row_cap) return HDSM_ROW_OVERFLOW;
+    return st;
   }
 
   // candidate sets of the root node: polytopes whose rows hold at the constant points (p_0, p_1, ...)
@@ -742,8 +955,8 @@ struct Solver {
           if (valid) {
             const int pos = cnt + __popc(m & lt);
             if (pos < stat_cap) {
-              double* r = rown + 4 * (n_nbr_rows + pos);
-              r[0] = n[0], r[1] = n[1], r[2] = n[2], r[3] = b;
+              double* r = rown + n_nbr_rows + pos;
+              r[0] = n[0], r[A.row_cap] = n[1], r[2 * A.row_cap] = n[2], r[3 * A.row_cap] = b;
             }
           }
           cnt += __popc(m);
@@ -758,80 +971,146 @@ struct Solver {
   // ---------------------------------------------------------------- K2: Mehrotra predictor-corrector
   // box row helpers: side 0 = upper (q <= hi), side 1 = lower (lo <= q); coefficient sign +1 / -1
   __device__ __forceinline__ double box_slack(int idx, int side, int a, int q) const {
-    return side == 0 ? T.qhi[a][q] - qv[idx] : qv[idx] - T.qlo[a][q];
+    return side == 0 ? sqhi[idx] - qv[idx] : qv[idx] - sqlo[idx];
   }
 
-  // LDL^T of Ks (lower part, in place), all threads of the block, one barrier per pivot.  Column j is
-  // kept unscaled (c_ij = L_ij d_j) while the trailing matrix is updated with c_ij c_kj / d_j, so no
-  // separate scaling pass (and no second barrier) is needed inside the loop.  A pivot that lost all its
-  // digits to cancellation (<= 1e-13 of the original diagonal) marks a direction the barrier function
-  // has pinned: the variable is frozen for this solve (1/d := 0) instead of aborting.  Only a
-  // non-positive / NaN original diagonal is a failure.  With four warps every thread keeps its <= PM
-  // (row, column) pairs in registers; with one warp the pairs come from the table.
-  // On exit both triangles hold the unit factor L_ik (at (i,k) and (k,i)) and invd[j] = 1/d_j, so the
-  // two solves have no multiply or divide on their critical path.
+  // LDL^T of Ks (lower part, in place), all threads of the block, one barrier per pivot - and, in the same
+  // sweep, the INVERSE of the unit factor, accumulated in the upper triangle, which the factorisation does not use:
+  // entry (k, i), k < i, ends up holding Linv[i][k].  Column j is kept unscaled (c_ij = L_ij d_j).  At step j the
+  // pair (i, k), k <= i, j < i, does exactly one of
+  //     j < k :  K[i][k]    -= c_ij c_kj / d_j            trailing matrix
+  //     j = k :  Linv[i][k]  = -c_ij / d_j                forward elimination applied to the identity
+  //     j > k :  Linv[i][k] -= (c_ij / d_j) Linv[j][k]
+  // and c_kj (lower triangle, j < k) and Linv[j][k] (upper triangle, j > k) are the SAME shared-memory word
+  // Ks[k][j]: one predicated multiply-add per pair and step whatever the case, so the inverse rides along at no
+  // extra latency (each thread holds its <= PM pairs in registers; one warp: pairs from the table).  With it the
+  // two triangular solves - 46 dependent shuffle + multiply-add steps on one warp - become two products that all
+  // threads share (solve_inplace).  A pivot that lost all its digits to cancellation (<= 1e-13 of the original
+  // diagonal) marks a direction the barrier function has pinned: the variable is frozen for this solve (1/d := 0)
+  // instead of aborting.  Only a non-positive / NaN original diagonal is a failure.
+  // Tried and measured slower on B200 (profiles/r3_experiments.md): skipping finished pair slots per warp (more
+  // branches than it saves), and the whole factorisation on one warp with the matrix in registers and columns by
+  // shuffle (5 k instructions of straight-line code per call: instruction fetch bound, 26 k cycles); every pair's
+  // running value in a register, stored only when another thread needs it (half the shared-memory traffic, but
+  // 226 k instead of 125 k cycles per agent in the factorisation: the conditional stores and selects cost more).
   static constexpr int PM = W == 1 ? 0 : (NW * (NW + 1) / 2 + NT - 1) / NT;
-  int pr_dst[PM > 0 ? PM : 1], pr_i[PM > 0 ? PM : 1], pr_k[PM > 0 ? PM : 1];
+  int pr_ik[PM > 0 ? PM : 1], pr_i[PM > 0 ? PM : 1], pr_k[PM > 0 ? PM : 1];
   __device__ __forceinline__ void init_pairs() {
 #pragma unroll
     for (int m = 0; m < PM; ++m) {
       const int t = tid + m * NT;
-      const int ik = t < NW * (NW + 1) / 2 ? tab[t] : 0, i = ik >> 8, kk = ik & 255;
-      pr_dst[m] = i * LD + kk, pr_i[m] = i * LD, pr_k[m] = kk * LD;
+      const int ik = t < NW * (NW + 1) / 2 ? tab[t] : 0, i = ik >> 8, kk = ik & 255;  // padding: pair (0, 0), never active
+      pr_ik[m] = ik, pr_i[m] = i * LD, pr_k[m] = kk * LD;
     }
   }
+  __device__ __forceinline__ void pair_step(int j, double inv, int i, int kk, int oi, int ok) {
+    const double l = Ks[oi + j] * inv;
+    if (j < kk) {
+      Ks[oi + kk] -= l * Ks[ok + j];
+    } else if (kk < i) {  // (a diagonal pair is finished once j reaches it)
+      const double old = j == kk ? 0.0 : Ks[ok + i], b = j == kk ? 1.0 : Ks[ok + j];
+      Ks[ok + i] = old - l * b;
+    }
+  }
+  bool fast_solve = true;  // set by factor(): no accepted pivot lost more than six digits (block-uniform)
   __device__ __forceinline__ bool factor() {
     bool ok = true;
+    fast_solve = true;
 #pragma unroll 1
-    for (int j = 0; j < NW; ++j) {
-      const double djj = Ks[j * LD + j], dor = diag0[j];
-      ok &= dor > 0.0;
-      const double inv = djj > 1e-13 * dor ? 1.0 / djj : 0.0;
-      if (tid == j) invd[j] = inv;
-      const int T_j = (NW - 1 - j) * (NW - j) / 2;
+    for (int j = 0; j < NW - 1; ++j) {
       if (W == 1) {
+        const double djj = Ks[j * LD + j], dor = diag0[j];
+        ok &= dor > 0.0;
+        const double inv = djj > 1e-13 * dor ? fast_rcp(djj) : 0.0;
+        fast_solve &= !(djj > 1e-13 * dor) || djj >= kFastPivot * dor;
+        if (tid == j) invd[j] = inv;
+        const int T_j = NW * (NW + 1) / 2 - (j + 1) * (j + 2) / 2;
 #pragma unroll 3
         for (int t = tid; t < T_j; t += NT) {
           const int ik = tab[t], i = ik >> 8, kk = ik & 255;
-          Ks[i * LD + kk] -= Ks[i * LD + j] * inv * Ks[kk * LD + j];
+          pair_step(j, inv, i, kk, i * LD, kk * LD);
         }
       } else {
+        // all loads of the thread's pairs in flight before the pivot's reciprocal is needed and before the first
+        // store: one shared-memory round trip per pivot instead of one per pair
+        constexpr int PA = PM > 0 ? PM : 1;
+        double a[PA], b[PA], old[PA];
+        int dst[PA];
 #pragma unroll
-        for (int m = 0; m < PM; ++m)
-          if (tid + m * NT < T_j) Ks[pr_dst[m]] -= Ks[pr_i[m] + j] * inv * Ks[pr_k[m] + j];
+        for (int m = 0; m < PM; ++m) {
+          const int i = pr_ik[m] >> 8, kk = pr_ik[m] & 255;
+          dst[m] = j < kk ? pr_i[m] + kk : pr_k[m] + i;
+          a[m] = b[m] = old[m] = 0.0;
+          if (j < i) a[m] = Ks[pr_i[m] + j], b[m] = Ks[pr_k[m] + j], old[m] = Ks[dst[m]];  // predicated: finished pairs cost no shared-memory bandwidth
+        }
+        const double djj = Ks[j * LD + j], dor = diag0[j];
+        ok &= dor > 0.0;
+        const double inv = djj > 1e-13 * dor ? fast_rcp(djj) : 0.0;
+        fast_solve &= !(djj > 1e-13 * dor) || djj >= kFastPivot * dor;
+        if (tid == j) invd[j] = inv;
+#pragma unroll
+        for (int m = 0; m < PM; ++m) {
+          const int i = pr_ik[m] >> 8, kk = pr_ik[m] & 255;
+          const double bb = j == kk ? 1.0 : b[m], oo = j == kk ? 0.0 : old[m];
+          const double r = oo - (a[m] * inv) * bb;
+          if (j < i) Ks[dst[m]] = r;
+        }
       }
       bsync();
     }
-    // unit factor in both triangles for the two solves
-    for (int t = tid; t < NW * (NW + 1) / 2; t += NT) {
-      const int ik = tab[t], i = ik >> 8, kk = ik & 255;
-      if (i != kk) {
-        const double l = Ks[i * LD + kk] * invd[kk];
-        Ks[i * LD + kk] = l;
-        Ks[kk * LD + i] = l;
-      }
+    {  // last pivot: nothing left to update
+      const double djj = Ks[(NW - 1) * LD + NW - 1], dor = diag0[NW - 1];
+      ok &= dor > 0.0;
+      fast_solve &= !(djj > 1e-13 * dor) || djj >= kFastPivot * dor;
+      if (tid == NW - 1) invd[NW - 1] = djj > 1e-13 * dor ? fast_rcp(djj) : 0.0;
     }
     bsync();
     return ok;
   }
-  // K x = v with K = L D L^T (unit L in both triangles), warp 0 only: v[NW] in shared memory is overwritten
-  __device__ __forceinline__ void solve_inplace(double* v) const {
-    if (wid == 0) {
+  // K x = v with K = L D L^T; v in shared memory is overwritten, `tmp` [NW] is scratch.
+  // Fast path: x = Linv^T D^-1 Linv v, two products with the inverse of the unit factor (upper triangle of Ks,
+  // see factor), TPR threads per row.  The explicit inverse is as accurate as substitution while the factor is
+  // well conditioned, and loses what the pivots lost beyond that: measured on the C port (ORC_LINLOG) the two
+  // differ by <= 5e-8 relative when every accepted pivot kept >= kFastPivot of its diagonal (94 % of all solves,
+  // iteration counts and statuses of 18 000 closed-loop solves identical to the Cholesky reference), and by up to
+  // 100 % below that - near convergence of a degenerate node, where the dual residual then stalls.  Those solves
+  // take the slow path: substitution on warp 0 with the unscaled columns of the lower triangle (backward stable).
+  __device__ __forceinline__ void solve_inplace(double* v, double* tmp) const {
+    if (fast_solve) {
+      const int row = tid / TPR, part = tid % TPR;
+      const bool act = row < NW;
+      double s = 0.0;
+      if (act) {
+#pragma unroll 2
+        for (int c = part; c < row; c += TPR) s += Ks[c * LD + row] * v[c];
+      }
+      s = tpr_sum(s);
+      if (act && part == 0) tmp[row] = (v[row] + s) * invd[row];
+      bsync();
+      s = 0.0;
+      if (act) {
+#pragma unroll 2
+        for (int i = row + 1 + part; i < NW; i += TPR) s += Ks[row * LD + i] * tmp[i];
+      }
+      s = tpr_sum(s);
+      if (act && part == 0) v[row] = tmp[row] + s;
+    } else if (wid == 0) {
+      const int me = lane < NW ? lane : 0;
       const double myinv = lane < NW ? invd[lane] : 0.0;
-      const double* myrow = Ks + (lane < NW ? lane : 0) * LD;
       double acc = lane < NW ? v[lane] : 0.0;
-#pragma unroll 6
-      for (int j = 0; j < NW - 1; ++j) {  // L z = rhs
-        const double zj = __shfl_sync(kFull, acc, j);
-        if (lane > j && lane < NW) acc -= myrow[j] * zj;
+#pragma unroll 4
+      for (int j = 0; j < NW - 1; ++j) {  // L z = v,  y = D^-1 z:  c_ij y_j = L_ij z_j
+        const double yj = __shfl_sync(kFull, acc * myinv, j);
+        if (lane > j && lane < NW) acc -= Ks[me * LD + j] * yj;
       }
-      acc *= myinv;  // y = D^-1 z
-#pragma unroll 6
-      for (int i = NW - 1; i > 0; --i) {  // L' x = y
-        const double xi = __shfl_sync(kFull, acc, i);
-        if (lane < i) acc -= myrow[i] * xi;
+      const double y = acc * myinv;
+      double sum = 0.0;
+#pragma unroll 4
+      for (int k = NW - 1; k > 0; --k) {  // L' x = y:  x_i = y_i - (1 / d_i) sum_{k > i} c_ki x_k
+        const double xk = __shfl_sync(kFull, y - myinv * sum, k);
+        if (lane < k) sum += Ks[k * LD + me] * xk;
       }
-      if (lane < NW) v[lane] = acc;
+      if (lane < NW) v[lane] = y - myinv * sum;
     }
     bsync();
   }
@@ -848,7 +1127,7 @@ struct Solver {
   };
   __device__ __forceinline__ static RowStep row_step(double s, double l, double slk, double cdw, double corr) {
     RowStep r;
-    const double rsl = 1.0 / (s * l);  // one division per row and pass
+    const double rsl = fast_rcp(s * l);  // one reciprocal per row and pass
     r.inv_s = l * rsl, r.inv_l = s * rsl;
     r.ds = -(s - slk) - cdw;
     r.dl = -l - (corr + l * r.ds) * r.inv_s;
@@ -863,19 +1142,19 @@ struct Solver {
     for (int c = 0; c < NZ; ++c) acc[c] = first ? T.Hw[ax][rr][c] : 0.0;
 #pragma unroll 1
     for (int q = q0; q < q1; ++q) {
-      const double f = DQ[ax * NQ + q] * T.EQ[ax][q][rr];
+      const double f = DQ[ax * NQ + q] * eq_row(ax, q)[rr];
 #pragma unroll
-      for (int c = 0; c < NZ; ++c) acc[c] += f * T.EQ[ax][q][c];
+      for (int c = 0; c < NZ; ++c) acc[c] += f * eq_row(ax, q)[c];
     }
     if (slots) {
       // symmetric 3x3 block stored as (00,01,02,11,12,22): entry (ax, b)
       const int mi = ax == b ? (ax == 0 ? 0 : ax == 1 ? 3 : 5) : (ax + b == 1 ? 1 : ax + b == 2 ? 2 : 4);
 #pragma unroll 1
       for (int slot = 0; slot < nkp; ++slot) {
-        const int kp = T.kp_of_slot[slot];
-        const double f = Mk[6 * slot + mi] * T.QP[ax][kp][rr];
+        const int kp = skp[slot];
+        const double f = Mk[6 * slot + mi] * qp_row(ax, kp)[rr];
 #pragma unroll
-        for (int c = 0; c < NZ; ++c) acc[c] += f * T.QP[b][kp][c];
+        for (int c = 0; c < NZ; ++c) acc[c] += f * qp_row(b, kp)[c];
       }
     }
   }
@@ -895,7 +1174,7 @@ struct Solver {
     int nrows = 0;
     for (int idx = tid; idx < NQ3; idx += NT) {
       const int a = idx / NQ, q = idx - a * NQ;
-      nrows += T.qconst[a][q] ? 0 : 2;
+      nrows += sqc[idx] ? 0 : 2;
     }
     if (tid < 2 * nkp) nrows += sege[tid] - segb[tid];
     double cnt4[4] = {(double)nrows, 0, 0, 0};
@@ -917,11 +1196,11 @@ struct Solver {
     double gm4[4] = {tid < NW ? fabs(g[tid]) : 0.0, 0, 0, 0};
     reduce4<1>(gm4);  // includes the barrier that publishes w
     const double gmax = gm4[0];
-    positions_of(T, w, pbar, p);
-    quantities_of(T, w, qbar, qv);
+    positions_of(w, pbar, p);
+    quantities_of(w, qbar, qv);
     bsync();
     {
-      const int kp = slot_of_thread < nkp ? T.kp_of_slot[slot_of_thread] : 0;
+      const int kp = slot_of_thread < nkp ? skp[slot_of_thread] : 0;
       const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
       for_my_rows([&](const double* r, double& s, double& l) {
         const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
@@ -932,8 +1211,8 @@ struct Solver {
 #pragma unroll 1
     for (int idx = tid; idx < NQ3; idx += NT) {
       const int a = idx / NQ, q = idx - a * NQ;
-      if (T.qconst[a][q]) continue;
-      const double sc = 0.05 * (T.qhi[a][q] - T.qlo[a][q]);
+      if (sqc[idx]) continue;
+      const double sc = 0.05 * (sqhi[idx] - sqlo[idx]);
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
         const double s = fmax(box_slack(idx, side, a, q), sc);
@@ -943,32 +1222,55 @@ struct Solver {
     bsync();
 
     tick(2);
+    // The step of one iteration is APPLIED at the top of the next one, in the same sweep over the rows that computes
+    // the next residuals: positions and box quantities are linear in w, so p + al dp and q + al dq are what
+    // positions_of / quantities_of of the new w would give, and neither a separate update sweep nor the two dense
+    // products and their barrier are needed.  (upd: a step is pending; al, smu and the two directions are those of
+    // the previous iteration.)
+    const int kp = slot_of_thread < nkp ? skp[slot_of_thread] : 0;
+    double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
+    double dx = 0, dy = 0, dz = 0, ex = 0, ey = 0, ez = 0, al = 0, smu = 0;
+    bool upd = false;
 #pragma unroll 1
     for (int it = 0;; ++it) {
-      const int kp = slot_of_thread < nkp ? T.kp_of_slot[slot_of_thread] : 0;
-      const double px = p[3 * kp], py = p[3 * kp + 1], pz = p[3 * kp + 2];
       tick(8);
-      // ---- pass 1: residuals and barrier blocks
+      // ---- (pending step, then) pass 1: residuals and barrier blocks
       double acc4[4] = {0, 0, 0, 0};  // mu, rcmax, lam.slack, sum lam
+      const double qx = upd ? px + al * ex : px, qy = upd ? py + al * ey : py, qz = upd ? pz + al * ez : pz;  // new positions
+      double p_own = 0.0;
+      if (upd && tid < K3) p_own = p[tid] + al * dpc[tid];
       {
         double m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, t0 = 0, t1 = 0, t2 = 0, f0 = 0, f1 = 0, f2 = 0;
         for_my_rows([&](const double* r, double& s, double& l) {
           const double nx = r[0], ny = r[1], nz = r[2];
-          const double slk = r[3] - (nx * px + ny * py + nz * pz);
-          const double rc = s - slk, d = l / s, t = d * rc;
+          if (upd) {
+            const double slk0 = r[3] - (nx * px + ny * py + nz * pz);
+            const double rc0 = s - slk0, inv_s = fast_rcp(s);
+            const double dsa = -rc0 - (nx * dx + ny * dy + nz * dz);
+            const double dla = -l - l * dsa * inv_s;
+            const double ds = -rc0 - (nx * ex + ny * ey + nz * ez);
+            const double dl = -l - ((dsa * dla - smu) + l * ds) * inv_s;
+            s += al * ds, l += al * dl;
+          }
+          const double slk = r[3] - (nx * qx + ny * qy + nz * qz);
+          const double rc = s - slk, d = l * fast_rcp(s), t = d * rc;
           acc4[0] += s * l, acc4[1] = fmax(acc4[1], fabs(rc)), acc4[2] += l * slk, acc4[3] += l;
           const double dx = d * nx, dy = d * ny, dz = d * nz;
           m0 += dx * nx, m1 += dx * ny, m2 += dx * nz, m3 += dy * ny, m4 += dy * nz, m5 += dz * nz;
           t0 += t * nx, t1 += t * ny, t2 += t * nz;
           f0 += l * nx, f1 += l * ny, f2 += l * nz;
         });
+        // twelve independent butterflies per step, inside the groups of lps lanes.  Every lane of the warp takes part
+        // (threads without a step carry zeros) so that the mask is the constant full one: with a run-time group mask
+        // the compiler guards every shuffle level with a MATCH.ANY / vote sequence
+        tick2(11);
+        for (int o = lps >> 1; o > 0; o >>= 1) {
+          m0 += __shfl_xor_sync(kFull, m0, o), m1 += __shfl_xor_sync(kFull, m1, o), m2 += __shfl_xor_sync(kFull, m2, o);
+          m3 += __shfl_xor_sync(kFull, m3, o), m4 += __shfl_xor_sync(kFull, m4, o), m5 += __shfl_xor_sync(kFull, m5, o);
+          t0 += __shfl_xor_sync(kFull, t0, o), t1 += __shfl_xor_sync(kFull, t1, o), t2 += __shfl_xor_sync(kFull, t2, o);
+          f0 += __shfl_xor_sync(kFull, f0, o), f1 += __shfl_xor_sync(kFull, f1, o), f2 += __shfl_xor_sync(kFull, f2, o);
+        }
         if (slot_of_thread < nkp) {
-          for (int o = lps >> 1; o > 0; o >>= 1) {  // twelve independent butterflies per step
-            m0 += __shfl_xor_sync(gmask, m0, o), m1 += __shfl_xor_sync(gmask, m1, o), m2 += __shfl_xor_sync(gmask, m2, o);
-            m3 += __shfl_xor_sync(gmask, m3, o), m4 += __shfl_xor_sync(gmask, m4, o), m5 += __shfl_xor_sync(gmask, m5, o);
-            t0 += __shfl_xor_sync(gmask, t0, o), t1 += __shfl_xor_sync(gmask, t1, o), t2 += __shfl_xor_sync(gmask, t2, o);
-            f0 += __shfl_xor_sync(gmask, f0, o), f1 += __shfl_xor_sync(gmask, f1, o), f2 += __shfl_xor_sync(gmask, f2, o);
-          }
           if (sub == 0) {
             double* M = Mk + 6 * slot_of_thread;
             M[0] = m0, M[1] = m1, M[2] = m2, M[3] = m3, M[4] = m4, M[5] = m5;
@@ -976,25 +1278,50 @@ struct Solver {
             Fk[3 * slot_of_thread] = f0, Fk[3 * slot_of_thread + 1] = f1, Fk[3 * slot_of_thread + 2] = f2;
           }
         }
+        tick2(12);
       }
 #pragma unroll 1
       for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         double dsum = 0, tsum = 0, fsum = 0;
-        if (!T.qconst[a][q]) {
-          const double irange = 1.0 / (T.qhi[a][q] - T.qlo[a][q]);
+        if (!sqc[idx]) {
+          const double irange = fast_rcp(sqhi[idx] - sqlo[idx]);
+          const double qold = qv[idx], qnew = upd ? qold + al * dqc[idx] : qold, dqa = upd ? dq[idx] : 0.0, dqb = upd ? dqc[idx] : 0.0;
 #pragma unroll
           for (int side = 0; side < 2; ++side) {
-            const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
-            const double rc = s - slk, d = l / s, sg = side == 0 ? 1.0 : -1.0;
+            const double sg = side == 0 ? 1.0 : -1.0;
+            double s = bs[2 * idx + side], l = bl[2 * idx + side];
+            if (upd) {
+              const double slk0 = side == 0 ? sqhi[idx] - qold : qold - sqlo[idx], inv_s = fast_rcp(s);
+              const double rc0 = s - slk0, dsa = -rc0 - sg * dqa, dla = -l - l * dsa * inv_s;
+              const double ds = -rc0 - sg * dqb;
+              const double dl = -l - ((dsa * dla - smu) + l * ds) * inv_s;
+              s += al * ds, l += al * dl;
+              bs[2 * idx + side] = s, bl[2 * idx + side] = l;
+            }
+            const double slk = side == 0 ? sqhi[idx] - qnew : qnew - sqlo[idx];
+            const double rc = s - slk, d = l * fast_rcp(s);
             acc4[0] += s * l, acc4[1] = fmax(acc4[1], fabs(rc) * irange), acc4[2] += l * slk, acc4[3] += l;
             dsum += d, tsum += sg * d * rc, fsum += sg * l;
           }
+          if (upd) qv[idx] = qnew;  // read and written by this thread only
         }
         DQ[idx] = dsum, TQ[idx] = tsum, FQ[idx] = fsum;
       }
+      if (upd && tid < NW) {  // nobody reads w or dwc in this phase
+        const double v = w[tid] + al * dwc[tid];
+        if (!isfinite(v)) acc4[1] = INFINITY;
+        w[tid] = v;
+      }
+      px = qx, py = qy, pz = qz;
       __syncwarp();
-      reduce4<2>(acc4);  // also the barrier that publishes Mk / Tk / Fk / DQ / TQ / FQ
+      tick2(13);
+      reduce4<2>(acc4);  // also the barrier that publishes Mk / Tk / Fk / DQ / TQ / FQ and w
+      if (upd && tid < K3) p[tid] = p_own;  // for publish(): every reader of p in here has it in registers, and the next barrier comes before any return
+      if (!(acc4[1] < INFINITY)) {  // a step produced a non-finite w
+        out.status = HDSM_NUMERICAL, out.iters = it > 0 ? it - 1 : 0;
+        return out;
+      }
       const double mu = acc4[0] * inv_m, rcmax = acc4[1], lamsl = acc4[2], lamsum = acc4[3];
 
       tick(3);
@@ -1005,12 +1332,12 @@ struct Solver {
         for (int c = part; c < NZ; c += TPR) hg += T.Hw[ax][rr][c] * w[ax * NZ + c];
 #pragma unroll 1
         for (int slot = part; slot < nkp; slot += TPR) {
-          const double qp = T.QP[ax][T.kp_of_slot[slot]][rr];
+          const double qp = qp_row(ax, skp[slot])[rr];
           fi += Fk[3 * slot + ax] * qp, ti += Tk[3 * slot + ax] * qp;
         }
 #pragma unroll 2
         for (int q = part; q < NQ; q += TPR) {
-          const double e = T.EQ[ax][q][rr];
+          const double e = eq_row(ax, q)[rr];
           fi += FQ[ax * NQ + q] * e, ti += TQ[ax * NQ + q] * e;
         }
       }
@@ -1118,12 +1445,12 @@ struct Solver {
 
       tick(6);
       // ---- predictor
-      solve_inplace(dw);
+      solve_inplace(dw, dwc);  // dwc is free until the corrector's right-hand side is written
       tick(7);
-      positions_of(T, dw, nullptr, dp);
-      quantities_of(T, dw, nullptr, dq);
+      positions_of(dw, nullptr, dp);
+      quantities_of(dw, nullptr, dq);
       bsync();
-      const double dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
+      dx = dp[3 * kp], dy = dp[3 * kp + 1], dz = dp[3 * kp + 2];
       tick(8);
       // largest relative decrease of any s or lam along the step: alpha_max = 1 / rmax
       double a4[4] = {0, 0, 0, 0};  // rmax, sum s.lam, sum (s dl + l ds), sum ds.dl
@@ -1136,7 +1463,7 @@ struct Solver {
 #pragma unroll 1
       for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
-        if (T.qconst[a][q]) continue;
+        if (sqc[idx]) continue;
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
@@ -1147,10 +1474,11 @@ struct Solver {
       }
       __syncwarp();
       reduce4<1>(a4);
+      tick2(14);
       const double alpha = a4[0] > 1.0 ? 1.0 / a4[0] : 1.0;
       const double mu_aff = fmax((a4[1] + alpha * a4[2] + alpha * alpha * a4[3]) * inv_m, 0.0);
       const double ratio = mu > 0 ? mu_aff / mu : 0.0;
-      const double smu = ratio * ratio * ratio * mu;
+      smu = ratio * ratio * ratio * mu;
 
       // ---- corrector right-hand side
       {
@@ -1161,17 +1489,16 @@ struct Solver {
           const double t = (l * (s - slk) - (e.ds * e.dl - smu)) * e.inv_s;
           t0 += t * r[0], t1 += t * r[1], t2 += t * r[2];
         });
-        if (slot_of_thread < nkp) {
-          for (int o = lps >> 1; o > 0; o >>= 1)
-            t0 += __shfl_xor_sync(gmask, t0, o), t1 += __shfl_xor_sync(gmask, t1, o), t2 += __shfl_xor_sync(gmask, t2, o);
-          if (sub == 0) Tk[3 * slot_of_thread] = t0, Tk[3 * slot_of_thread + 1] = t1, Tk[3 * slot_of_thread + 2] = t2;
-        }
+        for (int o = lps >> 1; o > 0; o >>= 1)  // all lanes, full mask (see pass 1)
+          t0 += __shfl_xor_sync(kFull, t0, o), t1 += __shfl_xor_sync(kFull, t1, o), t2 += __shfl_xor_sync(kFull, t2, o);
+        if (slot_of_thread < nkp && sub == 0)
+          Tk[3 * slot_of_thread] = t0, Tk[3 * slot_of_thread + 1] = t1, Tk[3 * slot_of_thread + 2] = t2;
       }
 #pragma unroll 1
       for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
         double tsum = 0;
-        if (!T.qconst[a][q]) {
+        if (!sqc[idx]) {
 #pragma unroll
           for (int side = 0; side < 2; ++side) {
             const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
@@ -1183,23 +1510,24 @@ struct Solver {
         TQ[idx] = tsum;
       }
       bsync();
+      tick2(15);
       double tc = 0;
       if (rowact) {
 #pragma unroll 1
-        for (int slot = part; slot < nkp; slot += TPR) tc += Tk[3 * slot + ax] * T.QP[ax][T.kp_of_slot[slot]][rr];
+        for (int slot = part; slot < nkp; slot += TPR) tc += Tk[3 * slot + ax] * qp_row(ax, skp[slot])[rr];
 #pragma unroll 2
-        for (int q = part; q < NQ; q += TPR) tc += TQ[ax * NQ + q] * T.EQ[ax][q][rr];
+        for (int q = part; q < NQ; q += TPR) tc += TQ[ax * NQ + q] * eq_row(ax, q)[rr];
       }
       tc = tpr_sum(tc);
       if (owner) dwc[row] = -hg - tc;
       bsync();
       tick(9);
-      solve_inplace(dwc);
+      solve_inplace(dwc, dw);  // the predictor direction lives on in dp / dq only
       tick(7);
-      positions_of(T, dwc, nullptr, dpc);
-      quantities_of(T, dwc, nullptr, dqc);
+      positions_of(dwc, nullptr, dpc);
+      quantities_of(dwc, nullptr, dqc);
       bsync();
-      const double ex = dpc[3 * kp], ey = dpc[3 * kp + 1], ez = dpc[3 * kp + 2];
+      ex = dpc[3 * kp], ey = dpc[3 * kp + 1], ez = dpc[3 * kp + 2];
 
       tick(8);
       // ---- step length of the combined direction
@@ -1215,7 +1543,7 @@ struct Solver {
 #pragma unroll 1
       for (int idx = tid; idx < NQ3; idx += NT) {
         const int a = idx / NQ, q = idx - a * NQ;
-        if (T.qconst[a][q]) continue;
+        if (sqc[idx]) continue;
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
           const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
@@ -1229,49 +1557,12 @@ struct Solver {
       }
       __syncwarp();
       reduce4<1>(m4);
+      tick2(14);
       // 0.97 of the way to the boundary: 0.995 leaves the blocking pair so far off the central path
       // that predictor and centring steps alternate without reducing mu on ~0.4% of the QPs
-      const double al = m4[0] > kStepFrac ? kStepFrac / m4[0] : 1.0;
-
-      // ---- update
-      for_my_rows([&](const double* r, double& s, double& l) {
-        const double slk = r[3] - (r[0] * px + r[1] * py + r[2] * pz);
-        const double rc = s - slk, inv_s = 1.0 / s;
-        const double dsa = -rc - (r[0] * dx + r[1] * dy + r[2] * dz);
-        const double dla = -l - l * dsa * inv_s;
-        const double ds = -rc - (r[0] * ex + r[1] * ey + r[2] * ez);
-        const double dl = -l - ((dsa * dla - smu) + l * ds) * inv_s;
-        s += al * ds, l += al * dl;
-      });
-#pragma unroll 1
-      for (int idx = tid; idx < NQ3; idx += NT) {
-        const int a = idx / NQ, q = idx - a * NQ;
-        if (T.qconst[a][q]) continue;
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-          const double s = bs[2 * idx + side], l = bl[2 * idx + side], slk = box_slack(idx, side, a, q);
-          const double sg = side == 0 ? 1.0 : -1.0, inv_s = 1.0 / s;
-          const double rc = s - slk, dsa = -rc - sg * dq[idx], dla = -l - l * dsa * inv_s;
-          const double ds = -rc - sg * dqc[idx];
-          const double dl = -l - ((dsa * dla - smu) + l * ds) * inv_s;
-          bs[2 * idx + side] = s + al * ds, bl[2 * idx + side] = l + al * dl;
-        }
-      }
-      double fin4[4] = {0, 0, 0, 0};
-      if (tid < NW) {
-        const double v = w[tid] + al * dwc[tid];
-        fin4[0] = isfinite(v) ? 0.0 : 1.0;
-        w[tid] = v;
-      }
-      reduce4<1>(fin4);  // also publishes w
-      if (fin4[0] > 0.0) {
-        out.status = HDSM_NUMERICAL, out.iters = it;
-        return out;
-      }
+      al = m4[0] > kStepFrac ? kStepFrac / m4[0] : 1.0;
+      upd = true;  // applied by the first sweep of the next iteration
       tick(9);
-      positions_of(T, w, pbar, p);
-      quantities_of(T, w, qbar, qv);
-      bsync();
     }
   }
 
@@ -1414,18 +1705,26 @@ struct Solver {
     const int width = min(max(A.width, 1), kMaxWidth);
     xch = rl + A.row_cap + (A.P * A.rmax + 7) / 8;
     unsigned char* pop = reinterpret_cast<unsigned char*>(xch + 2 * kMaxWidth * kMsgDoubles);  // [kMaxWidth][16] masks of the round
-    if (wid == 0) tick_start();
+    tick_init();
     load_and_index(agent);
     if (wid == 0) {
+      tick1(11);
       st = setup(agent);
       if (lane == 0) ctl[1] = st;
+      tick1(12);
     }
     bsync();
-    if (ctl[1] < 0) scan_neighbours(agent);  // uniform over the block
+    if (ctl[1] < 0) {  // uniform over the block
+      scan_neighbours(agent);
+      tick1(13);
+      const int sn = build_neighbour_rows(agent);
+      if (wid == 0) st = sn;
+    }
     if (wid == 0) {
-      if (st < 0) st = build_neighbour_rows(agent);
+      tick1(14);
       if (st < 0 && !root_sets(agent)) st = HDSM_INFEASIBLE;
       if (lane == 0) ctl[1] = st;
+      tick1(15);
     }
     bsync();
     if (ctl[1] < 0 && !(A.dbg & 1)) dominance_filter();  // uniform over the block
@@ -1655,7 +1954,7 @@ template <int N, int W>
 __global__ void __launch_bounds__(32 * W, W == 4 ? HDSM_MINBLOCKS : 1) hdsm_solve_kernel(const Tables* __restrict__ tables, const KernelArgs args) {
   extern __shared__ double smem[];
   // args.csize consecutive blocks (one thread-block cluster when csize > 1) work on one agent
-  const int slot = (int)blockIdx.x / args.csize, crank = (int)blockIdx.x - slot * args.csize;
+  const int lslot = (int)blockIdx.x / args.csize, crank = (int)blockIdx.x - lslot * args.csize, slot = lslot + args.slot0;
   if (slot >= args.n_local) return;
   const int agent = args.order ? args.order[slot] : slot;
   if (args.only_mask && !((args.only_mask >> (args.res[agent].status & 31)) & 1u)) return;

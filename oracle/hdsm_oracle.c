@@ -105,6 +105,64 @@ static void chol_solve(int n, const double *L, int lda, double *x) {
   }
 }
 
+/* Experiment knob (ORC_LINSOLVE=inv): the linear algebra the CUDA kernel uses since round 2 - right-looking
+ * LDL' that accumulates the inverse of the unit factor in the free upper triangle, the two triangular solves
+ * replaced by two products - run inside this port to measure, on the CPU, what the explicit inverse does to
+ * iteration counts and statuses before any GPU time is spent.  Default: the Cholesky above. */
+static __thread double g_minratio;
+static int ldlinv_factor(int n, double *A, int lda, double *invd) {
+  double d0[MAXNW];
+  for (int j = 0; j < n; j++) d0[j] = A[j * lda + j];
+  for (int j = 0; j < n; j++) {
+    const double djj = A[j * lda + j];
+    if (!(d0[j] > 0.0)) return 1;
+    const double inv = djj > 1e-13 * d0[j] ? 1.0 / djj : 0.0;
+    invd[j] = inv;
+    if (j == 0) g_minratio = 1.0;
+    if (inv > 0 && djj / d0[j] < g_minratio) g_minratio = djj / d0[j];
+    for (int i = j + 1; i < n; i++) {
+      const double lij = A[i * lda + j] * inv;
+      for (int k = 0; k <= i; k++) {
+        if (k == j) A[k * lda + i] = -lij;                           /* Linv[i][j] */
+        else if (k > j) A[i * lda + k] -= lij * A[k * lda + j];      /* trailing matrix */
+        else A[k * lda + i] -= lij * A[k * lda + j];                 /* Linv[i][k] -= L_ij Linv[j][k] */
+      }
+    }
+  }
+  return 0;
+}
+static void ldlinv_solve(int n, const double *A, int lda, const double *invd, double *x) {
+  double z[MAXNW];
+  for (int i = 0; i < n; i++) {
+    double v = x[i];
+    for (int c = 0; c < i; c++) v += A[c * lda + i] * x[c];
+    z[i] = v * invd[i];
+  }
+  for (int c = 0; c < n; c++) {
+    double v = z[c];
+    for (int i = c + 1; i < n; i++) v += A[c * lda + i] * z[i];
+    x[c] = v;
+  }
+}
+/* substitution on the same factor (lower triangle: unscaled columns c_ij = L_ij d_j) */
+static void ldlinv_solve_subst(int n, const double *A, int lda, const double *invd, double *x) {
+  double y[MAXNW];
+  for (int i = 0; i < n; i++) {
+    double v = x[i];
+    for (int j = 0; j < i; j++) v -= A[i * lda + j] * y[j];
+    y[i] = v * invd[i]; /* y = D^-1 z */
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double v = y[i];
+    for (int k = i + 1; k < n; k++) v -= A[k * lda + i] * invd[i] * x[k];
+    x[i] = v;
+  }
+}
+static int linsolve_inv(void) {
+  const char *e = getenv("ORC_LINSOLVE");
+  return e && !strcmp(e, "inv");
+}
+
 /* ModelODE restricted to one axis (agent_class.cpp:2155-2167): d/dt (p,v,a) = (v, a - c v, u) */
 static void ode_axis(const double s[3], double u, double c, double out[3]) {
   out[0] = s[1];
@@ -573,7 +631,9 @@ static void solve_qp(prob_t *pb, qp_out *out) {
           }
         }
     }
-    if (chol(nw, &K[0][0], MAXNW, 0)) {
+    double invd[MAXNW];
+    const int use_inv = linsolve_inv();
+    if (use_inv ? ldlinv_factor(nw, &K[0][0], MAXNW, invd) : chol(nw, &K[0][0], MAXNW, 0)) {
       out->status = ORC_NUMERICAL, out->iters = it, out->obj = INFINITY;
       return;
     }
@@ -586,7 +646,21 @@ static void solve_qp(prob_t *pb, qp_out *out) {
         for (int q = 0; q < nq; q++) v -= TQ[a][q] * T->EQ[a][q][r];
         dw[a * nz + r] = v;
       }
-    chol_solve(nw, &K[0][0], MAXNW, dw);
+    if (use_inv) {
+      if (getenv("ORC_LINLOG")) {
+        double xs[MAXNW], xi[MAXNW], dmax = 0, xmax = 0;
+        memcpy(xs, dw, sizeof(double) * nw), memcpy(xi, dw, sizeof(double) * nw);
+        ldlinv_solve_subst(nw, &K[0][0], MAXNW, invd, xs);
+        ldlinv_solve(nw, &K[0][0], MAXNW, invd, xi);
+        for (int i = 0; i < nw; i++) dmax = fmax(dmax, fabs(xs[i] - xi[i])), xmax = fmax(xmax, fabs(xs[i]));
+        FILE *f = fopen(getenv("ORC_LINLOG"), "a");
+        fprintf(f, "%d %.3e %.3e %.3e %.3e\n", it, mu, g_minratio, dmax / (xmax > 0 ? xmax : 1), rdmax / (1 + gmax));
+        fclose(f);
+      }
+      const char *thr = getenv("ORC_LINTHR");
+      if (thr && g_minratio < atof(thr)) ldlinv_solve_subst(nw, &K[0][0], MAXNW, invd, dw);
+      else ldlinv_solve(nw, &K[0][0], MAXNW, invd, dw);
+    } else chol_solve(nw, &K[0][0], MAXNW, dw);
     positions(pb, dw, dp, 0);
     quantities(pb, dw, dq, 0);
     double alpha = 1.0, s_sl = 0, s_x = 0, s_dd = 0;
@@ -647,7 +721,11 @@ static void solve_qp(prob_t *pb, qp_out *out) {
         for (int q = 0; q < nq; q++) v -= TQc[a][q] * T->EQ[a][q][r];
         dwc[a * nz + r] = v;
       }
-    chol_solve(nw, &K[0][0], MAXNW, dwc);
+    if (use_inv) {
+      const char *thr = getenv("ORC_LINTHR");
+      if (thr && g_minratio < atof(thr)) ldlinv_solve_subst(nw, &K[0][0], MAXNW, invd, dwc);
+      else ldlinv_solve(nw, &K[0][0], MAXNW, invd, dwc);
+    } else chol_solve(nw, &K[0][0], MAXNW, dwc);
     positions(pb, dwc, dpc, 0);
     quantities(pb, dwc, dqc, 0);
     /* final step length, then update */
