@@ -17,7 +17,12 @@ lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path
                                                           "multi_agent_pkgs_b200", "libhdsm.so")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, vals = rows[0], rows[2]
+LAUNCH = int(os.environ.get("LAUNCH", "0"))  # which profiled launch of the report (0 = first)
+hdr, vals = rows[0], rows[2 + LAUNCH]
+print("=" * 100)
+for name in ("Kernel Name", "Grid Size", "Block Size", "launch__cluster_dim_x"):
+    if name in hdr:
+        print(f"{name:70s} {vals[hdr.index(name)]}")
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
         "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -30,8 +35,9 @@ for i, h in enumerate(hdr):
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(sass)))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]  # one block per profiled launch
-end0 = starts[1] if len(starts) > 1 else len(rows)
-hdr, data = rows[starts[0] + 1], [r for r in rows[starts[0] + 2:end0] if len(r) == len(rows[starts[0] + 1])]
+s0 = starts[LAUNCH]
+end0 = starts[LAUNCH + 1] if len(starts) > LAUNCH + 1 else len(rows)
+hdr, data = rows[s0 + 1], [r for r in rows[s0 + 2:end0] if len(r) == len(rows[s0 + 1])]
 ix = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ix["# Samples"]]) for r in data)
 print("static instructions", len(data), "samples", tot)
