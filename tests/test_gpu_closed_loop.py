@@ -274,6 +274,36 @@ def test_single_warp_variant_gives_the_same_results():
         assert (np.abs(a["res"]["obj"][ok] - c["res"]["obj"][ok]) / np.maximum(1, np.abs(a["res"]["obj"][ok]))).max() <= 1e-9, kw
 
 
+def test_head_start_and_dispatch_order_never_change_a_result():
+    """From the second call on a large batch is solved in dispatch order (last call's iteration counts, longest first)
+    and the head of that order skips the first pass: a cluster launch on a second stream (HDSM_EARLY_DIV, default
+    n / 16).  Which launch solves an agent, and when, must not change a single bit of any output."""
+    sw = sc.config5_random(seed=23, n_rob=1536, side=120.0)
+    from oracle import c_oracle as co
+    for _ in range(2):
+        b = sw.make_batch()
+        r = co.solve_batch(b, max_nodes=64, width=4)
+        sw.advance(r["traj"], r["ctrl"], _ok(r["res"]))
+    b = sw.make_batch()
+    runs = {}
+    for div in ("0", "16", "4"):
+        os.environ["HDSM_EARLY_DIV"] = div
+        try:
+            pl = TrajectoryPlanner(sw.params, max_agents=b.n, max_neighbours=b.n, max_nodes=64, width=4)
+            runs[div] = [pl.solve_batch(b) for _ in range(3)]   # call 1: natural order; calls 2, 3: ordered (+ head start)
+            pl.close()
+        finally:
+            del os.environ["HDSM_EARLY_DIV"]
+    base = runs["0"][0]
+    assert (base["res"]["status"] == OPTIMAL).sum() > b.n // 2
+    for div, outs in runs.items():
+        for c, o in enumerate(outs):
+            for k in ("traj", "ctrl", "assign", "poly_used"):
+                assert np.array_equal(o[k], base[k]), (div, c, k)
+            for f in ("status", "nodes", "iters", "obj", "kkt_res"):
+                assert np.array_equal(o["res"][f], base["res"][f]), (div, c, f)
+
+
 def test_host_entry_point_rejects_bad_indices():
     sw = sc.config2_circle(n_swarms=1)
     b = sw.make_batch()

@@ -203,3 +203,29 @@ def test_fallback_shift():
     c = np.arange(30.0).reshape(10, 3)
     t2, c2 = o.fallback_shift(t, c)
     assert np.array_equal(t2[:-1], t[1:]) and np.array_equal(t2[-1], t[-1]) and np.array_equal(c2[-1], c[-1])
+
+
+def test_c_port_explicit_inverse_knob_agrees_with_cholesky():
+    """ORC_LINSOLVE=inv runs the linear algebra of the CUDA kernel inside the C port (LDL' with the inverse of the unit
+    factor accumulated on the side, two products instead of two triangular solves; ORC_LINTHR = the pivot threshold below
+    which it falls back to substitution, as the kernel does).  With the kernel's threshold the closed loop must end like
+    the Cholesky reference: same statuses and node counts, objectives to 1e-9."""
+    import os
+    from multi_agent_pkgs_b200 import scenarios as sc
+    from oracle import c_oracle as co
+    sw = sc.config5_random(seed=11, n_rob=200, side=50.0)
+    for step in range(4):
+        b = sw.make_batch()
+        ref = co.solve_batch(b, max_nodes=64)
+        os.environ["ORC_LINSOLVE"], os.environ["ORC_LINTHR"] = "inv", "1e-6"
+        try:
+            got = co.solve_batch(b, max_nodes=64)
+        finally:
+            del os.environ["ORC_LINSOLVE"], os.environ["ORC_LINTHR"]
+        assert np.array_equal(got["res"]["status"], ref["res"]["status"]), step
+        assert np.array_equal(got["res"]["nodes"], ref["res"]["nodes"]), step
+        ok = ref["res"]["status"] == 0
+        gap = np.abs(got["res"]["obj"][ok] - ref["res"]["obj"][ok]) / np.maximum(1, np.abs(ref["res"]["obj"][ok]))
+        assert gap.max() <= 1e-9, (step, gap.max())
+        st = ref["res"]["status"]
+        sw.advance(ref["traj"], ref["ctrl"], (st == 0) | ((st == 4) & np.isfinite(ref["res"]["obj"])))
