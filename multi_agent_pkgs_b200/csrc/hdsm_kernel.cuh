@@ -1,17 +1,20 @@
-// Batched trajectory optimisation for sm_100a: one agent per thread block (one warp).
+// Batched trajectory optimisation for sm_100a: one agent per thread block of four warps, or per cluster of such blocks.
 //
 // Replaces, per agent and per replanning step (multi_agent_planner/src/agent_class.cpp):
 //   K1  GenerateTimeAwareSafeCorridor  :1086-1215   inter-agent separating planes, built on device
 //   K2  SolveOptimizationProblem       :858-1023    + GRBModel::optimize :959  (primal-dual interior point)
-//   K3  the binaries b[k][p] / indicator rows :928-940  (exact branch and bound over candidate sets)
+//   K3  the binaries b[k][p] / indicator rows :928-940  (exact branch and bound over candidate sets, in rounds of
+//       independent nodes dealt to the blocks of a thread-block cluster)
 //   K4  PublishTrajectoryFull payload  :645-677     positions packed for the trajectory exchange
 //
-// Layout: every per-agent quantity lives in shared memory for the whole solve; HBM is touched once
-// for the inputs (coalesced per-agent blocks + the neighbour table, which is L2 resident) and once
-// for the outputs.  The 3(N-2)-square KKT matrix (the terminal equalities are eliminated by a
-// null-space basis, see hdsm_tables.h) is assembled, factorised (Cholesky) and solved by the warp
-// with one matrix row per lane held in registers.  FP64 throughout - the reference is double
-// (decomp_basis/data_type.h:50) and cond(K) reaches 1e14 near convergence.
+// Layout: every per-agent quantity lives in shared memory for the whole solve - rows, slacks, multipliers, the
+// 3(N-2)-square KKT matrix (the terminal equalities are eliminated by a null-space basis, see hdsm_tables.h) and copies
+// of the parameter tables the iterations walk; HBM is touched once for the inputs (coalesced per-agent blocks + the
+// neighbour table, which is L2 resident) and once for the outputs.  The KKT matrix is assembled with four threads per
+// row, factorised as LDL' with one block barrier per pivot in a sweep that also accumulates the inverse of the unit
+// factor, and the two systems of an iteration are solved as products with that inverse (substitution for
+// ill-conditioned factors).  FP64 throughout - the reference is double (decomp_basis/data_type.h:50) and cond(K)
+// reaches 1e14 near convergence.
 #pragma once
 #include <cuda_runtime.h>
 
