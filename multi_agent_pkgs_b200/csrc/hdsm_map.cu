@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -46,6 +47,7 @@ struct Args {
   size_t bits_bytes;                    // shared memory set aside for the occupancy bit rows
   const int2* pair_yz;                  // (dy, dz) and best value packed: x = dy | dz << 8 | best << 16, y unused
   const unsigned long long* pair_vals;  // eight int8 values, |dx| = 0..7
+  const int8_t* dist_tab;               // != null: the potential stencil is a function of the squared distance alone, [128] values (-128: none)
 };
 
 // ---- bulk asynchronous copies (TMA engine, sm_90+): one thread moves a whole grid between HBM and shared memory
@@ -70,9 +72,40 @@ __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// One axis of the exact squared-distance transform, in place: every entry of a column becomes the minimum over the
+// entries within +-RN of (old entry + offset^2), capped at 127.  A thread owns whole columns and carries the 2 RN + 1
+// old entries around its position in registers, so overwriting the column as it goes is safe.
+template <int RN>
+__device__ __forceinline__ void column_pass(uint8_t* q, int ncol, int inner, int outer_stride, int len, int stride, int tid) {
+  constexpr int kFar = 1000;
+  for (int c = tid; c < ncol; c += kThreads) {
+    uint8_t* col = q + (c % inner) + (size_t)(c / inner) * outer_stride;
+    int w[2 * RN + 1];
+#pragma unroll
+    for (int j = 0; j <= 2 * RN; ++j) w[j] = (j >= RN && j - RN < len) ? (int)col[(j - RN) * stride] : kFar;
+    for (int pos = 0; pos < len; ++pos) {
+      int best = kFar;
+#pragma unroll
+      for (int j = 0; j <= 2 * RN; ++j) best = min(best, w[j] + (j - RN) * (j - RN));
+      col[pos * stride] = (uint8_t)min(best, 127);
+#pragma unroll
+      for (int j = 0; j < 2 * RN; ++j) w[j] = w[j + 1];
+      w[2 * RN] = pos + RN + 1 < len ? (int)col[(pos + RN + 1) * stride] : kFar;
+    }
+  }
+}
+template <int RN>
+__device__ __forceinline__ void distance_passes(uint8_t* q, int dx, int dy, int dz, int tid) {
+  column_pass<RN>(q, dx * dz, dx, dx * dy, dy, dx, tid);  // along y: columns (x, z)
+  __syncthreads();
+  column_pass<RN>(q, dx * dy, dx * dy, 0, dz, dx * dy, tid);  // along z: columns (x, y)
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   extern __shared__ __align__(128) int8_t smem[];
   __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int8_t s_tab[128];
   const int g = blockIdx.x;
   if (g >= A.n_grids) return;
   const int dx = A.dims[3 * g], dy = A.dims[3 * g + 1], dz = A.dims[3 * g + 2];
@@ -87,6 +120,7 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   const int tid = threadIdx.x;
   for (int m = tid; m < A.n_inf; m += kThreads) st_inf[m] = reinterpret_cast<const int*>(A.inf_off)[m];
   for (int m = tid; m < A.n_pot; m += kThreads) st_pot[m] = reinterpret_cast<const int*>(A.pot_off)[m];
+  if (A.dist_tab && tid < 128) s_tab[tid] = A.dist_tab[tid];
   // ---- load: one bulk asynchronous copy of the whole grid (cp.async.bulk, completion on an mbarrier) where the grid
   // start allows it, issued by one thread while the others fetch the stencils; the last < 16 bytes by plain loads
   const bool bulk = (reinterpret_cast<size_t>(src) & 15) == 0 && (reinterpret_cast<size_t>(dst) & 15) == 0;
@@ -213,7 +247,49 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   // an 11-bit window, and because the value only falls with |dx| that one voxel decides the row.  Rows are
   // visited in order of their best value and the walk stops once no row can beat what the voxel already has.
   const bool rows_ok = A.n_pair > 0 && A.rn <= 7 && fits;
-  if (rows_ok) {
+  if (rows_ok && A.dist_tab) {
+    // Distance form.  Every stencil the reference's CreateMask produces is a non-increasing function of the Euclidean
+    // distance, cut off below (rn + 1) voxels (checked entry by entry when the handle is created): the largest value
+    // any occupied voxel offers is the table value at the squared distance to the NEAREST one.  That distance
+    // transform is separable and exact in integers: nearest occupied voxel along x from the bit rows (one window per
+    // voxel), then min over dy of (.. + dy^2) and min over dz of (.. + dz^2) down the columns - 2 rn + 2 row steps per
+    // voxel and axis instead of a walk over up to (2 rn + 1)^2 stencil rows.
+    for (int r = warp; r < dy * dz; r += nwarp)
+      for (int w = 0; w < nw; ++w) {
+        const int x = w * 32 + lane - 8;
+        const unsigned m = __ballot_sync(0xffffffffu, x >= 0 && x < dx && P[x + r * dx] == kOcc);
+        if (lane == 0) bits[r * nw + w] = m;
+      }
+    __syncthreads();
+    const int rn = A.rn;
+    const unsigned wmask = (1u << (2 * rn + 1)) - 1u, lmask = (1u << (rn + 1)) - 1u;
+    uint8_t* D = reinterpret_cast<uint8_t*>(Q);
+    for (int i = tid; i < nvox; i += kThreads) {
+      const int r = i / dx, x = i - r * dx;
+      const int bp = x - rn + 8;
+      const unsigned* row = bits + r * nw + (bp >> 5);
+      const unsigned win = (unsigned)((((unsigned long long)row[1] << 32) | row[0]) >> (bp & 31)) & wmask;
+      int d = 99;
+      const unsigned right = win >> rn, left = win & lmask;
+      if (right) d = __ffs(right) - 1;
+      if (left) d = min(d, rn - (31 - __clz(left)));
+      D[i] = (uint8_t)(d <= rn ? d * d : 127);
+    }
+    __syncthreads();
+    switch (rn) {
+      case 1: distance_passes<1>(D, dx, dy, dz, tid); break;
+      case 2: distance_passes<2>(D, dx, dy, dz, tid); break;
+      case 3: distance_passes<3>(D, dx, dy, dz, tid); break;
+      case 4: distance_passes<4>(D, dx, dy, dz, tid); break;
+      case 5: distance_passes<5>(D, dx, dy, dz, tid); break;
+      case 6: distance_passes<6>(D, dx, dy, dz, tid); break;
+      default: distance_passes<7>(D, dx, dy, dz, tid); break;
+    }
+    for (int i = tid; i < nvox; i += kThreads) {
+      const int v = P[i], val = s_tab[D[i]];
+      Q[i] = (int8_t)((v != kUnk && val > v) ? val : v);
+    }
+  } else if (rows_ok) {
     for (int r = warp; r < dy * dz; r += nwarp)
       for (int w = 0; w < nw; ++w) {
         const int x = w * 32 + lane - 8;
@@ -308,6 +384,7 @@ struct hdsm_map {
   int* d_irow = nullptr;
   int n_irow = 0, rn_inf = 0;
   unsigned long long* d_pvals = nullptr;
+  int8_t* d_tab = nullptr;  // distance form of the potential stencil (null: the stencil is not a function of the distance)
   int n_pair = 0, rn = 0;
   size_t bits_bytes = 0;
   unsigned char *d_buf = nullptr;
@@ -339,6 +416,7 @@ void hdsm_map_destroy(hdsm_map* h) {
   cudaFree(h->d_pair);
   cudaFree(h->d_irow);
   cudaFree(h->d_pvals);
+  cudaFree(h->d_tab);
   cudaFree(h->d_buf);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -358,6 +436,7 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
   // stencils: inflation (values unused), potential (entries of value 0 change nothing: dropped; sorted by value)
   std::vector<hdsm_mp::MaskEntry> inf = hdsm_mp::create_mask(p->voxel_size, p->inflation_dist, 1);
   std::vector<hdsm_mp::MaskEntry> pot = hdsm_mp::create_mask(p->voxel_size, p->potential_dist, (double)p->potential_pow);
+  const std::vector<hdsm_mp::MaskEntry> pot_full = pot;  // with the entries of value 0: the distance form below checks the whole mask
   pot.erase(std::remove_if(pot.begin(), pot.end(), [](const hdsm_mp::MaskEntry& e) { return e.v <= 0; }), pot.end());
   std::stable_sort(pot.begin(), pot.end(), [](const hdsm_mp::MaskEntry& a, const hdsm_mp::MaskEntry& b) { return a.v > b.v; });
   for (const auto& e : pot)
@@ -430,6 +509,44 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
     }
     h->n_pair = (int)rows.size();
   }
+  // distance form of the potential stencil: usable when the mask is a non-increasing function of x^2 + y^2 + z^2 that is
+  // complete inside the cube of half-width rn (every offset with a listed squared distance is in the mask, none after
+  // the first squared distance that is missing) - true for every mask CreateMask builds, verified here all the same
+  std::vector<int8_t> tab(128, (int8_t)-128);
+  bool dist_ok = h->rn >= 1 && h->rn <= 7 && !pot_full.empty() && !std::getenv("HDSM_MAP_NO_DIST");
+  for (const auto& e : pot_full) {
+    const int d2 = e.x * e.x + e.y * e.y + e.z * e.z;
+    if (!dist_ok) break;
+    if (d2 >= 127 || e.v == -128 || (tab[d2] != -128 && tab[d2] != e.v)) dist_ok = false;
+    else tab[d2] = e.v;
+  }
+  if (dist_ok) {
+    std::vector<char> present(128, 0), key(128, 0);
+    for (int x = -h->rn; x <= h->rn && dist_ok; ++x)
+      for (int y = -h->rn; y <= h->rn && dist_ok; ++y)
+        for (int z = -h->rn; z <= h->rn; ++z) {
+          const int d2 = x * x + y * y + z * z;
+          if (d2 >= 128) continue;  // beyond anything the table can hold: must not be in the mask (checked above)
+          key[d2] = 1;
+          bool in = false;
+          for (const auto& e : pot_full) in |= e.x == x && e.y == y && e.z == z;
+          if (in != (tab[d2] != -128)) {
+            dist_ok = false;
+            break;
+          }
+        }
+    int last = 127;
+    bool gone = false;
+    for (int d2 = 0; d2 < 128 && dist_ok; ++d2) {
+      if (!key[d2]) continue;
+      if (tab[d2] != -128) {
+        if (gone || tab[d2] > last) dist_ok = false;
+        last = tab[d2];
+      } else {
+        gone = true;
+      }
+    }
+  }
   smem += 4 + 4 * (size_t)((h->n_pair + 1) & ~1) + 8 * (size_t)h->n_pair;  // the row table (and its alignment slack)
   if (smem + 1024 < 227 * 1024) {  // whatever shared memory is left holds the bit rows
     h->bits_bytes = (227 * 1024 - 256 - smem) & ~size_t(15);  // 256 bytes stay free for the kernel's static shared memory (mbarrier)
@@ -448,6 +565,8 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
   if (e == cudaSuccess && h->n_pair) e = cudaMalloc(&h->d_pvals, pair_vals.size() * 8);
   if (e == cudaSuccess && h->n_pair) e = cudaMemcpy(h->d_pair, pair_yz.data(), pair_yz.size() * sizeof(int2), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && h->n_pair) e = cudaMemcpy(h->d_pvals, pair_vals.data(), pair_vals.size() * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && dist_ok) e = cudaMalloc(&h->d_tab, tab.size());
+  if (e == cudaSuccess && dist_ok) e = cudaMemcpy(h->d_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = hdsm::raise_smem_limit(hdsm_mp::map_kernel, device);
   if (e != cudaSuccess) {
     hdsm_map_destroy(h);
@@ -471,6 +590,7 @@ int hdsm_map_batch_device(hdsm_map* h, int n_grids, const int8_t* grids_in, cons
   a.in = grids_in, a.out = grids_out, a.dims = dims, a.inf_off = h->d_inf, a.pot_off = h->d_pot;
   a.n_pair = h->n_pair, a.rn = h->rn, a.pair_yz = h->d_pair, a.pair_vals = h->d_pvals, a.bits_bytes = h->bits_bytes;
   a.n_irow = h->n_irow, a.rn_inf = h->rn_inf, a.irow = h->d_irow;
+  a.dist_tab = h->d_tab;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   hdsm_mp::map_kernel<<<n_grids, hdsm_mp::kThreads, h->smem, s>>>(a);
   h->launches += 1;
