@@ -48,6 +48,7 @@ struct Args {
   const int2* pair_yz;                  // (dy, dz) and best value packed: x = dy | dz << 8 | best << 16, y unused
   const unsigned long long* pair_vals;  // eight int8 values, |dx| = 0..7
   const int8_t* dist_tab;               // != null: the potential stencil is a function of the squared distance alone, [128] values (-128: none)
+  int inf_cube;                         // 1: the inflation stencil is the full cube of half-width rn_inf
 };
 
 // ---- bulk asynchronous copies (TMA engine, sm_90+): one thread moves a whole grid between HBM and shared memory
@@ -151,10 +152,58 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
     const unsigned* row = bits + (yy + zz * dy) * nw + (bp >> 5);
     return (unsigned)((((unsigned long long)row[1] << 32) | row[0]) >> (bp & 31)) & ((1u << (2 * r + 1)) - 1u);
   };
+  // Dilation of a bit-packed voxel set by a cube of half-width r, one axis at a time (x inside the rows, y and z as
+  // ORs of whole words of neighbouring rows): a few word operations per thread where the gather form walks (2 r + 1)^2
+  // windows per voxel.  Needs a second set of bit rows; the result lands in bitsB.
+  const int nbw = nw * dy * dz;
+  const bool fits2 = (size_t)2 * nbw * 4 <= A.bits_bytes;
+  unsigned* bitsB = bits + nbw;
+  const auto dilate_cube = [&](int r) {
+    for (int idx = tid; idx < nbw; idx += kThreads) {  // x: bits -> bitsB
+      const int w = idx % nw;
+      const unsigned cur = bits[idx], lo = w > 0 ? bits[idx - 1] : 0u, hi = w < nw - 1 ? bits[idx + 1] : 0u;
+      unsigned o = cur;
+      for (int sft = 1; sft <= r; ++sft) o |= (cur << sft) | (lo >> (32 - sft)) | (cur >> sft) | (hi << (32 - sft));
+      bitsB[idx] = o;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nbw; idx += kThreads) {  // y: bitsB -> bits
+      const int w = idx % nw, row = idx / nw, y = row % dy, z = row / dy;
+      unsigned o = 0;
+      for (int yy = max(y - r, 0); yy <= min(y + r, dy - 1); ++yy) o |= bitsB[(yy + z * dy) * nw + w];
+      bits[idx] = o;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nbw; idx += kThreads) {  // z: bits -> bitsB
+      const int w = idx % nw, row = idx / nw, y = row % dy, z = row / dy;
+      unsigned o = 0;
+      for (int zz = max(z - r, 0); zz <= min(z + r, dz - 1); ++zz) o |= bits[(y + zz * dy) * nw + w];
+      bitsB[idx] = o;
+    }
+    __syncthreads();
+  };
+  const auto bit_of = [&](const unsigned* b, int row, int x) -> bool { return (b[row * nw + ((x + 8) >> 5)] >> ((x + 8) & 31)) & 1u; };
   // ---- SetUncertainToUnknown: P -> Q.  A voxel that is not occupied turns unknown when an unknown voxel of the
   // interior [c, dim - c) lies within the cube of half-width c around it.
   const int c = A.cube;
-  if (fits && c >= 1 && c <= 7) {
+  if (fits2 && c >= 1 && c <= 7) {
+    for (int r = warp; r < dy * dz; r += nwarp) {
+      const int y = r % dy, z = r / dy;
+      const bool row_in = y >= c && y < dy - c && z >= c && z < dz - c;
+      for (int w = 0; w < nw; ++w) {
+        const int x = w * 32 + lane - 8;
+        const unsigned m = __ballot_sync(0xffffffffu, row_in && x >= c && x < dx - c && P[x + r * dx] == kUnk);
+        if (lane == 0) bits[r * nw + w] = m;
+      }
+    }
+    __syncthreads();
+    dilate_cube(c);
+    for (int i = tid; i < nvox; i += kThreads) {
+      const int r = i / dx, x = i - r * dx;
+      const int8_t v = P[i];
+      Q[i] = (v != kOcc && bit_of(bitsB, r, x)) ? (int8_t)kUnk : v;
+    }
+  } else if (fits && c >= 1 && c <= 7) {
     for (int r = warp; r < dy * dz; r += nwarp) {
       const int y = r % dy, z = r / dy;
       const bool row_in = y >= c && y < dy - c && z >= c && z < dz - c;
@@ -201,7 +250,20 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   // ---- InflateObstacles: Q -> P.  A voxel becomes occupied when an occupied voxel (before the pass) has it in
   // its stencil: gather over the mirrored stencil - row form (per stencil row the largest |dx| it reaches), or
   // entry by entry.
-  if (fits && A.n_irow > 0 && A.rn_inf <= 7) {
+  if (fits2 && A.inf_cube && A.rn_inf >= 1 && A.rn_inf <= 7) {
+    for (int r = warp; r < dy * dz; r += nwarp)
+      for (int w = 0; w < nw; ++w) {
+        const int x = w * 32 + lane - 8;
+        const unsigned m = __ballot_sync(0xffffffffu, x >= 0 && x < dx && Q[x + r * dx] == kOcc);
+        if (lane == 0) bits[r * nw + w] = m;
+      }
+    __syncthreads();
+    dilate_cube(A.rn_inf);
+    for (int i = tid; i < nvox; i += kThreads) {
+      const int r = i / dx, x = i - r * dx;
+      P[i] = bit_of(bitsB, r, x) ? (int8_t)kOcc : Q[i];
+    }
+  } else if (fits && A.n_irow > 0 && A.rn_inf <= 7) {
     for (int r = warp; r < dy * dz; r += nwarp)
       for (int w = 0; w < nw; ++w) {
         const int x = w * 32 + lane - 8;
@@ -385,6 +447,7 @@ struct hdsm_map {
   int n_irow = 0, rn_inf = 0;
   unsigned long long* d_pvals = nullptr;
   int8_t* d_tab = nullptr;  // distance form of the potential stencil (null: the stencil is not a function of the distance)
+  int inf_cube = 0;         // the inflation stencil is the full cube of half-width rn_inf
   int n_pair = 0, rn = 0;
   size_t bits_bytes = 0;
   unsigned char *d_buf = nullptr;
@@ -480,6 +543,9 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
         if (reach >= 0) irow.push_back((dy & 0xff) | ((dz & 0xff) << 8) | (reach << 16));
       }
     h->n_irow = (int)irow.size();
+    // the full cube (true at the reference's default, inflation distance = voxel size): dilation by bit rows
+    const int side = 2 * h->rn_inf + 1;
+    h->inf_cube = (int)inf.size() == side * side * side && !std::getenv("HDSM_MAP_NO_DIST");
   }
   smem += 4 * (size_t)((h->n_irow + 3) & ~3);
   // row form of the potential stencil (used when the radius is at most 7 voxels and the bit rows fit)
@@ -590,7 +656,7 @@ int hdsm_map_batch_device(hdsm_map* h, int n_grids, const int8_t* grids_in, cons
   a.in = grids_in, a.out = grids_out, a.dims = dims, a.inf_off = h->d_inf, a.pot_off = h->d_pot;
   a.n_pair = h->n_pair, a.rn = h->rn, a.pair_yz = h->d_pair, a.pair_vals = h->d_pvals, a.bits_bytes = h->bits_bytes;
   a.n_irow = h->n_irow, a.rn_inf = h->rn_inf, a.irow = h->d_irow;
-  a.dist_tab = h->d_tab;
+  a.dist_tab = h->d_tab, a.inf_cube = h->inf_cube;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   hdsm_mp::map_kernel<<<n_grids, hdsm_mp::kThreads, h->smem, s>>>(a);
   h->launches += 1;
