@@ -8,11 +8,13 @@
 // hdsm_corridor_batch and hdsm_reftraj_batch read.
 //
 // Design.  A local grid (66 x 66 x 20 int8 = 87 KB) fits twice into the 227 KB of shared memory of one SM: the
-// block loads it once with 16-byte accesses, runs the three stencil passes ping-ponging between the two
-// copies, and writes the result once - HBM sees exactly one read and one write per voxel.  The reference
-// scatters from every occupied voxel; here every voxel gathers, which needs no atomics and is exact because
-// none of the three passes feeds on its own output (the potential stencil's only value of 100 is its centre).
-// The potential pass walks the stencil in order of decreasing value and stops at the first occupied hit.
+// block loads it once (one bulk asynchronous copy), runs the three passes ping-ponging between the two copies, and
+// writes the result once - HBM sees exactly one read and one write per voxel.  The reference scatters from every
+// occupied voxel; here every voxel gathers, which needs no atomics and is exact because none of the three passes
+// feeds on its own output (the potential stencil's only value of 100 is its centre).  All passes work on voxel sets
+// packed one bit per voxel along x.  The potential field is computed as an exact separable squared-distance transform
+// (the stencil is a function of the distance: verified on the host), unknown-space growth and the default 3x3x3
+// inflation as separable dilations of the bit rows; stencils of another shape keep the row / entry forms below.
 // The stencils are computed on the host when the handle is created, with the reference's formula.
 #include <cuda_runtime.h>
 
