@@ -77,12 +77,16 @@ __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
 
 // One axis of the exact squared-distance transform, in place: every entry of a column becomes the minimum over the
 // entries within +-RN of (old entry + offset^2), capped at 127.  A thread owns whole columns and carries the 2 RN + 1
-// old entries around its position in registers, so overwriting the column as it goes is safe.
-template <int RN>
-__device__ __forceinline__ void column_pass(uint8_t* q, int ncol, int inner, int outer_stride, int len, int stride, int tid) {
+// old entries around its position in registers, so overwriting the column as it goes is safe.  The last axis (FINAL)
+// writes the voxel's new value instead of the distance: the table value at that distance where it beats the value the
+// voxel has in `cur` (unknown voxels keep theirs).
+template <int RN, bool FINAL>
+__device__ __forceinline__ void column_pass(uint8_t* q, int ncol, int inner, int outer_stride, int len, int stride, int tid,
+                                            const int8_t* cur, const int8_t* tab) {
   constexpr int kFar = 1000;
   for (int c = tid; c < ncol; c += kThreads) {
-    uint8_t* col = q + (c % inner) + (size_t)(c / inner) * outer_stride;
+    const size_t base = (c % inner) + (size_t)(c / inner) * outer_stride;
+    uint8_t* col = q + base;
     int w[2 * RN + 1];
 #pragma unroll
     for (int j = 0; j <= 2 * RN; ++j) w[j] = (j >= RN && j - RN < len) ? (int)col[(j - RN) * stride] : kFar;
@@ -90,7 +94,13 @@ __device__ __forceinline__ void column_pass(uint8_t* q, int ncol, int inner, int
       int best = kFar;
 #pragma unroll
       for (int j = 0; j <= 2 * RN; ++j) best = min(best, w[j] + (j - RN) * (j - RN));
-      col[pos * stride] = (uint8_t)min(best, 127);
+      best = min(best, 127);
+      if (FINAL) {
+        const int v = cur[base + pos * stride], val = tab[best];
+        col[pos * stride] = (uint8_t)(int8_t)((v != kUnk && val > v) ? val : v);
+      } else {
+        col[pos * stride] = (uint8_t)best;
+      }
 #pragma unroll
       for (int j = 0; j < 2 * RN; ++j) w[j] = w[j + 1];
       w[2 * RN] = pos + RN + 1 < len ? (int)col[(pos + RN + 1) * stride] : kFar;
@@ -98,11 +108,10 @@ __device__ __forceinline__ void column_pass(uint8_t* q, int ncol, int inner, int
   }
 }
 template <int RN>
-__device__ __forceinline__ void distance_passes(uint8_t* q, int dx, int dy, int dz, int tid) {
-  column_pass<RN>(q, dx * dz, dx, dx * dy, dy, dx, tid);  // along y: columns (x, z)
+__device__ __forceinline__ void distance_passes(uint8_t* q, int dx, int dy, int dz, int tid, const int8_t* cur, const int8_t* tab) {
+  column_pass<RN, false>(q, dx * dz, dx, dx * dy, dy, dx, tid, cur, tab);  // along y: columns (x, z)
   __syncthreads();
-  column_pass<RN>(q, dx * dy, dx * dy, 0, dz, dx * dy, tid);  // along z: columns (x, y)
-  __syncthreads();
+  column_pass<RN, true>(q, dx * dy, dx * dy, 0, dz, dx * dy, tid, cur, tab);  // along z: columns (x, y), and the new values
 }
 
 __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
@@ -252,7 +261,8 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
   // ---- InflateObstacles: Q -> P.  A voxel becomes occupied when an occupied voxel (before the pass) has it in
   // its stencil: gather over the mirrored stencil - row form (per stencil row the largest |dx| it reaches), or
   // entry by entry.
-  if (fits2 && A.inf_cube && A.rn_inf >= 1 && A.rn_inf <= 7) {
+  const bool occ_bits_ready = fits2 && A.inf_cube && A.rn_inf >= 1 && A.rn_inf <= 7;  // bitsB will hold the occupancy after inflation
+  if (occ_bits_ready) {
     for (int r = warp; r < dy * dz; r += nwarp)
       for (int w = 0; w < nw; ++w) {
         const int x = w * 32 + lane - 8;
@@ -318,12 +328,20 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
     // transform is separable and exact in integers: nearest occupied voxel along x from the bit rows (one window per
     // voxel), then min over dy of (.. + dy^2) and min over dz of (.. + dz^2) down the columns - 2 rn + 2 row steps per
     // voxel and axis instead of a walk over up to (2 rn + 1)^2 stencil rows.
-    for (int r = warp; r < dy * dz; r += nwarp)
-      for (int w = 0; w < nw; ++w) {
-        const int x = w * 32 + lane - 8;
-        const unsigned m = __ballot_sync(0xffffffffu, x >= 0 && x < dx && P[x + r * dx] == kOcc);
-        if (lane == 0) bits[r * nw + w] = m;
+    if (occ_bits_ready) {  // the dilation that inflated the obstacles left their bit rows behind: cut to the grid's x range
+      for (int idx = tid; idx < nbw; idx += kThreads) {
+        const int w = idx % nw, lo = max(8, 32 * w), hi = min(dx + 8, 32 * w + 32);
+        const unsigned m = hi <= lo ? 0u : (hi - lo == 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u) << (lo - 32 * w));
+        bits[idx] = bitsB[idx] & m;
       }
+    } else {
+      for (int r = warp; r < dy * dz; r += nwarp)
+        for (int w = 0; w < nw; ++w) {
+          const int x = w * 32 + lane - 8;
+          const unsigned m = __ballot_sync(0xffffffffu, x >= 0 && x < dx && P[x + r * dx] == kOcc);
+          if (lane == 0) bits[r * nw + w] = m;
+        }
+    }
     __syncthreads();
     const int rn = A.rn;
     const unsigned wmask = (1u << (2 * rn + 1)) - 1u, lmask = (1u << (rn + 1)) - 1u;
@@ -341,17 +359,13 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const Args A) {
     }
     __syncthreads();
     switch (rn) {
-      case 1: distance_passes<1>(D, dx, dy, dz, tid); break;
-      case 2: distance_passes<2>(D, dx, dy, dz, tid); break;
-      case 3: distance_passes<3>(D, dx, dy, dz, tid); break;
-      case 4: distance_passes<4>(D, dx, dy, dz, tid); break;
-      case 5: distance_passes<5>(D, dx, dy, dz, tid); break;
-      case 6: distance_passes<6>(D, dx, dy, dz, tid); break;
-      default: distance_passes<7>(D, dx, dy, dz, tid); break;
-    }
-    for (int i = tid; i < nvox; i += kThreads) {
-      const int v = P[i], val = s_tab[D[i]];
-      Q[i] = (int8_t)((v != kUnk && val > v) ? val : v);
+      case 1: distance_passes<1>(D, dx, dy, dz, tid, P, s_tab); break;
+      case 2: distance_passes<2>(D, dx, dy, dz, tid, P, s_tab); break;
+      case 3: distance_passes<3>(D, dx, dy, dz, tid, P, s_tab); break;
+      case 4: distance_passes<4>(D, dx, dy, dz, tid, P, s_tab); break;
+      case 5: distance_passes<5>(D, dx, dy, dz, tid, P, s_tab); break;
+      case 6: distance_passes<6>(D, dx, dy, dz, tid, P, s_tab); break;
+      default: distance_passes<7>(D, dx, dy, dz, tid, P, s_tab); break;
     }
   } else if (rows_ok) {
     for (int r = warp; r < dy * dz; r += nwarp)
