@@ -326,6 +326,11 @@ typedef struct hdsm_map hdsm_map;
 
 /* grid_stride: voxels per grid slot; two copies must fit into shared memory (grid_stride <= 116 000). */
 int hdsm_map_create(const hdsm_map_params* params, int max_grids, size_t grid_stride, int device, hdsm_map** out);
+/* Host only, no device needed: the form of the potential stencil (CreateMask, voxel_grid.cpp:192-226) the kernel uses when
+ * the stencil is a function of the distance alone - tab128[d2] = value at squared voxel distance d2, -128 = not in the
+ * stencil.  Returns 1 if that form applies to these parameters (the kernel then computes the potential field as a
+ * squared-distance transform), 0 if the kernel keeps the stencil walk, < 0 on invalid arguments. */
+int hdsm_map_distance_table(const hdsm_map_params* params, int8_t* tab128);
 void hdsm_map_destroy(hdsm_map* h);
 const char* hdsm_map_last_error(const hdsm_map* h);
 int64_t hdsm_map_launch_count(const hdsm_map* h);

@@ -19,7 +19,7 @@ EXPORTS = ["hdsm_version", "hdsm_create", "hdsm_destroy", "hdsm_last_error", "hd
            "hdsm_reftraj_create", "hdsm_reftraj_destroy", "hdsm_reftraj_last_error", "hdsm_reftraj_launch_count",
            "hdsm_reftraj_batch", "hdsm_reftraj_batch_device",
            "hdsm_map_create", "hdsm_map_destroy", "hdsm_map_last_error", "hdsm_map_launch_count", "hdsm_map_batch",
-           "hdsm_map_batch_device",
+           "hdsm_map_batch_device", "hdsm_map_distance_table",
            "hdsm_sense_grid_dims", "hdsm_sense_create", "hdsm_sense_destroy", "hdsm_sense_last_error",
            "hdsm_sense_launch_count", "hdsm_sense_batch", "hdsm_sense_batch_device"]
 

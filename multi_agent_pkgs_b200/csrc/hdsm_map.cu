@@ -450,6 +450,45 @@ inline std::vector<MaskEntry> create_mask(double vox, double mask_dist, double p
   return m;
 }
 
+// Distance form of a stencil: tab[d2] = the value of every entry at squared distance d2 (-128: none).  Usable (returns
+// true) when the mask is a non-increasing function of x^2 + y^2 + z^2 that is complete inside the cube of half-width rn:
+// equal values at equal squared distances, every offset of the cube with a listed squared distance in the mask, and no
+// entry after the first squared distance of the cube that is missing - true for every mask CreateMask builds with
+// rn <= 7, verified here for the handle's own parameters all the same.  Pure host code.
+inline bool distance_table(const std::vector<MaskEntry>& mask, int rn, int8_t* tab) {
+  for (int i = 0; i < 128; ++i) tab[i] = (int8_t)-128;
+  if (rn < 1 || rn > 7 || mask.empty()) return false;
+  for (const auto& e : mask) {
+    const int d2 = e.x * e.x + e.y * e.y + e.z * e.z;
+    if (std::abs(e.x) > rn || std::abs(e.y) > rn || std::abs(e.z) > rn) return false;
+    if (d2 >= 127 || e.v == -128 || (tab[d2] != -128 && tab[d2] != e.v)) return false;  // 127 is the kernel's "farther than anything"
+    tab[d2] = e.v;
+  }
+  std::vector<char> key(128, 0);
+  for (int x = -rn; x <= rn; ++x)
+    for (int y = -rn; y <= rn; ++y)
+      for (int z = -rn; z <= rn; ++z) {
+        const int d2 = x * x + y * y + z * z;
+        if (d2 >= 128) continue;  // cannot be in the mask (checked above)
+        key[d2] = 1;
+        bool in = false;
+        for (const auto& e : mask) in |= e.x == x && e.y == y && e.z == z;
+        if (in != (tab[d2] != -128)) return false;
+      }
+  int last = 127;
+  bool gone = false;
+  for (int d2 = 0; d2 < 128; ++d2) {
+    if (!key[d2]) continue;
+    if (tab[d2] != -128) {
+      if (gone || tab[d2] > last) return false;
+      last = tab[d2];
+    } else {
+      gone = true;
+    }
+  }
+  return true;
+}
+
 }  // namespace hdsm_mp
 
 struct hdsm_map {
@@ -559,9 +598,12 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
         if (reach >= 0) irow.push_back((dy & 0xff) | ((dz & 0xff) << 8) | (reach << 16));
       }
     h->n_irow = (int)irow.size();
-    // the full cube (true at the reference's default, inflation distance = voxel size): dilation by bit rows
+    // the full cube, with or without its centre (an occupied voxel stays occupied either way; CreateMask leaves the
+    // centre out when the inflation distance equals the voxel size, the reference's default): dilation by bit rows
     const int side = 2 * h->rn_inf + 1;
-    h->inf_cube = (int)inf.size() == side * side * side && !std::getenv("HDSM_MAP_NO_DIST");
+    bool centre = false;
+    for (const auto& e : inf) centre |= e.x == 0 && e.y == 0 && e.z == 0;
+    h->inf_cube = (int)inf.size() + (centre ? 0 : 1) == side * side * side && !std::getenv("HDSM_MAP_NO_DIST");
   }
   smem += 4 * (size_t)((h->n_irow + 3) & ~3);
   // row form of the potential stencil (used when the radius is at most 7 voxels and the bit rows fit)
@@ -591,44 +633,9 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
     }
     h->n_pair = (int)rows.size();
   }
-  // distance form of the potential stencil: usable when the mask is a non-increasing function of x^2 + y^2 + z^2 that is
-  // complete inside the cube of half-width rn (every offset with a listed squared distance is in the mask, none after
-  // the first squared distance that is missing) - true for every mask CreateMask builds, verified here all the same
+  // distance form of the potential stencil (see hdsm_mp::distance_table)
   std::vector<int8_t> tab(128, (int8_t)-128);
-  bool dist_ok = h->rn >= 1 && h->rn <= 7 && !pot_full.empty() && !std::getenv("HDSM_MAP_NO_DIST");
-  for (const auto& e : pot_full) {
-    const int d2 = e.x * e.x + e.y * e.y + e.z * e.z;
-    if (!dist_ok) break;
-    if (d2 >= 127 || e.v == -128 || (tab[d2] != -128 && tab[d2] != e.v)) dist_ok = false;
-    else tab[d2] = e.v;
-  }
-  if (dist_ok) {
-    std::vector<char> present(128, 0), key(128, 0);
-    for (int x = -h->rn; x <= h->rn && dist_ok; ++x)
-      for (int y = -h->rn; y <= h->rn && dist_ok; ++y)
-        for (int z = -h->rn; z <= h->rn; ++z) {
-          const int d2 = x * x + y * y + z * z;
-          if (d2 >= 128) continue;  // beyond anything the table can hold: must not be in the mask (checked above)
-          key[d2] = 1;
-          bool in = false;
-          for (const auto& e : pot_full) in |= e.x == x && e.y == y && e.z == z;
-          if (in != (tab[d2] != -128)) {
-            dist_ok = false;
-            break;
-          }
-        }
-    int last = 127;
-    bool gone = false;
-    for (int d2 = 0; d2 < 128 && dist_ok; ++d2) {
-      if (!key[d2]) continue;
-      if (tab[d2] != -128) {
-        if (gone || tab[d2] > last) dist_ok = false;
-        last = tab[d2];
-      } else {
-        gone = true;
-      }
-    }
-  }
+  const bool dist_ok = !std::getenv("HDSM_MAP_NO_DIST") && hdsm_mp::distance_table(pot_full, h->rn, tab.data());
   smem += 4 + 4 * (size_t)((h->n_pair + 1) & ~1) + 8 * (size_t)h->n_pair;  // the row table (and its alignment slack)
   if (smem + 1024 < 227 * 1024) {  // whatever shared memory is left holds the bit rows
     h->bits_bytes = (227 * 1024 - 256 - smem) & ~size_t(15);  // 256 bytes stay free for the kernel's static shared memory (mbarrier)
@@ -656,6 +663,12 @@ int hdsm_map_create(const hdsm_map_params* p, int max_grids, size_t grid_stride,
   }
   *out = h;
   return HDSM_OK;
+}
+
+int hdsm_map_distance_table(const hdsm_map_params* p, int8_t* tab128) {
+  if (!p || !tab128 || !(p->voxel_size > 0) || p->potential_dist < 0) return HDSM_ERR_INVALID;
+  const int rn = p->potential_dist > 0 ? (int)std::ceil(p->potential_dist / p->voxel_size) : 0;
+  return hdsm_mp::distance_table(hdsm_mp::create_mask(p->voxel_size, p->potential_dist, (double)p->potential_pow), rn, tab128) ? 1 : 0;
 }
 
 const char* hdsm_map_last_error(const hdsm_map* h) { return h ? h->err.c_str() : "null handle"; }

@@ -48,3 +48,80 @@ def test_process_properties():
     assert out[known_free].min() >= 0 and out[known_free].max() < 100 and (out[known_free] > 0).any()
     again = om.c_process(out, 0.3, 0.0, 0.0, 4)                      # no inflation, no potential: identity
     assert np.array_equal(again, out)
+
+
+def _distance_transform_potential(g, tab, rn):
+    """The kernel's potential pass in NumPy: squared distance to the nearest occupied voxel by three one-axis passes with
+    windows of +-rn (capped at 127 like the kernel's bytes), then the table."""
+    occ = g == 100
+    Z, Y, X = g.shape
+    far = 10000
+
+    def shifted(a, d, axis, fill):
+        out = np.full(a.shape, fill, a.dtype)
+        n = a.shape[axis]
+        if abs(d) >= n:
+            return out
+        src = [slice(None)] * 3
+        dst = [slice(None)] * 3
+        src[axis] = slice(0, n - d) if d >= 0 else slice(-d, n)
+        dst[axis] = slice(d, n) if d >= 0 else slice(0, n + d)
+        out[tuple(dst)] = a[tuple(src)]
+        return out
+
+    g1 = np.full(g.shape, far, int)
+    for d in range(-rn, rn + 1):
+        g1 = np.where(shifted(occ, d, 2, False), np.minimum(g1, d * d), g1)
+    g1 = np.minimum(g1, 127)
+    for axis in (1, 0):
+        nxt = np.full(g.shape, far, int)
+        for d in range(-rn, rn + 1):
+            nxt = np.minimum(nxt, shifted(g1, d, axis, far) + d * d)
+        g1 = np.minimum(nxt, 127)
+    val = tab[g1].astype(int)
+    out = g.astype(int)
+    upd = (g != -1) & (val > out)
+    out[upd] = val[upd]
+    return out.astype(np.int8)
+
+
+def test_distance_table_and_the_distance_transform_form_of_the_potential_field():
+    """hdsm_map_distance_table (host code of the library, no device needed) against the checker's stencil, and the
+    algorithm the kernel runs with it - an exact separable squared-distance transform - against the checker's potential
+    pass: byte for byte, grids with pre-existing values and unknown voxels included."""
+    import ctypes as C
+    from multi_agent_pkgs_b200 import _lib
+
+    class MapParams(C.Structure):
+        _fields_ = [("voxel_size", C.c_double), ("inflation_dist", C.c_double), ("potential_dist", C.c_double),
+                    ("potential_pow", C.c_int32), ("reserved", C.c_int32)]
+
+    L = _lib.load(build=False)
+    L.hdsm_map_distance_table.restype = C.c_int
+    rng = np.random.default_rng(5)
+    # (0.3, 2.1): radius of 8 voxels, beyond the kernel's windows; (0.3, 0.3): CreateMask leaves the centre out when the
+    # distance equals the voxel size, so the mask is not complete from distance 0 on - both keep the stencil walk
+    for vox, pot, pw, expect in ((0.3, 1.5, 4, 1), (0.2, 0.9, 2, 1), (0.3, 1.5, 1, 1), (0.25, 1.0, 3, 1), (0.3, 2.1, 2, 0), (0.3, 0.3, 1, 0)):
+        tab = np.zeros(128, np.int8)
+        prm = MapParams(vox, 0.3, pot, pw, 0)
+        ok = L.hdsm_map_distance_table(C.byref(prm), tab.ctypes.data_as(C.c_void_p))
+        rn = int(np.ceil(pot / vox))
+        assert ok == expect, (vox, pot, pw)
+        if not ok:
+            continue
+        off, val = om.c_mask(vox, pot, pw)
+        d2 = (off.astype(int) ** 2).sum(1)
+        assert np.array_equal(tab[d2], val)                                   # every stencil entry is its table value
+        assert set(np.nonzero(tab != -128)[0]) == set(d2.tolist())             # and nothing else is in the table
+        for shape in ((20, 66, 66), (12, 30, 41), (7, 9, 8)):
+            g = np.zeros((4,) + shape, np.int8)
+            g[rng.random(g.shape) < 0.02] = 100
+            g[rng.random(g.shape) < 0.03] = -1
+            g[1][:] = 0
+            g[2][:] = 100
+            g[3][rng.random(shape) < 0.3] = 37
+            want = om.c_process(g, vox, 0.0, pot, pw)                        # inflation 0: the potential pass alone
+            got = np.stack([_distance_transform_potential(x, tab, rn) for x in g])
+            assert np.array_equal(got, want), (vox, pot, pw, shape)
+    prm = MapParams(0.3, 0.3, 0.0, 4, 0)
+    assert L.hdsm_map_distance_table(C.byref(prm), np.zeros(128, np.int8).ctypes.data_as(C.c_void_p)) == 0   # no stencil
