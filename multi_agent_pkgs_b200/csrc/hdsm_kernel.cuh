@@ -1175,10 +1175,7 @@ struct Solver {
     init_groups();
     init_pairs();
     int nrows = 0;
-    for (int idx = tid; idx < NQ3; idx += NT) {
-      const int a = idx / NQ, q = idx - a * NQ;
-      nrows += sqc[idx] ? 0 : 2;
-    }
+    for (int idx = tid; idx < NQ3; idx += NT) nrows += sqc[idx] ? 0 : 2;
     if (tid < 2 * nkp) nrows += sege[tid] - segb[tid];
     double cnt4[4] = {(double)nrows, 0, 0, 0};
     reduce4<0>(cnt4);
@@ -1285,7 +1282,6 @@ struct Solver {
       }
 #pragma unroll 1
       for (int idx = tid; idx < NQ3; idx += NT) {
-        const int a = idx / NQ, q = idx - a * NQ;
         double dsum = 0, tsum = 0, fsum = 0;
         if (!sqc[idx]) {
           const double irange = fast_rcp(sqhi[idx] - sqlo[idx]);
