@@ -303,7 +303,10 @@ int hdsm_create(const hdsm_params* params, int max_agents, int max_neighbours, i
     if ((e = cudaStreamCreateWithPriority(&h->stream_early, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(e, "stream_early");
     if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
-    if (const char* ev = std::getenv("HDSM_EARLY_DIV")) h->early_div = std::max(0, std::atoi(ev));
+    if (const char* ev = std::getenv("HDSM_EARLY_DIV")) {  // 0: no head start; otherwise at least 2 (the first pass keeps half of the batch)
+      const int v = std::atoi(ev);
+      h->early_div = v <= 0 ? 0 : std::max(2, v);
+    }
   }
   for (int c = 0; c < kMaxChunks; ++c)
     if ((e = cudaEventCreate(&h->ev_chunk[c])) != cudaSuccess || (e = cudaEventCreate(&h->ev_begin[c])) != cudaSuccess)
